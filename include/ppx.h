@@ -1,0 +1,236 @@
+/* ppx.h -- C ABI of libppx.so: the B200 (sm_100a) learner hot path of BoogaQ/PPO-exploration.
+ *
+ * The reference is pure Python (no FFI of its own); each entry point below names the
+ * reference method (file:line under /root/reference) whose arithmetic it replaces.  The Python
+ * package `ppo-exploration_b200` binds these with ctypes and mirrors the reference's class surface.
+ *
+ * Conventions
+ *   - every function returns 0 (PPX_OK) or a negative PPX_ERR_*; ppx_last_error() gives the
+ *     thread-local message.  Nothing is printed, no exception crosses the boundary.
+ *   - all data pointers are DEVICE pointers borrowed for the duration of the call (never freed,
+ *     never retained) unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, the caller syncs.
+ *   - rollout arrays are time-major [T,N,...] row-major exactly as buffer.py:153-161 allocates them;
+ *     "flat index i" means the env-major flatten of buffer.py:49-52: (t, n) = (i % T, i / T).
+ *   - weights of dense layers are stored IN-MAJOR: W[K_in][N_out] (transpose of torch's Linear.weight).
+ */
+#ifndef PPX_H_
+#define PPX_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPX_OK 0
+#define PPX_ERR_ARG (-1)
+#define PPX_ERR_CUDA (-2)
+#define PPX_ERR_CAPACITY (-3)
+#define PPX_ERR_UNSUPPORTED (-4)
+
+enum { PPX_ACT_NONE = 0, PPX_ACT_TANH = 1, PPX_ACT_LEAKY_RELU = 2, PPX_ACT_ELU = 3 };
+
+const char* ppx_last_error(void);
+int ppx_version(void);
+/* kernels launched by this library in this process (bench.py's gpu_launches) */
+uint64_t ppx_launch_count(void);
+int ppx_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- reverse scans ------------- */
+/* RolloutStorage.compute_returns_and_advantages, buffer.py:203-230.
+ * masks[t] is the `dones` stored by add() at step t (buffer.py:180); step t is cut by masks[t+1]
+ * and the last step by last_done (buffer.py:221-226).  f64 carry, f32 store. */
+int ppx_gae(const float* rewards, const float* values, const uint8_t* masks, const float* last_value,
+            const uint8_t* last_done, double gamma, double lam, int T, int N, float* advantages,
+            float* returns, void* stream);
+/* IntrinsicStorage.compute_returns_and_advantages, buffer.py:321-362: the extrinsic head as above
+ * plus the non-episodic intrinsic head (no terminal masking, its own gamma, same lambda). */
+int ppx_gae_dual(const float* rewards, const float* values, const uint8_t* masks, const float* last_value,
+                 const uint8_t* last_done, double gamma, double lam, const float* int_rewards,
+                 const float* int_values, const float* last_int_value, double int_gamma, int T, int N,
+                 float* advantages, float* returns, float* int_advantages, float* int_returns,
+                 void* stream);
+/* SilModule.discount_with_dones, sil_module.py:99-105: R_t = r_t + gamma*R_{t+1}*(1-done_t), per column. */
+int ppx_discount(const double* rewards, const uint8_t* dones, double gamma, int T, int N, double* out,
+                 void* stream);
+
+/* ---------------------------------------------------------------- SimHash ------------------- */
+/* bits of RolloutStorage.sim_hash, buffer.py:194: code bit b = (A[b,:] . obs[i,:] > 0), f64 dot.
+ * A is [k,D] f64 row-major, k <= 64. */
+int ppx_simhash_codes(const double* A, const float* obs, int k, int D, int64_t n, uint64_t* codes,
+                      void* stream);
+
+typedef struct ppx_count_table ppx_count_table;
+/* the persistent count_table of buffer.py:136 as an open-addressing device table (linear probing,
+ * 64-bit atomicCAS claim, 32-bit counts).  capacity is rounded up to a power of two. */
+int ppx_count_table_create(uint64_t capacity, ppx_count_table** out);
+int ppx_count_table_destroy(ppx_count_table* t);
+int ppx_count_table_clear(ppx_count_table* t, void* stream);
+/* buffer.py:197-198 on packed codes: counts_out[i] = count of codes[i] AFTER its own increment,
+ * with the reference's sequential semantics (element i sees every j < i of this and earlier calls).
+ * Returns PPX_ERR_CAPACITY (after syncing the stream) if the table filled up. */
+int ppx_count_table_update(ppx_count_table* t, const uint64_t* codes, int64_t n, uint32_t* counts_out,
+                           void* stream);
+/* whole sim_hash(obs, rewards), buffer.py:188-200, fused: codes from obs, sequential count update,
+ * rewards[i] += beta/sqrt(count_i) (bonus in f64, stored back in the dtype of `rewards`).
+ * obs is [n,D]; pass n = T*N with a [T,N,D] rollout to apply the bonus post hoc in the reference's
+ * t-major, env-minor order.  codes_out / counts_out may be NULL. */
+int ppx_simhash_update(ppx_count_table* t, const double* A, const float* obs, int k, int D, int64_t n,
+                       double beta, void* rewards_inout, int rewards_are_f64, uint64_t* codes_out,
+                       uint32_t* counts_out, void* stream);
+/* buffer.py:199 alone, from precomputed counts (multi-GPU path: counts come from gathered codes). */
+int ppx_simhash_bonus(const uint32_t* counts, int64_t n, double beta, void* rewards_inout,
+                      int rewards_are_f64, void* stream);
+/* synchronous helpers (tests / checkpointing): number of distinct keys; dump of (key,count) pairs. */
+int ppx_count_table_size(ppx_count_table* t, uint64_t* n_keys_host);
+int ppx_count_table_dump(ppx_count_table* t, uint64_t* keys_dev, uint32_t* counts_dev, uint64_t max_out,
+                         uint64_t* n_out_host);
+
+/* ---------------------------------------------------------------- shuffle-gather ------------ */
+/* RolloutStorage._get_samples, buffer.py:256-267 / :384-394, without materialising the env-major
+ * flatten: for each array a, dst_a[b,:] = src_a[(idx[b] % T) * N + idx[b] / T, :] (row_bytes[a] each).
+ * Up to PPX_MAX_GATHER arrays per launch. */
+#define PPX_MAX_GATHER 12
+int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
+                         int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream);
+/* mean and unbiased std of a contiguous f32 vector, accumulated in f64 (advantages.mean()/.std(),
+ * algorithms.py:219).  out[0]=mean, out[1]=std(ddof=1). */
+int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream);
+
+/* ---------------------------------------------------------------- dense layers (fp32) ------- */
+/* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.
+ * Strides (in elements) step X/W/bias/Y per batch entry; batch=1 ignores them.
+ * Replaces the nn.Linear+activation stacks of models.py:141-150, 220-234, 281-291. */
+int ppx_linear_fwd(const float* X, int ldx, const float* W, const float* bias, int M, int K, int N, int act,
+                   float* Y, int ldy, int batch, int64_t strideX, int64_t strideW, int64_t strideB,
+                   int64_t strideY, void* stream);
+/* dX[z] = (dY[z] @ W[z]^T) * act'(H[z]) where H is the post-activation output of the layer that
+ * produced X (NULL / PPX_ACT_NONE: no derivative factor). */
+int ppx_linear_bwd_data(const float* dY, int lddy, const float* W, int M, int K, int N, const float* H,
+                        int ldh, int act, float* dX, int lddx, int batch, int64_t strideDY, int64_t strideW,
+                        int64_t strideH, int64_t strideDX, void* stream);
+/* dW[z] = X[z]^T @ dY[z] ([K,N]), dbias[z] = colsum(dY[z]).  Deterministic split-M reduction through
+ * `workspace` (>= ppx_linear_bwd_weight_workspace(...) floats). */
+int64_t ppx_linear_bwd_weight_workspace(int M, int K, int N, int batch);
+int ppx_linear_bwd_weight(const float* X, int ldx, const float* dY, int lddy, int M, int K, int N, float* dW,
+                          float* dbias, float* workspace, int batch, int64_t strideX, int64_t strideDY,
+                          int64_t strideDW, int64_t strideDB, void* stream);
+
+/* ---------------------------------------------------------------- PPO loss ------------------ */
+/* Fused clipped-surrogate / clipped-value / entropy loss, forward and backward, for one minibatch:
+ * PPO.train algorithms.py:219-238, PPO_RND.train :431-460 (dual=1), PPO_ICM.train :670-692 (the
+ * policy_weight factor).  Inputs are the network outputs for the minibatch and the gathered sample
+ * fields; outputs are the gradients w.r.t. the network outputs and the loss scalars.
+ *
+ *   discrete = 0 (Box):  actor_out = pre-tanh means [B,A]; actions f64 [B,A]; old_log_probs [B,A];
+ *                        log-prob / ratio / surrogate evaluated in f64 like the reference
+ *                        (actions are f64, buffer.py:154).  d_log_std[A] is accumulated.
+ *   discrete = 1:        actor_out = logits [B,A]; actions f64 [B] (class ids); old_log_probs [B].
+ *   adv_stats / int_adv_stats: device {mean, std} from ppx_mean_std.
+ *   value head(s): values/old_values/returns [B]; the max-of-means branch (algorithms.py:232) is
+ *                  resolved on device; d_values is the gradient of the SELECTED branch * vf_coef.
+ *   losses_out[8] (device, f64): total, policy, value, entropy, int_value, 0, 0, 0.
+ * `workspace` needs ppx_ppo_loss_workspace(B, A) bytes. */
+typedef struct {
+  int64_t B;        /* minibatch rows held by this rank */
+  int64_t B_total;  /* rows of the global minibatch (0 = B); means and gradient scales use this */
+  int A;
+  int discrete;
+  int dual;
+  float clip_range, ent_coef, vf_coef, int_vf_coef, policy_weight;
+} ppx_ppo_cfg;
+int64_t ppx_ppo_loss_workspace(int64_t B, int A);
+int ppx_ppo_loss_fwd_bwd(const ppx_ppo_cfg* cfg_host, const float* actor_out, const float* log_std,
+                         const double* actions, const float* old_log_probs, const float* advantages,
+                         const double* adv_stats, const float* values, const float* old_values,
+                         const float* returns, const float* int_advantages, const double* int_adv_stats,
+                         const float* int_values, const float* old_int_values, const float* int_returns,
+                         float* d_actor_out, float* d_log_std, float* d_values, float* d_int_values,
+                         double* losses_out, void* workspace, void* stream);
+/* The same computation split at its only global dependency, for sharded minibatches:
+ * head   -> per-sample work + sums_out[32] (f64 partial sums of this rank);
+ *           all-reduce sums_out across ranks (one 256-byte message), then
+ * finish -> loss scalars, max-of-means branch, d_log_std, d_values from the GLOBAL sums. */
+int ppx_ppo_loss_head(const ppx_ppo_cfg* cfg_host, const float* actor_out, const float* log_std,
+                      const double* actions, const float* old_log_probs, const float* advantages,
+                      const double* adv_stats, const float* values, const float* old_values, const float* returns,
+                      const float* int_advantages, const double* int_adv_stats, const float* int_values,
+                      const float* old_int_values, const float* int_returns, float* d_actor_out, double* sums_out,
+                      void* workspace, void* stream);
+int ppx_ppo_loss_finish(const ppx_ppo_cfg* cfg_host, const double* sums, const float* log_std, const float* values,
+                        const float* old_values, const float* returns, const float* int_values,
+                        const float* old_int_values, const float* int_returns, float* d_log_std, float* d_values,
+                        float* d_int_values, double* losses_out, void* workspace, void* stream);
+
+/* MSE / cross-entropy pieces of the ICM and RND-predictor losses (algorithms.py:497, :686-688):
+ * loss = scale * mean((a-b)^2) over n elements; d_a = +g, d_b = -g (either may be NULL);
+ * the scalar is ADDED to *loss_accum (device f64). */
+int ppx_mse_fwd_bwd(const float* a, const float* b, int64_t n, double scale, float* d_a, float* d_b,
+                    double* loss_accum, void* stream);
+/* loss = scale * mean_b( -log softmax(logits[b])[target[b]] ), d_logits out; targets f64 class ids with
+ * element stride `target_stride` (util.py:61-78: nn.CrossEntropyLoss on the inverse model). */
+int ppx_xent_fwd_bwd(const float* logits, const double* targets, int target_stride, int64_t B, int C,
+                     double scale, float* d_logits, double* loss_accum, void* stream);
+
+/* ---------------------------------------------------------------- optimiser ----------------- */
+/* clip_grad_norm_(max_norm) + Adam step on a flat parameter vector (algorithms.py:243-244):
+ * coef = min(1, max_norm/(||g||+1e-6)) (skipped when max_norm <= 0), torch.optim.Adam update
+ * (no weight decay / amsgrad) with bias correction for `step` (1-based). */
+int ppx_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  double max_norm, int64_t n_clip /* grads [0,n_clip) enter the norm and are clipped */,
+                  double lr, double beta1, double beta2, double eps, int64_t step,
+                  int64_t* step_dev /* NULL, or device counter of steps done: incremented, then used (graph replay) */,
+                  double* norm_out, void* workspace /* >= 4096 doubles */, void* stream);
+
+/* ---------------------------------------------------------------- bonus-net epilogues ------- */
+/* RunningMeanStd.update (util.py:20-44), f64 moments on device: state = {mean[dim], var[dim], count}.
+ * x is [n, dim] with element type f32 (x_is_f64=0) or f64. */
+int ppx_rms_update(const void* x, int x_is_f64, int64_t n, int dim, double* mean, double* var, double* count,
+                   void* workspace, void* stream);
+/* BaseAlgorithm.normalize_obs (algorithms.py:111-118): out = f32(clip((obs-mean)/sqrt(var+1e-10),-5,5)), f64 math */
+int ppx_normalize_obs(const float* obs, int64_t n, int dim, const double* mean, const double* var, float* out,
+                      void* stream);
+/* RndNetwork.int_reward tail (models.py:265): r = (pred-target)^2 */
+int ppx_rnd_sqerr(const float* pred, const float* target, int64_t n, float* r, void* stream);
+/* algorithms.py:396-398 for a whole rollout: for t in 0..T-1: rms.update(r[t,:]); r[t,:] /= sqrt(var)+1e-8 */
+int ppx_rnd_normalize_rollout(float* r, int T, int N, double* mean, double* var, double* count, void* stream);
+/* ICM int_reward tail (models.py:319-320) + blend (algorithms.py:630):
+ * ri = clamp(mean_f((pred-feat)^2), -5, 5); rewards = (1-eta)*rewards + eta*ri; ri_out optional */
+int ppx_icm_bonus_tail(const float* pred_feat, const float* next_feat, int64_t n, int F, double eta,
+                       float* rewards_inout, float* ri_out, void* stream);
+/* rows of an embedding table (ICM action_encoder for Discrete, models.py:294): out[b,:] = table[id[b],:]
+ * ids are f64 (stored actions) or i64; out has leading dimension ldo. */
+int ppx_embedding_fwd(const float* table, int C, const void* ids, int ids_are_f64, int id_stride, int64_t B,
+                      float* out, int ldo, void* stream);
+int ppx_embedding_bwd(const float* d_out, int ldo, const void* ids, int ids_are_f64, int id_stride, int64_t B,
+                      int C, float* d_table, void* stream);
+
+/* ---------------------------------------------------------------- ES-NSRA ------------------- */
+/* fill a shared noise table with N(0,1) f32 (Philox4x32-10 + Box-Muller); build-side design, the
+ * reference draws fresh randn per member (evolution_strategies.py:172-182). */
+int ppx_noise_fill(float* table, int64_t n, uint64_t seed, void* stream);
+/* _get_weights_try for the whole population (evolution_strategies.py:137-145):
+ * out[p,j] = theta[j] + sigma * eps[p,j], eps[p,:] = noise[offsets[p] : offsets[p]+D] (offsets NULL:
+ * noise is dense [P,D]).  out is f64 (out_is_f64=1, reference dtype) or f32. */
+int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P, int D,
+                   void* out, int out_is_f64, void* stream);
+/* _update_weights (evolution_strategies.py:217-239): z-score rewards (ddof 0); skip entirely if std==0;
+ * theta += lr/(P*sigma) * sum_p w_p eps_p with w_p = ((1-nw)*z_p + nw*novelty)/2 (use_novelty=1) or z_p;
+ * then *lr_inout *= decay.  rank_mode=1 replaces the z-score by centred ranks (BASELINE north_star;
+ * not in the reference).  All scalars state lives on device: lr_inout[1]; status_out[0]=1 if skipped. */
+int64_t ppx_es_update_workspace(int P, int D);
+int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int D,
+                  double sigma, double novelty_param, double novelty, int use_novelty, int rank_mode,
+                  double decay, double* lr_inout, int* status_out, void* workspace, void* stream);
+/* centred ranks: rank_out[p] = #{q: r_q < r_p or (r_q == r_p and q < p)}, centred_out = rank/(P-1) - 0.5 */
+int ppx_rank_center(const double* r, int P, int64_t* rank_out, double* centred_out, void* stream);
+/* get_kNN + novelty (evolution_strategies.py:264-281, 318-325), batched over Q queries:
+ * sum_out[q] = sum of the S=min(K,M) smallest Euclidean distances (ascending order, f64, no FMA);
+ * novelty_out[q] = sum/S floored (<=1e-3 -> 5e-3).  K <= 32. */
+int ppx_knn_novelty(const double* archive, int64_t M, const double* queries, int Q, int dim, int K,
+                    double* sum_out, double* novelty_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPX_H_ */

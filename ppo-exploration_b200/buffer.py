@@ -1,0 +1,355 @@
+"""Device-resident rollout buffers with the reference's call surface.
+
+Mirrors buffer.py of the reference: BaseBuffer (:13-109), RolloutStorage (:111-267),
+IntrinsicStorage (:271-394).  Same constructor arguments, method names, attribute names and
+RolloutSample field order; the arrays are torch CUDA tensors in the reference's [T,N,...] layout and
+the arithmetic (GAE scan, SimHash counts, shuffle-gather) runs in libppx.so.
+
+Deliberate differences (documented in DESIGN.md):
+  * arrays are allocated once and zeroed on reset() instead of re-allocated (buffer.py:153-161);
+  * get() does not rewrite the attributes into the env-major flat layout (buffer.py:241-245): the
+    gather kernel decodes flat index -> (t, n) on the fly.  `flat(name)` returns the flat view;
+  * masks are uint8 (the reference stores int64 ones/zeros);
+  * the hash width k is a constructor argument (`hash_bits`, default 16 = buffer.py:137).
+The shuffle indices come from the same `np.random.permutation(T*N)` draw as the reference
+(buffer.py:239), so a seeded run visits identical minibatches.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _dev(x, dtype, device):
+    """numpy / torch (any device) -> contiguous CUDA tensor of `dtype`."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype, non_blocking=True)
+
+
+class BaseBuffer(object):
+    """buffer.py:13-109 (the parts the rollout path uses)."""
+
+    def __init__(self, buffer_size, observation_space, action_space, n_envs=1, device=None):
+        self.buffer_size = buffer_size
+        self.observation_space = observation_space
+        self.obs_shape = tuple(observation_space.shape)
+        self.action_space = action_space
+        self.pos = 0
+        self.full = False
+        self.n_envs = n_envs
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("ppx buffers live on a CUDA device; there is no CPU path")
+        self.action_dim = 1 if action_space.__class__.__name__ == "Discrete" else action_space.shape[0]
+
+    @staticmethod
+    def swap_and_flatten(arr):
+        """[T,N,...] -> [T*N,...] env-major, trailing dim added to 2-D input (buffer.py:40-52)."""
+        shape = tuple(arr.shape)
+        if len(shape) < 3:
+            shape = shape + (1,)
+        return arr.transpose(0, 1).reshape(shape[0] * shape[1], *shape[2:])
+
+    def size(self):
+        return self.buffer_size if self.full else self.pos
+
+    def reset(self):
+        self.pos = 0
+        self.full = False
+
+
+class CountTable:
+    """Persistent SimHash count table (buffer.py:136) living in device memory."""
+
+    def __init__(self, capacity=1 << 20):
+        h = C.c_void_p()
+        L.call("ppx_count_table_create", int(capacity), C.byref(h))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.call("ppx_count_table_destroy", self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def clear(self):
+        L.call("ppx_count_table_clear", self._h, L.stream())
+
+    def update_codes(self, codes):
+        """Sequential-semantics count update on packed uint64 codes -> uint32 counts."""
+        counts = torch.empty(codes.numel(), dtype=torch.int32, device=codes.device)
+        L.call("ppx_count_table_update", self._h, codes.data_ptr(), codes.numel(), counts.data_ptr(), L.stream())
+        return counts
+
+    def __len__(self):
+        n = C.c_uint64()
+        L.call("ppx_count_table_size", self._h, C.byref(n))
+        return int(n.value)
+
+    def items(self):
+        """{code: count} copied to the host (synchronous; tests and checkpointing)."""
+        n = len(self)
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+        counts = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+        got = C.c_uint64()
+        L.call("ppx_count_table_dump", self._h, keys.data_ptr(), counts.data_ptr(), n, C.byref(got))
+        k = keys[:n].cpu().numpy().view(np.uint64)
+        c = counts[:n].cpu().numpy()
+        return {int(a): int(b) for a, b in zip(k, c)}
+
+
+class RolloutStorage(BaseBuffer):
+    """buffer.py:111-267."""
+
+    def __init__(self, buffer_size, n_envs, obs_space, action_space, gae_lam=0.95, gamma=0.99, sim_hash=False,
+                 device=None, hash_bits=16, table_capacity=1 << 20):
+        super().__init__(buffer_size, obs_space, action_space, n_envs=n_envs, device=device)
+        self.gae_lam = gae_lam
+        self.gamma = gamma
+        self.generator_ready = False
+        self._alloc()
+        self.reset()
+        # same global-RNG draw, at the same point, as buffer.py:137 (made whether or not hashing is on)
+        self.A = np.random.randn(hash_bits, self.obs_shape[0])
+        self._A_dev = None
+        self.do_hash = bool(sim_hash)
+        self.beta = 0.1 if sim_hash else None
+        self.count_table = CountTable(table_capacity) if sim_hash else None
+        self.RolloutSample = namedtuple('RolloutSample', ['observations', 'actions', 'old_values', 'old_log_probs',
+                                                          'advantages', 'returns'])
+        self._fields = [('observations', 'observations'), ('actions', 'actions'), ('old_values', 'values'),
+                        ('old_log_probs', 'action_log_probs'), ('advantages', 'advantages'), ('returns', 'returns')]
+        self._mb = {}
+
+    # ------------------------------------------------------------------ storage
+    def _alloc(self):
+        T, N, dev = self.buffer_size, self.n_envs, self.device
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.observations = z(T, N, *self.obs_shape)
+        self.actions = z(T, N, self.action_dim, dt=torch.float64)            # f64, buffer.py:154
+        self.rewards = z(T, N)
+        self.int_rewards = z(T, N)
+        self.values = z(T, N)
+        self.returns = z(T, N)
+        self.action_log_probs = z(T, N, self.action_dim)
+        self.masks = torch.ones(T, N, dtype=torch.uint8, device=dev)         # ones, buffer.py:160
+        self.advantages = z(T, N)
+
+    def _zero(self):
+        for name in ('observations', 'actions', 'rewards', 'int_rewards', 'values', 'returns', 'action_log_probs',
+                     'advantages'):
+            getattr(self, name).zero_()
+        self.masks.fill_(1)
+
+    def reset(self):
+        """buffer.py:149-163 (zeroed in place instead of re-allocated)."""
+        self._zero()
+        self.generator_ready = False
+        super().reset()
+
+    def add(self, obs, action, reward, value, mask, log_prob):
+        """buffer.py:165-186: write row `pos`; SimHash bonus first when enabled."""
+        p, dev = self.pos, self.device
+        obs_d = _dev(obs, torch.float32, dev).reshape(self.n_envs, *self.obs_shape)
+        self.observations[p].copy_(obs_d)
+        if self.do_hash:
+            reward = self.sim_hash(obs_d, reward)
+        self.actions[p].copy_(_dev(action, torch.float64, dev).reshape(self.n_envs, self.action_dim))
+        self.rewards[p].copy_(_dev(reward, torch.float32, dev).reshape(self.n_envs))
+        self.masks[p].copy_(_dev(mask, torch.uint8, dev).reshape(self.n_envs))
+        self.values[p].copy_(_dev(value, torch.float32, dev).reshape(self.n_envs))
+        self.action_log_probs[p].copy_(_dev(log_prob, torch.float32, dev).reshape(self.n_envs, self.action_dim))
+        self.pos += 1
+        if self.pos == self.buffer_size:
+            self.full = True
+
+    def load_rollout(self, **arrays):
+        """Bulk fill from [T,N,...] host or device arrays (one H2D copy per field) and mark full."""
+        dt = {'actions': torch.float64, 'masks': torch.uint8}
+        for name, a in arrays.items():
+            dst = getattr(self, name)
+            dst.copy_(_dev(a, dt.get(name, torch.float32), self.device).reshape(dst.shape))
+        self.pos, self.full = self.buffer_size, True
+        self.generator_ready = False
+
+    # ------------------------------------------------------------------ SimHash
+    def _A(self):
+        if self._A_dev is None or self._A_dev_src is not self.A:
+            self._A_dev = torch.as_tensor(np.ascontiguousarray(self.A, dtype=np.float64)).to(self.device)
+            self._A_dev_src = self.A
+        return self._A_dev
+
+    def sim_hash(self, obs, rewards):
+        """buffer.py:188-200.  Mutates and returns `rewards` (numpy in -> numpy out, tensor in -> tensor).
+        A 3-D obs [T,N,D] with rewards [T,N] applies the bonus for a whole rollout in one launch, in the
+        reference's order (t-major, env-minor)."""
+        A = self._A()
+        k, D = A.shape
+        obs_d = _dev(obs, torch.float32, self.device).reshape(-1, D)
+        n = obs_d.shape[0]
+        is_np = not isinstance(rewards, torch.Tensor)
+        f64 = (rewards.dtype == np.float64) if is_np else (rewards.dtype == torch.float64)
+        if is_np or not rewards.is_cuda:
+            r_d = _dev(rewards, torch.float64 if f64 else torch.float32, self.device).reshape(n).clone()
+        else:
+            r_d = rewards if f64 else rewards  # in place on the caller's CUDA tensor
+            if r_d.dtype not in (torch.float32, torch.float64) or not r_d.is_contiguous():
+                raise RuntimeError("sim_hash: rewards must be a contiguous f32/f64 tensor")
+        L.call("ppx_simhash_update", self.count_table._h, A.data_ptr(), obs_d.data_ptr(), int(k), int(D), int(n),
+               float(self.beta), r_d.data_ptr(), int(f64), None, None, L.stream())
+        if is_np:
+            rewards[...] = r_d.cpu().numpy().reshape(rewards.shape)
+            return rewards
+        if not rewards.is_cuda:
+            rewards.copy_(r_d.cpu().reshape(rewards.shape))
+            return rewards
+        return rewards
+
+    def sim_hash_codes(self, obs):
+        """packed uint64 codes (bit b = sign bit b of buffer.py:194) as an int64 CUDA tensor."""
+        A = self._A()
+        k, D = A.shape
+        obs_d = _dev(obs, torch.float32, self.device).reshape(-1, D)
+        codes = torch.empty(obs_d.shape[0], dtype=torch.int64, device=self.device)
+        L.call("ppx_simhash_codes", A.data_ptr(), obs_d.data_ptr(), int(k), int(D), obs_d.shape[0], codes.data_ptr(),
+               L.stream())
+        return codes
+
+    # ------------------------------------------------------------------ GAE
+    def compute_returns_and_advantages(self, last_value, dones):
+        """buffer.py:203-230."""
+        lv = _dev(last_value, torch.float32, self.device).reshape(self.n_envs)
+        d = _dev(dones, torch.uint8, self.device).reshape(self.n_envs)
+        L.call("ppx_gae", self.rewards.data_ptr(), self.values.data_ptr(), self.masks.data_ptr(), lv.data_ptr(),
+               d.data_ptr(), float(self.gamma), float(self.gae_lam), self.buffer_size, self.n_envs,
+               self.advantages.data_ptr(), self.returns.data_ptr(), L.stream())
+
+    # ------------------------------------------------------------------ shuffle-gather
+    def flat(self, name):
+        """env-major flat view of a stored array, shaped like the reference's flattened attribute."""
+        return self.swap_and_flatten(getattr(self, name))
+
+    def _minibatch_buffers(self, B):
+        """Persistent gather destinations for minibatches of up to B samples (stable addresses)."""
+        key = int(B)
+        if key not in self._mb:
+            bufs = {}
+            for field, src in self._fields:
+                s = getattr(self, src)
+                bufs[field] = torch.empty((B,) + tuple(s.shape[2:]), dtype=s.dtype, device=self.device)
+            self._mb[key] = bufs
+        return self._mb[key]
+
+    def gather_into(self, idx_dev, bufs):
+        """One fused launch: every RolloutSample field for the flat indices `idx_dev` (int64, CUDA)."""
+        B = idx_dev.numel()
+        n = len(self._fields)
+        srcs = (C.c_void_p * n)()
+        dsts = (C.c_void_p * n)()
+        rb = (C.c_int * n)()
+        for i, (field, src) in enumerate(self._fields):
+            s = getattr(self, src)
+            srcs[i] = s.data_ptr()
+            dsts[i] = bufs[field].data_ptr()
+            rb[i] = int(s[0, 0].numel() * s.element_size()) if s.dim() > 2 else s.element_size()
+        L.call("ppx_gather_minibatch", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, self.n_envs,
+               L.stream())
+
+    def _sample_from(self, bufs, B):
+        out = []
+        for field, src in self._fields:
+            t = bufs[field][:B]
+            if field in ('advantages', 'int_advantages'):
+                t = t.reshape(B, 1)                                       # 2-D arrays gain a trailing dim
+            out.append(t)
+        return self.RolloutSample(*out)
+
+    def permutation(self):
+        """The epoch's shuffle: the reference's own host draw (buffer.py:239), uploaded once."""
+        idx = np.random.permutation(self.buffer_size * self.n_envs)
+        return torch.as_tensor(idx).to(self.device, non_blocking=True)
+
+    def get(self, batch_size=None):
+        """buffer.py:233-254: generator of RolloutSample minibatches (CUDA tensors; each sample owns
+        fresh storage, like the reference's torch.tensor copies)."""
+        assert self.full, ''
+        total = self.buffer_size * self.n_envs
+        idx = self.permutation()
+        self.generator_ready = True
+        if batch_size is None:
+            batch_size = total
+        start = 0
+        while start < total:
+            sl = idx[start:start + batch_size]
+            B = sl.numel()
+            bufs = {f: torch.empty((B,) + tuple(getattr(self, s).shape[2:]), dtype=getattr(self, s).dtype,
+                                   device=self.device) for f, s in self._fields}
+            self.gather_into(sl, bufs)
+            yield self._sample_from(bufs, B)
+            start += batch_size
+
+
+class IntrinsicStorage(RolloutStorage):
+    """buffer.py:271-394: two reward streams (RND)."""
+
+    def __init__(self, buffer_size, n_envs, obs_space, action_space, gae_lam=0.95, gamma=0.99, int_gamma=0.99,
+                 device=None):
+        super().__init__(buffer_size, n_envs, obs_space, action_space, gae_lam, gamma, device=device)
+        self.int_gamma = int_gamma
+        self.RolloutSample = namedtuple('RolloutSample', ['observations', 'actions', 'old_values', 'int_values',
+                                                          'old_log_probs', 'advantages', 'int_advantages', 'returns',
+                                                          'int_returns'])
+        self._fields = [('observations', 'observations'), ('actions', 'actions'), ('old_values', 'values'),
+                        ('int_values', 'int_values'), ('old_log_probs', 'action_log_probs'),
+                        ('advantages', 'advantages'), ('int_advantages', 'int_advantages'), ('returns', 'returns'),
+                        ('int_returns', 'int_returns')]
+
+    def _alloc(self):
+        super()._alloc()
+        T, N, dev = self.buffer_size, self.n_envs, self.device
+        for name in ('int_values', 'int_returns', 'int_advantages'):
+            setattr(self, name, torch.zeros(T, N, dtype=torch.float32, device=dev))
+
+    def _zero(self):
+        super()._zero()
+        for name in ('int_values', 'int_returns', 'int_advantages'):
+            getattr(self, name).zero_()
+
+    def add(self, obs, action, reward, int_reward, value, int_value, mask, log_prob):
+        """buffer.py:305-318."""
+        p, dev = self.pos, self.device
+        self.int_rewards[p].copy_(_dev(int_reward, torch.float32, dev).reshape(self.n_envs))
+        self.int_values[p].copy_(_dev(int_value, torch.float32, dev).reshape(self.n_envs))
+        super().add(obs, action, reward, value, mask, log_prob)
+
+    def compute_returns_and_advantages(self, last_value, last_int_value, dones):
+        """buffer.py:321-362.  Returns mean(int_rewards) as a 0-d CUDA tensor (the value the reference
+        logs at :335) so the caller can record it without forcing a sync here."""
+        lv = _dev(last_value, torch.float32, self.device).reshape(self.n_envs)
+        liv = _dev(last_int_value, torch.float32, self.device).reshape(self.n_envs)
+        d = _dev(dones, torch.uint8, self.device).reshape(self.n_envs)
+        L.call("ppx_gae_dual", self.rewards.data_ptr(), self.values.data_ptr(), self.masks.data_ptr(), lv.data_ptr(),
+               d.data_ptr(), float(self.gamma), float(self.gae_lam), self.int_rewards.data_ptr(),
+               self.int_values.data_ptr(), liv.data_ptr(), float(self.int_gamma), self.buffer_size, self.n_envs,
+               self.advantages.data_ptr(), self.returns.data_ptr(), self.int_advantages.data_ptr(),
+               self.int_returns.data_ptr(), L.stream())
+        return self.int_rewards.mean()
+
+
+def discount_with_dones(rewards, dones, gamma, device="cuda"):
+    """SilModule.discount_with_dones (sil_module.py:99-105) over [T] or [T,N] columns, f64."""
+    r = _dev(np.asarray(rewards, dtype=np.float64), torch.float64, device)
+    d = _dev(np.asarray(dones), torch.uint8, device)
+    shape = r.shape
+    r2 = r.reshape(shape[0], -1).contiguous()
+    d2 = d.reshape(shape[0], -1).contiguous()
+    out = torch.empty_like(r2)
+    L.call("ppx_discount", r2.data_ptr(), d2.data_ptr(), float(gamma), r2.shape[0], r2.shape[1], out.data_ptr(),
+           L.stream())
+    return out.reshape(shape)

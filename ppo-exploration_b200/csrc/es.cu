@@ -1,0 +1,299 @@
+// ES-NSRA step: shared noise table, population perturbation, fitness-shaped parameter update,
+// centred ranks and novelty k-NN over the behaviour archive.
+//
+// Replaces EvolutionStrategy._get_population/_get_weights_try (evolution_strategies.py:137-145,
+// 172-182), _update_weights (:217-239) and get_kNN + the novelty lines (:264-281, :318-325).
+//
+// The reference draws fresh randn per member and stacks a [P,in,out] f64 tensor per layer each
+// iteration.  Here a population member is an int64 offset into one resident f32 noise table
+// (ppx_noise_fill), theta is one flat f64 vector over all layers, and both hot kernels stream the
+// noise exactly once:
+//   perturb  out[p,:] = theta + sigma*eps_p            8*D  B/perturbation  (f32 out)
+//   update   theta   += f * sum_p c_p eps_p            4*D  B/perturbation  (GEMV, f64 accumulate,
+//                                                      split over members, fixed-order reduction)
+// Parity mode passes a dense [P,D] eps (offsets == NULL) holding the very values given to the
+// reference.  All state (theta, lr) stays on device; the std==0 early-out of :225-226 is a device flag.
+#include "common.cuh"
+
+namespace ppx {
+namespace {
+
+// ---------------- Philox4x32-10 + Box-Muller ----------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+}
+__global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ table, int64_t n, uint64_t seed) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // quad index
+  if (q * 4 >= n) return;
+  uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  float z[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;       // (0,1]
+    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (q * 4 + e < n) table[q * 4 + e] = z[e];
+}
+
+// ---------------- perturb ----------------
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+perturb_kernel(const double* __restrict__ theta, const float* __restrict__ noise, const int64_t* __restrict__ offsets,
+               double sigma, int P, int D, OutT* __restrict__ out) {
+  const int p = blockIdx.y;
+  const float* eps = noise + (offsets ? offsets[p] : (int64_t)p * D);
+  OutT* o = out + (int64_t)p * D;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < D; j += gridDim.x * blockDim.x) {
+    // w + SIGMA * eps with separate rounding of product and sum, like numpy (evolution_strategies.py:143-144)
+    o[j] = (OutT)__dadd_rn(theta[j], __dmul_rn(sigma, (double)ld_stream(eps + j)));
+  }
+}
+
+// ---------------- update ----------------
+// stats[0]=mean, stats[1]=std(ddof 0), stats[2]=skip flag
+__global__ void __launch_bounds__(1024) es_stats_kernel(const double* __restrict__ r, int P, int rank_mode, double* stats, int* status) {
+  __shared__ double s_red[32];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a += r[i];
+  const double mean = block_sum(a, s_red) / (double)P;
+  a = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { const double d = r[i] - mean; a += d * d; }
+  const double var = block_sum(a, s_red) / (double)P;
+  if (threadIdx.x == 0) {
+    const double sd = sqrt(var);
+    const bool skip = !rank_mode && (sd == 0.0);
+    stats[0] = mean; stats[1] = sd; stats[2] = skip ? 1.0 : 0.0;
+    if (status) *status = skip ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank_kernel(const double* __restrict__ r, int P, int64_t* __restrict__ rank_out, double* __restrict__ centred_out) {
+  __shared__ double s_r[256];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const double mine = p < P ? r[p] : 0.0;
+  int64_t cnt = 0;
+  for (int base = 0; base < P; base += 256) {
+    const int q = base + threadIdx.x;
+    s_r[threadIdx.x] = q < P ? r[q] : 0.0;
+    __syncthreads();
+    const int lim = min(256, P - base);
+    for (int t = 0; t < lim; ++t) {
+      const double o = s_r[t];
+      cnt += (o < mine) || (o == mine && (base + t) < p);
+    }
+    __syncthreads();
+  }
+  if (p < P) {
+    if (rank_out) rank_out[p] = cnt;
+    if (centred_out) centred_out[p] = (double)cnt / (double)(P - 1) - 0.5;
+  }
+}
+
+// coef[p] = f * shaped fitness (0 everywhere when the update is skipped)
+__global__ void __launch_bounds__(256)
+es_coef_kernel(const double* __restrict__ r, const double* __restrict__ centred, int P, const double* __restrict__ stats,
+               const double* __restrict__ lr, double sigma, double nw, double novelty, int use_novelty, int rank_mode,
+               double* __restrict__ coef) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  if (stats[2] != 0.0) { coef[p] = 0.0; return; }
+  const double f = *lr / ((double)P * sigma);                          // update_factor, :230
+  double z = rank_mode ? centred[p] : (r[p] - stats[0]) / stats[1];   // :227
+  if (use_novelty) z = ((1.0 - nw) * z + nw * novelty) / 2.0;          // :235
+  coef[p] = f * z;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(128)
+es_gemv_kernel(const float* __restrict__ noise, const int64_t* __restrict__ offsets, const double* __restrict__ coef, int P, int D,
+               int p_chunk, double* __restrict__ partial) {
+  const int j = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int p0 = blockIdx.y * p_chunk, p1 = min(P, p0 + p_chunk);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (j < D) {
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const float* eps = noise + (offsets ? __ldg(offsets + p) : (int64_t)p * D) + j;
+      const double c = __ldg(coef + p);
+      float4 e;
+      if (VEC) e = ld_stream4(reinterpret_cast<const float4*>(eps));
+      else {
+        e.x = ld_stream(eps);
+        e.y = j + 1 < D ? ld_stream(eps + 1) : 0.f;
+        e.z = j + 2 < D ? ld_stream(eps + 2) : 0.f;
+        e.w = j + 3 < D ? ld_stream(eps + 3) : 0.f;
+      }
+      a0 = fma(c, (double)e.x, a0); a1 = fma(c, (double)e.y, a1);
+      a2 = fma(c, (double)e.z, a2); a3 = fma(c, (double)e.w, a3);
+    }
+    double* out = partial + (int64_t)blockIdx.y * D + j;
+    out[0] = a0;
+    if (j + 1 < D) out[1] = a1;
+    if (j + 2 < D) out[2] = a2;
+    if (j + 3 < D) out[3] = a3;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+es_apply_kernel(double* __restrict__ theta, const double* __restrict__ partial, int splits, int D, const double* __restrict__ stats,
+                double decay, double* lr) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool skip = stats[2] != 0.0;
+  if (j < D && !skip) {
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * D + j];
+    theta[j] += s;
+  }
+  if (j == 0 && !skip) *lr *= decay;                                   // :239 (not reached on the early return)
+}
+
+// ---------------- novelty k-NN ----------------
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+knn_kernel(const double* __restrict__ archive, int64_t M, const double* __restrict__ queries, int Q, int dim, int K,
+           double* __restrict__ sum_out, double* __restrict__ nov_out) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int lane = threadIdx.x & 31;
+  const double* qv = queries + (int64_t)q * dim;
+  double best[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) best[i] = INFINITY;
+  const int S = (int)min((int64_t)K, M);
+  for (int64_t m = lane; m < M; m += 32) {
+    const double* a = archive + m * dim;
+    double d2 = 0.0;
+    for (int d = 0; d < dim; ++d) {
+      const double diff = __dsub_rn(a[d], qv[d]);
+      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));                      // no FMA contraction: match the CPU distance
+    }
+    double v = __dsqrt_rn(d2);
+    if (v < best[KMAX - 1]) {
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {                                 // sorted insert
+        if (v < best[i]) { const double t = best[i]; best[i] = v; v = t; }
+      }
+    }
+  }
+  // S rounds: pop the global minimum among the 32 sorted lists, summing in ascending order
+  double sum = 0.0;
+  for (int round = 0; round < S; ++round) {
+    double mn = best[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const unsigned who = __ballot_sync(0xffffffffu, best[0] == mn);
+    sum = __dadd_rn(sum, mn);
+    if (lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int i = 0; i + 1 < KMAX; ++i) best[i] = best[i + 1];
+      best[KMAX - 1] = INFINITY;
+    }
+  }
+  if (lane == 0) {
+    if (sum_out) sum_out[q] = sum;
+    if (nov_out) {
+      double nu = sum / (double)S;
+      if (nu <= 1e-3) nu = 5e-3;                                       // :323-324
+      nov_out[q] = nu;
+    }
+  }
+}
+
+int gemv_splits(int P, int D) {
+  const int64_t colblocks = ceil_div(D, 512);
+  int64_t s = ceil_div(4 * (int64_t)sm_count(), colblocks);
+  s = std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, P / 8)));
+  return (int)s;
+}
+
+}  // namespace
+}  // namespace ppx
+
+using namespace ppx;
+
+extern "C" int ppx_noise_fill(float* table, int64_t n, uint64_t seed, void* stream) {
+  PPX_REQUIRE(table && n >= 1, "noise_fill: bad arguments");
+  noise_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(table, n, seed);
+  return after_launch("noise_fill");
+}
+
+extern "C" int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P, int D,
+                              void* out, int out_is_f64, void* stream) {
+  PPX_REQUIRE(theta && noise && out && P >= 1 && D >= 1, "es_perturb: bad arguments");
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(D, 256), 64), (unsigned)P);
+  PPX_REQUIRE(P <= 65535, "es_perturb: P=%d exceeds grid.y limit; call in slices", P);
+  if (out_is_f64) perturb_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, noise, offsets, sigma, P, D, (double*)out);
+  else perturb_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, noise, offsets, sigma, P, D, (float*)out);
+  return after_launch("es_perturb");
+}
+
+extern "C" int64_t ppx_es_update_workspace(int P, int D) {
+  return (int64_t)sizeof(double) * (8 + 2 * (int64_t)P + (int64_t)gemv_splits(P, D) * D);
+}
+
+extern "C" int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int D,
+                             double sigma, double novelty_param, double novelty, int use_novelty, int rank_mode, double decay,
+                             double* lr_inout, int* status_out, void* workspace, void* stream) {
+  PPX_REQUIRE(theta && noise && rewards && lr_inout && workspace, "es_update: null pointer");
+  PPX_REQUIRE(P >= 2 && D >= 1 && sigma != 0.0, "es_update: P=%d D=%d sigma=%g", P, D, sigma);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* stats = (double*)workspace;
+  double* coef = stats + 8;
+  double* centred = coef + P;
+  double* partial = centred + P;
+  es_stats_kernel<<<1, 1024, 0, st>>>(rewards, P, rank_mode, stats, status_out);
+  int rc = after_launch("es_update(stats)");
+  if (rc) return rc;
+  if (rank_mode) {
+    rank_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(rewards, P, nullptr, centred);
+    rc = after_launch("es_update(rank)");
+    if (rc) return rc;
+  }
+  es_coef_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(rewards, centred, P, stats, lr_inout, sigma, novelty_param, novelty,
+                                                             use_novelty, rank_mode, coef);
+  rc = after_launch("es_update(coef)");
+  if (rc) return rc;
+  const int splits = gemv_splits(P, D);
+  const int p_chunk = (int)ceil_div(P, splits);
+  dim3 grid((unsigned)ceil_div(D, 512), (unsigned)splits);
+  bool vec = (D % 4 == 0) && ((uintptr_t)noise % 16 == 0) && offsets == nullptr;
+  // with offsets, vector loads need every offset to be a multiple of 4 -- the table sampler guarantees it
+  // (see host wrapper); dense parity inputs only need D % 4 == 0.
+  if (offsets) vec = (D % 4 == 0) && ((uintptr_t)noise % 16 == 0);
+  if (vec) es_gemv_kernel<true><<<grid, 128, 0, st>>>(noise, offsets, coef, P, D, p_chunk, partial);
+  else es_gemv_kernel<false><<<grid, 128, 0, st>>>(noise, offsets, coef, P, D, p_chunk, partial);
+  rc = after_launch("es_update(gemv)");
+  if (rc) return rc;
+  es_apply_kernel<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(theta, partial, splits, D, stats, decay, lr_inout);
+  return after_launch("es_update(apply)");
+}
+
+extern "C" int ppx_rank_center(const double* r, int P, int64_t* rank_out, double* centred_out, void* stream) {
+  PPX_REQUIRE(r && P >= 2 && (rank_out || centred_out), "rank_center: bad arguments");
+  rank_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(r, P, rank_out, centred_out);
+  return after_launch("rank_center");
+}
+
+extern "C" int ppx_knn_novelty(const double* archive, int64_t M, const double* queries, int Q, int dim, int K, double* sum_out,
+                               double* novelty_out, void* stream) {
+  PPX_REQUIRE(archive && queries && M >= 1 && Q >= 1 && dim >= 1, "knn_novelty: bad arguments");
+  PPX_REQUIRE(K >= 1 && K <= 32, "knn_novelty: K=%d (1..32)", K);
+  const unsigned grid = (unsigned)ceil_div(Q, 4);
+  if (K <= 16) knn_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>(archive, M, queries, Q, dim, K, sum_out, novelty_out);
+  else knn_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(archive, M, queries, Q, dim, K, sum_out, novelty_out);
+  return after_launch("knn_novelty");
+}

@@ -1,0 +1,100 @@
+// Global-norm gradient clipping fused with the Adam step on a flat parameter vector.
+//
+// Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (algorithms.py:243-244, :465-466,
+// :501-502, :697-699).  Two launches: per-CTA f64 sum of squares over the clipped prefix of the
+// gradient, then every CTA re-reduces those partials in the same fixed order (so all agree on the
+// clip coefficient without a grid sync) and applies the update.  32 B/param/step.
+#include "common.cuh"
+
+namespace ppx {
+namespace {
+
+constexpr int kNormBlocks = 512;
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)g[i];
+    s += v * v;
+  }
+  s = block_sum(s, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            const double* __restrict__ partials, int n_partials, float max_norm, int64_t n_clip, float w1 /*1-beta1*/,
+            double beta1, double beta2d, double lr, float beta2, float w2 /*1-beta2*/, float step_size, float bc2_sqrt,
+            float eps, const int64_t* __restrict__ step_dev, double* norm_out) {
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    if (step_dev) {                                          // device-resident step counter (CUDA-graph replay)
+      const double t = (double)(*step_dev);
+      s_step_size = (float)(lr / (1.0 - pow(beta1, t)));
+      s_bc2_sqrt = (float)sqrt(1.0 - pow(beta2d, t));
+    } else {
+      s_step_size = step_size;
+      s_bc2_sqrt = bc2_sqrt;
+    }
+    float coef = 1.f;
+    if (n_partials > 0) {
+      double s = 0.0;
+      for (int k = 0; k < n_partials; ++k) s += partials[k];
+      const float norm = (float)sqrt(s);
+      coef = fminf(max_norm / (norm + 1e-6f), 1.f);          // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
+      if (blockIdx.x == 0 && norm_out) *norm_out = sqrt(s);
+    }
+    s_coef = coef;
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  step_size = s_step_size;
+  bc2_sqrt = s_bc2_sqrt;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    if (i < n_clip) gi *= coef;
+    float mi = m[i], vi = v[i];
+    mi = mi + w1 * (gi - mi);                                 // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * beta2 + w2 * gi * gi;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);                   // param.addcdiv_(exp_avg, denom, -step_size)
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+__global__ void bump_step_kernel(int64_t* step) { *step += 1; }
+
+}  // namespace
+}  // namespace ppx
+
+extern "C" int ppx_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double max_norm,
+                             int64_t n_clip, double lr, double beta1, double beta2, double eps, int64_t step, int64_t* step_dev, double* norm_out,
+                             void* workspace, void* stream) {
+  using namespace ppx;
+  PPX_REQUIRE(params && grads && exp_avg && exp_avg_sq && workspace, "clip_adam: null pointer");
+  PPX_REQUIRE(n >= 1 && (step >= 1 || step_dev) && n_clip >= 0 && n_clip <= n, "clip_adam: n=%lld step=%lld n_clip=%lld", (long long)n, (long long)step, (long long)n_clip);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partials = (double*)workspace;
+  int n_partials = 0;
+  if (step_dev) {                                            // counter holds steps done; bump first, then use
+    bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+    int rc = after_launch("clip_adam step");
+    if (rc) return rc;
+    step = 1;
+  }
+  if (max_norm > 0.0 && n_clip > 0) {
+    n_partials = (int)std::min<int64_t>(kNormBlocks, ceil_div(n_clip, 1024));
+    sumsq_kernel<<<n_partials, 256, 0, st>>>(grads, n_clip, partials);
+    int rc = after_launch("clip_adam sumsq");
+    if (rc) return rc;
+  }
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 1024), (int64_t)sm_count() * 8);
+  adam_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, n_partials, (float)max_norm, n_clip,
+                                    (float)(1.0 - beta1), beta1, beta2, lr, (float)beta2, (float)(1.0 - beta2),
+                                    (float)(lr / bc1), (float)sqrt(bc2), (float)eps, step_dev, norm_out);
+  return after_launch("clip_adam");
+}

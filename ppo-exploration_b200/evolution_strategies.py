@@ -1,0 +1,178 @@
+"""ES-NSRA step on the GPU with the reference's method names.
+
+Mirrors EvolutionStrategy of evolution_strategies.py (:100-384) for the parts on the learner hot
+path: _get_population (:172-182), _get_weights_try (:137-145), _update_weights (:217-239), get_kNN
+(:264-281), the novelty lines (:318-325) and calc_noveltiy_distribution (:283-290).  Episode
+evaluation (evaluate / get_behavior_char / run's env loop) is the simulator side and stays with the
+caller: feed the fitness vector back through `_update_weights`.
+
+Build-side design: the population is a vector of offsets into ONE resident f32 noise
+table instead of P fresh f64 randn tensors; theta is one flat f64 device vector over all layers.
+Parity mode: pass a dense eps array ([P, D] float32-representable values, or the reference's nested
+list-of-layers population) wherever a population is expected.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class EvolutionStrategy(object):
+    def __init__(self, env_id=None, hidden_sizes=(64, 64), nsr_plateu=1.5, nsr_range=(0, 1), nsr_update=0.05,
+                 population_size=50, sigma=0.1, learning_rate=0.01, decay=0.9995, novelty_param=0.5, num_threads=1,
+                 obs_dim=None, n_actions=None, device="cuda", noise_table_size=1 << 24, noise_seed=0,
+                 fitness_shaping="zscore"):
+        if obs_dim is None or n_actions is None:
+            raise ValueError("pass obs_dim= and n_actions= (the reference reads them from gym.make(env_id), "
+                             "evolution_strategies.py:121; the env layer is out of scope here)")
+        self.env_id = env_id
+        self.device = torch.device(device)
+        self.hidden_sizes = list(hidden_sizes)
+        sizes = [obs_dim, *hidden_sizes, n_actions]
+        self.shapes = [(sizes[i], sizes[i + 1]) for i in range(len(sizes) - 1)]       # :33-35, bias-free
+        self.layer_sizes = [a * b for a, b in self.shapes]
+        self.D = int(sum(self.layer_sizes))
+        # same global-RNG draws as FeedForwardNetwork.__init__ (:34-35)
+        w0 = [np.random.randn(*s) for s in self.shapes]
+        self.theta = torch.as_tensor(np.concatenate([w.ravel() for w in w0])).to(self.device)
+        self.POPULATION_SIZE = population_size
+        self.SIGMA = sigma
+        self._lr = torch.full((1,), float(learning_rate), dtype=torch.float64, device=self.device)
+        self.decay = decay
+        self.novelty_param = novelty_param
+        self.K = 10
+        self.nsr_plateu, self.nsr_range, self.nsr_update = nsr_plateu, list(nsr_range), nsr_update
+        self.fitness_shaping = fitness_shaping
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ws = None
+        self._noise = None
+        self._noise_size, self._noise_seed = int(noise_table_size), int(noise_seed)
+        self._rng = np.random.RandomState(noise_seed + 1)
+
+    # ---- state views ----
+    @property
+    def learning_rate(self):
+        return float(self._lr.item())
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self._lr.fill_(float(v))
+
+    @property
+    def weights(self):
+        return self.get_weights()
+
+    def get_weights(self):
+        """list of [in,out] f64 numpy arrays, like FeedForwardNetwork.get_weights (:63-64)."""
+        flat = self.theta.cpu().numpy()
+        out, o = [], 0
+        for s, n in zip(self.shapes, self.layer_sizes):
+            out.append(flat[o:o + n].reshape(s).copy())
+            o += n
+        return out
+
+    def set_weights(self, weights):
+        self.theta.copy_(torch.as_tensor(np.concatenate([np.asarray(w, np.float64).ravel() for w in weights])))
+
+    # ---- noise table / population ----
+    def noise_table(self):
+        if self._noise is None:
+            self._noise = torch.empty(self._noise_size, dtype=torch.float32, device=self.device)
+            L.call("ppx_noise_fill", self._noise.data_ptr(), self._noise_size, self._noise_seed, L.stream())
+        return self._noise
+
+    def _get_population(self):
+        """:172-182.  Returns int64 offsets [P] (multiples of 4, so rows are 16-byte aligned) into the table."""
+        self.noise_table()
+        hi = (self._noise_size - self.D) // 4
+        off = self._rng.randint(0, hi, size=self.POPULATION_SIZE).astype(np.int64) * 4
+        return torch.as_tensor(off).to(self.device)
+
+    def _as_eps(self, population):
+        """-> (noise tensor f32, offsets tensor or None)."""
+        if isinstance(population, torch.Tensor) and population.dtype == torch.int64:
+            return self.noise_table(), population
+        if isinstance(population, list):                             # reference nested list [P][L] of arrays
+            population = np.array([np.concatenate([np.asarray(l).ravel() for l in m]) for m in population])
+        eps = torch.as_tensor(np.ascontiguousarray(population)).to(self.device)
+        if eps.dtype != torch.float32:
+            e32 = eps.float()
+            if not torch.equal(e32.double(), eps.double()):
+                raise ValueError("dense eps must be float32-representable (the device noise is f32)")
+            eps = e32
+        return eps.contiguous(), None
+
+    def perturb_all(self, population, out_f64=False):
+        """theta + sigma*eps for every member: [P, D] CUDA (f32 by default, f64 = reference dtype)."""
+        noise, off = self._as_eps(population)
+        P = off.numel() if off is not None else noise.shape[0]
+        out = torch.empty(P, self.D, dtype=torch.float64 if out_f64 else torch.float32, device=self.device)
+        L.call("ppx_es_perturb", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
+               float(self.SIGMA), P, self.D, out.data_ptr(), int(out_f64), L.stream())
+        return out
+
+    def _get_weights_try(self, w, p):
+        """:137-145 for ONE member given as the reference's list of per-layer eps arrays; returns a list of
+        f64 numpy arrays.  (`w` is accepted for signature compatibility; theta on device is what is used.)"""
+        flat = self.perturb_all([p], out_f64=True)[0].cpu().numpy()
+        out, o = [], 0
+        for s, n in zip(self.shapes, self.layer_sizes):
+            out.append(flat[o:o + n].reshape(s))
+            o += n
+        return out
+
+    # ---- update ----
+    def _update_weights(self, rewards, population, novelty=None):
+        """:217-239.  Asynchronous; `self.update_skipped` reads back the std==0 flag."""
+        noise, off = self._as_eps(population)
+        P = off.numel() if off is not None else noise.shape[0]
+        r = torch.as_tensor(np.asarray(rewards, dtype=np.float64)).to(self.device) if not isinstance(rewards, torch.Tensor) \
+            else rewards.to(self.device, torch.float64)
+        need = L.call("ppx_es_update_workspace", P, self.D)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=self.device)
+        L.call("ppx_es_update", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
+               r.data_ptr(), P, self.D, float(self.SIGMA), float(self.novelty_param),
+               float(novelty) if novelty is not None else 0.0, int(novelty is not None),
+               int(self.fitness_shaping == "centered_rank"), float(self.decay), self._lr.data_ptr(),
+               self._status.data_ptr(), self._ws.data_ptr(), L.stream())
+
+    @property
+    def update_skipped(self):
+        return bool(self._status.item())
+
+    def centered_ranks(self, rewards):
+        r = torch.as_tensor(np.asarray(rewards, dtype=np.float64)).to(self.device)
+        ranks = torch.empty(r.numel(), dtype=torch.int64, device=self.device)
+        cen = torch.empty(r.numel(), dtype=torch.float64, device=self.device)
+        L.call("ppx_rank_center", r.data_ptr(), r.numel(), ranks.data_ptr(), cen.data_ptr(), L.stream())
+        return ranks, cen
+
+    # ---- novelty ----
+    def novelty_batch(self, archive, queries, K=None):
+        """archive [M,dim], queries [Q,dim] -> (knn distance sums [Q], novelties [Q]) f64 CUDA."""
+        a = torch.as_tensor(np.concatenate(archive) if isinstance(archive, list) else np.asarray(archive)) \
+            if not isinstance(archive, torch.Tensor) else archive
+        a = a.to(self.device, torch.float64).contiguous()
+        q = (torch.as_tensor(np.asarray(queries)) if not isinstance(queries, torch.Tensor) else queries)
+        q = q.to(self.device, torch.float64).reshape(-1, a.shape[1]).contiguous()
+        K = self.K if K is None else K
+        s = torch.empty(q.shape[0], dtype=torch.float64, device=self.device)
+        nov = torch.empty_like(s)
+        L.call("ppx_knn_novelty", a.data_ptr(), a.shape[0], q.data_ptr(), q.shape[0], a.shape[1], int(K), s.data_ptr(),
+               nov.data_ptr(), L.stream())
+        return s, nov
+
+    def get_kNN(self, archive, bc, n_neighbors):
+        """:264-281: summed distance to the n_neighbors nearest archive entries (python float)."""
+        s, _ = self.novelty_batch(archive, bc, K=n_neighbors)
+        return float(s[0].item())
+
+    def get_novelty_from_bc(self, archive, bc):
+        """:318-325 (dup :208-214) given the behaviour characterisation instead of a policy rollout."""
+        _, nov = self.novelty_batch(archive, bc)
+        return float(nov[0].item())
+
+    def calc_noveltiy_distribution(self, novelties):
+        """:283-290 (host; MPS = 2 scalars)."""
+        return [round((n / (sum(novelties))), 4) for n in novelties]

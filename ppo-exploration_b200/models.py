@@ -1,0 +1,560 @@
+"""Networks of the learner hot path as flat device parameter banks driven by libppx kernels.
+
+Mirrors models.py of the reference: Policy (:15-124) over MlpNetwork / MlpIntrinsic (:137-213),
+RndNetwork (:216-267) and IntrinsicCuriosityModule (:270-320).  Same class names, constructor
+arguments, method names and state_dict keys (so weights move both ways), but:
+  * every network keeps its parameters, gradients and Adam moments in ONE flat f32 CUDA vector
+    (one clip+Adam launch per optimiser step, one flat-buffer all-reduce when sharded);
+  * weights are stored in-major ([K_in, N_out]); actor / critic / int_critic first layers are
+    concatenated along N and their second layers run as one strided-batched launch;
+  * forward AND backward are explicit kernel sequences (ppx_linear_fwd / _bwd_data / _bwd_weight) --
+    there is no autograd graph.
+Initialisation replays the reference's own torch calls on the CPU in the same order
+(nn.Linear default init, then orthogonal_(sqrt 2) / constant_), so identical seeds give identical
+weights; that is host-side setup, not the hot path.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3}
+F4 = 4  # bytes per float
+
+
+class ParamBank:
+    """Flat parameter / gradient / Adam-moment vectors with named views."""
+
+    def __init__(self, specs, device):
+        self.device = device
+        self.offsets, self.shapes = {}, {}
+        off = 0
+        for name, shape in specs:
+            n = int(np.prod(shape))
+            self.offsets[name], self.shapes[name] = off, tuple(shape)
+            off += (n + 3) // 4 * 4                    # keep every tensor 16-byte aligned
+        self.size = off
+        z = lambda: torch.zeros(off, dtype=torch.float32, device=device)
+        self.flat, self.grad, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.norm_dev = torch.zeros(1, dtype=torch.float64, device=device)
+        self._ws = torch.zeros(4096, dtype=torch.float64, device=device)
+
+    def view(self, name, grad=False):
+        o, s = self.offsets[name], self.shapes[name]
+        return (self.grad if grad else self.flat)[o:o + int(np.prod(s))].view(s)
+
+    def p(self, name, extra=0):
+        return self.flat.data_ptr() + (self.offsets[name] + extra) * F4
+
+    def g(self, name, extra=0):
+        return self.grad.data_ptr() + (self.offsets[name] + extra) * F4
+
+    def adam_step(self, lr, max_norm=0.0, betas=(0.9, 0.999), eps=1e-8):
+        """clip_grad_norm_(max_norm) over the whole bank + Adam (device-side step counter)."""
+        L.call("ppx_clip_adam", self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+               self.exp_avg_sq.data_ptr(), self.size, float(max_norm), self.size if max_norm > 0 else 0, float(lr),
+               float(betas[0]), float(betas[1]), float(eps), 0, self.step_dev.data_ptr(), self.norm_dev.data_ptr(),
+               self._ws.data_ptr(), L.stream())
+
+
+class _Scratch:
+    """Named persistent device buffers that grow on demand (stable addresses between calls of equal size)."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def get(self, name, numel, dtype=torch.float32):
+        b = self.bufs.get(name)
+        if b is None or b.numel() < numel or b.dtype != dtype:
+            b = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+            self.bufs[name] = b
+        return b
+
+
+def linear_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, batch=1, sx=0, sw=0, sb=0, sy=0):
+    L.call("ppx_linear_fwd", x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, batch, sx, sw, sb, sy, L.stream())
+
+
+def linear_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx, batch=1, sdy=0, sw=0, sh=0, sdx=0):
+    L.call("ppx_linear_bwd_data", dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx, batch, sdy, sw, sh, sdx,
+           L.stream())
+
+
+def linear_bwd_weight(scratch, x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, batch=1, sx=0, sdy=0, sdw=0, sdb=0):
+    need = L.call("ppx_linear_bwd_weight_workspace", M, K, N, batch)
+    ws = scratch.get("wgrad_ws", need)
+    L.call("ppx_linear_bwd_weight", x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, ws.data_ptr(), batch, sx, sdy,
+           sdw, sdb, L.stream())
+
+
+class DenseStack:
+    """A chain of Linear(+activation) layers living inside a ParamBank under `prefix`.
+
+    layers: [(K, N, act_name)], last activation must be "none".  Reference state_dict names are
+    f"{prefix}.{2*i}.weight/bias" (nn.Sequential indices with the activations interleaved)."""
+
+    def __init__(self, bank, prefix, layers, scratch):
+        self.bank, self.prefix, self.layers, self.scratch = bank, prefix, layers, scratch
+        assert layers[-1][2] == "none"
+
+    @staticmethod
+    def specs(prefix, layers):
+        out = []
+        for i, (K, N, _) in enumerate(layers):
+            out += [(f"{prefix}.{2 * i}.weight", (K, N)), (f"{prefix}.{2 * i}.bias", (N,))]
+        return out
+
+    def forward(self, x, tag=""):
+        """x: [M, K0] contiguous f32 CUDA.  Returns the list of activations [x, h1, ..., y]."""
+        M = x.shape[0]
+        acts = [x]
+        for i, (K, N, act) in enumerate(self.layers):
+            y = self.scratch.get(f"{self.prefix}{tag}.h{i}", M * N)[:M * N].view(M, N)
+            linear_fwd(acts[-1].data_ptr(), acts[-1].stride(0), self.bank.p(f"{self.prefix}.{2 * i}.weight"),
+                       self.bank.p(f"{self.prefix}.{2 * i}.bias"), M, K, N, ACT[act], y.data_ptr(), N)
+            acts.append(y)
+        return acts
+
+    def backward(self, acts, d_y, need_dx=False, accumulate_tag=""):
+        """Gradients into bank.grad (overwrites this stack's slices).  d_y: [M, N_last] contiguous.
+        Returns dX ([M,K0]) if need_dx."""
+        M = d_y.shape[0]
+        d = d_y
+        for i in range(len(self.layers) - 1, -1, -1):
+            K, N, _ = self.layers[i]
+            x = acts[i]
+            linear_bwd_weight(self.scratch, x.data_ptr(), x.stride(0), d.data_ptr(), d.stride(0), M, K, N,
+                              self.bank.g(f"{self.prefix}.{2 * i}.weight"), self.bank.g(f"{self.prefix}.{2 * i}.bias"))
+            if i == 0 and not need_dx:
+                return None
+            prev_act = self.layers[i - 1][2] if i > 0 else "none"
+            dx = self.scratch.get(f"{self.prefix}{accumulate_tag}.d{i}", M * K)[:M * K].view(M, K)
+            linear_bwd_data(d.data_ptr(), d.stride(0), self.bank.p(f"{self.prefix}.{2 * i}.weight"), M, K, N,
+                            x.data_ptr() if i > 0 else None, x.stride(0) if i > 0 else K, ACT[prev_act],
+                            dx.data_ptr(), K)
+            d = dx
+        return d
+
+
+def _to_in_major(w):
+    return w.detach().t().contiguous()
+
+
+class _TorchInit:
+    """CPU replay of the reference's module construction, only to consume the torch RNG identically."""
+
+    @staticmethod
+    def linear(i, o):
+        return torch.nn.Linear(i, o)
+
+    @staticmethod
+    def orthogonal(lin):
+        torch.nn.init.orthogonal_(lin.weight, math.sqrt(2))
+        torch.nn.init.constant_(lin.bias, 0)
+
+
+class ParallelMLP:
+    """G independent D-h-h-out_g tanh MLPs sharing one input (actor | critic | int_critic), batched.
+
+    Parameters (in `bank`): W1 [D, G*h], b1 [G*h], W2 [G,h,h], b2 [G,h], W3.g [h,out_g], b3.g [out_g]."""
+
+    def __init__(self, bank, names, D, h, outs, scratch):
+        self.bank, self.names, self.D, self.h, self.outs, self.scratch = bank, names, D, h, outs, scratch
+        self.G = len(names)
+
+    @staticmethod
+    def specs(names, D, h, outs):
+        G = len(names)
+        s = [("W1", (D, G * h)), ("b1", (G * h,)), ("W2", (G, h, h)), ("b2", (G, h))]
+        for g, o in zip(names, outs):
+            s += [(f"W3.{g}", (h, o)), (f"b3.{g}", (o,))]
+        return s
+
+    def forward(self, x):
+        M, G, h, D, b = x.shape[0], self.G, self.h, self.D, self.bank
+        H1 = self.scratch.get("pmlp.H1", M * G * h)[:M * G * h].view(M, G * h)
+        H2 = self.scratch.get("pmlp.H2", M * G * h)[:M * G * h].view(M, G * h)
+        linear_fwd(x.data_ptr(), x.stride(0), b.p("W1"), b.p("b1"), M, D, G * h, ACT["tanh"], H1.data_ptr(), G * h)
+        linear_fwd(H1.data_ptr(), G * h, b.p("W2"), b.p("b2"), M, h, h, ACT["tanh"], H2.data_ptr(), G * h,
+                   batch=G, sx=h, sw=h * h, sb=h, sy=h)
+        outs = []
+        for gi, (g, o) in enumerate(zip(self.names, self.outs)):
+            y = self.scratch.get(f"pmlp.out.{g}", M * o)[:M * o].view(M, o)
+            linear_fwd(H2.data_ptr() + gi * h * F4, G * h, b.p(f"W3.{g}"), b.p(f"b3.{g}"), M, h, o, ACT["none"],
+                       y.data_ptr(), o)
+            outs.append(y)
+        self._saved = (x, H1, H2)
+        return outs
+
+    def backward(self, d_outs):
+        """d_outs[g]: [M, out_g] contiguous.  Fills bank.grad for every MLP parameter."""
+        x, H1, H2 = self._saved
+        M, G, h, D, b, sc = x.shape[0], self.G, self.h, self.D, self.bank, self.scratch
+        dP2 = sc.get("pmlp.dP2", M * G * h)[:M * G * h].view(M, G * h)
+        dP1 = sc.get("pmlp.dP1", M * G * h)[:M * G * h].view(M, G * h)
+        for gi, (g, o) in enumerate(zip(self.names, self.outs)):
+            d = d_outs[gi]
+            linear_bwd_weight(sc, H2.data_ptr() + gi * h * F4, G * h, d.data_ptr(), o, M, h, o, b.g(f"W3.{g}"),
+                              b.g(f"b3.{g}"))
+            linear_bwd_data(d.data_ptr(), o, b.p(f"W3.{g}"), M, h, o, H2.data_ptr() + gi * h * F4, G * h, ACT["tanh"],
+                            dP2.data_ptr() + gi * h * F4, G * h)
+        linear_bwd_weight(sc, H1.data_ptr(), G * h, dP2.data_ptr(), G * h, M, h, h, b.g("W2"), b.g("b2"),
+                          batch=G, sx=h, sdy=h, sdw=h * h, sdb=h)
+        linear_bwd_data(dP2.data_ptr(), G * h, b.p("W2"), M, h, h, H1.data_ptr(), G * h, ACT["tanh"], dP1.data_ptr(),
+                        G * h, batch=G, sdy=h, sw=h * h, sh=h, sdx=h)
+        linear_bwd_weight(sc, x.data_ptr(), x.stride(0), dP1.data_ptr(), G * h, M, D, G * h, b.g("W1"), b.g("b1"))
+
+
+class Policy:
+    """models.py:15-124.  `env` only needs .observation_space.shape and .action_space (class name
+    "Discrete" with .n, or "Box" with .shape)."""
+
+    def __init__(self, env, hidden_size, intrinsic_model=False, device="cuda"):
+        self.env = env
+        self.device = torch.device(device)
+        self.state_dim = env.observation_space.shape[0]
+        self.action_type = env.action_space.__class__.__name__
+        self.action_dim = env.action_space.n if self.action_type == "Discrete" else env.action_space.shape[0]
+        self.intrinsic = intrinsic_model
+        self.hidden_size = hidden_size
+        self.names = ["actor", "critic"] + (["int_critic"] if intrinsic_model else [])
+        self.outs = [self.action_dim, 1] + ([1] if intrinsic_model else [])
+        specs = ParallelMLP.specs(self.names, self.state_dim, hidden_size, self.outs)
+        specs.append(("action_log_std", (self.action_dim,)))
+        self.bank = ParamBank(specs, self.device)
+        self.scratch = _Scratch(self.device)
+        self.mlp = ParallelMLP(self.bank, self.names, self.state_dim, hidden_size, self.outs, self.scratch)
+        self.net = self                                           # reference code reaches policy.net.parameters()
+        self._init_like_reference()
+
+    # ---- initialisation / weight exchange ----
+    def _init_like_reference(self):
+        """models.py:141-154 / 177-195: construct actor, critic(, int_critic) Linears in order, then
+        init_weights(): orthogonal(sqrt 2) weights and zero biases in module order."""
+        lins = {}
+        D, h = self.state_dim, self.hidden_size
+        for g, o in zip(self.names, self.outs):
+            lins[g] = [_TorchInit.linear(D, h), _TorchInit.linear(h, h), _TorchInit.linear(h, o)]
+        for g in self.names:
+            for lin in lins[g]:
+                _TorchInit.orthogonal(lin)
+        sd = {"action_log_std": torch.zeros(1, self.action_dim)}
+        for g in self.names:
+            for li, lin in zip((0, 2, 4), lins[g]):
+                sd[f"{g}.{li}.weight"], sd[f"{g}.{li}.bias"] = lin.weight.detach(), lin.bias.detach()
+        self.load_state_dict(sd)
+
+    def load_state_dict(self, sd):
+        """Accepts the reference's MlpNetwork / MlpIntrinsic state_dict (torch tensors or numpy)."""
+        t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).float()
+        h, b = self.hidden_size, self.bank
+        W1, b1, W2, b2 = b.view("W1"), b.view("b1"), b.view("W2"), b.view("b2")
+        for gi, g in enumerate(self.names):
+            W1[:, gi * h:(gi + 1) * h].copy_(_to_in_major(t(sd[f"{g}.0.weight"])))
+            b1[gi * h:(gi + 1) * h].copy_(t(sd[f"{g}.0.bias"]))
+            W2[gi].copy_(_to_in_major(t(sd[f"{g}.2.weight"])))
+            b2[gi].copy_(t(sd[f"{g}.2.bias"]))
+            b.view(f"W3.{g}").copy_(_to_in_major(t(sd[f"{g}.4.weight"])))
+            b.view(f"b3.{g}").copy_(t(sd[f"{g}.4.bias"]))
+        b.view("action_log_std").copy_(t(sd["action_log_std"]).reshape(-1))
+
+    def state_dict(self, grad=False):
+        h, b = self.hidden_size, self.bank
+        v = lambda n: b.view(n, grad=grad).detach().cpu()
+        sd = {"action_log_std": v("action_log_std").reshape(1, -1).clone()}
+        for gi, g in enumerate(self.names):
+            sd[f"{g}.0.weight"] = v("W1")[:, gi * h:(gi + 1) * h].t().contiguous()
+            sd[f"{g}.0.bias"] = v("b1")[gi * h:(gi + 1) * h].clone()
+            sd[f"{g}.2.weight"] = v("W2")[gi].t().contiguous()
+            sd[f"{g}.2.bias"] = v("b2")[gi].clone()
+            sd[f"{g}.4.weight"] = v(f"W3.{g}").t().contiguous()
+            sd[f"{g}.4.bias"] = v(f"b3.{g}").clone()
+        return sd
+
+    def parameters(self):
+        return [self.bank.flat]
+
+    # ---- forward passes ----
+    def forward_raw(self, obs):
+        """obs [B,D] f32 CUDA -> (actor_out [B,A] (pre-tanh means / logits), values [B,1](, int_values [B,1]))."""
+        return self.mlp.forward(obs)
+
+    def _dist(self, actor_out):
+        if self.action_type == "Discrete":
+            return torch.distributions.Categorical(torch.softmax(actor_out, dim=-1))
+        mean = torch.tanh(actor_out)
+        return torch.distributions.Normal(mean, torch.exp(self.bank.view("action_log_std").expand_as(mean)))
+
+    def act(self, obs):
+        """models.py:30-50 / 75-99 (rollout side; sampling uses torch's CUDA generator)."""
+        obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).float()
+        outs = self.forward_raw(obs.contiguous())
+        dist = self._dist(outs[0])
+        actions = dist.sample()
+        lp = dist.log_prob(actions)
+        vals = [o.squeeze(-1).clone() for o in outs[1:]]
+        if self.intrinsic:
+            return actions, vals[0], vals[1], lp
+        return actions, vals[0], lp
+
+    def evaluate(self, obs, actions):
+        """models.py:52-73 / 101-124 as plain tensors (train() uses the fused loss kernel instead)."""
+        obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).float()
+        actions = actions.to(self.device)
+        outs = self.forward_raw(obs.contiguous())
+        dist = self._dist(outs[0])
+        if self.action_type == "Discrete":
+            lp = dist.log_prob(actions.flatten()).unsqueeze(1)
+        else:
+            lp = dist.log_prob(actions)
+        ent = dist.entropy()
+        vals = [o.squeeze(-1).clone() for o in outs[1:]]
+        if self.intrinsic:
+            return vals[0], vals[1], lp, ent
+        return vals[0], lp, ent
+
+
+class RndNetwork:
+    """models.py:216-267: predictor D-h-h-h-1 (LeakyReLU, LeakyReLU, ELU), frozen target D-h-h-1
+    (LeakyReLU x2); constant init (target w=.01 b=1, predictor w=1 b=.01).  Only the predictor lives in
+    the optimiser bank."""
+
+    def __init__(self, input_size, hidden_size=32, device="cuda"):
+        self.device = torch.device(device)
+        D, h = input_size, hidden_size
+        self.input_size, self.hidden_size = D, h
+        self.p_layers = [(D, h, "leaky_relu"), (h, h, "leaky_relu"), (h, h, "elu"), (h, 1, "none")]
+        self.t_layers = [(D, h, "leaky_relu"), (h, h, "leaky_relu"), (h, 1, "none")]
+        self.bank = ParamBank(DenseStack.specs("predictor", self.p_layers), self.device)
+        self.target_bank = ParamBank(DenseStack.specs("target", self.t_layers), self.device)
+        self.scratch = _Scratch(self.device)
+        self.predictor = DenseStack(self.bank, "predictor", self.p_layers, self.scratch)
+        self.target = DenseStack(self.target_bank, "target", self.t_layers, self.scratch)
+        # the reference still constructs default-initialised Linears first (RNG consumption), models.py:220-234
+        for (i, o, _) in self.p_layers + self.t_layers:
+            _TorchInit.linear(i, o)
+        for i in range(len(self.p_layers)):
+            self.bank.view(f"predictor.{2 * i}.weight").fill_(1.0)
+            self.bank.view(f"predictor.{2 * i}.bias").fill_(0.01)
+        for i in range(len(self.t_layers)):
+            self.target_bank.view(f"target.{2 * i}.weight").fill_(0.01)
+            self.target_bank.view(f"target.{2 * i}.bias").fill_(1.0)
+
+    def load_state_dict(self, sd):
+        t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).float()
+        for name, bank, n in (("predictor", self.bank, 4), ("target", self.target_bank, 3)):
+            for i in range(n):
+                bank.view(f"{name}.{2 * i}.weight").copy_(_to_in_major(t(sd[f"{name}.{2 * i}.weight"])))
+                bank.view(f"{name}.{2 * i}.bias").copy_(t(sd[f"{name}.{2 * i}.bias"]))
+
+    def state_dict(self):
+        sd = {}
+        for name, bank, n in (("predictor", self.bank, 4), ("target", self.target_bank, 3)):
+            for i in range(n):
+                sd[f"{name}.{2 * i}.weight"] = bank.view(f"{name}.{2 * i}.weight").detach().cpu().t().contiguous()
+                sd[f"{name}.{2 * i}.bias"] = bank.view(f"{name}.{2 * i}.bias").detach().cpu().clone()
+        return sd
+
+    def forward(self, x):
+        """x [M,D] f32 CUDA contiguous -> (predict [M,1], target [M,1]); keeps predictor activations."""
+        self._p_acts = self.predictor.forward(x)
+        t_acts = self.target.forward(x)
+        return self._p_acts[-1], t_acts[-1]
+
+    __call__ = forward
+
+    def int_reward(self, obs):
+        """models.py:261-267: (pred - target)^2, squeezed -> [M] f32 CUDA."""
+        obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).float()
+        obs = obs.reshape(-1, self.input_size).contiguous()
+        pred, tgt = self.forward(obs)
+        r = torch.empty(obs.shape[0], dtype=torch.float32, device=self.device)
+        L.call("ppx_rnd_sqerr", pred.data_ptr(), tgt.data_ptr(), obs.shape[0], r.data_ptr(), L.stream())
+        return r
+
+    def train_step(self, x, loss_accum, B_total=0):
+        """MSE(pred, target) forward+backward into bank.grad (algorithms.py:495-500).  x already normalised.
+        Sharded: B_total = rows of the global minibatch, so the mean (and its gradient) is global."""
+        pred, tgt = self.forward(x)
+        M = x.shape[0]
+        d_pred = self.scratch.get("rnd.dpred", M)[:M].view(M, 1)
+        L.call("ppx_mse_fwd_bwd", pred.data_ptr(), tgt.data_ptr(), M, float(M) / float(B_total) if B_total else 1.0,
+               d_pred.data_ptr(), None,
+               loss_accum.data_ptr(), L.stream())
+        self.predictor.backward(self._p_acts, d_pred)
+
+
+class ActionConverter:
+    """util.py:47-78 (shape contract only)."""
+
+    def __init__(self, action_space):
+        self.action_type = action_space.__class__.__name__
+        if self.action_type == "Discrete":
+            self.num_actions, self.action_output = action_space.n, 1
+        elif self.action_type == "Box":
+            self.num_actions = action_space.shape[0]
+            self.action_output = self.num_actions
+
+
+class IntrinsicCuriosityModule:
+    """models.py:270-320: state encoder D-h-f, forward model (n+f)-h-f, inverse model 2f-h-n,
+    action encoder Embedding(n,n) / Linear(n,n); f = h; orthogonal(sqrt 2) Linears."""
+
+    def __init__(self, input_size, action_converter, hidden_size, device="cuda"):
+        self.device = torch.device(device)
+        self.action_converter = action_converter
+        self.discrete = action_converter.action_type == "Discrete"
+        D, h = input_size, hidden_size
+        f, n = hidden_size, action_converter.num_actions
+        self.input_size, self.feature_size, self.n_actions, self.hidden = D, f, n, h
+        self.enc_layers = [(D, h, "leaky_relu"), (h, f, "none")]
+        self.fwd_layers = [(n + f, h, "leaky_relu"), (h, f, "none")]
+        self.inv_layers = [(2 * f, h, "leaky_relu"), (h, n, "none")]
+        specs = (DenseStack.specs("state_encoder", self.enc_layers) + DenseStack.specs("forward_model", self.fwd_layers)
+                 + DenseStack.specs("inverse_model", self.inv_layers))
+        specs += [("action_encoder.weight", (n, n))] + ([] if self.discrete else [("action_encoder.bias", (n,))])
+        self.bank = ParamBank(specs, self.device)
+        self.scratch = _Scratch(self.device)
+        self.enc = DenseStack(self.bank, "state_encoder", self.enc_layers, self.scratch)
+        self.fwd = DenseStack(self.bank, "forward_model", self.fwd_layers, self.scratch)
+        self.inv = DenseStack(self.bank, "inverse_model", self.inv_layers, self.scratch)
+        self._init_like_reference()
+
+    def _init_like_reference(self):
+        order = [("state_encoder", self.enc_layers), ("forward_model", self.fwd_layers), ("inverse_model", self.inv_layers)]
+        lins = [(name, i, _TorchInit.linear(K, N)) for name, layers in order for i, (K, N, _) in enumerate(layers)]
+        n = self.n_actions
+        sd = {}
+        if self.discrete:
+            emb = torch.nn.Embedding(n, n)
+        else:
+            emb = _TorchInit.linear(n, n)
+        for name, i, lin in lins:                                   # init_weights(): module order, Linears only
+            _TorchInit.orthogonal(lin)
+            sd[f"{name}.{2 * i}.weight"], sd[f"{name}.{2 * i}.bias"] = lin.weight.detach(), lin.bias.detach()
+        if not self.discrete:
+            _TorchInit.orthogonal(emb)
+            sd["action_encoder.bias"] = emb.bias.detach()
+        sd["action_encoder.weight"] = emb.weight.detach()
+        self.load_state_dict(sd)
+
+    def load_state_dict(self, sd):
+        t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).float()
+        for name, layers in (("state_encoder", self.enc_layers), ("forward_model", self.fwd_layers),
+                             ("inverse_model", self.inv_layers)):
+            for i in range(len(layers)):
+                self.bank.view(f"{name}.{2 * i}.weight").copy_(_to_in_major(t(sd[f"{name}.{2 * i}.weight"])))
+                self.bank.view(f"{name}.{2 * i}.bias").copy_(t(sd[f"{name}.{2 * i}.bias"]))
+        if self.discrete:
+            self.bank.view("action_encoder.weight").copy_(t(sd["action_encoder.weight"]))      # table [n, n]
+        else:
+            self.bank.view("action_encoder.weight").copy_(_to_in_major(t(sd["action_encoder.weight"])))
+            self.bank.view("action_encoder.bias").copy_(t(sd["action_encoder.bias"]))
+
+    def state_dict(self):
+        sd = {}
+        for name, layers in (("state_encoder", self.enc_layers), ("forward_model", self.fwd_layers),
+                             ("inverse_model", self.inv_layers)):
+            for i in range(len(layers)):
+                sd[f"{name}.{2 * i}.weight"] = self.bank.view(f"{name}.{2 * i}.weight").detach().cpu().t().contiguous()
+                sd[f"{name}.{2 * i}.bias"] = self.bank.view(f"{name}.{2 * i}.bias").detach().cpu().clone()
+        w = self.bank.view("action_encoder.weight").detach().cpu()
+        sd["action_encoder.weight"] = w.clone() if self.discrete else w.t().contiguous()
+        if not self.discrete:
+            sd["action_encoder.bias"] = self.bank.view("action_encoder.bias").detach().cpu().clone()
+        return sd
+
+    # ---- pieces shared by int_reward and the training forward ----
+    def _encode_action(self, action, M, out, ldo):
+        """action_encoder into columns [0,n) of `out` (leading dim ldo).  Discrete: ids (f64 or i64, one per
+        row); Box: f32 [M,n]."""
+        n = self.n_actions
+        if self.discrete:
+            ids = action.reshape(-1).contiguous()
+            is_f64 = ids.dtype == torch.float64
+            if not is_f64:
+                ids = ids.long()
+            L.call("ppx_embedding_fwd", self.bank.p("action_encoder.weight"), n, ids.data_ptr(), int(is_f64), 1, M,
+                   out, ldo, L.stream())
+            return ids
+        a = action.float().reshape(M, n).contiguous()
+        linear_fwd(a.data_ptr(), n, self.bank.p("action_encoder.weight"), self.bank.p("action_encoder.bias"), M, n, n,
+                   ACT["none"], out, ldo)
+        return a
+
+    def int_reward(self, state, next_state, action, rewards=None, eta=0.0):
+        """models.py:311-320 (+ the reward blend of algorithms.py:630 when `rewards` is given, in place)."""
+        dev, f, n = self.device, self.feature_size, self.n_actions
+        s = torch.as_tensor(np.asarray(state) if not isinstance(state, torch.Tensor) else state).to(dev).float().contiguous()
+        ns = torch.as_tensor(np.asarray(next_state) if not isinstance(next_state, torch.Tensor) else next_state).to(dev).float().contiguous()
+        action = action.to(dev) if isinstance(action, torch.Tensor) else torch.as_tensor(np.asarray(action)).to(dev)
+        M = s.shape[0]
+        both = self.scratch.get("icm.both", 2 * M * self.input_size)[:2 * M * self.input_size].view(2 * M, self.input_size)
+        both[:M].copy_(s)
+        both[M:].copy_(ns)
+        feats = self.enc.forward(both, tag=".bonus")[-1]                         # [2M, f]: phi(s) ; phi(s')
+        fin = self.scratch.get("icm.bonus.fin", M * (f + n))[:M * (f + n)].view(M, f + n)
+        fin[:, :f].copy_(feats[:M])
+        self._encode_action(action, M, fin.data_ptr() + f * F4, f + n)
+        pred = self.fwd.forward(fin, tag=".bonus")[-1]
+        ri = torch.empty(M, dtype=torch.float32, device=dev)
+        L.call("ppx_icm_bonus_tail", pred.data_ptr(), feats[M:].data_ptr(), M, f, float(eta),
+               rewards.data_ptr() if rewards is not None else None, ri.data_ptr(), L.stream())
+        return ri
+
+    def train_step(self, obs, actions, beta, loss_accum):
+        """Forward (models.py:300-309) + 0.8*inverse + 0.2*forward loss (algorithms.py:684-688) + backward into
+        bank.grad, on the shuffled-consecutive rows obs[:-1] -> obs[1:], actions[:-1]."""
+        f, n, D = self.feature_size, self.n_actions, self.input_size
+        B = obs.shape[0]
+        M = B - 1
+        sc = self.scratch
+        feats_acts = self.enc.forward(obs, tag=".train")                         # encoder once over all B rows
+        feats = feats_acts[-1]                                                   # [B, f]
+        s_ft, ns_ft = feats[:M], feats[1:]
+        fin = sc.get("icm.fin", M * (f + n))[:M * (f + n)].view(M, f + n)
+        iin = sc.get("icm.iin", M * 2 * f)[:M * 2 * f].view(M, 2 * f)
+        fin[:, :f].copy_(s_ft)
+        iin[:, :f].copy_(s_ft)
+        iin[:, f:].copy_(ns_ft)
+        act_in = self._encode_action(actions[:M], M, fin.data_ptr() + f * F4, f + n)
+        fwd_acts = self.fwd.forward(fin, tag=".train")
+        inv_acts = self.inv.forward(iin, tag=".train")
+        ns_hat, a_hat = fwd_acts[-1], inv_acts[-1]
+        # losses + gradients w.r.t. the three heads
+        d_ns_hat = sc.get("icm.d_ns_hat", M * f)[:M * f].view(M, f)
+        d_ns_ft = sc.get("icm.d_ns_ft", M * f)[:M * f].view(M, f)
+        d_a_hat = sc.get("icm.d_a_hat", M * n)[:M * n].view(M, n)
+        ns_c = sc.get("icm.ns_c", M * f)[:M * f].view(M, f)
+        ns_c.copy_(ns_ft)
+        L.call("ppx_mse_fwd_bwd", ns_c.data_ptr(), ns_hat.data_ptr(), M * f, float(beta), d_ns_ft.data_ptr(),
+               d_ns_hat.data_ptr(), loss_accum.data_ptr(), L.stream())
+        if self.discrete:
+            tgt = actions[:M].reshape(-1).double().contiguous()
+            L.call("ppx_xent_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), 1, M, n, float(1 - beta), d_a_hat.data_ptr(),
+                   loss_accum.data_ptr(), L.stream())
+        else:
+            tgt = actions[:M].float().reshape(M, n).contiguous()
+            L.call("ppx_mse_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), M * n, float(1 - beta), d_a_hat.data_ptr(),
+                   None, loss_accum.data_ptr(), L.stream())
+        # backward through the two heads down to their inputs
+        d_fin = self.fwd.backward(fwd_acts, d_ns_hat, need_dx=True)              # [M, f+n]
+        d_iin = self.inv.backward(inv_acts, d_a_hat, need_dx=True)               # [M, 2f]
+        # action encoder gradient
+        if self.discrete:
+            d_act = d_fin[:, f:].contiguous()
+            L.call("ppx_embedding_bwd", d_act.data_ptr(), n, act_in.data_ptr(), int(act_in.dtype == torch.float64), 1, M,
+                   n, self.bank.g("action_encoder.weight"), L.stream())
+        else:
+            d_act = d_fin[:, f:].contiguous()
+            linear_bwd_weight(sc, act_in.data_ptr(), n, d_act.data_ptr(), n, M, n, n, self.bank.g("action_encoder.weight"),
+                              self.bank.g("action_encoder.bias"))
+        # gradient w.r.t. the encoder output rows: row i gets s_ft grads (i < M) and ns_ft grads (i >= 1)
+        d_feats = sc.get("icm.d_feats", B * f)[:B * f].view(B, f)
+        d_feats.zero_()
+        d_feats[:M].add_(d_fin[:, :f]).add_(d_iin[:, :f])
+        d_feats[1:].add_(d_iin[:, f:]).add_(d_ns_ft)
+        self.enc.backward(feats_acts, d_feats)

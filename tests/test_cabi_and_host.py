@@ -1,0 +1,91 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol; host logic; hygiene."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "ppo-exploration_b200")
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ppx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ppo_exploration_b200 as ppx
+    lib = ppx._lib.load()                                     # dlopen only: no CUDA call, works without a GPU
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ppx.h but not exported by libppx.so"
+    assert set(syms) == set(ppx._lib.SIGNATURES), set(syms) ^ set(ppx._lib.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", ppx._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ppx_[a-z0-9_]+)", out))
+    assert set(syms) <= exported
+    assert ppx._lib.call("ppx_version") == 100
+    assert ppx._lib.launch_count() == 0
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(PKG, "libppx.so")], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_touches_the_oracle_or_cpu_fallbacks():
+    bad = []
+    for dp, _, fs in os.walk(PKG):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M) or "/root/reference" in s:
+                    bad.append(f)
+    assert not bad, bad
+    for f in ("bench.py", "__graft_entry__.py"):
+        s = open(os.path.join(ROOT, f)).read()
+        assert "/root/reference" not in s.replace('os.path.isdir("/root/reference")', ""), f
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    import ppo_exploration_b200 as ppx
+    monkeypatch.setattr(ppx._lib, "_lib", None)
+    monkeypatch.setattr(ppx._lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ppx._lib.load()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    import ppo_exploration_b200 as ppx
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ppx.RolloutStorage(4, 2, ppx.Box((3,)), ppx.Box((1,)), device="cpu")
+    with pytest.raises(ValueError):
+        ppx.PPO(env_id="Swimmer-v2")
+    with pytest.raises(ValueError):
+        ppx.EvolutionStrategy("Swimmer-v2", [64, 64])
+
+
+def test_spaces_and_synthetic_env():
+    import ppo_exploration_b200 as ppx
+    env = ppx.SyntheticVecEnv(5, 3, ppx.Discrete(4), seed=2)
+    o = env.reset()
+    o2, r, d, info = env.step(np.zeros(5))
+    assert o.shape == o2.shape == (5, 3) and o.dtype == np.float32 and r.shape == (5,) and d.dtype == bool and len(info) == 5
+    assert ppx.ActionConverter(ppx.Discrete(4)).action_output == 1 and ppx.ActionConverter(ppx.Box((3,))).num_actions == 3
+
+
+def test_swap_and_flatten_matches_reference_layout():
+    import torch
+    import ppo_exploration_b200 as ppx
+    from oracle import rollout as OR
+    a = np.arange(24, dtype=np.float32).reshape(4, 3, 2)
+    b = np.arange(12, dtype=np.float32).reshape(4, 3)
+    for x in (a, b):
+        got = ppx.BaseBuffer.swap_and_flatten(torch.tensor(x)).numpy()
+        assert np.array_equal(got, OR.swap_and_flatten(x))
