@@ -270,6 +270,13 @@ def run_ppx(args):
             dist.barrier()
         return float(ms.item())
 
+    if args.profile:
+        for _ in range(args.warmup):
+            step_resident()
+        ms = timed(step_resident, args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "launches": L.launch_count()}))
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
@@ -332,6 +339,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ppx", choices=["ppx", "reference"])
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: W warm-up + K steps only, no e2e/CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

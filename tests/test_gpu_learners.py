@@ -41,9 +41,11 @@ def _check_sd(got, g, prefix, atol):
 def _loss_close(got, want, n_first=4):
     want = np.asarray(want)
     scale = np.maximum(np.abs(want), 1e-3)
-    # the first minibatches see identical parameters: strict 1e-5; later ones inherit Adam drift
-    assert np.all(np.abs(got[:n_first] - want[:n_first]) <= 1e-5 * scale[:n_first] + 1e-7), (got[:n_first], want[:n_first])
-    assert np.all(np.abs(got - want) <= 2e-4 * scale + 1e-6), np.abs(got - want).max()
+    # the first minibatches see identical parameters: strict 1e-5 relative; the absolute floor 2e-6 covers the
+    # policy loss, a mean of O(1) normalised-advantage terms that cancels to ~1e-7 when ratio == 1
+    assert np.all(np.abs(got[:n_first] - want[:n_first]) <= 1e-5 * scale[:n_first] + 2e-6), (got[:n_first], want[:n_first])
+    # later minibatches inherit Adam's amplification of summation-order noise
+    assert np.all(np.abs(got - want) <= 2e-4 * scale + 2e-6), np.abs(got - want).max()
 
 
 @pytest.mark.parametrize("name", list(PPO_CASES))
