@@ -289,9 +289,12 @@ def run_ppx(args):
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     # per-op device timing of the dense-layer calls over one more pass (CUDA events on the launching stream)
+    m.use_cuda_graph = False                            # per-op events need the individual launches, not a graph replay
+    step_resident()
     with OpTimer(L, torch) as ot:
         step_resident()
     agg = ot.summary()
+    m.use_cuda_graph = True
 
     trans = T * N * world
     value = trans * args.steps / (ms / 1e3)
@@ -311,7 +314,7 @@ def run_ppx(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed every step (256 MiB memset inside the timed region)",
                        "shuffle": "np.random.permutation on the host each epoch (bit-exact reference stream), inside the timed region",
-                       "global_minibatch": B * world},
+                       "global_minibatch": B * world, "cuda_graph": "per-minibatch launch sequence replayed as a CUDA graph (N=1)"},
             "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d + perm_bytes // world),
                     "d2h_bytes_per_step": int(HP["n_epochs"] * N_MINIBATCH * 64), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -97,6 +97,15 @@ int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, c
  * algorithms.py:219).  out[0]=mean, out[1]=std(ddof=1). */
 int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream);
 
+/* Host-side (no GPU): bit-exact replay of numpy's legacy `np.random.permutation(n)` (the draw of
+ * buffer.py:239) from numpy's own MT19937 state (np.random.get_state(): key[624], pos); the advanced
+ * state is written back so the caller can np.random.set_state it.  `_draws` + `_apply` are the same
+ * computation split into its RNG-bound and its memory-bound half so two host threads can pipeline
+ * consecutive epochs. */
+int ppx_np_permutation(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* out_host);
+int ppx_np_shuffle_draws(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* j_out_host);
+int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host);
+
 /* ---------------------------------------------------------------- dense layers (fp32) ------- */
 /* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.
  * Strides (in elements) step X/W/bias/Y per batch entry; batch=1 ignores them.

@@ -45,6 +45,9 @@ SIGNATURES = {
     "ppx_count_table_dump": (c_i, [c_p, c_p, c_p, c_u, C.POINTER(c_u)]),
     "ppx_gather_minibatch": (c_i, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_p, c_l, c_i, c_i, c_p]),
     "ppx_mean_std": (c_i, [c_p, c_l, c_p, c_p]),
+    "ppx_np_permutation": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),
+    "ppx_np_shuffle_draws": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),
+    "ppx_np_shuffle_apply": (c_i, [c_p, c_l, c_p]),
     "ppx_linear_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_l, c_l, c_l, c_l, c_p]),
     "ppx_linear_bwd_data": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_l, c_l, c_l, c_l, c_p]),
     "ppx_linear_bwd_weight_workspace": (c_l, [c_i, c_i, c_i, c_i]),
@@ -104,8 +107,11 @@ def call(name, *args):
     return rc
 
 
+extra_launches = 0      # kernels launched through CUDA-graph replays (not seen by the C-side counter)
+
+
 def launch_count():
-    return int(load().ppx_launch_count())
+    return int(load().ppx_launch_count()) + extra_launches
 
 
 def stream():

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib as L
 from . import dist as D
-from .buffer import RolloutStorage, IntrinsicStorage, _dev
+from .buffer import RolloutStorage, IntrinsicStorage, HostRngStream, _dev
 from .models import Policy, RndNetwork, IntrinsicCuriosityModule, ActionConverter, _Scratch
 from .util import RunningMeanStd, normalize_obs
 
@@ -59,6 +59,10 @@ class BaseAlgorithm(object):
         self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._sums = torch.zeros(32, dtype=torch.float64, device=self.device)
         self.scale_batch_with_world = True     # sharded runs: batch_size is per rank (weak scaling)
+        self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
+        self._graphs = {}
+        self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._perm_static = None
 
     # ---- shared pieces of the fused update --------------------------------------------------
     def _record(self, key, value):
@@ -113,25 +117,60 @@ class BaseAlgorithm(object):
                d_ival.data_ptr() if dual else None, losses_row, ws, L.stream())
         pol.mlp.backward([d_actor, d_val] + ([d_ival] if dual else []))
 
-    def _epoch_minibatches(self, ro):
-        """Yields (idx_dev, B_local, B_total) for one epoch.  Single GPU: slices of the reference's permutation
-        (buffer.py:239,251-254).  Sharded: every rank draws the SAME permutation over the global [T, W*N]
-        index space and keeps the rows of each global minibatch whose env it owns (owner-computes)."""
+    def _graph_call(self, key, fn):
+        """Run fn() -- a fixed sequence of libppx launches on static buffers -- through a CUDA graph: eager the
+        first time a key is seen (allocations settle), captured the second time, replayed afterwards."""
+        if not self.use_cuda_graph or D.world_size() > 1:
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "warm"
+            return fn()
+        if ent == "warm":
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # the RNG worker thread may pin memory meanwhile
+                fn()
+            ent = (g, L.launch_count() - n0)
+            L.extra_launches -= ent[1]                      # the capture pass launched nothing
+            self._graphs[key] = ent
+        ent[0].replay()
+        L.extra_launches += ent[1]
+
+    def _rng_script(self, ro, randn_per_minibatch=False):
+        W = D.world_size()
+        total = ro.buffer_size * ro.n_envs * W
+        Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
+        n_mb = -(-total // Bg)
+        script = []
+        for _ in range(self.n_epochs):
+            script.append(('perm', total))
+            script += [('randn',)] * (n_mb if randn_per_minibatch else 0)
+        return script
+
+    def _epoch_minibatches(self, ro, rng):
+        """Yields (idx_dev, B_local, B_total, offset) for one epoch.  Single GPU: slices of the reference's
+        permutation (buffer.py:239,251-254), staged in a static device buffer.  Sharded: every rank draws the
+        SAME permutation over the global [T, W*N] index space and keeps the rows of each global minibatch whose
+        env it owns (owner-computes)."""
         W, r = D.world_size(), D.rank()
         T, N = ro.buffer_size, ro.n_envs
         total = T * N * W
         Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
+        perm = rng.next()                                       # pinned int64 [total]
         if W == 1:
-            idx = ro.permutation()
+            if self._perm_static is None or self._perm_static.numel() != total:
+                self._perm_static = torch.empty(total, dtype=torch.int64, device=self.device)
+            self._perm_static.copy_(perm, non_blocking=True)
             for s in range(0, total, Bg):
-                sl = idx[s:s + Bg]
-                yield sl, sl.numel(), 0
+                sl = self._perm_static[s:s + Bg]
+                yield sl, sl.numel(), 0, s
             return
-        perm = np.random.permutation(total)
+        perm = perm.numpy()
         for s in range(0, total, Bg):
             g = perm[s:s + Bg]
             loc = D.owned_slice(g, T, N, r)
-            yield torch.as_tensor(loc).to(self.device, non_blocking=True), len(loc), len(g)
+            yield torch.as_tensor(loc).to(self.device, non_blocking=True), len(loc), len(g), s
 
     def _sync_grads(self, bank):
         if D.world_size() > 1:
@@ -210,12 +249,16 @@ class PPO(BaseAlgorithm):
         losses = torch.zeros(self.n_epochs * n_mb, 8, dtype=torch.float64, device=self.device)
         bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
         step = 0
+        rng = HostRngStream(self._rng_script(ro))
         for _ in range(self.n_epochs):
-            for sl, b, bt in self._epoch_minibatches(ro):
-                ro.gather_into(sl, bufs)
-                self._policy_step(bufs, b, losses.data_ptr() + step * 64, B_total=bt)
-                self._sync_grads(self.policy.bank)
-                self.policy.bank.adam_step(self.lr, self.max_grad_norm)
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+                def fn(sl=sl, b=b, bt=bt):
+                    ro.gather_into(sl, bufs)
+                    self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt)
+                    self._sync_grads(self.policy.bank)
+                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)
+                self._graph_call(("ppo", off, b, bt), fn)
+                losses[step].copy_(self._loss_row)
                 step += 1
         ro.generator_ready = True
         self._finish_train(losses[:step], ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
@@ -308,15 +351,19 @@ class PPO_RND(BaseAlgorithm):
         bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
         step = 0
         self.rnd_trained_steps = 0
+        rng = HostRngStream(self._rng_script(ro, randn_per_minibatch=True))
         for _ in range(self.n_epochs):
-            for sl, b, bt in self._epoch_minibatches(ro):
-                ro.gather_into(sl, bufs)
-                self._policy_step(bufs, b, losses.data_ptr() + step * 64, dual=True, int_vf_coef=self.int_vf_coef,
-                                  B_total=bt)
-                self._sync_grads(self.policy.bank)
-                self.policy.bank.adam_step(self.lr, self.max_grad_norm)
-                if np.random.randn() < 0.25:                        # algorithms.py:468, same host RNG stream
-                    self.train_rnd(bufs['observations'][:b], bt)
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+                def fn(sl=sl, b=b, bt=bt):
+                    ro.gather_into(sl, bufs)
+                    self._policy_step(bufs, b, self._loss_row.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
+                                      B_total=bt)
+                    self._sync_grads(self.policy.bank)
+                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)
+                self._graph_call(("rnd_policy", off, b, bt), fn)
+                losses[step].copy_(self._loss_row)
+                if rng.next() < 0.25:                               # algorithms.py:468, same host RNG stream
+                    self._graph_call(("rnd_pred", b, bt), lambda b=b, bt=bt: self.train_rnd(bufs['observations'][:b], bt))
                     self.rnd_trained_steps += 1
                 step += 1
         ro.generator_ready = True
@@ -391,14 +438,21 @@ class PPO_ICM(BaseAlgorithm):
         icm_losses = torch.zeros(self.n_epochs * n_mb, dtype=torch.float64, device=self.device)
         bufs = ro._minibatch_buffers(B)
         step = 0
+        rng = HostRngStream(self._rng_script(ro))
+        icm_row = torch.zeros(1, dtype=torch.float64, device=self.device) if not hasattr(self, "_icm_row") else self._icm_row
+        self._icm_row = icm_row
         for _ in range(self.n_epochs):
-            for sl, b, bt in self._epoch_minibatches(ro):
-                ro.gather_into(sl, bufs)
-                self._policy_step(bufs, b, losses.data_ptr() + step * 64, policy_weight=float(self.policy_weight))
-                self.intrinsic_module.train_step(bufs['observations'][:b], bufs['actions'][:b], self.beta,
-                                                 icm_losses[step:step + 1])
-                self.policy.bank.adam_step(self.lr, self.max_grad_norm)     # only policy grads are clipped (:697)
-                self.intrinsic_module.bank.adam_step(self.int_lr, 0.0)
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+                def fn(sl=sl, b=b):
+                    ro.gather_into(sl, bufs)
+                    self._policy_step(bufs, b, self._loss_row.data_ptr(), policy_weight=float(self.policy_weight))
+                    icm_row.zero_()
+                    self.intrinsic_module.train_step(bufs['observations'][:b], bufs['actions'][:b], self.beta, icm_row)
+                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)     # only policy grads are clipped (:697)
+                    self.intrinsic_module.bank.adam_step(self.int_lr, 0.0)
+                self._graph_call(("icm", off, b), fn)
+                losses[step].copy_(self._loss_row)
+                icm_losses[step:step + 1].copy_(icm_row)
                 step += 1
         ro.generator_ready = True
         losses[:, 5] = icm_losses

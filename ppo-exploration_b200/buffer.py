@@ -15,6 +15,8 @@ The shuffle indices come from the same `np.random.permutation(T*N)` draw as the 
 (buffer.py:239), so a seeded run visits identical minibatches.
 """
 import ctypes as C
+import queue
+import threading
 from collections import namedtuple
 
 import numpy as np
@@ -28,6 +30,81 @@ def _dev(x, dtype, device):
     if isinstance(x, torch.Tensor):
         return x.detach().to(device=device, dtype=dtype, non_blocking=True).contiguous()
     return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype, non_blocking=True)
+
+
+def np_permutation(n):
+    """np.random.permutation(n) (the draw of buffer.py:239), bit-exact and ~3x faster: libppx replays numpy's
+    legacy MT19937 shuffle from numpy's own global state and hands the advanced state back."""
+    st = np.random.get_state()
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int(int(st[2]))
+    out = np.empty(int(n), np.int64)
+    L.call("ppx_np_permutation", key.ctypes.data, C.byref(pos), int(n), out.ctypes.data)
+    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+    return out
+
+
+class HostRngStream:
+    """Replays a fixed script of draws from the GLOBAL numpy RNG in worker threads, in order, so the host
+    shuffle (buffer.py:239) and RND's per-minibatch randn() (algorithms.py:468) overlap the GPU work while
+    consuming exactly the reference's random stream.  script items: ('perm', n) | ('randn',).
+
+    Two pipelined stages (both release the GIL inside libppx): stage 1 owns the RNG -- it draws the
+    Fisher-Yates partner sequence of each permutation (RNG-bound) and the scalar randn()s; stage 2 applies
+    the swaps into a pinned buffer (memory-bound) while stage 1 already works on the next epoch."""
+
+    def __init__(self, script):
+        self.q, self.mid = queue.Queue(), queue.Queue()
+        self.err = None
+        self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
+        self.t2 = threading.Thread(target=self._apply, daemon=True)
+        self.t1.start()
+        self.t2.start()
+
+    def _draw(self, script):
+        try:
+            for op in script:
+                if op[0] == 'perm':
+                    n = int(op[1])
+                    st = np.random.get_state()
+                    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+                    pos = C.c_int(int(st[2]))
+                    j = np.empty(max(n, 1), np.int64)
+                    L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
+                    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+                    self.mid.put(('perm', j, n))
+                else:
+                    self.mid.put(('val', float(np.random.randn())))
+        except Exception as e:
+            self.err = e
+        self.mid.put(None)
+
+    def _apply(self):
+        try:
+            while True:
+                item = self.mid.get()
+                if item is None:
+                    break
+                if item[0] == 'perm':
+                    _, j, n = item
+                    out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
+                    L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
+                    self.q.put(out)
+                else:
+                    self.q.put(item[1])
+        except Exception as e:
+            self.err = e
+        self.q.put(None)
+
+    def next(self):
+        v = self.q.get()
+        if v is None:
+            raise self.err if self.err is not None else RuntimeError("HostRngStream: script exhausted")
+        return v
+
+    def drain(self):
+        self.t1.join()
+        self.t2.join()
 
 
 class BaseBuffer(object):
@@ -272,7 +349,7 @@ class RolloutStorage(BaseBuffer):
 
     def permutation(self):
         """The epoch's shuffle: the reference's own host draw (buffer.py:239), uploaded once."""
-        idx = np.random.permutation(self.buffer_size * self.n_envs)
+        idx = np_permutation(self.buffer_size * self.n_envs)
         return torch.as_tensor(idx).to(self.device, non_blocking=True)
 
     def get(self, batch_size=None):

@@ -38,21 +38,32 @@ gather_kernel(GatherArgs args, const int64_t* __restrict__ idx, int64_t B, int T
   else gather_rows<int>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N);
 }
 
-// one CTA, two passes (mean, then centred sum of squares), f64 accumulation, fixed order -> deterministic
-__global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+// mean / unbiased std in two small launches: per-CTA f64 (sum, sum of squares) partials, then one CTA
+// combines them in a fixed order.  f64 keeps sum-of-squares cancellation below 1e-12 relative for
+// advantage-like data (|mean| <~ 1e3 std); deterministic.
+constexpr int kStatBlocks = 256;
+__global__ void __launch_bounds__(256) moments_partial_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ part) {
   __shared__ double s_red[32];
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
-  const double mean = block_sum(s, s_red) / (double)n;
-  double q = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double d = (double)x[i] - mean;
-    q += d * d;
+  double s = 0.0, q = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i];
+    s += v;
+    q += v * v;
   }
+  s = block_sum(s, s_red);
+  q = block_sum(q, s_red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = q; }
+}
+__global__ void __launch_bounds__(256) moments_final_kernel(const double* __restrict__ part, int nb, int64_t n, double* __restrict__ out) {
+  __shared__ double s_red[32];
+  double s = 0.0, q = 0.0;
+  if ((int)threadIdx.x < nb) { s = part[2 * threadIdx.x]; q = part[2 * threadIdx.x + 1]; }
+  s = block_sum(s, s_red);
   q = block_sum(q, s_red);
   if (threadIdx.x == 0) {
+    const double mean = s / (double)n;
     out[0] = mean;
-    out[1] = sqrt(q / (double)(n - 1));          // unbiased, like torch.Tensor.std()
+    out[1] = sqrt(fmax(q - s * mean, 0.0) / (double)(n - 1));          // unbiased, like torch.Tensor.std()
   }
 }
 
@@ -87,6 +98,12 @@ extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* d
 
 extern "C" int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream) {
   PPX_REQUIRE(x && out2 && n >= 1, "mean_std: bad arguments");
-  ppx::mean_std_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out2);
+  static double* part = nullptr;                       // per-process scratch; calls are stream-ordered (one learner thread)
+  if (!part) PPX_CUDA(cudaMalloc((void**)&part, 2 * ppx::kStatBlocks * sizeof(double)));
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(ppx::kStatBlocks, ppx::ceil_div(n, 2048)));
+  ppx::moments_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, n, part);
+  int rc = ppx::after_launch("mean_std(partials)");
+  if (rc) return rc;
+  ppx::moments_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(part, nb, n, out2);
   return ppx::after_launch("mean_std");
 }

@@ -1,0 +1,134 @@
+// Host-side, bit-exact replay of numpy's legacy shuffle:  np.random.permutation(n)  (buffer.py:239).
+//
+// The reference draws one permutation per epoch from the GLOBAL legacy RandomState (MT19937).  To keep
+// "bit-exact shuffle indices" without paying numpy's generic shuffle loop (7-18 ms per 512k on the
+// host, which would bound the whole learner pass), this restates numpy's algorithm in C:
+//   RandomState.permutation(n): arr = arange(n, int64); shuffle(arr)
+//   shuffle (1-d fast path):    for i = n-1 .. 1:  j = random_interval(i);  swap(arr[i], arr[j])
+//   random_interval(max):       mask = next_pow2(max+1)-1;  do v = next_uint32() & mask while v > max
+//                               (64-bit draws when max > 0xffffffff)
+//   next_uint32:                MT19937 genrand with the standard tempering
+// The caller passes numpy's own state (np.random.get_state(): key[624], pos) and writes the advanced
+// state back with np.random.set_state, so interleaved numpy calls (e.g. RND's randn()) stay in sequence.
+// Two stages so they can pipeline across epochs: drawing the j sequence is RNG-bound, applying the
+// swaps is cache-miss-bound.
+#include <stdlib.h>
+#include "common.cuh"
+
+extern "C" int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host);
+
+namespace {
+constexpr int MT_N = 624, MT_M = 397;
+constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+
+// MT19937 with block generation: the 624-word state update and the tempering run as straight loops
+// over whole blocks (auto-vectorised), extraction is a buffered load.  Same output sequence as numpy's
+// word-at-a-time mt19937_next.
+struct Mt {
+  uint32_t* key;
+  int pos;
+  uint32_t out[MT_N];
+  int avail_from;            // out[] holds the tempered words of the CURRENT key block for indices >= avail_from
+  Mt(uint32_t* k, int p) : key(k), pos(p), avail_from(MT_N) { temper_from(p); }
+  inline void temper_from(int from) {
+    uint32_t* __restrict__ o = out;
+    const uint32_t* __restrict__ k = key;
+    for (int i = from; i < MT_N; ++i) {
+      uint32_t y = k[i];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      o[i] = y;
+    }
+    avail_from = from;
+  }
+  inline void gen() {
+    uint32_t* k = key;
+    int i;
+    uint32_t y;
+    for (i = 0; i < MT_N - MT_M; i++) {
+      y = (k[i] & UPPER) | (k[i + 1] & LOWER);
+      k[i] = k[i + MT_M] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    }
+    for (; i < MT_N - 1; i++) {
+      y = (k[i] & UPPER) | (k[i + 1] & LOWER);
+      k[i] = k[i + (MT_M - MT_N)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    }
+    y = (k[MT_N - 1] & UPPER) | (k[0] & LOWER);
+    k[MT_N - 1] = k[MT_M - 1] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    pos = 0;
+    temper_from(0);
+  }
+  inline uint32_t next32() {
+    if (pos == MT_N) gen();
+    return out[pos++];
+  }
+  inline uint64_t next64() {                       // numpy: (uint64)next32() << 32 | next32()
+    const uint64_t hi = next32();
+    return (hi << 32) | next32();
+  }
+};
+
+inline uint64_t random_interval(Mt& mt, uint64_t max) {
+  if (max == 0) return 0;
+  uint64_t mask = max, value;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+  if (max <= 0xffffffffull) {
+    while ((value = (mt.next32() & mask)) > max) {}
+  } else {
+    while ((value = (mt.next64() & mask)) > max) {}
+  }
+  return value;
+}
+}  // namespace
+
+// Branch-free form of the rejection loop for 32-bit bounds: every draw is stored, the position only
+// advances when the draw is accepted.  Identical draw sequence, no data-dependent branch to mispredict.
+static inline void draw_partners(Mt& mt, int64_t n, int64_t* j_out) {
+  int64_t i = n - 1;
+  for (; i >= 1 && (uint64_t)i > 0xffffffffull; --i) j_out[i] = (int64_t)random_interval(mt, (uint64_t)i);
+  while (i >= 1) {
+    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+    const uint32_t v = mt.next32() & mask;
+    j_out[i] = (int64_t)v;
+    i -= (int64_t)(v <= (uint32_t)i);
+  }
+}
+
+// stage 1: the swap partners j_i for i = n-1 .. 1 (j_out[i] = partner of position i; j_out[0] unused)
+extern "C" int ppx_np_shuffle_draws(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* j_out_host) {
+  PPX_REQUIRE(key624_host && pos_host && j_out_host && n >= 0, "np_shuffle_draws: bad arguments");
+  PPX_REQUIRE(*pos_host >= 0 && *pos_host <= MT_N, "np_shuffle_draws: MT19937 pos=%d out of range", *pos_host);
+  Mt mt(key624_host, *pos_host);
+  draw_partners(mt, n, j_out_host);
+  *pos_host = mt.pos;
+  return PPX_OK;
+}
+
+// stage 2: arange(n) with the swaps applied
+extern "C" int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host) {
+  PPX_REQUIRE(j_host && out_host && n >= 0, "np_shuffle_apply: bad arguments");
+  for (int64_t i = 0; i < n; ++i) out_host[i] = i;
+  for (int64_t i = n - 1; i >= 1; --i) {
+    const int64_t j = j_host[i];
+    const int64_t t = out_host[j];
+    out_host[j] = out_host[i];
+    out_host[i] = t;
+  }
+  return PPX_OK;
+}
+
+// both stages back to back (single-threaded callers); out_host doubles as the partner buffer
+extern "C" int ppx_np_permutation(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* out_host) {
+  PPX_REQUIRE(key624_host && pos_host && out_host && n >= 0, "np_permutation: bad arguments");
+  PPX_REQUIRE(*pos_host >= 0 && *pos_host <= MT_N, "np_permutation: MT19937 pos=%d out of range", *pos_host);
+  Mt mt(key624_host, *pos_host);
+  int64_t* j = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
+  if (!j) return ppx::fail(PPX_ERR_ARG, "np_permutation: out of host memory");
+  draw_partners(mt, n, j);
+  *pos_host = mt.pos;
+  const int rc = ppx_np_shuffle_apply(j, n, out_host);
+  free(j);
+  return rc;
+}

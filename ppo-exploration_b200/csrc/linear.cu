@@ -198,16 +198,33 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmP p) {
   }
 }
 
-// out[e] = sum_s part[s*stride + e], fixed order
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n,
-                                       float* __restrict__ out, int batch, int64_t part_bstride, int64_t out_bstride) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// out[e] = sum_s part[s*stride + e].  32 outputs x 8 split-phases per CTA: every thread keeps its loads
+// independent (in flight together), the 8 phase sums are combined through shared memory in a fixed order
+// -> deterministic.  One launch reduces the weight block [0,n_w) into out_w and the bias block into out_b.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n_w, int64_t n_b,
+                       float* __restrict__ out_w, float* __restrict__ out_b, int batch, int64_t part_bstride,
+                       int64_t outw_bstride, int64_t outb_bstride) {
+  __shared__ float s_p[8][33];
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;
   const int z = blockIdx.y;
-  if (e >= n || z >= batch) return;
-  const float* p = part + z * part_bstride + e;
+  const int64_t n = n_w + (out_b ? n_b : 0);
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += p[k * stride];
-  out[z * out_bstride + e] = s;
+  if (e < n) {
+    const float* p = part + z * part_bstride + e;
+#pragma unroll 4
+    for (int k = ph; k < splits; k += 8) s += p[(int64_t)k * stride];
+  }
+  s_p[ph][lane] = s;
+  __syncthreads();
+  if (ph == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += s_p[q][lane];
+    if (e < n_w) out_w[z * outw_bstride + e] = t;
+    else out_b[z * outb_bstride + (e - n_w)] = t;
+  }
 }
 
 // ---------------- narrow outputs (N <= 4): value heads, action means ----------------
@@ -376,13 +393,10 @@ extern "C" int ppx_linear_bwd_weight(const float* X, int ldx, const float* dY, i
 #undef PPX_WS
     int rc = after_launch("linear_bwd_weight(small)");
     if (rc) return rc;
-    dim3 rg((unsigned)ceil_div((int64_t)K * N, 256), (unsigned)batch);
-    reduce_partials_kernel<<<rg, 256, 0, st>>>(workspace, ctas, per, (int64_t)K * N, dW, batch, (int64_t)ctas * per, strideDW);
-    rc = after_launch("linear_bwd_weight(reduce)");
-    if (rc || !dbias) return rc;
-    dim3 bg(1, (unsigned)batch);
-    reduce_partials_kernel<<<bg, 256, 0, st>>>(workspace + (int64_t)K * N, ctas, per, N, dbias, batch, (int64_t)ctas * per, strideDB);
-    return after_launch("linear_bwd_weight(reduce bias)");
+    dim3 rg((unsigned)ceil_div(per, 32), (unsigned)batch);
+    reduce_partials_kernel<<<rg, 256, 0, st>>>(workspace, ctas, per, (int64_t)K * N, N, dW, dbias, batch, (int64_t)ctas * per,
+                                               strideDW, strideDB);
+    return after_launch("linear_bwd_weight(reduce)");
   }
   const int splits = wgrad_splits(M, K, N, batch);
   GemmP p{};
@@ -393,11 +407,8 @@ extern "C" int ppx_linear_bwd_weight(const float* X, int ldx, const float* dY, i
   gemm_kernel<false, true, EPI_WGRAD><<<grid, NT, 0, st>>>(p);
   int rc = after_launch("linear_bwd_weight");
   if (rc) return rc;
-  dim3 rg((unsigned)ceil_div((int64_t)K * N, 256), (unsigned)batch);
-  reduce_partials_kernel<<<rg, 256, 0, st>>>(workspace, splits, per, (int64_t)K * N, dW, batch, (int64_t)splits * per, strideDW);
-  rc = after_launch("linear_bwd_weight(reduce)");
-  if (rc || !dbias) return rc;
-  dim3 bg((unsigned)ceil_div(N, 256), (unsigned)batch);
-  reduce_partials_kernel<<<bg, 256, 0, st>>>(workspace + (int64_t)K * N, splits, per, N, dbias, batch, (int64_t)splits * per, strideDB);
-  return after_launch("linear_bwd_weight(reduce bias)");
+  dim3 rg((unsigned)ceil_div(per, 32), (unsigned)batch);
+  reduce_partials_kernel<<<rg, 256, 0, st>>>(workspace, splits, per, (int64_t)K * N, N, dW, dbias, batch, (int64_t)splits * per,
+                                             strideDW, strideDB);
+  return after_launch("linear_bwd_weight(reduce)");
 }

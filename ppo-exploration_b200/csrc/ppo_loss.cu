@@ -160,12 +160,21 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
   }
 }
 
-// sums[e] = sum over CTAs of partials[cta][e], fixed order
-__global__ void __launch_bounds__(32) sum_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
-  const int lane = threadIdx.x;
+// sums[e] = sum over CTAs of partials[cta][e]: 8 warps take interleaved CTAs, combined in a fixed order
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
+  __shared__ double s_p[8][kPart];
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
   double acc = 0.0;
-  for (int k = 0; k < nblocks; ++k) acc += partials[(int64_t)k * kPart + lane];
-  sums[lane] = acc;
+#pragma unroll 4
+  for (int k = ph; k < nblocks; k += 8) acc += partials[(int64_t)k * kPart + lane];
+  s_p[ph][lane] = acc;
+  __syncthreads();
+  if (ph == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += s_p[q][lane];
+    sums[lane] = t;
+  }
 }
 
 struct FinalArgs {
@@ -279,7 +288,7 @@ __global__ void accum_loss_kernel(const double* __restrict__ partials, int n, do
 
 int grid_for(int64_t n) {
   int64_t g = ceil_div(n, 256);
-  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 4);
+  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 2);
   return (int)std::max<int64_t>(1, std::min(g, cap));
 }
 
@@ -333,7 +342,7 @@ extern "C" int ppx_ppo_loss_head(const ppx_ppo_cfg* c, const float* actor_out, c
   else head_kernel<false><<<g, 256, 0, st>>>(h);
   rc = after_launch("ppo_loss head");
   if (rc) return rc;
-  sum_partials_kernel<<<1, 32, 0, st>>>(partials, g, sums_out);
+  sum_partials_kernel<<<1, 256, 0, st>>>(partials, g, sums_out);
   return after_launch("ppo_loss sums");
 }
 

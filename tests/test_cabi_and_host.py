@@ -89,3 +89,27 @@ def test_swap_and_flatten_matches_reference_layout():
     for x in (a, b):
         got = ppx.BaseBuffer.swap_and_flatten(torch.tensor(x)).numpy()
         assert np.array_equal(got, OR.swap_and_flatten(x))
+
+
+def test_host_permutation_is_bit_exact_numpy_replay():
+    """libppx's host-side MT19937 shuffle == np.random.permutation, and leaves the global stream in step."""
+    from ppo_exploration_b200.buffer import np_permutation, HostRngStream
+    for n in (0, 1, 2, 3, 17, 1000, 524288):
+        np.random.seed(n)
+        want = [np.random.permutation(n) for _ in range(2)] + [np.random.randn(3)]
+        np.random.seed(n)
+        got = [np_permutation(n) for _ in range(2)] + [np.random.randn(3)]
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), n
+    np.random.seed(3)
+    want = []
+    for _ in range(3):                                       # RND's stream: perm, then one randn per minibatch
+        want.append(np.random.permutation(1000))
+        want += [np.random.randn() for _ in range(2)]
+    tail = np.random.randn()
+    np.random.seed(3)
+    s = HostRngStream(sum([[('perm', 1000), ('randn',), ('randn',)] for _ in range(3)], []))
+    for w in want:
+        g = s.next()
+        assert np.array_equal(g.numpy(), w) if isinstance(w, np.ndarray) else g == w
+    s.drain()
+    assert np.random.randn() == tail
