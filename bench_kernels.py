@@ -1,0 +1,209 @@
+"""Per-kernel roofline microbenchmark of libppx (not the driver's bench: see bench.py for that contract).
+
+For every hot kernel: the shape the headline configs use AND a shape large enough to be bandwidth-bound,
+timed with CUDA events on the launching stream after warm-up, with an L2 flush (256 MiB memset) before
+every timed launch.  achieved = ALGORITHMIC bytes per launch (SURVEY §8d / DESIGN.md) / time;
+frac = achieved / MEASURED_PEAKS.json hbm_gbs.  Writes one JSON line per case and, with --md, a table.
+
+  python bench_kernels.py [--only gae,simhash,...] [--md profiles/kernels_rNN.md] [--iters 20]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import ppo_exploration_b200 as ppx  # noqa: E402
+from ppo_exploration_b200 import _lib as L  # noqa: E402
+from ppo_exploration_b200 import models as PM  # noqa: E402
+
+DEV = "cuda"
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+TF = PEAKS.get("bf16_tflops", 1590.0)
+_flush = None
+
+
+def timed(fn, iters, warm=3):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        _flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts = np.array(ts)
+    return float(np.median(ts)), float(ts.min())
+
+
+def report(rows, name, shape, bytes_, flops, ms, ms_min, launches=1, note=""):
+    r = {"kernel": name, "shape": shape, "ms_median": ms, "ms_min": ms_min, "launches": launches, "note": note}
+    if bytes_:
+        r.update(alg_bytes=int(bytes_), gbs=bytes_ / ms / 1e6, hbm_frac=bytes_ / ms / 1e6 / HBM)
+    if flops:
+        r.update(flops=float(flops), tflops=flops / ms / 1e9, tensor_frac=flops / ms / 1e9 / TF)
+    rows.append(r)
+    print(json.dumps(r), flush=True)
+
+
+def bench_gae(rows, iters):
+    for T, N, dual in ((256, 2048, False), (256, 131072, False), (128, 128, True), (128, 131072, True)):
+        o, a = ppx.Box((4,)), ppx.Box((1,))
+        cls = ppx.IntrinsicStorage if dual else ppx.RolloutStorage
+        buf = cls(T, N, o, a)
+        g = torch.Generator(device=DEV).manual_seed(0)
+        for nm in ("rewards", "values") + (("int_rewards", "int_values") if dual else ()):
+            getattr(buf, nm).copy_(torch.randn(T, N, device=DEV, generator=g))
+        buf.masks.copy_((torch.rand(T, N, device=DEV, generator=g) < 0.02).to(torch.uint8))
+        lv = torch.randn(N, device=DEV); d = buf.masks[-1].clone()
+        fn = (lambda: buf.compute_returns_and_advantages(lv, lv, d)) if dual else (lambda: buf.compute_returns_and_advantages(lv, d))
+        ms, mn = timed(fn, iters)
+        report(rows, "gae_dual" if dual else "gae", f"T={T} N={N}", T * N * (33 if dual else 17), 0, ms, mn)
+        del buf
+
+
+def bench_simhash(rows, iters):
+    for n, D, k in ((2048, 8, 64), (524288, 8, 64), (8 << 20, 8, 64)):
+        np.random.seed(0)
+        buf = ppx.RolloutStorage(1, 1, ppx.Box((D,)), ppx.Box((1,)), sim_hash=True, hash_bits=k, table_capacity=1 << 25)
+        obs = torch.randn(n, D, device=DEV)
+        r = torch.zeros(n, device=DEV)
+        fn = lambda: buf.sim_hash(obs, r)
+        ms, mn = timed(fn, min(iters, 10))
+        report(rows, "simhash_update", f"n={n} D={D} k={k}", n * (4 * D + 8 + 8 + 16), 0, ms, mn,
+               note="codes + ordered count update + bonus; includes the 8-byte ctrl memset")
+        codes = buf.sim_hash_codes(obs)
+        ms, mn = timed(lambda: buf.sim_hash_codes(obs), iters)
+        report(rows, "simhash_codes", f"n={n} D={D} k={k}", n * (4 * D + 8), 0, ms, mn)
+        del buf
+
+
+def bench_gather(rows, iters):
+    for T, N, D, A, B in ((256, 2048, 8, 2, 131072), (256, 2048, 8, 2, 524288), (128, 128, 28224, 1, 4096)):
+        buf = ppx.RolloutStorage(T, N, ppx.Box((D,)), ppx.Box((A,)))
+        buf.observations.normal_()
+        idx = torch.randperm(T * N, device=DEV)[:B].contiguous()
+        bufs = buf._minibatch_buffers(B)
+        ms, mn = timed(lambda: buf.gather_into(idx, bufs), iters)
+        per = 2 * (4 * D + 8 * A + 4 * A + 12) + 8
+        report(rows, "gather_minibatch", f"T={T} N={N} D={D} A={A} B={B}", B * per, 0, ms, mn)
+        del buf, bufs
+
+
+def bench_loss(rows, iters):
+    for B, A, disc in ((131072, 2, 0), (4 << 20, 2, 0), (131072, 18, 1), (4 << 20, 1, 0)):
+        f = lambda *s: torch.randn(*s, device=DEV)
+        actor, lstd = f(B, A), torch.zeros(A, device=DEV)
+        actions = (torch.randint(0, A, (B,), device=DEV).double() if disc else f(B, A).double())
+        oldlp = -1.0 + 0.1 * f(B, A if not disc else 1)
+        adv, val, oval, ret = f(B), f(B), f(B), f(B)
+        stats = torch.tensor([0.0, 1.0], dtype=torch.float64, device=DEV)
+        d_actor, d_lstd, d_val = torch.empty(B, A, device=DEV), torch.empty(A, device=DEV), torch.empty(B, device=DEV)
+        losses = torch.zeros(8, dtype=torch.float64, device=DEV)
+        ws = torch.empty(L.call("ppx_ppo_loss_workspace", B, A) // 8 + 1, dtype=torch.float64, device=DEV)
+        cfg = L.PpoCfg(B, 0, A, disc, 0, 0.2, 0.01, 1.0, 0.0, 1.0)
+        fn = lambda: L.call("ppx_ppo_loss_fwd_bwd", C.byref(cfg), actor.data_ptr(), lstd.data_ptr(), actions.data_ptr(),
+                            oldlp.data_ptr(), adv.data_ptr(), stats.data_ptr(), val.data_ptr(), oval.data_ptr(),
+                            ret.data_ptr(), None, None, None, None, None, d_actor.data_ptr(), d_lstd.data_ptr(),
+                            d_val.data_ptr(), None, losses.data_ptr(), ws.data_ptr(), L.stream())
+        ms, mn = timed(fn, iters)
+        # actor_out 4A + actions 8A(Box)/8 + old_lp 4A(/4) + adv 4 + v,ov,R 12 (twice: head + dvalue) ; writes d_actor 4A + d_v 4
+        byt = B * ((4 * A + 8 * A + 4 * A + 4 * A) if not disc else (4 * A + 8 + 4 + 4 * A)) + B * (4 + 12 + 12 + 4)
+        report(rows, "ppo_loss_fwd_bwd", f"B={B} A={A} discrete={disc}", byt, 0, ms, mn, launches=4,
+               note="head + sum + finalize + dvalue")
+
+
+def bench_adam(rows, iters):
+    for n in (9732, 16 << 20):
+        bank = PM.ParamBank([("w", (n,))], torch.device(DEV))
+        bank.flat.normal_(); bank.grad.normal_()
+        ms, mn = timed(lambda: bank.adam_step(3e-4, 5.0), iters)
+        report(rows, "clip_adam", f"n={n}", n * 32, 0, ms, mn, launches=3, note="step bump + sumsq + adam")
+
+
+def bench_es(rows, iters):
+    P, D = 10000, 4736
+    np.random.seed(0)
+    es = ppx.EvolutionStrategy(hidden_sizes=[64, 64], obs_dim=8, n_actions=2, population_size=P, noise_table_size=1 << 28)
+    ms, mn = timed(lambda: L.call("ppx_noise_fill", es.noise_table().data_ptr(), 1 << 28, 1, L.stream()), 5)
+    report(rows, "noise_fill", "n=2^28 f32", (1 << 28) * 4, 0, ms, mn)
+    off = es._get_population()
+    r = torch.randn(P, dtype=torch.float64, device=DEV)
+    out = torch.empty(P, D, device=DEV)
+    fnp = lambda: L.call("ppx_es_perturb", es.theta.data_ptr(), es.noise_table().data_ptr(), off.data_ptr(), 0.1, P, D,
+                         out.data_ptr(), 0, L.stream())
+    ms, mn = timed(fnp, iters)
+    report(rows, "es_perturb", f"P={P} D={D} f32 out", P * D * 8, 0, ms, mn)
+    ms, mn = timed(lambda: es._update_weights(r, off, 0.5), iters)
+    report(rows, "es_update", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=4, note="stats + coef + gemv + apply")
+    es.fitness_shaping = "centered_rank"
+    ms, mn = timed(lambda: es._update_weights(r, off, 0.5), iters)
+    report(rows, "es_update(rank)", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=5)
+    for M, Q in ((10000, 2), (10000, 1024)):
+        arch = torch.randn(M, 2, dtype=torch.float64, device=DEV)
+        q = torch.randn(Q, 2, dtype=torch.float64, device=DEV)
+        ms, mn = timed(lambda: es.novelty_batch(arch, q), iters)
+        report(rows, "knn_novelty", f"M={M} Q={Q} K=10", 0, 0, ms, mn, note=f"{Q / ms * 1e3:.0f} queries/s (latency-bound, archive is L2-resident)")
+
+
+def bench_linear(rows, iters):
+    sc = PM._Scratch(torch.device(DEV))
+    for M, K, N, batch in ((131072, 8, 128, 1), (131072, 64, 64, 2), (131072, 64, 2, 1), (4096, 28224, 384, 1), (16384, 28224, 256, 1)):
+        ld = N * batch
+        x = torch.randn(M, K * batch, device=DEV)
+        w = torch.randn(batch, K, N, device=DEV) / np.sqrt(K)
+        b = torch.randn(batch, N, device=DEV)
+        y = torch.empty(M, ld, device=DEV)
+        dy = torch.randn(M, ld, device=DEV)
+        dx = torch.empty(M, K * batch, device=DEV)
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+        fl = 2.0 * M * K * N * batch
+        ms, mn = timed(lambda: PM.linear_fwd(x.data_ptr(), K * batch, w.data_ptr(), b.data_ptr(), M, K, N, 1, y.data_ptr(), ld,
+                                             batch, K, K * N, N, N), iters)
+        report(rows, "linear_fwd", f"M={M} K={K} N={N} b={batch}", 4 * M * (K + N) * batch, fl, ms, mn)
+        ms, mn = timed(lambda: PM.linear_bwd_data(dy.data_ptr(), ld, w.data_ptr(), M, K, N, x.data_ptr(), K * batch, 1, dx.data_ptr(),
+                                                  K * batch, batch, N, K * N, K, K), iters)
+        report(rows, "linear_bwd_data", f"M={M} K={K} N={N} b={batch}", 4 * M * (2 * K + N) * batch, fl, ms, mn)
+        ms, mn = timed(lambda: PM.linear_bwd_weight(sc, x.data_ptr(), K * batch, dy.data_ptr(), ld, M, K, N, dw.data_ptr(), db.data_ptr(),
+                                                    batch, K, N, K * N, N), iters)
+        report(rows, "linear_bwd_weight", f"M={M} K={K} N={N} b={batch}", 4 * M * (K + N) * batch, fl, ms, mn, launches=2)
+        del x, y, dy, dx
+
+
+ALL = {"gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
+       "es": bench_es, "linear": bench_linear}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=",".join(ALL))
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--md", default=None)
+    args = ap.parse_args()
+    rows = []
+    for k in args.only.split(","):
+        ALL[k](rows, args.iters)
+        torch.cuda.empty_cache()
+    if args.md:
+        with open(args.md, "w") as f:
+            f.write(f"| kernel | shape | ms (median) | alg. bytes | GB/s | frac of measured HBM ({HBM:.0f} GB/s) | TFLOP/s | note |\n|---|---|---|---|---|---|---|---|\n")
+            for r in rows:
+                f.write(f"| {r['kernel']} | {r['shape']} | {r['ms_median']:.4f} | {r.get('alg_bytes', '')} | "
+                        f"{r.get('gbs', 0):.0f} | {r.get('hbm_frac', 0):.3f} | {r.get('tflops', 0):.2f} | {r['note']} |\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -54,8 +54,9 @@ class HostRngStream:
     the swaps into a pinned buffer (memory-bound) while stage 1 already works on the next epoch."""
 
     def __init__(self, script):
-        self.q, self.mid = queue.Queue(), queue.Queue()
+        self.q, self.mid = queue.Queue(), queue.Queue(maxsize=2)
         self.err = None
+        self._jbufs = {}                                        # rotating partner buffers (<= 4 alive per size)
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
         self.t2 = threading.Thread(target=self._apply, daemon=True)
         self.t1.start()
@@ -69,7 +70,9 @@ class HostRngStream:
                     st = np.random.get_state()
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
-                    j = np.empty(max(n, 1), np.int64)
+                    pool = self._jbufs.setdefault(n, [[np.empty(max(n, 1), np.int64) for _ in range(4)], 0])
+                    j = pool[0][pool[1] % 4]
+                    pool[1] += 1
                     L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
                     np.random.set_state((st[0], key, pos.value, st[3], st[4]))
                     self.mid.put(('perm', j, n))
