@@ -183,7 +183,21 @@ def bench_linear(rows, iters):
         del x, y, dy, dx
 
 
-ALL = {"gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
+def bench_tc(rows, iters):
+    for M, R, N in ((131072, 64, 64), (131072, 8, 128), (131072, 64, 128), (131072, 128, 128)):
+        A = torch.randn(M, R, device=DEV)
+        W = torch.randn(N, R, device=DEV) / np.sqrt(R)
+        hi, lo = torch.empty_like(W), torch.empty_like(W)
+        L.call("ppx_tc_split", W.data_ptr(), N, R, hi.data_ptr(), lo.data_ptr(), None, None, L.stream())
+        b = torch.randn(N, device=DEV)
+        Cc = torch.empty(M, N, device=DEV)
+        fn = lambda: L.call("ppx_tc_linear", A.data_ptr(), R, hi.data_ptr(), lo.data_ptr(), R, M, R, N, b.data_ptr(), None, 0, 1, 0,
+                            Cc.data_ptr(), N, L.stream())
+        ms, mn = timed(fn, iters)
+        report(rows, "tc_linear(3xTF32)", f"M={M} R={R} N={N}", 4 * M * (R + N), 2.0 * M * R * N, ms, mn)
+
+
+ALL = {"tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
        "es": bench_es, "linear": bench_linear}
 
 

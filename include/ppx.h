@@ -125,6 +125,17 @@ int ppx_linear_bwd_weight(const float* X, int ldx, const float* dY, int lddy, in
                           float* dbias, float* workspace, int batch, int64_t strideX, int64_t strideDY,
                           int64_t strideDW, int64_t strideDB, void* stream);
 
+/* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
+/* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma
+ * kind::tf32 and a 3-pass hi/lo split (fp32-equivalent, error ~2^-21), TMA-fed, TMEM accumulators.
+ *   forward:  A = X [M,K],   B = W^T [N,K] (ppx_tc_split hiT/loT of the in-major W), epi = act(acc + bias)
+ *   dgrad:    A = dY [M,N],  B = W   [K,N] (ppx_tc_split hi/lo),                     epi = acc * act'(H)
+ * ppx_tc_supported says whether a shape/alignment can take this path (TMA needs 16-byte pitches). */
+int ppx_tc_supported(int M, int R, int N, int lda, int ldb, const void* A, const void* B);
+int ppx_tc_split(const float* src, int rows, int cols, float* hi, float* lo, float* hiT, float* loT, void* stream);
+int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
+                  const float* bias, const float* H, int ldh, int act, int dgrad, float* C, int ldc, void* stream);
+
 /* ---------------------------------------------------------------- PPO loss ------------------ */
 /* Fused clipped-surrogate / clipped-value / entropy loss, forward and backward, for one minibatch:
  * PPO.train algorithms.py:219-238, PPO_RND.train :431-460 (dual=1), PPO_ICM.train :670-692 (the

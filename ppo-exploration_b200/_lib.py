@@ -52,6 +52,9 @@ SIGNATURES = {
     "ppx_linear_bwd_data": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_l, c_l, c_l, c_l, c_p]),
     "ppx_linear_bwd_weight_workspace": (c_l, [c_i, c_i, c_i, c_i]),
     "ppx_linear_bwd_weight": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_l, c_l, c_l, c_l, c_p]),
+    "ppx_tc_supported": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "ppx_tc_split": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "ppx_tc_linear": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_p]),
     "ppx_ppo_loss_workspace": (c_l, [c_l, c_i]),
     "ppx_ppo_loss_fwd_bwd": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 21),
     "ppx_ppo_loss_head": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 18),
@@ -73,7 +76,7 @@ SIGNATURES = {
     "ppx_rank_center": (c_i, [c_p, c_i, c_p, c_p, c_p]),
     "ppx_knn_novelty": (c_i, [c_p, c_l, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
 }
-_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n != "ppx_version"}
+_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n not in ("ppx_version", "ppx_tc_supported")}
 
 _lib = None
 

@@ -1,0 +1,403 @@
+// Blackwell tensor-core dense layer:  C[M,N] = epi( A[M,R] . B[N,R]^T )  in fp32-equivalent precision.
+//
+// tcgen05.mma kind::tf32 with a 3-pass hi/lo split ("3xTF32"): x = hi + lo with hi = x truncated to
+// tf32 (exact), lo = x - hi (exact in fp32, tf32-truncated by the tensor core):
+//      A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi          (dropped term lo.lo ~ 2^-22 relative)
+// accumulated in fp32 in TMEM.  Error ~2^-21 per product, inside the 1e-5 parity bound that rules out
+// single-pass tf32/bf16 (SURVEY "Hard parts").  Used for the forward (A = activations, B = W^T) and the
+// data-gradient (A = dY, B = W) of dense layers; B is pre-split once per optimiser step
+// (ppx_tc_split), A is split on the fly in shared memory so activations are read from HBM once.
+//
+// Pipeline (one 128 x BN output tile per CTA, 320 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (raw), B_hi, B_lo, 128B-swizzled,
+//               K-major, 32 fp32 (=128 B) of K per stage, mbarrier complete_tx
+//   warps 2-5   splitters: in-place hi = x & ~0x1fff, lo -> second buffer (element-wise, so the TMA
+//               swizzle pattern is preserved), fence.proxy.async, arrive
+//   warp 1      MMA issuer: one elected lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=BN, K=8) per
+//               stage; tcgen05.commit releases the stage / signals the epilogue; owns TMEM alloc/dealloc
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 (warp q reads TMEM lanes 32q..32q+31 = tile rows),
+//               bias+activation (forward) or activation-derivative (dgrad), 128-byte row stores
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ppx {
+namespace tc {
+
+constexpr int BM = 128;          // tile rows = UMMA M
+constexpr int BK = 32;           // fp32 elements of K per stage = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32
+constexpr int kThreads = 320;
+constexpr int kSplitThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
+// rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (>>4), bits [16,30): 1 as CuTe sets it
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset (>>4), bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell), bits [46,48)
+  d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case PPX_ACT_TANH: return tanhf(x);
+    case PPX_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
+    case PPX_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_bwd(float h, int act) {
+  switch (act) {
+    case PPX_ACT_TANH: return 1.f - h * h;
+    case PPX_ACT_LEAKY_RELU: return h > 0.f ? 1.f : 0.01f;
+    case PPX_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;
+    default: return 1.f;
+  }
+}
+
+struct Params {
+  int M, N, R;                  // C is [M,N]; reduction length R
+  int ldc;
+  float* C;
+  const float* bias;            // forward epilogue (may be null)
+  const float* H; int ldh;      // dgrad epilogue: post-activation of the producer layer (may be null)
+  int act;
+  int dgrad;                    // 0: C = act(acc + bias)   1: C = acc * act'(H)
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+               const __grid_constant__ CUtensorMap mapBlo, Params p) {
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_kb = (p.R + BK - 1) / BK;
+
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto ready_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + s]); };
+  const uint32_t tmem_full_bar = smem_u32(&bars[3 * STAGES]);
+  auto a_hi = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+  auto a_lo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_BYTES; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * STAGE_BYTES + 2 * A_BYTES; };
+  auto b_lo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), kSplitThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation by one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+        tma_load_2d(smem_u32(a_hi(s)), &mapA, full_bar(s), kb * BK, m0);
+        tma_load_2d(smem_u32(b_hi(s)), &mapBhi, full_bar(s), kb * BK, n0);
+        tma_load_2d(smem_u32(b_lo(s)), &mapBlo, full_bar(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc(BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(ready_bar(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t ah = smem_u32(a_hi(s)), al = smem_u32(a_lo(s)), bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint32_t off = kk * UMMA_K * 4;            // 32 bytes along K inside the swizzle atom
+          const uint64_t dah = make_desc(ah + off), dal = make_desc(al + off);
+          const uint64_t dbh = make_desc(bh + off), dbl = make_desc(bl + off);
+          umma_tf32(tmem_base, dal, dbh, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));                          // stage free once these MMAs have read it
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ------------------------------ splitters (warps 2..5) ------------------------------
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(full_bar(s), ph);
+      uint4* hi = reinterpret_cast<uint4*>(a_hi(s));
+      uint4* lo = reinterpret_cast<uint4*>(a_lo(s));
+#pragma unroll
+      for (int i = 0; i < (int)(A_BYTES / 16) / kSplitThreads; ++i) {
+        const int e = t + i * kSplitThreads;
+        uint4 v = hi[e];
+        uint4 h, l;
+        h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+        l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+        l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+        l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+        l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+        hi[e] = h;
+        lo[e] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(ready_bar(s));
+    }
+  } else {
+    // ------------------------------ epilogue (warps 6..9) ------------------------------
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (row < p.M) {
+        float* dst = p.C + (size_t)row * p.ldc + n0 + c0;
+        const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (n0 + c0 + 32 <= p.N);
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          float x = __uint_as_float(v[j]);
+          if (col < p.N) {
+            if (!p.dgrad) {
+              if (p.bias) x += __ldg(p.bias + col);
+              x = act_fwd(x, p.act);
+            } else if (p.H) {
+              x *= act_bwd(__ldg(p.H + (size_t)row * p.ldh + col), p.act);
+            }
+          }
+          o[j] = x;
+        }
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) dst[j] = o[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// hi/lo split of a matrix, optionally transposed: src [rows, cols] -> hi/lo [rows, cols] and/or hiT/loT [cols, rows]
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo,
+             float* __restrict__ hiT, float* __restrict__ loT) {
+  __shared__ float th[32][33], tl[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i;
+    float h = 0.f, l = 0.f;
+    if (r < rows && c < cols) {
+      const float v = src[(size_t)r * cols + c];
+      h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      l = v - h;
+      if (hi) { hi[(size_t)r * cols + c] = h; lo[(size_t)r * cols + c] = l; }
+    }
+    th[i][threadIdx.x] = h;
+    tl[i][threadIdx.x] = l;
+  }
+  __syncthreads();
+  if (hiT) {
+    const int rr = r0 + threadIdx.x;                         // transposed: output row = source column
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int cc = blockIdx.x * 32 + i;
+      if (rr < rows && cc < cols) {
+        hiT[(size_t)cc * rows + rr] = th[threadIdx.x][i];
+        loT[(size_t)cc * rows + rr] = tl[threadIdx.x][i];
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+// 2D fp32 tensor [rows, cols] with row pitch ld (elements); box = 32 cols x box_rows, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (!enc) return fail(PPX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PPX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+  return PPX_OK;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const Params& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(p.M, BM), (unsigned)ceil_div(p.N, BN));
+  tc_gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(ma, mbh, mbl, p);
+  return after_launch("tc_gemm");
+}
+
+}  // namespace tc
+}  // namespace ppx
+
+using namespace ppx;
+
+extern "C" int ppx_tc_supported(int M, int R, int N, int lda, int ldb, const void* A, const void* B) {
+  if (R < 4 || N < 16 || M < 1) return 0;
+  if (R % 4 || lda % 4 || ldb % 4) return 0;                 // TMA: 16-byte pitches
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return 0;
+  return 1;
+}
+
+extern "C" int ppx_tc_split(const float* src, int rows, int cols, float* hi, float* lo, float* hiT, float* loT, void* stream) {
+  PPX_REQUIRE(src && rows > 0 && cols > 0 && ((hi && lo) || (hiT && loT)), "tc_split: bad arguments");
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+  tc::split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, rows, cols, hi, lo, hiT, loT);
+  return after_launch("tc_split");
+}
+
+extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
+                             const float* bias, const float* H, int ldh, int act, int dgrad, float* C, int ldc, void* stream) {
+  PPX_REQUIRE(A && Bhi && Blo && C, "tc_linear: null pointer");
+  PPX_REQUIRE(ppx_tc_supported(M, R, N, lda, ldb, A, Bhi) && !((uintptr_t)Blo & 15), "tc_linear: shape/alignment not supported (M=%d R=%d N=%d lda=%d ldb=%d)", M, R, N, lda, ldb);
+  const int BN = N <= 64 ? 64 : 128;
+  CUtensorMap ma, mbh, mbl;
+  int rc = tc::make_map(&ma, A, M, R, lda, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_map(&mbh, Bhi, N, R, ldb, BN);
+  if (rc) return rc;
+  rc = tc::make_map(&mbl, Blo, N, R, ldb, BN);
+  if (rc) return rc;
+  tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad};
+  if (BN == 64) return tc::launch<64, 4>(ma, mbh, mbl, p, (cudaStream_t)stream);
+  return tc::launch<128, 3>(ma, mbh, mbl, p, (cudaStream_t)stream);
+}

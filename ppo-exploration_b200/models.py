@@ -20,8 +20,15 @@ import torch
 
 from . import _lib as L
 
+import os
+
 ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3}
 F4 = 4  # bytes per float
+# tcgen05 3xTF32 path for forward / data-gradient of dense layers (PPX_TC=0 forces the SIMT fp32 kernels).
+# The reduction length is capped: the tensor core accumulates in fp32 with truncation, so one TMEM
+# accumulation chain is kept to <= 128 products (error ~1e-6); longer K needs chunked draining.
+TC_ENABLED = os.environ.get("PPX_TC", "0") == "1"   # opt-in: at h<=128 the SIMT path is faster (profiles/)
+TC_MAX_R = 128
 
 
 class ParamBank:
@@ -41,6 +48,11 @@ class ParamBank:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.norm_dev = torch.zeros(1, dtype=torch.float64, device=device)
         self._ws = torch.zeros(4096, dtype=torch.float64, device=device)
+        self.tc_weights = []                       # TcWeight shadows to refresh after every step
+
+    def refresh_tc(self):
+        for t in self.tc_weights:
+            t.refresh()
 
     def view(self, name, grad=False):
         o, s = self.offsets[name], self.shapes[name]
@@ -58,6 +70,45 @@ class ParamBank:
                self.exp_avg_sq.data_ptr(), self.size, float(max_norm), self.size if max_norm > 0 else 0, float(lr),
                float(betas[0]), float(betas[1]), float(eps), 0, self.step_dev.data_ptr(), self.norm_dev.data_ptr(),
                self._ws.data_ptr(), L.stream())
+        self.refresh_tc()
+
+
+class TcWeight:
+    """hi/lo tf32 split of one in-major weight matrix W [K,N] (and of its transpose), refreshed after every
+    optimiser step: forward uses W^T [N,K] as the K-major B operand, the data-gradient uses W [K,N]."""
+
+    def __init__(self, w_ptr, K, N, device):
+        self.w_ptr, self.K, self.N = w_ptr, K, N
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.hi, self.lo, self.hiT, self.loT = e(K, N), e(K, N), e(N, K), e(N, K)
+        self.refresh()
+
+    def refresh(self):
+        L.call("ppx_tc_split", self.w_ptr, self.K, self.N, self.hi.data_ptr(), self.lo.data_ptr(), self.hiT.data_ptr(),
+               self.loT.data_ptr(), L.stream())
+
+
+def tc_ok(M, R, N, lda, ldb, a_ptr, b_ptr):
+    return (TC_ENABLED and R <= TC_MAX_R and M >= 128 and
+            L.call("ppx_tc_supported", M, R, N, lda, ldb, a_ptr, b_ptr) == 1)
+
+
+def dense_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, tcw=None):
+    """act(X @ W + b): tensor-core path when the shape allows it, SIMT fp32 otherwise."""
+    if tcw is not None and tc_ok(M, K, N, ldx, K, x_ptr, tcw.hiT.data_ptr()):
+        L.call("ppx_tc_linear", x_ptr, ldx, tcw.hiT.data_ptr(), tcw.loT.data_ptr(), K, M, K, N, b_ptr, None, 0, act, 0,
+               y_ptr, ldy, L.stream())
+    else:
+        linear_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy)
+
+
+def dense_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx, tcw=None):
+    """(dY @ W^T) * act'(H): tensor-core path when the shape allows it."""
+    if tcw is not None and tc_ok(M, N, K, lddy, N, dy_ptr, tcw.hi.data_ptr()):
+        L.call("ppx_tc_linear", dy_ptr, lddy, tcw.hi.data_ptr(), tcw.lo.data_ptr(), N, M, N, K, None, h_ptr, ldh, act, 1,
+               dx_ptr, lddx, L.stream())
+    else:
+        linear_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx)
 
 
 class _Scratch:
@@ -164,6 +215,17 @@ class ParallelMLP:
     def __init__(self, bank, names, D, h, outs, scratch):
         self.bank, self.names, self.D, self.h, self.outs, self.scratch = bank, names, D, h, outs, scratch
         self.G = len(names)
+        self.tc1 = self.tc2 = None
+
+    def enable_tc(self):
+        """(Re)build the tensor-core weight shadows; call after the parameters were (re)loaded."""
+        if not TC_ENABLED:
+            return
+        b, G, h, D, dev = self.bank, self.G, self.h, self.D, self.bank.device
+        b.tc_weights = [t for t in b.tc_weights if t not in ([self.tc1] if self.tc1 else []) + (self.tc2 or [])]
+        self.tc1 = TcWeight(b.p("W1"), D, G * h, dev)
+        self.tc2 = [TcWeight(b.p("W2", g * h * h), h, h, dev) for g in range(G)]
+        b.tc_weights += [self.tc1] + self.tc2
 
     @staticmethod
     def specs(names, D, h, outs):
@@ -177,9 +239,14 @@ class ParallelMLP:
         M, G, h, D, b = x.shape[0], self.G, self.h, self.D, self.bank
         H1 = self.scratch.get("pmlp.H1", M * G * h)[:M * G * h].view(M, G * h)
         H2 = self.scratch.get("pmlp.H2", M * G * h)[:M * G * h].view(M, G * h)
-        linear_fwd(x.data_ptr(), x.stride(0), b.p("W1"), b.p("b1"), M, D, G * h, ACT["tanh"], H1.data_ptr(), G * h)
-        linear_fwd(H1.data_ptr(), G * h, b.p("W2"), b.p("b2"), M, h, h, ACT["tanh"], H2.data_ptr(), G * h,
-                   batch=G, sx=h, sw=h * h, sb=h, sy=h)
+        dense_fwd(x.data_ptr(), x.stride(0), b.p("W1"), b.p("b1"), M, D, G * h, ACT["tanh"], H1.data_ptr(), G * h, self.tc1)
+        if self.tc2 is not None and tc_ok(M, h, h, G * h, h, H1.data_ptr(), self.tc2[0].hiT.data_ptr()):
+            for g in range(G):
+                dense_fwd(H1.data_ptr() + g * h * F4, G * h, b.p("W2", g * h * h), b.p("b2", g * h), M, h, h, ACT["tanh"],
+                          H2.data_ptr() + g * h * F4, G * h, self.tc2[g])
+        else:
+            linear_fwd(H1.data_ptr(), G * h, b.p("W2"), b.p("b2"), M, h, h, ACT["tanh"], H2.data_ptr(), G * h,
+                       batch=G, sx=h, sw=h * h, sb=h, sy=h)
         outs = []
         for gi, (g, o) in enumerate(zip(self.names, self.outs)):
             y = self.scratch.get(f"pmlp.out.{g}", M * o)[:M * o].view(M, o)
@@ -203,8 +270,13 @@ class ParallelMLP:
                             dP2.data_ptr() + gi * h * F4, G * h)
         linear_bwd_weight(sc, H1.data_ptr(), G * h, dP2.data_ptr(), G * h, M, h, h, b.g("W2"), b.g("b2"),
                           batch=G, sx=h, sdy=h, sdw=h * h, sdb=h)
-        linear_bwd_data(dP2.data_ptr(), G * h, b.p("W2"), M, h, h, H1.data_ptr(), G * h, ACT["tanh"], dP1.data_ptr(),
-                        G * h, batch=G, sdy=h, sw=h * h, sh=h, sdx=h)
+        if self.tc2 is not None and tc_ok(M, h, h, G * h, h, dP2.data_ptr(), self.tc2[0].hi.data_ptr()):
+            for g in range(G):
+                dense_bwd_data(dP2.data_ptr() + g * h * F4, G * h, b.p("W2", g * h * h), M, h, h, H1.data_ptr() + g * h * F4,
+                               G * h, ACT["tanh"], dP1.data_ptr() + g * h * F4, G * h, self.tc2[g])
+        else:
+            linear_bwd_data(dP2.data_ptr(), G * h, b.p("W2"), M, h, h, H1.data_ptr(), G * h, ACT["tanh"], dP1.data_ptr(),
+                            G * h, batch=G, sdy=h, sw=h * h, sh=h, sdx=h)
         linear_bwd_weight(sc, x.data_ptr(), x.stride(0), dP1.data_ptr(), G * h, M, D, G * h, b.g("W1"), b.g("b1"))
 
 
@@ -260,6 +332,7 @@ class Policy:
             b.view(f"W3.{g}").copy_(_to_in_major(t(sd[f"{g}.4.weight"])))
             b.view(f"b3.{g}").copy_(t(sd[f"{g}.4.bias"]))
         b.view("action_log_std").copy_(t(sd["action_log_std"]).reshape(-1))
+        self.mlp.enable_tc()
 
     def state_dict(self, grad=False):
         h, b = self.hidden_size, self.bank

@@ -1,0 +1,54 @@
+"""GPU numerics: tcgen05 3xTF32 dense-layer kernel vs an fp64 reference (fp32-equivalent accuracy)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {0: lambda x: x, 1: torch.tanh, 2: F.leaky_relu, 3: F.elu}
+
+
+def _run(M, R, N, act, dgrad, seed=0):
+    from ppo_exploration_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(M, R, device="cuda", generator=g)
+    W = torch.randn(N, R, device="cuda", generator=g) / np.sqrt(R)           # B operand [N, R], R contiguous
+    bias = torch.randn(N, device="cuda", generator=g)
+    H = torch.tanh(torch.randn(M, N, device="cuda", generator=g))
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    L.call("ppx_tc_split", W.data_ptr(), N, R, hi.data_ptr(), lo.data_ptr(), None, None, L.stream())
+    assert torch.equal(hi + lo, W) and torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
+    C = torch.full((M, N), float("nan"), device="cuda")
+    assert L.call("ppx_tc_supported", M, R, N, R, R, A.data_ptr(), hi.data_ptr()) == 1
+    L.call("ppx_tc_linear", A.data_ptr(), R, hi.data_ptr(), lo.data_ptr(), R, M, R, N, bias.data_ptr(), H.data_ptr(), N, act,
+           dgrad, C.data_ptr(), N, L.stream())
+    torch.cuda.synchronize()
+    acc = A.double() @ W.double().t()
+    if dgrad:
+        d = {0: torch.ones_like(H), 1: 1 - H * H, 2: torch.where(H > 0, 1.0, 0.01), 3: torch.where(H > 0, 1.0, H + 1)}[act]
+        ref = acc * d.double()
+    else:
+        ref = ACTS[act](acc + bias.double())
+    return C.double(), ref, acc
+
+
+@pytest.mark.parametrize("M,R,N,act,dgrad", [(128, 32, 64, 0, 0), (128, 64, 64, 1, 0), (1000, 8, 128, 1, 0), (300, 64, 100, 2, 0),
+                                             (131072, 64, 64, 1, 0), (131072, 64, 64, 1, 1), (257, 100, 16, 3, 1),
+                                             (64, 36, 40, 0, 0)])
+def test_tc_linear_matches_fp64(M, R, N, act, dgrad):
+    C, ref, acc = _run(M, R, N, act, dgrad)
+    assert torch.isfinite(C).all()
+    scale = float(acc.abs().max())
+    err = float((C - ref).abs().max())
+    # 3xTF32: dropped lo*lo term ~2^-22 per product + fp32 accumulation -> well inside 1e-5 of the output scale
+    assert err <= 4e-6 * max(scale, 1.0), (err, scale)
+
+
+def test_tc_split_transposed():
+    from ppo_exploration_b200 import _lib as L
+    W = torch.randn(70, 45, device="cuda")
+    hiT, loT = torch.empty(45, 70, device="cuda"), torch.empty(45, 70, device="cuda")
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    L.call("ppx_tc_split", W.data_ptr(), 70, 45, hi.data_ptr(), lo.data_ptr(), hiT.data_ptr(), loT.data_ptr(), L.stream())
+    assert torch.equal(hi.t().contiguous(), hiT) and torch.equal(lo.t().contiguous(), loT) and torch.equal(hi + lo, W)
