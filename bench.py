@@ -157,7 +157,8 @@ class ClockSampler:
 
 class OpTimer:
     """CUDA-event brackets around selected C-ABI calls on the launching stream (roofline measurement)."""
-    SHAPE_ARGS = {"ppx_linear_fwd": (4, 5, 6, 10), "ppx_linear_bwd_data": (3, 4, 5, 11), "ppx_linear_bwd_weight": (4, 5, 6, 10)}
+    SHAPE_ARGS = {"ppx_linear_fwd": (4, 5, 6, 10), "ppx_linear_bwd_data": (3, 4, 5, 11), "ppx_linear_bwd_weight": (4, 5, 6, 10),
+                  "ppx_mlp3_fwd": (2, 3, 4, 5), "ppx_mlp3_bwd": (2, 3, 4, 5)}
 
     def __init__(self, L, torch):
         self.L, self.torch, self.rec, self.orig = L, torch, [], L.call
@@ -306,7 +307,12 @@ def run_ppx(args):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     top = max(agg.items(), key=lambda kv: kv[1][0])
     (op, (M_, K_, N_, b_)), (tot_ms, cnt) = top
-    flops = 2.0 * M_ * K_ * N_ * b_
+    if op == "ppx_mlp3_fwd":          # shape = (M, D, H, G): 2 flops per MAC of the three layers of every net
+        flops = 2.0 * M_ * (b_ * (K_ * N_ + N_ * N_) + N_ * (A + b_ - 1))
+    elif op == "ppx_mlp3_bwd":        # dgrad (layers 3,2) + wgrad (layers 3,2,1)
+        flops = 2.0 * M_ * (b_ * (K_ * N_ + 2 * N_ * N_) + 2 * N_ * (A + b_ - 1))
+    else:
+        flops = 2.0 * M_ * K_ * N_ * b_
     achieved = flops / (tot_ms / cnt / 1e3) / 1e12
     ops = sorted(((f"{k[0]}{list(k[1])}", round(v[0], 3), v[1]) for k, v in agg.items()), key=lambda x: -x[1])[:8]
     line = {"metric": "transitions/s through GAE+bonus+PPO update", "value": value, "unit": "transitions/s",
@@ -319,10 +325,11 @@ def run_ppx(args):
                     "d2h_bytes_per_step": int(HP["n_epochs"] * N_MINIBATCH * 64), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": f"gemm_kernel via {op} M={M_} K={K_} N={N_} batch={b_}",
+            "roofline": {"bound": "tensor", "kernel": f"{op} M={M_} K/D={K_} N/H={N_} batch/G={b_}",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                         "note": "exact-fp32 SIMT GEMM (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak",
+                         "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
+                         "fp32_frac": achieved / 74.4,
                          "ms_per_launch": tot_ms / cnt, "launches_per_step": cnt, "top_ops_ms_per_step": ops}}
     if world == 1 and rank == 0:
         v, det = cpu_reference_pass(hash_envs=512, hash_steps=64, train_minibatches=8)

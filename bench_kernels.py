@@ -197,7 +197,28 @@ def bench_tc(rows, iters):
         report(rows, "tc_linear(3xTF32)", f"M={M} R={R} N={N}", 4 * M * (R + N), 2.0 * M * R * N, ms, mn)
 
 
-ALL = {"tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
+def bench_mlp3(rows, iters):
+    """Fused policy-MLP forward / backward (mlp_fused.cu) at the C2 minibatch and at the RND/C1 width."""
+    for M, D, h, space, intr in ((131072, 8, 64, ppx.Box((2,)), False), (131072, 8, 64, ppx.Box((2,)), True),
+                                 (16384, 4, 128, ppx.Discrete(2), False)):
+        env = ppx.SyntheticVecEnv(4, D, space, seed=0)
+        pol = ppx.models.Policy(env, h, intrinsic_model=intr, device=DEV)
+        assert pol.mlp._fused_args()["ok"]
+        G, so = len(pol.outs), sum(pol.outs)
+        x = torch.randn(M, D, device=DEV)
+        outs = pol.forward_raw(x)
+        d = [torch.randn_like(o) / M for o in outs]
+        ms, mn = timed(lambda: pol.forward_raw(x), iters)
+        fl = 2.0 * M * (G * (D * h + h * h) + h * so)
+        report(rows, "mlp3_fwd", f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn,
+               note=f"fp32 SIMT: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
+        ms, mn = timed(lambda: pol.mlp.backward(d), iters)
+        fl = 2.0 * M * (G * (D * h + 2 * h * h) + 2 * h * so)
+        report(rows, "mlp3_bwd", f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn, launches=2,
+               note=f"bwd + partial reduce; fp32 SIMT: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
+
+
+ALL = {"mlp3": bench_mlp3, "tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
        "es": bench_es, "linear": bench_linear}
 
 

@@ -125,6 +125,24 @@ int ppx_linear_bwd_weight(const float* X, int ldx, const float* dY, int lddy, in
                           float* dbias, float* workspace, int batch, int64_t strideX, int64_t strideDY,
                           int64_t strideDW, int64_t strideDB, void* stream);
 
+/* ---------------------------------------------------------------- fused policy MLPs ---------- */
+/* G independent D -> H -> H -> o_g tanh MLPs over one minibatch (actor | critic | int_critic of
+ * models.py:137-213), forward and backward each as ONE persistent kernel (mlp_fused.cu).
+ * Parameter layout = the policy bank's: W1 [D, G*H], b1 [G*H], W2 [G,H,H] (in-major), b2 [G,H],
+ * W3[g] [H,o_g], b3[g] [o_g].  H1/H2 [M, G*H] are the saved tanh activations.  `outs`, `W3`, `b3`,
+ * `out`, `dOut`, `dW3`, `db3` are HOST arrays of G entries.  Supported: H in {64,128}, D <= 32,
+ * o_g <= 32, G <= 4 (ppx_mlp3_supported); other shapes take the layer-by-layer ppx_linear_* path. */
+int ppx_mlp3_supported(int D, int H, int G, const int* outs_host);
+int ppx_mlp3_fwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W1,
+                 const float* b1, const float* W2, const float* b2, const float* const* W3_host,
+                 const float* const* b3_host, float* H1, float* H2, float* const* out_host, void* stream);
+/* workspace size in floats (-1: unsupported shape) */
+int64_t ppx_mlp3_bwd_workspace(int M, int D, int H, int G, const int* outs_host);
+int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W2,
+                 const float* const* W3_host, const float* H1, const float* H2, const float* const* dOut_host,
+                 float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
+                 float* workspace, void* stream);
+
 /* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
 /* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma
  * kind::tf32 and a 3-pass hi/lo split (fp32-equivalent, error ~2^-21), TMA-fed, TMEM accumulators.

@@ -15,6 +15,7 @@ The shuffle indices come from the same `np.random.permutation(T*N)` draw as the 
 (buffer.py:239), so a seeded run visits identical minibatches.
 """
 import ctypes as C
+import os
 import queue
 import threading
 from collections import namedtuple
@@ -56,6 +57,12 @@ class HostRngStream:
     def __init__(self, script):
         self.q, self.mid = queue.Queue(), queue.Queue(maxsize=2)
         self.err = None
+        if os.environ.get("PPX_DIAG_REUSE_PERM") == "1":        # diagnosis only: isolates the host shuffle cost
+            seen, sc = False, []
+            for op in script:
+                sc.append(('reuse',) if (op[0] == 'perm' and seen) else op)
+                seen = seen or op[0] == 'perm'
+            script = sc
         self._jbufs = {}                                        # rotating partner buffers (<= 4 alive per size)
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
         self.t2 = threading.Thread(target=self._apply, daemon=True)
@@ -76,6 +83,8 @@ class HostRngStream:
                     L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
                     np.random.set_state((st[0], key, pos.value, st[3], st[4]))
                     self.mid.put(('perm', j, n))
+                elif op[0] == 'reuse':
+                    self.mid.put(('reuse',))
                 else:
                     self.mid.put(('val', float(np.random.randn())))
         except Exception as e:
@@ -92,7 +101,10 @@ class HostRngStream:
                     _, j, n = item
                     out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
                     L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
+                    self._last = out
                     self.q.put(out)
+                elif item[0] == 'reuse':
+                    self.q.put(self._last)
                 else:
                     self.q.put(item[1])
         except Exception as e:

@@ -20,6 +20,7 @@ import torch
 
 from . import _lib as L
 
+import ctypes as C
 import os
 
 ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3}
@@ -29,6 +30,8 @@ F4 = 4  # bytes per float
 # accumulation chain is kept to <= 128 products (error ~1e-6); longer K needs chunked draining.
 TC_ENABLED = os.environ.get("PPX_TC", "0") == "1"   # opt-in: at h<=128 the SIMT path is faster (profiles/)
 TC_MAX_R = 128
+# fused forward / backward of the D-h-h-o policy MLPs (mlp_fused.cu); PPX_FUSED_MLP=0 forces the layer-by-layer path
+FUSED_ENABLED = os.environ.get("PPX_FUSED_MLP", "1") != "0"
 
 
 class ParamBank:
@@ -216,6 +219,7 @@ class ParallelMLP:
         self.bank, self.names, self.D, self.h, self.outs, self.scratch = bank, names, D, h, outs, scratch
         self.G = len(names)
         self.tc1 = self.tc2 = None
+        self._fa = None
 
     def enable_tc(self):
         """(Re)build the tensor-core weight shadows; call after the parameters were (re)loaded."""
@@ -235,10 +239,30 @@ class ParallelMLP:
             s += [(f"W3.{g}", (h, o)), (f"b3.{g}", (o,))]
         return s
 
+    def _fused_args(self):
+        """Host-side pointer tables for ppx_mlp3_* (built once; bank addresses never change)."""
+        if self._fa is None:
+            G, b = self.G, self.bank
+            ia, pa = (C.c_int * G), (C.c_void_p * G)
+            outs = ia(*self.outs)
+            ok = FUSED_ENABLED and L.call("ppx_mlp3_supported", self.D, self.h, G, outs) == 1
+            self._fa = dict(ok=ok, outs=outs, W3=pa(*[b.p(f"W3.{g}") for g in self.names]),
+                            b3=pa(*[b.p(f"b3.{g}") for g in self.names]),
+                            dW3=pa(*[b.g(f"W3.{g}") for g in self.names]), db3=pa(*[b.g(f"b3.{g}") for g in self.names]))
+        return self._fa
+
     def forward(self, x):
         M, G, h, D, b = x.shape[0], self.G, self.h, self.D, self.bank
         H1 = self.scratch.get("pmlp.H1", M * G * h)[:M * G * h].view(M, G * h)
         H2 = self.scratch.get("pmlp.H2", M * G * h)[:M * G * h].view(M, G * h)
+        fa = self._fused_args()
+        if fa["ok"]:
+            outs = [self.scratch.get(f"pmlp.out.{g}", M * o)[:M * o].view(M, o) for g, o in zip(self.names, self.outs)]
+            L.call("ppx_mlp3_fwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W1"), b.p("b1"), b.p("W2"),
+                   b.p("b2"), fa["W3"], fa["b3"], H1.data_ptr(), H2.data_ptr(),
+                   (C.c_void_p * G)(*[o.data_ptr() for o in outs]), L.stream())
+            self._saved = (x, H1, H2)
+            return outs
         dense_fwd(x.data_ptr(), x.stride(0), b.p("W1"), b.p("b1"), M, D, G * h, ACT["tanh"], H1.data_ptr(), G * h, self.tc1)
         if self.tc2 is not None and tc_ok(M, h, h, G * h, h, H1.data_ptr(), self.tc2[0].hiT.data_ptr()):
             for g in range(G):
@@ -260,6 +284,13 @@ class ParallelMLP:
         """d_outs[g]: [M, out_g] contiguous.  Fills bank.grad for every MLP parameter."""
         x, H1, H2 = self._saved
         M, G, h, D, b, sc = x.shape[0], self.G, self.h, self.D, self.bank, self.scratch
+        fa = self._fused_args()
+        if fa["ok"]:
+            ws = sc.get("pmlp.fused_ws", L.call("ppx_mlp3_bwd_workspace", M, D, h, G, fa["outs"]))
+            L.call("ppx_mlp3_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
+                   H2.data_ptr(), (C.c_void_p * G)(*[d.data_ptr() for d in d_outs]), b.g("W1"), b.g("b1"), b.g("W2"),
+                   b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), L.stream())
+            return
         dP2 = sc.get("pmlp.dP2", M * G * h)[:M * G * h].view(M, G * h)
         dP1 = sc.get("pmlp.dP1", M * G * h)[:M * G * h].view(M, G * h)
         for gi, (g, o) in enumerate(zip(self.names, self.outs)):
