@@ -138,8 +138,17 @@ int ppx_mlp3_fwd(const float* X, int ldx, int M, int D, int H, int G, const int*
                  const float* const* b3_host, float* H1, float* H2, float* const* out_host, void* stream);
 /* workspace size in floats (-1: unsupported shape) */
 int64_t ppx_mlp3_bwd_workspace(int M, int D, int H, int G, const int* outs_host);
+/* A value head (o_g = 1) may have its output gradient evaluated inside the backward kernel from the loss
+ * inputs instead of being read from dOut[g]: d = scale * (w1*-2(R-v) + w2*-2(R-v_clip)*[|v-v_old|<=clip]) / B_total
+ * with {w1,w2} = branch[0..1] written by ppx_ppo_loss_head_final (the max-of-means branch, algorithms.py:232). */
+typedef struct {
+  const float* values; const float* old_values; const float* returns;   /* [M]; values == NULL: read dOut[g] */
+  const double* branch;                                                 /* device, 2 doubles */
+  float scale;                                                          /* policy_weight*vf_coef or int_vf_coef */
+} ppx_value_head;
 int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W2,
                  const float* const* W3_host, const float* H1, const float* H2, const float* const* dOut_host,
+                 const ppx_value_head* value_heads_host /* G entries or NULL */, float clip_range, int64_t B_total,
                  float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
                  float* workspace, void* stream);
 
@@ -185,6 +194,16 @@ int ppx_ppo_loss_fwd_bwd(const ppx_ppo_cfg* cfg_host, const float* actor_out, co
                          const float* int_values, const float* old_int_values, const float* int_returns,
                          float* d_actor_out, float* d_log_std, float* d_values, float* d_int_values,
                          double* losses_out, void* workspace, void* stream);
+/* Single-GPU fast path: head + fixed-order sum of the CTA partials + loss scalars / branch / d_log_std in ONE
+ * launch (the last CTA to finish does the tail).  branch_out[4] = {w1, w2, int_w1, int_w2}; the value-head
+ * gradients are then evaluated inside ppx_mlp3_bwd (ppx_value_head) or by ppx_ppo_loss_finish. */
+int ppx_ppo_loss_head_final(const ppx_ppo_cfg* cfg_host, const float* actor_out, const float* log_std,
+                            const double* actions, const float* old_log_probs, const float* advantages,
+                            const double* adv_stats, const float* values, const float* old_values,
+                            const float* returns, const float* int_advantages, const double* int_adv_stats,
+                            const float* int_values, const float* old_int_values, const float* int_returns,
+                            float* d_actor_out, float* d_log_std, double* losses_out, double* branch_out,
+                            void* workspace, void* stream);
 /* The same computation split at its only global dependency, for sharded minibatches:
  * head   -> per-sample work + sums_out[32] (f64 partial sums of this rank);
  *           all-reduce sums_out across ranks (one 256-byte message), then

@@ -25,6 +25,10 @@ class PpoCfg(C.Structure):
                 ("policy_weight", C.c_float)]
 
 
+class ValueHead(C.Structure):
+    _fields_ = [("values", c_p), ("old_values", c_p), ("returns", c_p), ("branch", c_p), ("scale", C.c_float)]
+
+
 # name -> (restype, argtypes).  Functions returning int are status codes checked by `call`.
 SIGNATURES = {
     "ppx_last_error": (C.c_char_p, []),
@@ -55,12 +59,13 @@ SIGNATURES = {
     "ppx_mlp3_supported": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i, c_p]),
-    "ppx_mlp3_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ppx_mlp3_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_float, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_tc_supported": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "ppx_tc_split": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "ppx_tc_linear": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_p]),
     "ppx_ppo_loss_workspace": (c_l, [c_l, c_i]),
     "ppx_ppo_loss_fwd_bwd": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 21),
+    "ppx_ppo_loss_head_final": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 20),
     "ppx_ppo_loss_head": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 18),
     "ppx_ppo_loss_finish": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 14),
     "ppx_mse_fwd_bwd": (c_i, [c_p, c_p, c_l, c_d, c_p, c_p, c_p, c_p]),

@@ -58,6 +58,7 @@ class BaseAlgorithm(object):
         self._scratch = _Scratch(self.device)
         self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._sums = torch.zeros(32, dtype=torch.float64, device=self.device)
+        self._branch = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.scale_batch_with_world = True     # sharded runs: batch_size is per rank (weak scaling)
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
         self._graphs = {}
@@ -98,17 +99,30 @@ class BaseAlgorithm(object):
             if dual:
                 self._stats[2:4].copy_(D.merge_mean_std(self._stats[2:4], B))
         d_actor = sc.get("d_actor", B * A)[:B * A].view(B, A)
-        d_val = sc.get("d_val", B)[:B].view(B, 1)
-        d_ival = sc.get("d_ival", B)[:B].view(B, 1)
         cfg = L.PpoCfg(B, int(B_total), A, int(self.discrete), int(dual), float(self.clip_range), float(self.ent_coef),
                        float(self.vf_coef), float(int_vf_coef), float(policy_weight))
         g = lambda k: bufs[k][:B].data_ptr() if k in bufs else None
         ws = self._loss_workspace().data_ptr()
-        L.call("ppx_ppo_loss_head", C.byref(cfg), outs[0].data_ptr(), pol.bank.p("action_log_std"), g('actions'),
-               g('old_log_probs'), adv.data_ptr(), self._stats.data_ptr(), outs[1].data_ptr(), g('old_values'),
-               g('returns'), g('int_advantages'), self._stats.data_ptr() + 16,
-               outs[2].data_ptr() if dual else None, g('int_values'), g('int_returns'), d_actor.data_ptr(),
-               self._sums.data_ptr(), ws, L.stream())
+        head_args = (C.byref(cfg), outs[0].data_ptr(), pol.bank.p("action_log_std"), g('actions'),
+                     g('old_log_probs'), adv.data_ptr(), self._stats.data_ptr(), outs[1].data_ptr(), g('old_values'),
+                     g('returns'), g('int_advantages'), self._stats.data_ptr() + 16,
+                     outs[2].data_ptr() if dual else None, g('int_values'), g('int_returns'), d_actor.data_ptr())
+        if not sharded and pol.mlp.fused():
+            # single GPU: head + partial sums + loss scalars / branch in ONE launch; the value-head gradients are
+            # evaluated inside the fused MLP backward from the branch weights
+            L.call("ppx_ppo_loss_head_final", *head_args, pol.bank.g("action_log_std"), losses_row,
+                   self._branch.data_ptr(), ws, L.stream())
+            vh = {1: (outs[1], bufs['old_values'][:B], bufs['returns'][:B], self._branch.data_ptr(),
+                      float(policy_weight) * float(self.vf_coef))}
+            if dual:
+                vh[2] = (outs[2], bufs['int_values'][:B], bufs['int_returns'][:B], self._branch.data_ptr() + 16,
+                         float(int_vf_coef))
+            pol.mlp.backward([d_actor, None] + ([None] if dual else []), value_heads=vh, clip_range=self.clip_range,
+                             B_total=B)
+            return
+        d_val = sc.get("d_val", B)[:B].view(B, 1)
+        d_ival = sc.get("d_ival", B)[:B].view(B, 1)
+        L.call("ppx_ppo_loss_head", *head_args, self._sums.data_ptr(), ws, L.stream())
         if sharded:
             D.all_reduce_sum_(self._sums)
         L.call("ppx_ppo_loss_finish", C.byref(cfg), self._sums.data_ptr(), pol.bank.p("action_log_std"),

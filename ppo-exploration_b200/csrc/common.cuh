@@ -63,6 +63,25 @@ __device__ __forceinline__ T block_sum(T v, T* smem32) {
   return r;
 }
 
+// "Last block done" reduction tail: every thread of every block calls this after writing its block's partial
+// results to global memory; it returns true in exactly one block -- the last to arrive -- whose threads may
+// then read all partials (use __ldcg) and finish the reduction in a fixed order.  The ticket (zero before the
+// first launch) is re-armed by the last block, so stream-ordered launches can share one counter.
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == total - 1);
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
 // streaming (read-once) loads: keep them out of L1
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;

@@ -42,7 +42,11 @@ gather_kernel(GatherArgs args, const int64_t* __restrict__ idx, int64_t B, int T
 // combines them in a fixed order.  f64 keeps sum-of-squares cancellation below 1e-12 relative for
 // advantage-like data (|mean| <~ 1e3 std); deterministic.
 constexpr int kStatBlocks = 256;
-__global__ void __launch_bounds__(256) moments_partial_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ part) {
+__device__ unsigned int g_stat_ticket = 0;
+// mean / unbiased std in ONE launch: per-CTA f64 (sum, sum of squares) partials; the last CTA to finish combines
+// them in a fixed order (deterministic).  f64 keeps sum-of-squares cancellation below 1e-12 relative for
+// advantage-like data (|mean| <~ 1e3 std).
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ part, double* __restrict__ out) {
   __shared__ double s_red[32];
   double s = 0.0, q = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,11 +57,10 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(const float* __res
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
   if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = q; }
-}
-__global__ void __launch_bounds__(256) moments_final_kernel(const double* __restrict__ part, int nb, int64_t n, double* __restrict__ out) {
-  __shared__ double s_red[32];
-  double s = 0.0, q = 0.0;
-  if ((int)threadIdx.x < nb) { s = part[2 * threadIdx.x]; q = part[2 * threadIdx.x + 1]; }
+  if (!last_block_done(&g_stat_ticket)) return;
+  const int nb = gridDim.x;
+  s = 0.0; q = 0.0;
+  if ((int)threadIdx.x < nb) { s = __ldcg(part + 2 * threadIdx.x); q = __ldcg(part + 2 * threadIdx.x + 1); }
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
   if (threadIdx.x == 0) {
@@ -101,9 +104,6 @@ extern "C" int ppx_mean_std(const float* x, int64_t n, double* out2, void* strea
   static double* part = nullptr;                       // per-process scratch; calls are stream-ordered (one learner thread)
   if (!part) PPX_CUDA(cudaMalloc((void**)&part, 2 * ppx::kStatBlocks * sizeof(double)));
   const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(ppx::kStatBlocks, ppx::ceil_div(n, 2048)));
-  ppx::moments_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, n, part);
-  int rc = ppx::after_launch("mean_std(partials)");
-  if (rc) return rc;
-  ppx::moments_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(part, nb, n, out2);
+  ppx::moments_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, n, part, out2);
   return ppx::after_launch("mean_std");
 }

@@ -38,7 +38,11 @@ struct BwdP {
   const float* W2; const float* W3[MAXG]; int o[MAXG];
   const float* H1; const float* H2; int ldh;
   const float* dOut[MAXG];
-  float* ws2;        // [G][nCta*NG][H*H]     dW2 partials
+  // value heads (o = 1) whose output gradient is evaluated here from the loss inputs instead of being read:
+  // d = scale * (w1 * -2(R - v) + w2 * -2(R - v_clip) * [|v - v_old| <= clip]) / B_total   (ppo_loss.cu dvalue)
+  const float* vh_v[MAXG]; const float* vh_ov[MAXG]; const float* vh_R[MAXG]; const double* vh_branch[MAXG];
+  float vh_scale[MAXG]; float vh_clip; float vh_Bt;
+  float* ws2;        // [G][nCta][H*H]        dW2 partials
   float* wsr;        // [G][nCta][RS]         dW1 | db1 | db2 | dW3 | db3 partials
   int RS;
 };
@@ -231,8 +235,9 @@ __device__ __forceinline__ void cross_reduce(float (&v)[NV], float* part, int ti
 }
 
 template <int H> struct BwdCfg {
-  static constexpr int KC = (H == 64) ? 8 : 4;          // outputs j / inputs d handled per thin-reduction pass
-  static constexpr int NV = (H / 16) * (KC + 1);
+  static constexpr int KC = (H == 64) ? 8 : 4;          // inputs d handled per dW1 pass
+  static constexpr int KO = 4;                          // outputs j handled per dW3 pass
+  static constexpr int NV = (H / 16) * (KC + 1);        // part[] is sized for the larger of the two
 };
 
 template <int H>
@@ -240,11 +245,12 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
   constexpr int CT = H / 16, CQ = H / 64;
   constexpr int NG = NT / (2 * H);            // row groups of the dW2 accumulation (2 for H=64, 1 for H=128)
   constexpr int KC = BwdCfg<H>::KC, NV = BwdCfg<H>::NV, KS = KC + 1;
+  constexpr int KO = BwdCfg<H>::KO, NVO = CT * (KO + 1), KSO = KO + 1;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int g = blockIdx.y, o = p.o[g], D = p.D, Dp = round4(D);
   float* W2Ts = sm;                          // [H][H]   W2Ts[j][i] = W2[i][j]
-  float* W3s = W2Ts + H * H;                 // [H][o]
+  float* W3s = W2Ts + H * H;                 // [o][H]   W3s[j][c] = W3[c][j]
   float* H1s = W3s + round4(H * o);          // [TM][H]  H1
   float* H2s = H1s + TM * H;                 // [TM][H]  H2, then dP2
   float* Xs = H2s + TM * H;                  // [TM][Dp]
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
     const int i = e / H, j = e % H;
     W2Ts[j * H + i] = __ldg(p.W2 + (size_t)g * H * H + e);
   }
-  for (int e = tid; e < H * o; e += NT) W3s[e] = __ldg(p.W3[g] + e);
+  for (int e = tid; e < H * o; e += NT) W3s[(e % o) * H + e / o] = __ldg(p.W3[g] + e);
   for (int e = tid; e < p.RS; e += NT) accR[e] = 0.f;
 
   float dW2[8][CT];
@@ -288,7 +294,24 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
       const int r = e / Dp, k = e % Dp;
       Xs[e] = (m0 + r < p.M && k < D) ? ld_stream(p.X + (size_t)(m0 + r) * p.ldx + k) : 0.f;
     }
-    for (int e = tid; e < TM * o; e += NT) dOs[e] = (m0 + e / o < p.M) ? ld_stream(p.dOut[g] + (size_t)m0 * o + e) : 0.f;
+    if (p.vh_v[g] != nullptr) {                            // o == 1 (checked on the host)
+      if (tid < TM) {
+        float dv = 0.f;
+        const int b = m0 + tid;
+        if (b < p.M) {
+          const float w1 = (float)p.vh_branch[g][0], w2 = (float)p.vh_branch[g][1], clip = p.vh_clip;
+          const float v = ld_stream(p.vh_v[g] + b), ov = ld_stream(p.vh_ov[g] + b), R = ld_stream(p.vh_R[g] + b);
+          const float d = v - ov;
+          const float vc = ov + fminf(fmaxf(d, -clip), clip);
+          const float pass = (d >= -clip && d <= clip) ? 1.f : 0.f;
+          const float gv = w1 * (-2.f * (R - v)) + w2 * (-2.f * (R - vc)) * pass;
+          dv = p.vh_scale[g] * gv / p.vh_Bt;
+        }
+        dOs[tid] = dv;
+      }
+    } else {
+      for (int e = tid; e < TM * o; e += NT) dOs[e] = (m0 + e / o < p.M) ? ld_stream(p.dOut[g] + (size_t)m0 * o + e) : 0.f;
+    }
     __syncthreads();
 
     // ---- db3 += colsum(dOut) (o threads, 4 independent partial sums) ----
@@ -299,17 +322,17 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
       }
       accR[offb3 + tid] += (s0 + s1) + (s2 + s3);
     }
-    // ---- wide heads only (o > KC): dW3 columns j >= KC, while H2s still holds H2 ----
-    for (int jc = KC; jc < o; jc += KC) {
-      float v[NV];
+    // ---- wide heads only (o > KO): dW3 columns j >= KO, while H2s still holds H2 ----
+    for (int jc = KO; jc < o; jc += KO) {
+      float v[NVO];
 #pragma unroll
-      for (int n = 0; n < NV; ++n) v[n] = 0.f;
+      for (int n = 0; n < NVO; ++n) v[n] = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = ty * 8 + i;
-        float d[KC];
+        float d[KO];
 #pragma unroll
-        for (int jj = 0; jj < KC; ++jj) d[jj] = (jc + jj < o) ? dOs[r * o + jc + jj] : 0.f;
+        for (int jj = 0; jj < KO; ++jj) d[jj] = (jc + jj < o) ? dOs[r * o + jc + jj] : 0.f;
 #pragma unroll
         for (int q = 0; q < CQ; ++q) {
           const float4 h = *reinterpret_cast<const float4*>(&H2s[r * H + q * 64 + tx * 4]);
@@ -317,49 +340,57 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
-            for (int jj = 0; jj < KC; ++jj) v[(q * 4 + cc) * KS + jj] = fmaf(hv[cc], d[jj], v[(q * 4 + cc) * KS + jj]);
+            for (int jj = 0; jj < KO; ++jj) v[(q * 4 + cc) * KSO + jj] = fmaf(hv[cc], d[jj], v[(q * 4 + cc) * KSO + jj]);
         }
       }
-      cross_reduce<NV>(v, part, tid, [&](int n, int txx, float s) {
-        const int k = n % KS;
-        if (k < KC && jc + k < o) accR[offW3 + col_of(n / KS, txx) * o + jc + k] += s;
+      cross_reduce<NVO>(v, part, tid, [&](int n, int txx, float s) {
+        const int k = n % KSO;
+        if (k < KO && jc + k < o) accR[offW3 + col_of(n / KSO, txx) * o + jc + k] += s;
       });
     }
-    // ---- A: dP2 = (dOut W3^T)(1 - H2^2) in place over H2s;  dW3[:, j < KC] += H2^T dOut;  db2 += colsum(dP2) ----
+    // ---- A: dP2 = (dOut W3^T)(1 - H2^2) in place over H2s;  dW3[:, j < KO] += H2^T dOut;  db2 += colsum(dP2) ----
     {
-      float v[NV];
+      float v[NVO];
 #pragma unroll
-      for (int n = 0; n < NV; ++n) v[n] = 0.f;
+      for (int n = 0; n < NVO; ++n) v[n] = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = ty * 8 + i;
-        float d[KC];
+        float d[KO];
 #pragma unroll
-        for (int jj = 0; jj < KC; ++jj) d[jj] = (jj < o) ? dOs[r * o + jj] : 0.f;
+        for (int jj = 0; jj < KO; ++jj) d[jj] = (jj < o) ? dOs[r * o + jj] : 0.f;
 #pragma unroll
         for (int q = 0; q < CQ; ++q) {
           const int c0 = q * 64 + tx * 4;
           const float4 h = *reinterpret_cast<const float4*>(&H2s[r * H + c0]);
           const float hv[4] = {h.x, h.y, h.z, h.w};
+          float sp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int jj = 0; jj < KO; ++jj)
+            if (jj < o) {                                   // CTA-uniform
+              const float4 w = *reinterpret_cast<const float4*>(&W3s[jj * H + c0]);
+              sp[0] = fmaf(d[jj], w.x, sp[0]); sp[1] = fmaf(d[jj], w.y, sp[1]);
+              sp[2] = fmaf(d[jj], w.z, sp[2]); sp[3] = fmaf(d[jj], w.w, sp[3]);
+            }
+          for (int j = KO; j < o; ++j) {
+            const float dj = dOs[r * o + j];
+            const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0]);
+            sp[0] = fmaf(dj, w.x, sp[0]); sp[1] = fmaf(dj, w.y, sp[1]); sp[2] = fmaf(dj, w.z, sp[2]); sp[3] = fmaf(dj, w.w, sp[3]);
+          }
           float dp[4];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            float s = 0.f;
+            dp[cc] = sp[cc] * (1.f - hv[cc] * hv[cc]);
 #pragma unroll
-            for (int jj = 0; jj < KC; ++jj)
-              if (jj < o) s = fmaf(d[jj], W3s[(c0 + cc) * o + jj], s);
-            for (int j = KC; j < o; ++j) s = fmaf(dOs[r * o + j], W3s[(c0 + cc) * o + j], s);
-            dp[cc] = s * (1.f - hv[cc] * hv[cc]);
-#pragma unroll
-            for (int jj = 0; jj < KC; ++jj) v[(q * 4 + cc) * KS + jj] = fmaf(hv[cc], d[jj], v[(q * 4 + cc) * KS + jj]);
-            v[(q * 4 + cc) * KS + KC] += dp[cc];
+            for (int jj = 0; jj < KO; ++jj) v[(q * 4 + cc) * KSO + jj] = fmaf(hv[cc], d[jj], v[(q * 4 + cc) * KSO + jj]);
+            v[(q * 4 + cc) * KSO + KO] += dp[cc];
           }
           *reinterpret_cast<float4*>(&H2s[r * H + c0]) = make_float4(dp[0], dp[1], dp[2], dp[3]);
         }
       }
-      cross_reduce<NV>(v, part, tid, [&](int n, int txx, float s) {
-        const int k = n % KS, c = col_of(n / KS, txx);
-        if (k < KC) { if (k < o) accR[offW3 + c * o + k] += s; }
+      cross_reduce<NVO>(v, part, tid, [&](int n, int txx, float s) {
+        const int k = n % KSO, c = col_of(n / KSO, txx);
+        if (k < KO) { if (k < o) accR[offW3 + c * o + k] += s; }
         else accR[offb2 + c] += s;
       });
     }
@@ -426,34 +457,62 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
   __syncthreads();
   float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
   for (int e = tid; e < p.RS; e += NT) wr[e] = accR[e];
-  float* w2 = p.ws2 + ((size_t)(g * gridDim.x + blockIdx.x) * NG + gr) * H * H;
+  // dW2: the NG row groups are combined here in a fixed order (through H1s, free by now) -> one partial per CTA
+  float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
+  if (NG > 1) {
+    if (gr == 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int q = 0; q < CQ; ++q)
-      *reinterpret_cast<float4*>(&w2[(ti * 8 + i) * H + q * 64 + tx * 4]) =
-          make_float4(dW2[i][q * 4], dW2[i][q * 4 + 1], dW2[i][q * 4 + 2], dW2[i][q * 4 + 3]);
+        for (int q = 0; q < CQ; ++q)
+          *reinterpret_cast<float4*>(&H1s[(ti * 8 + i) * H + q * 64 + tx * 4]) =
+              make_float4(dW2[i][q * 4], dW2[i][q * 4 + 1], dW2[i][q * 4 + 2], dW2[i][q * 4 + 3]);
+    }
+    __syncthreads();
+  }
+  if (gr == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) {
+        float4 o4 = make_float4(dW2[i][q * 4], dW2[i][q * 4 + 1], dW2[i][q * 4 + 2], dW2[i][q * 4 + 3]);
+        if (NG > 1) {
+          const float4 t = *reinterpret_cast<const float4*>(&H1s[(ti * 8 + i) * H + q * 64 + tx * 4]);
+          o4.x += t.x; o4.y += t.y; o4.z += t.z; o4.w += t.w;
+        }
+        *reinterpret_cast<float4*>(&w2[(ti * 8 + i) * H + q * 64 + tx * 4]) = o4;
+      }
+  }
 }
 
-// grads[e] = sum over CTA partials in a fixed order; one thread per parameter of net blockIdx.y
+// grads[e] = sum over CTA partials in a fixed order.  Block = 32 consecutive parameters x 8 slices of the
+// partial list (slice s takes partials s, s+8, ...: many independent loads in flight), slices combined 0..7.
 template <int H>
 __global__ void __launch_bounds__(256) mlp3_reduce_kernel(RedP p) {
+  __shared__ float sl[8][33];
   const int g = blockIdx.y, o = p.o[g], D = p.D;
-  const int e = blockIdx.x * 256 + threadIdx.x;
+  const int el = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + el;
   const int R = D * H + 2 * H + H * o + o;
-  if (e >= H * H + R) return;
   float s = 0.f;
-  if (e < H * H) {
-    const float* src = p.ws2 + (size_t)g * p.n2 * H * H + e;
-#pragma unroll 4
-    for (int k = 0; k < p.n2; ++k) s += src[(size_t)k * H * H];
-    p.dW2[(size_t)g * H * H + e] = s;
-    return;
+  if (e < H * H + R) {
+    const bool w2 = e < H * H;
+    const int n = w2 ? p.n2 : p.nr;
+    const size_t stride = w2 ? (size_t)H * H : (size_t)p.RS;
+    const float* src = w2 ? p.ws2 + (size_t)g * p.n2 * H * H + e : p.wsr + (size_t)g * p.nr * p.RS + (e - H * H);
+    float s0 = 0.f, s1 = 0.f;
+    int k = slice;
+    for (; k + 8 < n; k += 16) { s0 += src[(size_t)k * stride]; s1 += src[(size_t)(k + 8) * stride]; }
+    if (k < n) s0 += src[(size_t)k * stride];
+    s = s0 + s1;
   }
+  sl[slice][el] = s;
+  __syncthreads();
+  if (slice != 0 || e >= H * H + R) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) s += sl[q][el];
+  if (e < H * H) { p.dW2[(size_t)g * H * H + e] = s; return; }
   const int r = e - H * H;
-  const float* src = p.wsr + (size_t)g * p.nr * p.RS + r;
-#pragma unroll 4
-  for (int k = 0; k < p.nr; ++k) s += src[(size_t)k * p.RS];
   if (r < D * H) p.dW1[(size_t)(r / H) * (p.G * H) + g * H + r % H] = s;
   else if (r < D * H + H) p.db1[g * H + (r - D * H)] = s;
   else if (r < D * H + 2 * H) p.db2[g * H + (r - D * H - H)] = s;
@@ -548,12 +607,12 @@ extern "C" int64_t ppx_mlp3_bwd_workspace(int M, int D, int H, int G, const int*
   mf::Shape s;
   if (!outs || !mf::shape_ok(D, H, G, outs, &s)) return -1;
   const int n = bwd_grid(M, H, G);
-  const int NG = mf::NT / (2 * H);
-  return (int64_t)G * n * ((int64_t)NG * H * H + s.RS);
+  return (int64_t)G * n * ((int64_t)H * H + s.RS);
 }
 
 extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs, const float* W2,
                             const float* const* W3, const float* H1, const float* H2, const float* const* dOut,
+                            const ppx_value_head* vh, float clip_range, int64_t B_total,
                             float* dW1, float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3,
                             float* workspace, void* stream) {
   mf::Shape s;
@@ -564,8 +623,18 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
   const int NG = mf::NT / (2 * H);
   mf::BwdP p{};
   p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.W2 = W2; p.H1 = H1; p.H2 = H2; p.ldh = G * H;
-  p.ws2 = workspace; p.wsr = workspace + (size_t)G * n * NG * H * H; p.RS = s.RS;
-  for (int g = 0; g < G; ++g) { p.W3[g] = W3[g]; p.o[g] = outs[g]; p.dOut[g] = dOut[g]; }
+  p.ws2 = workspace; p.wsr = workspace + (size_t)G * n * H * H; p.RS = s.RS;
+  p.vh_clip = clip_range; p.vh_Bt = (float)(B_total > 0 ? B_total : M);
+  for (int g = 0; g < G; ++g) {
+    p.W3[g] = W3[g]; p.o[g] = outs[g]; p.dOut[g] = dOut[g];
+    if (vh && vh[g].values) {
+      PPX_REQUIRE(outs[g] == 1 && vh[g].old_values && vh[g].returns && vh[g].branch, "mlp3_bwd: value head %d needs o=1 and all inputs", g);
+      p.vh_v[g] = vh[g].values; p.vh_ov[g] = vh[g].old_values; p.vh_R[g] = vh[g].returns; p.vh_branch[g] = vh[g].branch;
+      p.vh_scale[g] = vh[g].scale;
+    } else {
+      PPX_REQUIRE(dOut[g], "mlp3_bwd: dOut[%d] is null", g);
+    }
+  }
   const size_t smem = mf::bwd_smem(H, D, s.omax, s.RS);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)n, (unsigned)G);
@@ -583,10 +652,10 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
   int rc = after_launch("mlp3_bwd");
   if (rc) return rc;
   mf::RedP r{};
-  r.ws2 = p.ws2; r.wsr = p.wsr; r.n2 = n * NG; r.nr = n; r.RS = s.RS; r.D = D; r.G = G;
+  r.ws2 = p.ws2; r.wsr = p.wsr; r.n2 = n; r.nr = n; r.RS = s.RS; r.D = D; r.G = G;
   r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2;
   for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
-  dim3 rgrid((unsigned)ceil_div(H * H + mf::rest_size(H, D, s.omax), 256), (unsigned)G);
+  dim3 rgrid((unsigned)ceil_div(H * H + mf::rest_size(H, D, s.omax), 32), (unsigned)G);
   if (H == 64) mf::mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
   else mf::mlp3_reduce_kernel<128><<<rgrid, 256, 0, st>>>(r);
   return after_launch("mlp3_reduce");

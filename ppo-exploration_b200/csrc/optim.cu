@@ -11,8 +11,9 @@ namespace {
 
 constexpr int kNormBlocks = 512;
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials, int64_t* step_dev) {
   __shared__ double s_red[32];
+  if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;      // read by adam_kernel (next launch)
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = (double)g[i];
@@ -78,15 +79,18 @@ extern "C" int ppx_clip_adam(float* params, const float* grads, float* exp_avg, 
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)workspace;
   int n_partials = 0;
+  const bool clip = max_norm > 0.0 && n_clip > 0;
   if (step_dev) {                                            // counter holds steps done; bump first, then use
-    bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
-    int rc = after_launch("clip_adam step");
-    if (rc) return rc;
+    if (!clip) {
+      bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+      int rc = after_launch("clip_adam step");
+      if (rc) return rc;
+    }
     step = 1;
   }
-  if (max_norm > 0.0 && n_clip > 0) {
+  if (clip) {
     n_partials = (int)std::min<int64_t>(kNormBlocks, ceil_div(n_clip, 1024));
-    sumsq_kernel<<<n_partials, 256, 0, st>>>(grads, n_clip, partials);
+    sumsq_kernel<<<n_partials, 256, 0, st>>>(grads, n_clip, partials, step_dev);
     int rc = after_launch("clip_adam sumsq");
     if (rc) return rc;
   }

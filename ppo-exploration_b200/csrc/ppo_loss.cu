@@ -25,6 +25,61 @@ constexpr int kMaxBoxA = 16;
 constexpr double kHalfLog2Pi = 0.91893853320467274178;   // log(sqrt(2*pi))
 constexpr float kProbEps = 1.1920928955078125e-07f;      // torch.finfo(float32).eps (clamp_probs)
 
+struct FinalArgs {
+  const double* sums;
+  const float* log_std; float* d_log_std;
+  double* losses; double* branch;       // branch[0..3] = w1, w2, iw1, iw2
+  int64_t B; int A; int discrete; int dual;
+  float ent_coef, vf_coef, int_vf_coef, pw;
+};
+
+// one thread: the five loss scalars, the max-of-means branch weights, d_log_std, from the 32 global sums s[]
+__device__ void finalize_body(const FinalArgs& p, const double* s) {
+  const double Bd = (double)p.B;
+  const double n_terms = p.discrete ? Bd : Bd * p.A;
+  const double pl = -s[0] / n_terms;
+  const double m1 = s[1] / Bd, m2 = s[2] / Bd;
+  // compare as the reference does, on the float32 means
+  const float m1f = (float)m1, m2f = (float)m2;
+  double w1 = m1f > m2f ? 1.0 : (m1f < m2f ? 0.0 : 0.5);
+  const double vl = fmax(m1, m2);
+  double ivl = 0.0, iw1 = 0.0;
+  if (p.dual) {
+    const double i1 = s[3] / Bd, i2 = s[4] / Bd;
+    const float i1f = (float)i1, i2f = (float)i2;
+    iw1 = i1f > i2f ? 1.0 : (i1f < i2f ? 0.0 : 0.5);
+    ivl = fmax(i1, i2);
+  }
+  double el;
+  if (p.discrete) {
+    el = -s[5] / Bd;
+  } else {
+    double e = 0.0;
+    for (int a = 0; a < p.A; ++a) {
+      const float ent = 0.5f + 0.5f * 1.8378770664093453f + logf(expf(p.log_std[a]));   // Normal.entropy
+      e += (double)ent;
+      // d total / d log_std[a]: surrogate part + entropy part (d(-mean ent)/ds_a = -1/A)
+      p.d_log_std[a] = (float)(s[8 + a] - (double)p.pw * (double)p.ent_coef / (double)p.A);
+    }
+    el = -e / (double)p.A;
+  }
+  const double total = (double)p.pw * (pl + (double)p.ent_coef * el + (double)p.vf_coef * vl) +
+                       (p.dual ? (double)p.int_vf_coef * ivl : 0.0);
+  p.losses[0] = total; p.losses[1] = pl; p.losses[2] = vl; p.losses[3] = el; p.losses[4] = ivl;
+  p.losses[5] = 0.0; p.losses[6] = 0.0; p.losses[7] = 0.0;
+  p.branch[0] = w1; p.branch[1] = 1.0 - w1; p.branch[2] = iw1; p.branch[3] = 1.0 - iw1;
+}
+
+__global__ void __launch_bounds__(32) finalize_kernel(FinalArgs p) {
+  const int lane = threadIdx.x;
+  __shared__ double s[kPart];
+  s[lane] = p.sums[lane];
+  __syncwarp();
+  if (lane == 0) finalize_body(p, s);
+}
+
+__device__ unsigned int g_head_ticket = 0;
+
 struct HeadArgs {
   const float* actor_out; const float* log_std; const double* actions; const float* old_lp;
   const float* adv; const double* adv_stats; const float* values; const float* old_values; const float* returns;
@@ -34,6 +89,8 @@ struct HeadArgs {
   double* partials;
   int64_t B; int64_t Bt; int A; int dual;       // B = rows on this rank, Bt = rows of the global minibatch
   float clip, ent_coef, pw;
+  double* sums_out;                     // [32] sum of the CTA partials (written by the last CTA to finish)
+  int do_final; FinalArgs fin;          // do_final: the last CTA also runs finalize_body (single-GPU path)
 };
 
 __device__ __forceinline__ float norm_adv(float a, const double* st) {
@@ -158,72 +215,25 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
       if (threadIdx.x == 0) out[8 + a] = r;
     }
   }
-}
-
-// sums[e] = sum over CTAs of partials[cta][e]: 8 warps take interleaved CTAs, combined in a fixed order
-__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
+  // ---- tail: the last CTA sums the partials in a fixed order (8 warps take interleaved CTAs, then 0..7) ----
+  if (!last_block_done(&g_head_ticket)) return;
   __shared__ double s_p[8][kPart];
-  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  __shared__ double s_sum[kPart];
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5, nblocks = gridDim.x;
   double acc = 0.0;
 #pragma unroll 4
-  for (int k = ph; k < nblocks; k += 8) acc += partials[(int64_t)k * kPart + lane];
+  for (int k = ph; k < nblocks; k += 8) acc += __ldcg(p.partials + (int64_t)k * kPart + lane);
   s_p[ph][lane] = acc;
   __syncthreads();
   if (ph == 0) {
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += s_p[q][lane];
-    sums[lane] = t;
+    s_sum[lane] = t;
+    p.sums_out[lane] = t;
   }
-}
-
-struct FinalArgs {
-  const double* sums;
-  const float* log_std; float* d_log_std;
-  double* losses; double* branch;       // branch[0..3] = w1, w2, iw1, iw2
-  int64_t B; int A; int discrete; int dual;
-  float ent_coef, vf_coef, int_vf_coef, pw;
-};
-
-__global__ void __launch_bounds__(32) finalize_kernel(FinalArgs p) {
-  const int lane = threadIdx.x;
-  __shared__ double s[kPart];
-  s[lane] = p.sums[lane];
-  __syncwarp();
-  if (lane != 0) return;
-  const double Bd = (double)p.B;
-  const double n_terms = p.discrete ? Bd : Bd * p.A;
-  const double pl = -s[0] / n_terms;
-  const double m1 = s[1] / Bd, m2 = s[2] / Bd;
-  // compare as the reference does, on the float32 means
-  const float m1f = (float)m1, m2f = (float)m2;
-  double w1 = m1f > m2f ? 1.0 : (m1f < m2f ? 0.0 : 0.5);
-  const double vl = fmax(m1, m2);
-  double ivl = 0.0, iw1 = 0.0;
-  if (p.dual) {
-    const double i1 = s[3] / Bd, i2 = s[4] / Bd;
-    const float i1f = (float)i1, i2f = (float)i2;
-    iw1 = i1f > i2f ? 1.0 : (i1f < i2f ? 0.0 : 0.5);
-    ivl = fmax(i1, i2);
-  }
-  double el;
-  if (p.discrete) {
-    el = -s[5] / Bd;
-  } else {
-    double e = 0.0;
-    for (int a = 0; a < p.A; ++a) {
-      const float ent = 0.5f + 0.5f * 1.8378770664093453f + logf(expf(p.log_std[a]));   // Normal.entropy
-      e += (double)ent;
-      // d total / d log_std[a]: surrogate part + entropy part (d(-mean ent)/ds_a = -1/A)
-      p.d_log_std[a] = (float)(s[8 + a] - (double)p.pw * (double)p.ent_coef / (double)p.A);
-    }
-    el = -e / (double)p.A;
-  }
-  const double total = (double)p.pw * (pl + (double)p.ent_coef * el + (double)p.vf_coef * vl) +
-                       (p.dual ? (double)p.int_vf_coef * ivl : 0.0);
-  p.losses[0] = total; p.losses[1] = pl; p.losses[2] = vl; p.losses[3] = el; p.losses[4] = ivl;
-  p.losses[5] = 0.0; p.losses[6] = 0.0; p.losses[7] = 0.0;
-  p.branch[0] = w1; p.branch[1] = 1.0 - w1; p.branch[2] = iw1; p.branch[3] = 1.0 - iw1;
+  __syncthreads();
+  if (p.do_final && threadIdx.x == 0) finalize_body(p.fin, s_sum);
 }
 
 __global__ void __launch_bounds__(256)
@@ -318,12 +328,12 @@ int check_cfg(const ppx_ppo_cfg* c) {
 inline int64_t total_rows(const ppx_ppo_cfg* c) { return c->B_total > 0 ? c->B_total : c->B; }
 }  // namespace
 
-extern "C" int ppx_ppo_loss_head(const ppx_ppo_cfg* c, const float* actor_out, const float* log_std, const double* actions,
-                                 const float* old_log_probs, const float* advantages, const double* adv_stats,
-                                 const float* values, const float* old_values, const float* returns,
-                                 const float* int_advantages, const double* int_adv_stats, const float* int_values,
-                                 const float* old_int_values, const float* int_returns, float* d_actor_out,
-                                 double* sums_out, void* workspace, void* stream) {
+namespace {
+int launch_head(const ppx_ppo_cfg* c, const float* actor_out, const float* log_std, const double* actions,
+                const float* old_log_probs, const float* advantages, const double* adv_stats, const float* values,
+                const float* old_values, const float* returns, const float* int_advantages, const double* int_adv_stats,
+                const float* int_values, const float* old_int_values, const float* int_returns, float* d_actor_out,
+                double* sums_out, void* workspace, float* d_log_std, double* losses_out, double* branch_out, void* stream) {
   int rc = check_cfg(c);
   if (rc) return rc;
   PPX_REQUIRE(actor_out && actions && old_log_probs && advantages && adv_stats && values && old_values && returns,
@@ -337,13 +347,42 @@ extern "C" int ppx_ppo_loss_head(const ppx_ppo_cfg* c, const float* actor_out, c
   const int g = grid_for(c->B);
   HeadArgs h{actor_out, log_std, actions, old_log_probs, advantages, adv_stats, values, old_values, returns,
              int_advantages, int_adv_stats, int_values, old_int_values, int_returns, d_actor_out, partials,
-             c->B, total_rows(c), c->A, c->dual, c->clip_range, c->ent_coef, c->policy_weight};
+             c->B, total_rows(c), c->A, c->dual, c->clip_range, c->ent_coef, c->policy_weight, sums_out, 0, FinalArgs{}};
+  if (losses_out) {
+    PPX_REQUIRE(branch_out && (c->discrete || d_log_std), "ppo_loss: fused finalize needs branch_out / d_log_std");
+    h.do_final = 1;
+    h.fin = FinalArgs{nullptr, log_std, d_log_std, losses_out, branch_out, total_rows(c), c->A, c->discrete, c->dual,
+                      c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight};
+  }
   if (c->discrete) head_kernel<true><<<g, 256, 0, st>>>(h);
   else head_kernel<false><<<g, 256, 0, st>>>(h);
-  rc = after_launch("ppo_loss head");
-  if (rc) return rc;
-  sum_partials_kernel<<<1, 256, 0, st>>>(partials, g, sums_out);
-  return after_launch("ppo_loss sums");
+  return after_launch("ppo_loss head");
+}
+}  // namespace
+
+extern "C" int ppx_ppo_loss_head(const ppx_ppo_cfg* c, const float* actor_out, const float* log_std, const double* actions,
+                                 const float* old_log_probs, const float* advantages, const double* adv_stats,
+                                 const float* values, const float* old_values, const float* returns,
+                                 const float* int_advantages, const double* int_adv_stats, const float* int_values,
+                                 const float* old_int_values, const float* int_returns, float* d_actor_out,
+                                 double* sums_out, void* workspace, void* stream) {
+  return launch_head(c, actor_out, log_std, actions, old_log_probs, advantages, adv_stats, values, old_values, returns,
+                     int_advantages, int_adv_stats, int_values, old_int_values, int_returns, d_actor_out, sums_out,
+                     workspace, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int ppx_ppo_loss_head_final(const ppx_ppo_cfg* c, const float* actor_out, const float* log_std,
+                                       const double* actions, const float* old_log_probs, const float* advantages,
+                                       const double* adv_stats, const float* values, const float* old_values,
+                                       const float* returns, const float* int_advantages, const double* int_adv_stats,
+                                       const float* int_values, const float* old_int_values, const float* int_returns,
+                                       float* d_actor_out, float* d_log_std, double* losses_out, double* branch_out,
+                                       void* workspace, void* stream) {
+  PPX_REQUIRE(workspace && losses_out && branch_out, "ppo_loss_head_final: null pointer");
+  double* sums = (double*)workspace + (int64_t)kMaxBlocks * kPart;
+  return launch_head(c, actor_out, log_std, actions, old_log_probs, advantages, adv_stats, values, old_values, returns,
+                     int_advantages, int_adv_stats, int_values, old_int_values, int_returns, d_actor_out, sums,
+                     workspace, d_log_std, losses_out, branch_out, stream);
 }
 
 extern "C" int ppx_ppo_loss_finish(const ppx_ppo_cfg* c, const double* sums, const float* log_std, const float* values,

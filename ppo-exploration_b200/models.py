@@ -280,17 +280,29 @@ class ParallelMLP:
         self._saved = (x, H1, H2)
         return outs
 
-    def backward(self, d_outs):
-        """d_outs[g]: [M, out_g] contiguous.  Fills bank.grad for every MLP parameter."""
+    def fused(self):
+        return self._fused_args()["ok"]
+
+    def backward(self, d_outs, value_heads=None, clip_range=0.0, B_total=0):
+        """d_outs[g]: [M, out_g] contiguous (None for a net listed in `value_heads`).  Fills bank.grad for every
+        MLP parameter.  value_heads (fused path only): {g_index: (values, old_values, returns, branch_ptr, scale)}
+        -- the clipped-value-loss gradient of that head is evaluated inside the backward kernel."""
         x, H1, H2 = self._saved
         M, G, h, D, b, sc = x.shape[0], self.G, self.h, self.D, self.bank, self.scratch
         fa = self._fused_args()
         if fa["ok"]:
             ws = sc.get("pmlp.fused_ws", L.call("ppx_mlp3_bwd_workspace", M, D, h, G, fa["outs"]))
+            vh = None
+            if value_heads:
+                vh = (L.ValueHead * G)()
+                for gi, (v, ov, R, br, scale) in value_heads.items():
+                    vh[gi] = L.ValueHead(v.data_ptr(), ov.data_ptr(), R.data_ptr(), br, float(scale))
+            dptr = (C.c_void_p * G)(*[(d.data_ptr() if d is not None else None) for d in d_outs])
             L.call("ppx_mlp3_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
-                   H2.data_ptr(), (C.c_void_p * G)(*[d.data_ptr() for d in d_outs]), b.g("W1"), b.g("b1"), b.g("W2"),
+                   H2.data_ptr(), dptr, vh, float(clip_range), int(B_total), b.g("W1"), b.g("b1"), b.g("W2"),
                    b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), L.stream())
             return
+        assert not value_heads, "value_heads needs the fused MLP path"
         dP2 = sc.get("pmlp.dP2", M * G * h)[:M * G * h].view(M, G * h)
         dP1 = sc.get("pmlp.dP1", M * G * h)[:M * G * h].view(M, G * h)
         for gi, (g, o) in enumerate(zip(self.names, self.outs)):
