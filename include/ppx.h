@@ -105,6 +105,9 @@ int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream);
 int ppx_np_permutation(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* out_host);
 int ppx_np_shuffle_draws(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* j_out_host);
 int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host);
+/* n <= 2^31 - 1: int32 partner list / scratch (constant-mask draw loop, cache-resident swaps); same stream. */
+int ppx_np_shuffle_draws32(uint32_t* key624_host, int* pos_host, int64_t n, int32_t* j_out_host);
+int ppx_np_shuffle_apply32(const int32_t* j_host, int64_t n, int32_t* scratch_host, int64_t* out_host);
 
 /* ---------------------------------------------------------------- dense layers (fp32) ------- */
 /* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.

@@ -64,6 +64,7 @@ class HostRngStream:
                 seen = seen or op[0] == 'perm'
             script = sc
         self._jbufs = {}                                        # rotating partner buffers (<= 4 alive per size)
+        self._scratch32 = None
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
         self.t2 = threading.Thread(target=self._apply, daemon=True)
         self.t1.start()
@@ -77,10 +78,12 @@ class HostRngStream:
                     st = np.random.get_state()
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
-                    pool = self._jbufs.setdefault(n, [[np.empty(max(n, 1), np.int64) for _ in range(4)], 0])
+                    small = n <= 0x7fffffff
+                    pool = self._jbufs.setdefault(n, [[np.empty(max(n, 1), np.int32 if small else np.int64) for _ in range(4)], 0])
                     j = pool[0][pool[1] % 4]
                     pool[1] += 1
-                    L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
+                    L.call("ppx_np_shuffle_draws32" if small else "ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n,
+                           j.ctypes.data)
                     np.random.set_state((st[0], key, pos.value, st[3], st[4]))
                     self.mid.put(('perm', j, n))
                 elif op[0] == 'reuse':
@@ -100,7 +103,12 @@ class HostRngStream:
                 if item[0] == 'perm':
                     _, j, n = item
                     out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
-                    L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
+                    if j.dtype == np.int32:
+                        if self._scratch32 is None or self._scratch32.size < n:
+                            self._scratch32 = np.empty(max(n, 1), np.int32)
+                        L.call("ppx_np_shuffle_apply32", j.ctypes.data, n, self._scratch32.ctypes.data, out.data_ptr())
+                    else:
+                        L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
                     self._last = out
                     self.q.put(out)
                 elif item[0] == 'reuse':

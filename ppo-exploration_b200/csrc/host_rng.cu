@@ -96,6 +96,28 @@ static inline void draw_partners(Mt& mt, int64_t n, int64_t* j_out) {
   }
 }
 
+// 32-bit variant of draw_partners for n <= 2^31: the mask only changes when i crosses a power of two, so the
+// inner loop runs with a constant mask straight over the tempered block (no per-draw clz, no call per word),
+// and the partner list is int32 (half the cache footprint for stage 2).  Same draw sequence.
+static inline void draw_partners32(Mt& mt, int64_t n, int32_t* j_out) {
+  int64_t i = n - 1;
+  while (i >= 1) {
+    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+    const int64_t lo = (int64_t)(mask >> 1) + 1;            // positions [lo, mask] share this mask
+    while (i >= lo) {
+      if (mt.pos == MT_N) mt.gen();
+      const uint32_t* __restrict__ o = mt.out;
+      int p = mt.pos;
+      while (p < MT_N && i >= lo) {
+        const uint32_t v = o[p++] & mask;
+        j_out[i] = (int32_t)v;
+        i -= (int64_t)(v <= (uint32_t)i);
+      }
+      mt.pos = p;
+    }
+  }
+}
+
 // stage 1: the swap partners j_i for i = n-1 .. 1 (j_out[i] = partner of position i; j_out[0] unused)
 extern "C" int ppx_np_shuffle_draws(uint32_t* key624_host, int* pos_host, int64_t n, int64_t* j_out_host) {
   PPX_REQUIRE(key624_host && pos_host && j_out_host && n >= 0, "np_shuffle_draws: bad arguments");
@@ -103,6 +125,31 @@ extern "C" int ppx_np_shuffle_draws(uint32_t* key624_host, int* pos_host, int64_
   Mt mt(key624_host, *pos_host);
   draw_partners(mt, n, j_out_host);
   *pos_host = mt.pos;
+  return PPX_OK;
+}
+
+extern "C" int ppx_np_shuffle_draws32(uint32_t* key624_host, int* pos_host, int64_t n, int32_t* j_out_host) {
+  PPX_REQUIRE(key624_host && pos_host && j_out_host && n >= 0 && n <= 0x7fffffffll, "np_shuffle_draws32: bad arguments");
+  PPX_REQUIRE(*pos_host >= 0 && *pos_host <= MT_N, "np_shuffle_draws32: MT19937 pos=%d out of range", *pos_host);
+  Mt mt(key624_host, *pos_host);
+  draw_partners32(mt, n, j_out_host);
+  *pos_host = mt.pos;
+  return PPX_OK;
+}
+
+// stage 2 for the int32 partner list: swaps on an int32 scratch array (n*4 bytes: cache resident), widened into
+// the int64 output at the end
+extern "C" int ppx_np_shuffle_apply32(const int32_t* j_host, int64_t n, int32_t* scratch_host, int64_t* out_host) {
+  PPX_REQUIRE(j_host && scratch_host && out_host && n >= 0 && n <= 0x7fffffffll, "np_shuffle_apply32: bad arguments");
+  int32_t* __restrict__ a = scratch_host;
+  for (int64_t i = 0; i < n; ++i) a[i] = (int32_t)i;
+  for (int64_t i = n - 1; i >= 1; --i) {
+    const int32_t j = j_host[i];
+    const int32_t t = a[j];
+    a[j] = a[i];
+    a[i] = t;
+  }
+  for (int64_t i = 0; i < n; ++i) out_host[i] = (int64_t)a[i];
   return PPX_OK;
 }
 
