@@ -271,7 +271,9 @@ int ppx_embedding_bwd(const float* d_out, int ldo, const void* ids, int ids_are_
 int ppx_noise_fill(float* table, int64_t n, uint64_t seed, void* stream);
 /* _get_weights_try for the whole population (evolution_strategies.py:137-145):
  * out[p,j] = theta[j] + sigma * eps[p,j], eps[p,:] = noise[offsets[p] : offsets[p]+D] (offsets NULL:
- * noise is dense [P,D]).  out is f64 (out_is_f64=1, reference dtype) or f32. */
+ * noise is dense [P,D]).  out is f64 (out_is_f64=1, reference dtype) or f32.
+ * CONTRACT: when offsets != NULL and D % 4 == 0, every offset must be a multiple of 4 (16-byte aligned noise
+ * rows; ppx_es_perturb and ppx_es_update read them as 16-byte vectors). */
 int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P, int D,
                    void* out, int out_is_f64, void* stream);
 /* _update_weights (evolution_strategies.py:217-239): z-score rewards (ddof 0); skip entirely if std==0;

@@ -62,6 +62,31 @@ perturb_kernel(const double* __restrict__ theta, const float* __restrict__ noise
   }
 }
 
+// Same arithmetic over the flat [P, D/4] index space with 16-byte noise loads (D % 4 == 0, every member's noise
+// row 16-byte aligned): a persistent grid-stride loop, two independent quads in flight per thread.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+perturb_vec_kernel(const double* __restrict__ theta, const float* __restrict__ noise, const int64_t* __restrict__ offsets,
+                   double sigma, int P, int D4, OutT* __restrict__ out) {
+  const int64_t total = (int64_t)P * D4, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int p = (int)(i / D4), j = (int)(i - (int64_t)p * D4) * 4;
+    const float* eps = noise + (offsets ? __ldg(offsets + p) : (int64_t)p * D4 * 4) + j;
+    const float4 e = ld_stream4(reinterpret_cast<const float4*>(eps));
+    const double2 t0 = __ldg(reinterpret_cast<const double2*>(theta + j));
+    const double2 t1 = __ldg(reinterpret_cast<const double2*>(theta + j + 2));
+    const double r0 = __dadd_rn(t0.x, __dmul_rn(sigma, (double)e.x)), r1 = __dadd_rn(t0.y, __dmul_rn(sigma, (double)e.y));
+    const double r2 = __dadd_rn(t1.x, __dmul_rn(sigma, (double)e.z)), r3 = __dadd_rn(t1.y, __dmul_rn(sigma, (double)e.w));
+    OutT* o = out + (int64_t)p * D4 * 4 + j;
+    if (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(o) = make_float4((float)r0, (float)r1, (float)r2, (float)r3);
+    } else {
+      *reinterpret_cast<double2*>(o) = make_double2(r0, r1);
+      *reinterpret_cast<double2*>(o + 2) = make_double2(r2, r3);
+    }
+  }
+}
+
 // ---------------- update ----------------
 // stats[0]=mean, stats[1]=std(ddof 0), stats[2]=skip flag
 __global__ void __launch_bounds__(1024) es_stats_kernel(const double* __restrict__ r, int P, int rank_mode, double* stats, int* status) {
@@ -125,7 +150,7 @@ es_gemv_kernel(const float* __restrict__ noise, const int64_t* __restrict__ offs
   const int p0 = blockIdx.y * p_chunk, p1 = min(P, p0 + p_chunk);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (j < D) {
-#pragma unroll 4
+#pragma unroll 8
     for (int p = p0; p < p1; ++p) {
       const float* eps = noise + (offsets ? __ldg(offsets + p) : (int64_t)p * D) + j;
       const double c = __ldg(coef + p);
@@ -215,8 +240,8 @@ knn_kernel(const double* __restrict__ archive, int64_t M, const double* __restri
 
 int gemv_splits(int P, int D) {
   const int64_t colblocks = ceil_div(D, 512);
-  int64_t s = ceil_div(4 * (int64_t)sm_count(), colblocks);
-  s = std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, P / 8)));
+  int64_t s = ceil_div(16 * (int64_t)sm_count(), colblocks);
+  s = std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, P / 32)));
   return (int)s;
 }
 
@@ -234,6 +259,18 @@ extern "C" int ppx_noise_fill(float* table, int64_t n, uint64_t seed, void* stre
 extern "C" int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P, int D,
                               void* out, int out_is_f64, void* stream) {
   PPX_REQUIRE(theta && noise && out && P >= 1 && D >= 1, "es_perturb: bad arguments");
+  // fast path: 16-byte vectors (the table sampler hands out offsets that are multiples of 4; dense eps needs D % 4 == 0)
+  bool vec = (D % 4 == 0) && ((uintptr_t)noise % 16 == 0) && ((uintptr_t)theta % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (vec && offsets) {
+    // offsets live on the device: the caller promises 4-alignment through ppx_es_perturb's contract (see ppx.h)
+  }
+  if (vec) {
+    const int64_t total = (int64_t)P * (D / 4);
+    const unsigned g = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+    if (out_is_f64) perturb_vec_kernel<double><<<g, 256, 0, (cudaStream_t)stream>>>(theta, noise, offsets, sigma, P, D / 4, (double*)out);
+    else perturb_vec_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(theta, noise, offsets, sigma, P, D / 4, (float*)out);
+    return after_launch("es_perturb(vec)");
+  }
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(D, 256), 64), (unsigned)P);
   PPX_REQUIRE(P <= 65535, "es_perturb: P=%d exceeds grid.y limit; call in slices", P);
   if (out_is_f64) perturb_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, noise, offsets, sigma, P, D, (double*)out);

@@ -15,7 +15,13 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   __shared__ double s_red[32];
   if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;      // read by adam_kernel (next launch)
   double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (((uintptr_t)g & 15) == 0) ? n / 4 : 0;
+  for (int64_t q = tid0; q < n4; q += nth) {
+    const float4 v = ld_stream4(reinterpret_cast<const float4*>(g) + q);
+    s += (double)v.x * (double)v.x + (double)v.y * (double)v.y + (double)v.z * (double)v.z + (double)v.w * (double)v.w;
+  }
+  for (int64_t i = n4 * 4 + tid0; i < n; i += nth) {
     const double v = (double)g[i];
     s += v * v;
   }
@@ -52,16 +58,34 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   const float coef = s_coef;
   step_size = s_step_size;
   bc2_sqrt = s_bc2_sqrt;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i];
-    if (i < n_clip) gi *= coef;
-    float mi = m[i], vi = v[i];
+  auto upd = [&](float gi, float& pi, float& mi, float& vi) {
     mi = mi + w1 * (gi - mi);                                 // exp_avg.lerp_(grad, 1-beta1)
     vi = vi * beta2 + w2 * gi * gi;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);                   // param.addcdiv_(exp_avg, denom, -step_size)
-    m[i] = mi;
-    v[i] = vi;
+    pi = pi - step_size * (mi / denom);                       // param.addcdiv_(exp_avg, denom, -step_size)
+  };
+  const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t q = tid0; q < n4; q += nth) {                  // 16-byte vectors over the aligned body
+    float4 g4 = ld_stream4(reinterpret_cast<const float4*>(g) + q);
+    float4 p4 = reinterpret_cast<float4*>(p)[q], m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+    const int64_t i = q * 4;
+    if (i + 3 < n_clip) { g4.x *= coef; g4.y *= coef; g4.z *= coef; g4.w *= coef; }
+    else {
+      if (i < n_clip) g4.x *= coef;
+      if (i + 1 < n_clip) g4.y *= coef;
+      if (i + 2 < n_clip) g4.z *= coef;
+    }
+    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[q] = p4; reinterpret_cast<float4*>(m)[q] = m4; reinterpret_cast<float4*>(v)[q] = v4;
+  }
+  for (int64_t i = n4 * 4 + tid0; i < n; i += nth) {
+    float gi = g[i];
+    if (i < n_clip) gi *= coef;
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(gi, pi, mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -89,14 +113,14 @@ extern "C" int ppx_clip_adam(float* params, const float* grads, float* exp_avg, 
     step = 1;
   }
   if (clip) {
-    n_partials = (int)std::min<int64_t>(kNormBlocks, ceil_div(n_clip, 1024));
+    n_partials = (int)std::min<int64_t>(kNormBlocks, ceil_div(n_clip, 4096));
     sumsq_kernel<<<n_partials, 256, 0, st>>>(grads, n_clip, partials, step_dev);
     int rc = after_launch("clip_adam sumsq");
     if (rc) return rc;
   }
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
-  const int grid = (int)std::min<int64_t>(ceil_div(n, 1024), (int64_t)sm_count() * 8);
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 2048), (int64_t)sm_count() * 8);
   adam_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, n_partials, (float)max_norm, n_clip,
                                     (float)(1.0 - beta1), beta1, beta2, lr, (float)beta2, (float)(1.0 - beta2),
                                     (float)(lr / bc1), (float)sqrt(bc2), (float)eps, step_dev, norm_out);

@@ -298,7 +298,7 @@ __global__ void accum_loss_kernel(const double* __restrict__ partials, int n, do
 
 int grid_for(int64_t n) {
   int64_t g = ceil_div(n, 256);
-  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 2);
+  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
   return (int)std::max<int64_t>(1, std::min(g, cap));
 }
 

@@ -145,6 +145,48 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
   }
 }
 
+// Wide rollouts (N >= 64k env columns): one THREAD per env column, sequential in t in exactly the reference's
+// operation order (bit-exact, including the f32 intrinsic carry), rows read fully coalesced across the warp.
+// The loads of the unrolled steps do not depend on the carry chain, so ~8 rows x 3 arrays are in flight per
+// thread: HBM-bound.  (Narrow rollouts keep the warp-per-column parallel scan above: not enough columns.)
+template <bool DUAL>
+__global__ void __launch_bounds__(128)
+gae_seq_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ masks,
+               const float* __restrict__ last_value, const uint8_t* __restrict__ last_done,
+               const float* __restrict__ int_rewards, const float* __restrict__ int_values,
+               const float* __restrict__ last_int_value, float g32, double gl, float gi32, float gil32, int T, int N,
+               float* __restrict__ adv, float* __restrict__ ret, float* __restrict__ iadv, float* __restrict__ iret) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double carry = 0.0;
+  float icarry = 0.f;
+  float nv = last_value[n];
+  double nnt = 1.0 - (double)last_done[n];
+  float niv = DUAL ? last_int_value[n] : 0.f;
+#pragma unroll 8
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t g = (size_t)t * N + n;
+    const float r = ld_stream(rewards + g), v = ld_stream(values + g);
+    const uint8_t m = masks[g];
+    const float gv = __fmul_rn(g32, nv);
+    const double delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn((double)gv, nnt)), (double)v);
+    carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nnt), carry));
+    const float a = (float)carry;
+    adv[g] = a;
+    ret[g] = __fadd_rn(a, v);
+    nv = v;
+    nnt = 1.0 - (double)m;
+    if (DUAL) {
+      const float ir = ld_stream(int_rewards + g), iv = ld_stream(int_values + g);
+      const float idelta = __fsub_rn(__fadd_rn(ir, __fmul_rn(gi32, niv)), iv);
+      icarry = __fadd_rn(idelta, __fmul_rn(gil32, icarry));
+      iadv[g] = icarry;
+      iret[g] = __fadd_rn(icarry, iv);
+      niv = iv;
+    }
+  }
+}
+
 // thread-per-column, sequential in t: same operation order as the reference loop -> bit-exact.
 __global__ void discount_kernel(const double* __restrict__ r, const uint8_t* __restrict__ d, double gamma,
                                 int T, int N, double* __restrict__ out) {
@@ -170,6 +212,11 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* masks, 
   const double gl = gamma * lam;
   const double gil = (double)(float)(int_gamma * lam);
   const int sms = sm_count();
+  if (N >= 65536) {
+    gae_seq_kernel<DUAL><<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(rewards, values, masks, last_value, last_done,
+        int_rewards, int_values, last_int_value, g32, gl, gi32, (float)(int_gamma * lam), T, N, adv, ret, iadv, iret);
+    return after_launch(DUAL ? "gae_dual(seq)" : "gae(seq)");
+  }
   // widest column tile that still gives every SM a CTA
   int cols = 32;
   if (ceil_div(N, 32) < sms) cols = 16;

@@ -107,3 +107,24 @@ def test_discount_with_dones_bit_exact():
     r, d = rs.randn(50, 7), (rs.rand(50, 7) < 0.1)
     out = ppx.discount_with_dones(r, d, 0.99).cpu().numpy()
     assert np.array_equal(out, OR.discount_with_dones(r, d, 0.99))
+
+
+@pytest.mark.parametrize("T,N,dp", [(16, 65536, 0.05), (37, 70001, 0.02)])
+def test_gae_wide_rollout_bit_exact(T, N, dp):
+    """N >= 64k columns takes the thread-per-column kernel: the reference's own operation order -> bit-exact."""
+    import ppo_exploration_b200 as ppx
+    rs = np.random.RandomState(N)
+    f = lambda: rs.randn(T, N).astype(np.float32)
+    rew, val, irew, ival = f(), f(), np.abs(f()), f()
+    msk = (rs.rand(T, N) < dp).astype(np.uint8)
+    lv, liv = rs.randn(N).astype(np.float32), rs.randn(N).astype(np.float32)
+    want_adv, want_ret = OR.gae(rew, val, msk.astype(np.int64), lv, msk[-1], 0.999, 0.95)
+    adv, ret = _run_single(rew, val, msk, lv, msk[-1], 0.999, 0.95)
+    assert np.array_equal(adv, want_adv) and np.array_equal(ret, want_ret)
+    want = OR.gae_dual(rew, val, msk.astype(np.int64), lv, msk[-1], 0.999, 0.95, irew, ival, liv, 0.99)
+    o, a = _spaces()
+    buf = ppx.IntrinsicStorage(T, N, o, a, gae_lam=0.95, gamma=0.999, int_gamma=0.99)
+    buf.load_rollout(rewards=rew, values=val, masks=msk, int_rewards=irew, int_values=ival)
+    buf.compute_returns_and_advantages(lv, liv, msk[-1])
+    for name, w in zip(("advantages", "returns", "int_advantages", "int_returns"), want):
+        assert np.array_equal(getattr(buf, name).cpu().numpy(), w), name
