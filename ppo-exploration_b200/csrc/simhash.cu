@@ -5,18 +5,21 @@
 // Semantics that must survive parallelisation: the reference walks the batch in env order,
 // `count[key] += 1; reward[i] += beta/sqrt(count[key])`, so the j-th occurrence of a key inside one
 // batch sees count c+j.  A bare atomicAdd gives the right final table but hands the bonuses to the
-// wrong envs.  Here the batch is cut into chunks of CH consecutive elements, one CTA per chunk:
-//   1. (parallel)  codes: bit b = (A[b,:] . obs[i,:] > 0), f64 dot            (buffer.py:194)
-//   2. (parallel)  bitonic sort of (code, local index) in shared memory -> for every element its
-//                  rank among equal codes of the chunk in index order, and one representative
-//                  (the last of each run) that knows the run length m
-//   3. (parallel)  representatives find / claim their slot: linear probing, atomicCAS on the 64-bit key
-//   4. (ordered)   chunks pass a baton in chunk order (tickets are taken at CTA start, so a CTA only
-//                  ever waits for CTAs that are already running): representative does
-//                  base = atomicAdd(count[slot], m); the critical section is one L2 atomic round trip
-//   5. (parallel)  count_i = base + rank_i + 1; reward_i += beta / sqrt(count_i)  (f64, buffer.py:199)
-// Steps 1-3 of later chunks overlap the baton of earlier ones.  All 2^64 codes are valid keys: the
-// all-ones code (the EMPTY sentinel) lives in a dedicated extra slot.
+// wrong envs.  Two launches, no inter-CTA ordering:
+//   A. (parallel over observations)  codes: bit b = (A[b,:] . obs[i,:] > 0), f64 dot (buffer.py:194), plus a
+//      16-bit BUCKET id = hash(code) % NB.  A is staged in shared memory, two observations per thread.
+//   B. (one CTA per bucket)  a bucket OWNS its codes, so everything order-dependent happens inside one CTA:
+//      the CTA streams the bucket ids in index order, compacts the indices of its own elements (a stable
+//      block scan keeps them in index order) into batches of <= 4096, and per batch
+//        1. bitonic sort of (code, position) in shared memory -> rank among equal codes in index order and
+//           one representative (the run tail) that knows the run length m
+//        2. representatives find / claim their slot (linear probing, 64-bit atomicCAS: other buckets claim
+//           other keys in the same table concurrently), read base = count[slot] and store base + m (plain
+//           accesses: nobody else touches this key during the launch)
+//        3. count_i = base + rank_i + 1; reward_i += beta / sqrt(count_i)  (f64, buffer.py:199)
+//      Batches of one bucket run in index order inside the CTA, so skewed inputs (few distinct codes) stay
+//      exact -- they only serialise.  Inputs above 2^20 observations are cut into stream-ordered launches.
+// All 2^64 codes are valid keys: the all-ones code (the EMPTY sentinel) lives in a dedicated extra slot.
 // Algorithmic traffic: 4D + 8 + 8 + 16 B/obs.
 #include "common.cuh"
 
@@ -26,20 +29,28 @@ struct ppx_count_table {
   uint64_t capacity;     // power of two
   uint32_t* ctrl;        // [0] ticket, [1] chunks done, [2] keys in use, [3] overflow flag
   uint64_t used_bound;   // host-side upper bound of keys in use (avoids a sync per call)
+  uint64_t* scratch_codes;   // [scratch_n] codes of the launch in flight
+  uint16_t* scratch_bucket;  // [scratch_n] bucket ids
+  int64_t scratch_n;
 };
 
 namespace ppx {
 namespace {
 
 constexpr uint64_t kEmpty = ~0ull;
-constexpr int CH = 2048;          // elements per chunk
-constexpr int CT = 1024;          // threads per CTA (2 elements each)
+constexpr int CAP = 4096;         // elements per sorted batch
+constexpr int CT = 1024;          // threads per bucket CTA (4 elements each)
+constexpr int64_t LMAX = 1 << 20; // observations per launch
+constexpr int TARGET = 3072;      // expected elements per bucket
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {     // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
   x ^= x >> 31;
   return x;
+}
+__device__ __forceinline__ uint32_t bucket_of(uint64_t code, uint32_t nb) {
+  return (uint32_t)(((mix64(code ^ 0x9e3779b97f4a7c15ull) >> 32) * (uint64_t)nb) >> 32);
 }
 
 __device__ __forceinline__ uint64_t find_or_claim(uint64_t* keys, uint64_t cap, uint32_t* ctrl, uint64_t code) {
@@ -71,127 +82,167 @@ __device__ __forceinline__ uint64_t code_of(const double* __restrict__ A, const 
   return code;
 }
 
-__global__ void codes_kernel(const double* __restrict__ A, const float* __restrict__ obs, int k, int D, int64_t n,
-                             uint64_t* __restrict__ codes) {
+// codes (+ bucket ids).  DMAX > 0: A staged in shared memory as f64, the observation rows held in registers, two
+// observations per thread so every shared-memory load of A feeds two FMAs (same sequential fma order over d as
+// code_of -> identical bits).  DMAX == 0: any D, straight from global / L1.
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+codes_kernel(const double* __restrict__ A, const float* __restrict__ obs, int k, int D, int64_t n,
+             uint64_t* __restrict__ codes, uint16_t* __restrict__ bucket, uint32_t nb) {
+  if (DMAX == 0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+      const uint64_t c = code_of(A, obs + i * D, k, D);
+      codes[i] = c;
+      if (bucket) bucket[i] = (uint16_t)bucket_of(c, nb);
+    }
+    return;
+  }
+  constexpr int DM = DMAX > 0 ? DMAX : 1;
+  __shared__ double As[64 * DM];
+  for (int e = threadIdx.x; e < k * DM; e += blockDim.x) {
+    const int b = e / DM, d = e - b * DM;
+    As[e] = d < D ? A[(size_t)b * D + d] : 0.0;
+  }
+  __syncthreads();
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i0 >= n) return;
+  const bool two = i0 + 1 < n;
+  double x0[DM], x1[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    x0[d] = d < D ? (double)ld_stream(obs + i0 * D + d) : 0.0;
+    x1[d] = (two && d < D) ? (double)ld_stream(obs + (i0 + 1) * D + d) : 0.0;
+  }
+  uint64_t c0 = 0, c1 = 0;
+  for (int b = 0; b < k; ++b) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+      const double a = As[b * DM + d];
+      if (d < D) { a0 = fma(a, x0[d], a0); a1 = fma(a, x1[d], a1); }
+    }
+    c0 |= (uint64_t)(a0 > 0.0) << b;
+    c1 |= (uint64_t)(a1 > 0.0) << b;
+  }
+  codes[i0] = c0;
+  if (bucket) bucket[i0] = (uint16_t)bucket_of(c0, nb);
+  if (two) {
+    codes[i0 + 1] = c1;
+    if (bucket) bucket[i0 + 1] = (uint16_t)bucket_of(c1, nb);
+  }
+}
+
+__global__ void __launch_bounds__(256) bucket_ids_kernel(const uint64_t* __restrict__ codes, int64_t n, uint16_t* __restrict__ bucket, uint32_t nb) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) codes[i] = code_of(A, obs + i * D, k, D);
+  if (i < n) bucket[i] = (uint16_t)bucket_of(codes[i], nb);
 }
 
 __device__ __forceinline__ bool key_gt(uint64_t ca, uint16_t ia, uint64_t cb, uint16_t ib) {
   return ca > cb || (ca == cb && ia > ib);
 }
 
-template <bool FROM_OBS>
-__global__ void __launch_bounds__(CT)
-update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap, uint32_t* ctrl,
-              const double* __restrict__ A, const float* __restrict__ obs, int k, int D,
-              const uint64_t* __restrict__ codes_in, int64_t n, double beta, void* rewards, int rewards_f64,
-              uint64_t* __restrict__ codes_out, uint32_t* __restrict__ counts_out) {
-  __shared__ uint64_t s_code[CH];
-  __shared__ uint32_t s_base[CH];
-  __shared__ uint16_t s_idx[CH];
-  __shared__ int s_warp[32];
-  __shared__ uint32_t s_chunk;
+struct BucketSmem {
+  uint64_t code[CAP];
+  uint32_t elem[CAP];       // element index inside the launch, in index order (the compacted list)
+  uint32_t base[CAP];
+  uint16_t pos[CAP];        // position in elem[] carried through the sort
+  int warp[32];
+  int total;
+};
 
+// one sorted batch: elements elem[0..m) (index order) of this bucket
+__device__ void process_batch(BucketSmem& S, int m, uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap,
+                              uint32_t* ctrl, const uint64_t* __restrict__ codes, int64_t e0, double beta, void* rewards,
+                              int rewards_f64, uint32_t* __restrict__ counts_out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) s_chunk = atomicAdd(&ctrl[0], 1u);            // ticket = chunk id, in CTA start order
-  __syncthreads();
-  const uint32_t chunk = s_chunk;
-  const int64_t e0 = (int64_t)chunk * CH;
-  const int nv = (int)min((int64_t)CH, n - e0);               // valid elements in this chunk
-
-  // 1. codes
-  for (int j = tid; j < CH; j += CT) {
-    uint64_t c = kEmpty;
-    uint16_t id = 0xFFFF;
-    if (j < nv) {
-      c = FROM_OBS ? code_of(A, obs + (e0 + j) * D, k, D) : codes_in[e0 + j];
-      id = (uint16_t)j;
-      if (codes_out) codes_out[e0 + j] = c;
-    }
-    s_code[j] = c;
-    s_idx[j] = id;
+  int SZ = 64;
+  while (SZ < m) SZ <<= 1;                                   // sort size: next power of two (>= 64)
+  for (int j = tid; j < SZ; j += CT) {
+    const bool valid = j < m;
+    S.code[j] = valid ? __ldg(codes + S.elem[j]) : kEmpty;
+    S.pos[j] = valid ? (uint16_t)j : (uint16_t)0xFFFF;
   }
   __syncthreads();
-
-  // 2. bitonic sort by (code, idx); padding (kEmpty, 0xFFFF) sorts last
-  for (int kk = 2; kk <= CH; kk <<= 1) {
+  // 1. bitonic sort by (code, pos); padding (kEmpty, 0xFFFF) sorts last
+  for (int kk = 2; kk <= SZ; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));
-      const int l = i | j;
-      const bool up = (i & kk) == 0;
-      const uint64_t ci = s_code[i], cl = s_code[l];
-      const uint16_t ii = s_idx[i], il = s_idx[l];
-      if (key_gt(ci, ii, cl, il) == up) {
-        s_code[i] = cl; s_code[l] = ci;
-        s_idx[i] = il; s_idx[l] = ii;
+      for (int t = tid; t < SZ / 2; t += CT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = (i & kk) == 0;
+        const uint64_t ci = S.code[i], cl = S.code[l];
+        const uint16_t ii = S.pos[i], il = S.pos[l];
+        if (key_gt(ci, ii, cl, il) == up) {
+          S.code[i] = cl; S.code[l] = ci;
+          S.pos[i] = il; S.pos[l] = ii;
+        }
       }
       __syncthreads();
     }
   }
-
-  // run starts: inclusive max-scan of (is_head ? p : 0); thread owns positions 2*tid, 2*tid+1
-  const int p0 = 2 * tid, p1 = p0 + 1;
-  const uint64_t c0 = s_code[p0], c1 = s_code[p1];
-  const bool h0 = p0 < nv && (p0 == 0 || s_code[p0 - 1] != c0);
-  const bool h1 = p1 < nv && (c1 != c0);
-  int v = h1 ? p1 : (h0 ? p0 : 0);
-  int incl = v;
+  // run starts: inclusive max-scan of (is_head ? p : 0); thread owns positions 4*tid .. 4*tid+3
+  const int p0 = 4 * tid;
+  uint64_t c[4];
+  bool head[4], tail[4];
+  int start[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) c[q] = (p0 + q < SZ) ? S.code[p0 + q] : kEmpty;
+  const uint64_t cprev = (p0 > 0 && p0 - 1 < SZ) ? S.code[p0 - 1] : kEmpty;
+  const uint64_t cnext = (p0 + 4 < SZ) ? S.code[p0 + 4] : kEmpty;
+  int run = 0;                                               // latest head position seen by this thread (0 if none)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int p = p0 + q;
+    const uint64_t before = q == 0 ? cprev : c[q - 1];
+    const uint64_t after = q == 3 ? cnext : c[q + 1];
+    head[q] = p < m && (p == 0 || before != c[q]);
+    tail[q] = p < m && (p == m - 1 || after != c[q]);
+    if (head[q]) run = p;
+  }
+  int incl = run;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int o = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl = max(incl, o);
   }
-  if (lane == 31) s_warp[wid] = incl;
+  if (lane == 31) S.warp[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int x = s_warp[lane];
+    int x = S.warp[lane];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int o = __shfl_up_sync(0xffffffffu, x, d);
       if (lane >= d) x = max(x, o);
     }
-    s_warp[lane] = x;
+    S.warp[lane] = x;
   }
   __syncthreads();
   int before = __shfl_up_sync(0xffffffffu, incl, 1);
   if (lane == 0) before = 0;
-  if (wid > 0) before = max(before, s_warp[wid - 1]);
-  const int start0 = h0 ? p0 : before;
-  const int start1 = h1 ? p1 : start0;
-  const bool t0 = p0 < nv && (p0 == nv - 1 || c1 != c0);
-  const bool t1 = p1 < nv && (p1 == nv - 1 || s_code[min(p1 + 1, CH - 1)] != c1);
-
-  // 3. representatives (run tails) locate their slot
-  uint64_t slot0 = 0, slot1 = 0;
-  if (t0) slot0 = find_or_claim(keys, cap, ctrl, c0);
-  if (t1) slot1 = find_or_claim(keys, cap, ctrl, c1);
-
-  // 4. ordered section
-  if (tid == 0) {
-    unsigned done;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(ctrl + 1) : "memory");
-      if (done < chunk) __nanosleep(32);
-    } while (done < chunk);
-  }
-  __syncthreads();
-  if (t0) s_base[start0] = atomicAdd(&counts[slot0], (uint32_t)(p0 - start0 + 1));
-  if (t1) s_base[start1] = atomicAdd(&counts[slot1], (uint32_t)(p1 - start1 + 1));
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctrl + 1), "r"(chunk + 1) : "memory");
-  }
-
-  // 5. counts and bonus, scattered back to element order
+  if (wid > 0) before = max(before, S.warp[wid - 1]);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int p = q ? p1 : p0;
-    if (p >= nv) continue;
-    const int st = q ? start1 : start0;
-    const uint32_t cnt = s_base[st] + (uint32_t)(p - st) + 1u;
-    const int64_t e = e0 + s_idx[p];
+  for (int q = 0; q < 4; ++q) {
+    if (head[q]) before = p0 + q;
+    start[q] = before;
+  }
+  // 2. run tails: slot, base count, new count (this CTA owns the key for the whole launch)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!tail[q]) continue;
+    const uint64_t slot = find_or_claim(keys, cap, ctrl, c[q]);
+    const uint32_t base = __ldcg(counts + slot);
+    S.base[start[q]] = base;
+    __stcg(counts + slot, base + (uint32_t)(p0 + q - start[q] + 1));
+  }
+  __syncthreads();
+  // 3. counts and bonus, scattered back to element order
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int p = p0 + q;
+    if (p >= m) continue;
+    const uint32_t cnt = S.base[start[q]] + (uint32_t)(p - start[q]) + 1u;
+    const int64_t e = e0 + S.elem[S.pos[p]];
     if (counts_out) counts_out[e] = cnt;
     if (rewards) {
       const double bonus = beta / sqrt((double)cnt);
@@ -199,6 +250,64 @@ update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64
       else ((float*)rewards)[e] = (float)((double)((float*)rewards)[e] + bonus);
     }
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(CT)
+bucket_update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap, uint32_t* ctrl,
+                     const uint64_t* __restrict__ codes, const uint16_t* __restrict__ bucket, int n, int64_t e0, double beta,
+                     void* rewards, int rewards_f64, uint32_t* __restrict__ counts_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BucketSmem& S = *reinterpret_cast<BucketSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint16_t mine = (uint16_t)blockIdx.x;
+  int fill = 0;
+  // stream the bucket ids in index order, CAP elements per step (4 per thread), stable compaction of the matches
+  for (int b0 = 0; b0 < n; b0 += CAP) {
+    const int i0 = b0 + 4 * tid;
+    bool mt[4];
+    if (i0 + 3 < n) {
+      const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(bucket + i0));
+      mt[0] = v.x == mine; mt[1] = v.y == mine; mt[2] = v.z == mine; mt[3] = v.w == mine;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mt[q] = (i0 + q < n) && (__ldg(bucket + i0 + q) == mine);
+    }
+    const int cnt = (int)mt[0] + (int)mt[1] + (int)mt[2] + (int)mt[3];
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) S.warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int x = S.warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += o;
+      }
+      S.warp[lane] = x;
+      if (lane == 31) S.total = x;
+    }
+    __syncthreads();
+    const int total = S.total;
+    int excl = incl - cnt + (wid > 0 ? S.warp[wid - 1] : 0);
+    __syncthreads();                                         // S.warp / S.total are reused below and next step
+    if (total == 0) continue;
+    if (fill + total > CAP) {                                // batch full: settle it before appending (index order)
+      process_batch(S, fill, keys, counts, cap, ctrl, codes, e0, beta, rewards, rewards_f64, counts_out);
+      fill = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (mt[q]) S.elem[fill + excl++] = (uint32_t)(i0 + q);
+    fill += total;
+    __syncthreads();
+  }
+  if (fill > 0) process_batch(S, fill, keys, counts, cap, ctrl, codes, e0, beta, rewards, rewards_f64, counts_out);
 }
 
 __global__ void bonus_kernel(const uint32_t* __restrict__ counts, int64_t n, double beta, void* rewards, int f64) {
@@ -277,20 +386,56 @@ int reserve(ppx_count_table* t, int64_t incoming, cudaStream_t st) {
   return PPX_OK;
 }
 
+int ensure_scratch(ppx_count_table* t, int64_t n) {
+  if (t->scratch_n >= n) return PPX_OK;
+  cudaFree(t->scratch_codes); cudaFree(t->scratch_bucket);
+  t->scratch_codes = nullptr; t->scratch_bucket = nullptr; t->scratch_n = 0;
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_codes, (size_t)n * sizeof(uint64_t)));
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_bucket, (size_t)(n + 8) * sizeof(uint16_t)));
+  t->scratch_n = n;
+  return PPX_OK;
+}
+
+int launch_codes(const double* A, const float* obs, int k, int D, int64_t n, uint64_t* codes, uint16_t* bucket, uint32_t nb,
+                 cudaStream_t st) {
+  if (D <= 8) codes_kernel<8><<<(unsigned)ceil_div(n, 256), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
+  else if (D <= 16) codes_kernel<16><<<(unsigned)ceil_div(n, 256), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
+  else codes_kernel<0><<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
+  return after_launch("simhash codes");
+}
+
 int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int D, const uint64_t* codes_in, int64_t n,
                double beta, void* rewards, int rewards_f64, uint64_t* codes_out, uint32_t* counts_out, cudaStream_t st) {
   if (n == 0) return PPX_OK;
   int rc = reserve(t, n, st);
   if (rc) return rc;
-  PPX_CUDA(cudaMemsetAsync(t->ctrl, 0, 2 * sizeof(uint32_t), st));       // ticket + baton
-  const unsigned grid = (unsigned)ceil_div(n, CH);
-  if (obs)
-    update_kernel<true><<<grid, CT, 0, st>>>(t->keys, t->counts, t->capacity, t->ctrl, A, obs, k, D, nullptr, n, beta,
-                                              rewards, rewards_f64, codes_out, counts_out);
-  else
-    update_kernel<false><<<grid, CT, 0, st>>>(t->keys, t->counts, t->capacity, t->ctrl, nullptr, nullptr, 0, 0, codes_in, n,
-                                               beta, rewards, rewards_f64, codes_out, counts_out);
-  return after_launch("simhash update");
+  rc = ensure_scratch(t, std::min<int64_t>(n, LMAX));
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(bucket_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+    configured = true;
+  }
+  for (int64_t e0 = 0; e0 < n; e0 += LMAX) {                  // stream-ordered launches keep the index order
+    const int64_t nl = std::min<int64_t>(LMAX, n - e0);
+    const uint32_t nb = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, TARGET), 65535));
+    const uint64_t* codes = codes_in ? codes_in + e0 : (codes_out ? codes_out + e0 : t->scratch_codes);
+    if (obs) {
+      rc = launch_codes(A, obs + e0 * D, k, D, nl, const_cast<uint64_t*>(codes), t->scratch_bucket, nb, st);
+      if (rc) return rc;
+    } else {
+      bucket_ids_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(codes, nl, t->scratch_bucket, nb);
+      rc = after_launch("simhash bucket ids");
+      if (rc) return rc;
+    }
+    const size_t sz = rewards_f64 ? sizeof(double) : sizeof(float);
+    bucket_update_kernel<<<nb, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, t->scratch_bucket,
+                                                            (int)nl, 0, beta, rewards ? (char*)rewards + e0 * sz : nullptr,
+                                                            rewards_f64, counts_out ? counts_out + e0 : nullptr);
+    rc = after_launch("simhash update");
+    if (rc) return rc;
+  }
+  return PPX_OK;
 }
 
 }  // namespace
@@ -300,8 +445,7 @@ extern "C" int ppx_simhash_codes(const double* A, const float* obs, int k, int D
   PPX_REQUIRE(A && obs && codes, "simhash_codes: null pointer");
   PPX_REQUIRE(k >= 1 && k <= 64 && D >= 1 && n >= 0, "simhash_codes: k=%d (1..64) D=%d n=%lld", k, D, (long long)n);
   if (n == 0) return PPX_OK;
-  ppx::codes_kernel<<<(unsigned)ppx::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(A, obs, k, D, n, codes);
-  return ppx::after_launch("simhash_codes");
+  return ppx::launch_codes(A, obs, k, D, n, codes, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int ppx_count_table_create(uint64_t capacity, ppx_count_table** out) {
@@ -322,7 +466,7 @@ extern "C" int ppx_count_table_create(uint64_t capacity, ppx_count_table** out) 
 
 extern "C" int ppx_count_table_destroy(ppx_count_table* t) {
   if (!t) return PPX_OK;
-  cudaFree(t->keys); cudaFree(t->counts); cudaFree(t->ctrl);
+  cudaFree(t->keys); cudaFree(t->counts); cudaFree(t->ctrl); cudaFree(t->scratch_codes); cudaFree(t->scratch_bucket);
   delete t;
   return PPX_OK;
 }
