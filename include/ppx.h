@@ -108,6 +108,14 @@ int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host);
 /* n <= 2^31 - 1: int32 partner list / scratch (constant-mask draw loop, cache-resident swaps); same stream. */
 int ppx_np_shuffle_draws32(uint32_t* key624_host, int* pos_host, int64_t n, int32_t* j_out_host);
 int ppx_np_shuffle_apply32(const int32_t* j_host, int64_t n, int32_t* scratch_host, int64_t* out_host);
+/* Streaming pair for two host threads working on the SAME permutation: _draws32_stream writes the accepted
+ * partners in acceptance order (acc[r] belongs to position n-1-r; AVX-512 block rejection when available) and
+ * publishes the count of final entries through *progress_host (start it at 0); _apply32_stream consumes them as
+ * they appear, so the permutation is ready ~max(stage) instead of sum(stages) after the call. */
+int ppx_np_shuffle_draws32_stream(uint32_t* key624_host, int* pos_host, int64_t n, int32_t* acc_host,
+                                  int64_t* progress_host);
+int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int64_t* progress_host,
+                                  int32_t* scratch_host, int64_t* out_host);
 
 /* ---------------------------------------------------------------- dense layers (fp32) ------- */
 /* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.

@@ -63,7 +63,7 @@ class BaseAlgorithm(object):
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
         self._graphs = {}
         self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
-        self._perm_static = None
+        self._perm_bufs, self._perm_ready, self._perm_free, self._copy_stream = None, [None, None], [None, None], None
 
     # ---- shared pieces of the fused update --------------------------------------------------
     def _record(self, key, value):
@@ -162,25 +162,49 @@ class BaseAlgorithm(object):
             script += [('randn',)] * (n_mb if randn_per_minibatch else 0)
         return script
 
-    def _epoch_minibatches(self, ro, rng):
-        """Yields (idx_dev, B_local, B_total, offset) for one epoch.  Single GPU: slices of the reference's
-        permutation (buffer.py:239,251-254), staged in a static device buffer.  Sharded: every rank draws the
-        SAME permutation over the global [T, W*N] index space and keeps the rows of each global minibatch whose
-        env it owns (owner-computes)."""
+    def _perm_prefetch(self, rng, total, slot):
+        """Upload the next epoch's permutation on a side stream into one of two static device buffers, so the
+        4 MB H2D copy overlaps the previous epoch's kernels instead of sitting in the compute stream."""
+        perm = rng.next()                                       # pinned int64 [total]
+        if self._perm_bufs is None or self._perm_bufs[0].numel() != total:
+            self._perm_bufs = [torch.empty(total, dtype=torch.int64, device=self.device) for _ in range(2)]
+            self._perm_free = [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._perm_free[slot] is not None:               # the epoch that last read this buffer must be done
+                self._copy_stream.wait_event(self._perm_free[slot])
+            self._perm_bufs[slot].copy_(perm, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._perm_ready[slot] = (ev, perm)                     # keep the pinned source alive until the copy ran
+
+    def _epoch_minibatches(self, ro, rng, epoch=0, n_epochs=1):
+        """Yields (idx_dev, B_local, B_total, key) for one epoch.  Single GPU: slices of the reference's
+        permutation (buffer.py:239,251-254), staged in a static device buffer (double-buffered, prefetched on a
+        copy stream).  Sharded: every rank draws the SAME permutation over the global [T, W*N] index space and
+        keeps the rows of each global minibatch whose env it owns (owner-computes)."""
         W, r = D.world_size(), D.rank()
         T, N = ro.buffer_size, ro.n_envs
         total = T * N * W
         Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
-        perm = rng.next()                                       # pinned int64 [total]
         if W == 1:
-            if self._perm_static is None or self._perm_static.numel() != total:
-                self._perm_static = torch.empty(total, dtype=torch.int64, device=self.device)
-            self._perm_static.copy_(perm, non_blocking=True)
+            slot = epoch & 1
+            if epoch == 0 or self._perm_ready[slot] is None:
+                self._perm_prefetch(rng, total, slot)
+            ev, _keep = self._perm_ready[slot]
+            torch.cuda.current_stream().wait_event(ev)
+            buf = self._perm_bufs[slot]
             for s in range(0, total, Bg):
-                sl = self._perm_static[s:s + Bg]
-                yield sl, sl.numel(), 0, s
+                sl = buf[s:s + Bg]
+                yield sl, sl.numel(), 0, (slot, s)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            self._perm_free[slot] = done
+            self._perm_ready[slot] = None
+            if epoch + 1 < n_epochs:                            # after this epoch's randn()s were consumed (RND)
+                self._perm_prefetch(rng, total, slot ^ 1)
             return
-        perm = perm.numpy()
+        perm = rng.next().numpy()
         for s in range(0, total, Bg):
             g = perm[s:s + Bg]
             loc = D.owned_slice(g, T, N, r)
@@ -264,8 +288,9 @@ class PPO(BaseAlgorithm):
         bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
         step = 0
         rng = HostRngStream(self._rng_script(ro))
-        for _ in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+        self._perm_ready = [None, None]
+        for ep in range(self.n_epochs):
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b, bt=bt):
                     ro.gather_into(sl, bufs)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt)
@@ -366,8 +391,9 @@ class PPO_RND(BaseAlgorithm):
         step = 0
         self.rnd_trained_steps = 0
         rng = HostRngStream(self._rng_script(ro, randn_per_minibatch=True))
-        for _ in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+        self._perm_ready = [None, None]
+        for ep in range(self.n_epochs):
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b, bt=bt):
                     ro.gather_into(sl, bufs)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
@@ -455,8 +481,9 @@ class PPO_ICM(BaseAlgorithm):
         rng = HostRngStream(self._rng_script(ro))
         icm_row = torch.zeros(1, dtype=torch.float64, device=self.device) if not hasattr(self, "_icm_row") else self._icm_row
         self._icm_row = icm_row
-        for _ in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng):
+        self._perm_ready = [None, None]
+        for ep in range(self.n_epochs):
+            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b):
                     ro.gather_into(sl, bufs)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), policy_weight=float(self.policy_weight))

@@ -63,7 +63,7 @@ class HostRngStream:
                 sc.append(('reuse',) if (op[0] == 'perm' and seen) else op)
                 seen = seen or op[0] == 'perm'
             script = sc
-        self._jbufs = {}                                        # rotating partner buffers (<= 4 alive per size)
+        self._jbufs = {}                                        # rotating partner buffers (<= 4 in flight per size)
         self._scratch32 = None
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
         self.t2 = threading.Thread(target=self._apply, daemon=True)
@@ -79,13 +79,24 @@ class HostRngStream:
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
                     small = n <= 0x7fffffff
-                    pool = self._jbufs.setdefault(n, [[np.empty(max(n, 1), np.int32 if small else np.int64) for _ in range(4)], 0])
-                    j = pool[0][pool[1] % 4]
+                    pool = self._jbufs.setdefault(n, [[(np.empty(max(n, 1), np.int32 if small else np.int64),
+                                                        np.zeros(1, np.int64)) for _ in range(6)], 0])
+                    j, prog = pool[0][pool[1] % 6]
                     pool[1] += 1
-                    L.call("ppx_np_shuffle_draws32" if small else "ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n,
-                           j.ctypes.data)
+                    if small:
+                        # streaming: hand the buffer to stage 2 first, it runs behind the published progress counter
+                        prog[0] = 0
+                        self.mid.put(('perm', j, n, prog))
+                        try:
+                            L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, j.ctypes.data,
+                                   prog.ctypes.data)
+                        except Exception:
+                            prog[0] = 1 << 62                   # never leave stage 2 spinning on a failed draw
+                            raise
+                    else:
+                        L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
+                        self.mid.put(('perm', j, n, None))
                     np.random.set_state((st[0], key, pos.value, st[3], st[4]))
-                    self.mid.put(('perm', j, n))
                 elif op[0] == 'reuse':
                     self.mid.put(('reuse',))
                 else:
@@ -101,12 +112,13 @@ class HostRngStream:
                 if item is None:
                     break
                 if item[0] == 'perm':
-                    _, j, n = item
+                    _, j, n, prog = item
                     out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
-                    if j.dtype == np.int32:
+                    if prog is not None:
                         if self._scratch32 is None or self._scratch32.size < n:
                             self._scratch32 = np.empty(max(n, 1), np.int32)
-                        L.call("ppx_np_shuffle_apply32", j.ctypes.data, n, self._scratch32.ctypes.data, out.data_ptr())
+                        L.call("ppx_np_shuffle_apply32_stream", j.ctypes.data, n, prog.ctypes.data,
+                               self._scratch32.ctypes.data, out.data_ptr())
                     else:
                         L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
                     self._last = out

@@ -10,9 +10,13 @@
 //   next_uint32:                MT19937 genrand with the standard tempering
 // The caller passes numpy's own state (np.random.get_state(): key[624], pos) and writes the advanced
 // state back with np.random.set_state, so interleaved numpy calls (e.g. RND's randn()) stay in sequence.
-// Two stages so they can pipeline across epochs: drawing the j sequence is RNG-bound, applying the
-// swaps is cache-miss-bound.
+// Two stages so they can pipeline across epochs AND inside one permutation: stage 1 draws the partner
+// sequence (RNG-bound; AVX-512 block rejection with compress-store when the CPU has it), stage 2 applies the
+// swaps (cache-miss-bound) and, in the streaming variant, starts as soon as the first partners are published.
+// Compiled by g++ (not nvcc): it uses target attributes / immintrin.
 #include <stdlib.h>
+#include <immintrin.h>
+#include <time.h>
 #include "common.cuh"
 
 extern "C" int ppx_np_shuffle_apply(const int64_t* j_host, int64_t n, int64_t* out_host);
@@ -178,4 +182,116 @@ extern "C" int ppx_np_permutation(uint32_t* key624_host, int* pos_host, int64_t 
   const int rc = ppx_np_shuffle_apply(j, n, out_host);
   free(j);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming pair: stage 1 writes the accepted partners in ACCEPTANCE order (acc[r] is the partner of position
+// i = n-1-r) and publishes how many are final through *progress (release); stage 2 runs behind it (acquire).
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline void publish(volatile int64_t* progress, int64_t r) { __atomic_store_n(progress, r, __ATOMIC_RELEASE); }
+
+#define PPX_DRAW_SCALAR_STEP()                                   \
+  {                                                              \
+    const uint32_t v = o[p++] & mask;                            \
+    acc[r] = (int32_t)v;                                         \
+    const int64_t ok = (int64_t)(v <= (uint32_t)i);              \
+    r += ok;                                                     \
+    i -= ok;                                                     \
+  }
+
+void draw_acc_base(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress) {
+  int64_t i = n - 1, r = 0, last_pub = 0;
+  while (i >= 1) {
+    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+    const int64_t lo = (int64_t)(mask >> 1) + 1;
+    while (i >= lo) {
+      if (mt.pos == MT_N) mt.gen();
+      const uint32_t* __restrict__ o = mt.out;
+      int p = mt.pos;
+      while (p < MT_N && i >= lo) PPX_DRAW_SCALAR_STEP()
+      mt.pos = p;
+      if (r - last_pub >= 8192) { publish(progress, r); last_pub = r; }
+    }
+  }
+  publish(progress, r);
+}
+
+// 16 draws per step: a draw is certainly accepted if v <= i-15 (at most 15 accepts precede it in the block) and
+// certainly rejected if v > i; blocks with a draw in between (probability ~ 16*15/2^k) take the scalar path.
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,popcnt")))
+void draw_acc_avx512(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress) {
+  int64_t i = n - 1, r = 0, last_pub = 0;
+  while (i >= 1) {
+    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+    const int64_t lo = (int64_t)(mask >> 1) + 1;
+    const __m512i maskv = _mm512_set1_epi32((int)mask);
+    while (i >= lo) {
+      if (mt.pos == MT_N) mt.gen();
+      const uint32_t* __restrict__ o = mt.out;
+      int p = mt.pos;
+      while (p + 16 <= MT_N && i - 16 >= lo) {
+        const __m512i v = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p)), maskv);
+        const uint32_t ii = (uint32_t)i;
+        const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)(ii - 15u)));
+        const __mmask16 maybe = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)ii));
+        if (sure == maybe) {
+          _mm512_mask_compressstoreu_epi32((void*)(acc + r), sure, v);
+          const int64_t c = (int64_t)__builtin_popcount((unsigned)sure);
+          r += c;
+          i -= c;
+          p += 16;
+        } else {
+          for (int q = 0; q < 16; ++q) PPX_DRAW_SCALAR_STEP()
+        }
+      }
+      while (p < MT_N && i >= lo && (p + 16 > MT_N || i - 16 < lo)) PPX_DRAW_SCALAR_STEP()
+      mt.pos = p;
+      if (r - last_pub >= 8192) { publish(progress, r); last_pub = r; }
+    }
+  }
+  publish(progress, r);
+}
+
+bool has_avx512() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq");
+  return ok;
+}
+}  // namespace
+
+extern "C" int ppx_np_shuffle_draws32_stream(uint32_t* key624_host, int* pos_host, int64_t n, int32_t* acc_host,
+                                             int64_t* progress_host) {
+  PPX_REQUIRE(key624_host && pos_host && acc_host && progress_host && n >= 0 && n <= 0x7fffffffll, "np_shuffle_draws32_stream: bad arguments");
+  PPX_REQUIRE(*pos_host >= 0 && *pos_host <= MT_N, "np_shuffle_draws32_stream: MT19937 pos=%d out of range", *pos_host);
+  Mt mt(key624_host, *pos_host);
+  if (has_avx512()) draw_acc_avx512(mt, n, acc_host, progress_host);
+  else draw_acc_base(mt, n, acc_host, progress_host);
+  *pos_host = mt.pos;
+  return PPX_OK;
+}
+
+extern "C" int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int64_t* progress_host,
+                                             int32_t* scratch_host, int64_t* out_host) {
+  if (n == 0) return PPX_OK;
+  PPX_REQUIRE(acc_host && progress_host && scratch_host && out_host && n >= 0 && n <= 0x7fffffffll, "np_shuffle_apply32_stream: bad arguments");
+  int32_t* __restrict__ a = scratch_host;
+  for (int64_t i = 0; i < n; ++i) a[i] = (int32_t)i;
+  int64_t avail = 0;
+  for (int64_t r = 0; r + 1 < n; ++r) {
+    if (r >= avail) {
+      int spins = 0;
+      while ((avail = __atomic_load_n(progress_host, __ATOMIC_ACQUIRE)) <= r) {
+        if (++spins < 256) _mm_pause();
+        else { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); }     // be polite on shared / throttled hosts
+      }
+    }
+    const int64_t i = n - 1 - r;
+    const int32_t j = acc_host[r];
+    const int32_t t = a[j];
+    a[j] = a[i];
+    a[i] = t;
+  }
+  for (int64_t i = 0; i < n; ++i) out_host[i] = (int64_t)a[i];
+  return PPX_OK;
 }
