@@ -121,9 +121,15 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_fwd_kernel(FwdP p) {
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     const int m0 = tile * TM;
     __syncthreads();                                        // staging done / previous tile finished with Xs, As
-    for (int e = tid; e < TM * Dp; e += NT) {
-      const int r = e / Dp, k = e % Dp;
-      Xs[e] = (m0 + r < p.M && k < D) ? ld_stream(p.X + (size_t)(m0 + r) * p.ldx + k) : 0.f;
+    if (Dp == D && p.ldx == D) {                            // dense rows: the tile is one contiguous run (no div/mod)
+      const int lim = min(TM, p.M - m0) * D;
+      const float* src = p.X + (size_t)m0 * D;
+      for (int e = tid; e < TM * Dp; e += NT) Xs[e] = e < lim ? ld_stream(src + e) : 0.f;
+    } else {
+      for (int e = tid; e < TM * Dp; e += NT) {
+        const int r = e / Dp, k = e % Dp;
+        Xs[e] = (m0 + r < p.M && k < D) ? ld_stream(p.X + (size_t)(m0 + r) * p.ldx + k) : 0.f;
+      }
     }
     __syncthreads();
 
@@ -290,9 +296,15 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
       reinterpret_cast<float4*>(H1s)[e] = v1;
       reinterpret_cast<float4*>(H2s)[e] = v2;
     }
-    for (int e = tid; e < TM * Dp; e += NT) {
-      const int r = e / Dp, k = e % Dp;
-      Xs[e] = (m0 + r < p.M && k < D) ? ld_stream(p.X + (size_t)(m0 + r) * p.ldx + k) : 0.f;
+    if (Dp == D && p.ldx == D) {                            // dense rows: the tile is one contiguous run (no div/mod)
+      const int lim = min(TM, p.M - m0) * D;
+      const float* src = p.X + (size_t)m0 * D;
+      for (int e = tid; e < TM * Dp; e += NT) Xs[e] = e < lim ? ld_stream(src + e) : 0.f;
+    } else {
+      for (int e = tid; e < TM * Dp; e += NT) {
+        const int r = e / Dp, k = e % Dp;
+        Xs[e] = (m0 + r < p.M && k < D) ? ld_stream(p.X + (size_t)(m0 + r) * p.ldx + k) : 0.f;
+      }
     }
     if (p.vh_v[g] != nullptr) {                            // o == 1 (checked on the host)
       if (tid < TM) {
@@ -310,7 +322,8 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
         dOs[tid] = dv;
       }
     } else {
-      for (int e = tid; e < TM * o; e += NT) dOs[e] = (m0 + e / o < p.M) ? ld_stream(p.dOut[g] + (size_t)m0 * o + e) : 0.f;
+      const int lim = min(TM, p.M - m0) * o;
+      for (int e = tid; e < TM * o; e += NT) dOs[e] = e < lim ? ld_stream(p.dOut[g] + (size_t)m0 * o + e) : 0.f;
     }
     __syncthreads();
 
