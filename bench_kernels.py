@@ -184,7 +184,7 @@ def bench_linear(rows, iters):
 
 
 def bench_tc(rows, iters):
-    for M, R, N in ((131072, 64, 64), (131072, 8, 128), (131072, 64, 128), (131072, 128, 128)):
+    for M, R, N in ((131072, 64, 64), (131072, 128, 128), (16384, 28224, 256), (16384, 28224, 128), (32768, 3136, 512)):
         A = torch.randn(M, R, device=DEV)
         W = torch.randn(N, R, device=DEV) / np.sqrt(R)
         hi, lo = torch.empty_like(W), torch.empty_like(W)
@@ -218,7 +218,40 @@ def bench_mlp3(rows, iters):
                note=f"bwd + partial reduce; fp32 SIMT: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
 
 
-ALL = {"mlp3": bench_mlp3, "tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
+def bench_bonus(rows, iters):
+    """Bonus nets at the Atari-shaped configs: C3 RND (16384 obs x 28224, h=128) and C4 ICM (32768 pairs x 3136, h=f=512)."""
+    np.random.seed(0); torch.manual_seed(0)
+    M, D, h = 16384, 28224, 128
+    env = ppx.SyntheticVecEnv(4, 8, ppx.Discrete(18), seed=0)
+    rnd = ppx.RndNetwork(D, hidden_size=h, device=DEV)
+    obs = torch.rand(M, D, device=DEV)
+    rms = ppx.RunningMeanStd(shape=(D,), device=DEV)
+    fl = 2.0 * M * (2 * D * h + 3 * h * h + 2 * h)
+    for tag, tc in (("tcgen05 3xTF32 first layers", True), ("SIMT fp32", False)):
+        if not tc:
+            rnd.predictor.tc, rnd.target.tc = {}, {}
+        fn = lambda: rnd.int_reward(ppx.normalize_obs(obs, rms))
+        ms, mn = timed(fn, max(3, iters // 4))
+        report(rows, "rnd_bonus", f"C3: M={M} D={D} h={h}", 4 * M * D, fl, ms, mn, launches=9,
+               note=f"{tag}; normalize_obs + target/predictor forward + (p-t)^2; {M / ms * 1e3:.0f} obs/s; alg bytes = one read of the observations")
+    del rnd, obs, rms
+    torch.cuda.empty_cache()
+    M, D, h, nA = 32768, 3136, 512, 18
+    icm = ppx.IntrinsicCuriosityModule(D, ppx.ActionConverter(ppx.Discrete(nA)), hidden_size=h, device=DEV)
+    s0, s1 = torch.rand(M, D, device=DEV), torch.rand(M, D, device=DEV)
+    act = torch.randint(0, nA, (M,), device=DEV)
+    fl = 2.0 * (2 * M * (D * h + h * h) + M * ((nA + h) * h + h * h))
+    for tag, tc in (("tcgen05 3xTF32 first layer", True), ("SIMT fp32", False)):
+        if not tc:
+            for st in (icm.enc, icm.fwd, icm.inv):
+                st.tc = {}
+        fn = lambda: icm.int_reward(s0, s1, act)
+        ms, mn = timed(fn, max(3, iters // 4))
+        report(rows, "icm_bonus", f"C4: M={M} D={D} h=f={h}", 4 * 2 * M * D, fl, ms, mn, launches=8,
+               note=f"{tag}; encoder(s), encoder(s'), forward model, clamp(mse); {M / ms * 1e3:.0f} transitions/s")
+
+
+ALL = {"bonus": bench_bonus, "mlp3": bench_mlp3, "tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
        "es": bench_es, "linear": bench_linear}
 
 

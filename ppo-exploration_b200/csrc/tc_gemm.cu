@@ -4,7 +4,10 @@
 // tf32 (exact), lo = x - hi (exact in fp32, tf32-truncated by the tensor core):
 //      A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi          (dropped term lo.lo ~ 2^-22 relative)
 // accumulated in fp32 in TMEM.  Error ~2^-21 per product, inside the 1e-5 parity bound that rules out
-// single-pass tf32/bf16 (SURVEY "Hard parts").  Used for the forward (A = activations, B = W^T) and the
+// single-pass tf32/bf16 (SURVEY "Hard parts").  The tensor core's fp32 accumulator TRUNCATES, so a long
+// reduction drifts (measured 2.4e-5 relative at K = 3136): the reduction is therefore cut into chunks of
+// 128 products that ping-pong between two TMEM accumulators; the epilogue warps drain each finished chunk
+// (tcgen05.ld) and add it into fp32 registers with round-to-nearest while the next chunk's MMAs run.  Used for the forward (A = activations, B = W^T) and the
 // data-gradient (A = dY, B = W) of dense layers; B is pre-split once per optimiser step
 // (ppx_tc_split), A is split on the fly in shared memory so activations are read from HBM once.
 //
@@ -15,8 +18,9 @@
 //               swizzle pattern is preserved), fence.proxy.async, arrive
 //   warp 1      MMA issuer: one elected lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=BN, K=8) per
 //               stage; tcgen05.commit releases the stage / signals the epilogue; owns TMEM alloc/dealloc
-//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 (warp q reads TMEM lanes 32q..32q+31 = tile rows),
-//               bias+activation (forward) or activation-derivative (dgrad), 128-byte row stores
+//   warps 6-9   epilogue: per 128-product chunk tcgen05.ld 32x32b.x32 (warp q reads TMEM lanes 32q..32q+31 =
+//               tile rows) + register accumulation; at the end bias+activation (forward) or
+//               activation-derivative (dgrad), 128-byte row stores
 #include <cuda.h>
 #include "common.cuh"
 
@@ -28,6 +32,7 @@ constexpr int BK = 32;           // fp32 elements of K per stage = one 128-byte 
 constexpr int UMMA_K = 8;        // tf32
 constexpr int kThreads = 320;
 constexpr int kSplitThreads = 128;
+constexpr int KBC = 4;           // k-blocks (of BK) per TMEM accumulation chunk = 128 products
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -145,21 +150,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapBlo, Params p) {
   constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));   // two accumulators
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // N tiles of one row block run side by side (A tile shared through L2)
   const int num_kb = (p.R + BK - 1) / BK;
 
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto ready_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + s]); };
-  const uint32_t tmem_full_bar = smem_u32(&bars[3 * STAGES]);
+  auto tmem_full_bar = [&](int b) { return smem_u32(&bars[3 * STAGES + b]); };
+  auto tmem_empty_bar = [&](int b) { return smem_u32(&bars[3 * STAGES + 2 + b]); };
+  const int num_chunks = (num_kb + KBC - 1) / KBC;
   auto a_hi = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
   auto a_lo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_BYTES; };
   auto b_hi = [&](int s) { return smem + (size_t)s * STAGE_BYTES + 2 * A_BYTES; };
@@ -171,7 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(ready_bar(s), kSplitThreads);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation by one full warp
@@ -203,21 +210,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
+      const int chunk = kb / KBC, buf = chunk & 1;
+      const bool chunk_first = (kb % KBC) == 0, chunk_last = (kb % KBC) == KBC - 1 || kb == num_kb - 1;
+      if (chunk_first) {                                      // the epilogue must have drained this accumulator
+        mbar_wait(tmem_empty_bar(buf), ((chunk >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       mbar_wait(ready_bar(s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t ah = smem_u32(a_hi(s)), al = smem_u32(a_lo(s)), bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint32_t off = kk * UMMA_K * 4;            // 32 bytes along K inside the swizzle atom
           const uint64_t dah = make_desc(ah + off), dal = make_desc(al + off);
           const uint64_t dbh = make_desc(bh + off), dbl = make_desc(bl + off);
-          umma_tf32(tmem_base, dal, dbh, idesc, (kb | kk) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          umma_tf32(tacc, dal, dbh, idesc, (chunk_first && kk == 0) ? 0u : 1u);   // small terms first
+          umma_tf32(tacc, dah, dbl, idesc, 1u);
+          umma_tf32(tacc, dah, dbh, idesc, 1u);
         }
         umma_commit(empty_bar(s));                          // stage free once these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
+        if (chunk_last) umma_commit(tmem_full_bar(buf));    // this chunk's accumulator is complete
       }
       __syncwarp();
     }
@@ -250,20 +264,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ------------------------------ epilogue (warps 6..9) ------------------------------
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (row < p.M) {
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int chunk = 0; chunk < num_chunks; ++chunk) {
+      const int buf = chunk & 1;
+      mbar_wait(tmem_full_bar(buf), (chunk >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);     // round-to-nearest fp32 adds
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+    }
+    if (row < p.M) {
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         float* dst = p.C + (size_t)row * p.ldc + n0 + c0;
         const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (n0 + c0 + 32 <= p.N);
         float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = n0 + c0 + j;
-          float x = __uint_as_float(v[j]);
+          float x = acc[c0 + j];
           if (col < p.N) {
             if (!p.dgrad) {
               if (p.bias) x += __ldg(p.bias + col);
@@ -361,7 +389,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorM
     PPX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.M, BM), (unsigned)ceil_div(p.N, BN));
+  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM));
   tc_gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(ma, mbh, mbl, p);
   return after_launch("tc_gemm");
 }

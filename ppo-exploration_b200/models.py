@@ -25,11 +25,13 @@ import os
 
 ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3}
 F4 = 4  # bytes per float
-# tcgen05 3xTF32 path for forward / data-gradient of dense layers (PPX_TC=0 forces the SIMT fp32 kernels).
-# The reduction length is capped: the tensor core accumulates in fp32 with truncation, so one TMEM
-# accumulation chain is kept to <= 128 products (error ~1e-6); longer K needs chunked draining.
-TC_ENABLED = os.environ.get("PPX_TC", "0") == "1"   # opt-in: at h<=128 the SIMT path is faster (profiles/)
-TC_MAX_R = 128
+# tcgen05 3xTF32 path (tc_gemm.cu) for the forward of WIDE dense layers -- the bonus nets' first layers (RND
+# D=28224, ICM D=3136): K >= TC_MIN_K.  PPX_TC=0 forces the SIMT fp32 kernels everywhere.  The narrow policy MLPs
+# (K <= 128) run the fused SIMT kernel instead (mlp_fused.cu); PPX_TC_POLICY=1 routes them through tcgen05 for
+# comparison (slower at these widths, see profiles/).
+TC_ENABLED = os.environ.get("PPX_TC", "1") != "0"
+TC_POLICY = os.environ.get("PPX_TC_POLICY", "0") == "1"
+TC_MIN_K = 256
 # fused forward / backward of the D-h-h-o policy MLPs (mlp_fused.cu); PPX_FUSED_MLP=0 forces the layer-by-layer path
 FUSED_ENABLED = os.environ.get("PPX_FUSED_MLP", "1") != "0"
 
@@ -80,20 +82,20 @@ class TcWeight:
     """hi/lo tf32 split of one in-major weight matrix W [K,N] (and of its transpose), refreshed after every
     optimiser step: forward uses W^T [N,K] as the K-major B operand, the data-gradient uses W [K,N]."""
 
-    def __init__(self, w_ptr, K, N, device):
+    def __init__(self, w_ptr, K, N, device, transposed_only=False):
         self.w_ptr, self.K, self.N = w_ptr, K, N
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
-        self.hi, self.lo, self.hiT, self.loT = e(K, N), e(K, N), e(N, K), e(N, K)
+        self.hi, self.lo = (None, None) if transposed_only else (e(K, N), e(K, N))
+        self.hiT, self.loT = e(N, K), e(N, K)
         self.refresh()
 
     def refresh(self):
-        L.call("ppx_tc_split", self.w_ptr, self.K, self.N, self.hi.data_ptr(), self.lo.data_ptr(), self.hiT.data_ptr(),
+        L.call("ppx_tc_split", self.w_ptr, self.K, self.N, L.ptr(self.hi), L.ptr(self.lo), self.hiT.data_ptr(),
                self.loT.data_ptr(), L.stream())
 
 
 def tc_ok(M, R, N, lda, ldb, a_ptr, b_ptr):
-    return (TC_ENABLED and R <= TC_MAX_R and M >= 128 and
-            L.call("ppx_tc_supported", M, R, N, lda, ldb, a_ptr, b_ptr) == 1)
+    return (TC_ENABLED and M >= 128 and L.call("ppx_tc_supported", M, R, N, lda, ldb, a_ptr, b_ptr) == 1)
 
 
 def dense_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, tcw=None):
@@ -153,6 +155,20 @@ class DenseStack:
     def __init__(self, bank, prefix, layers, scratch):
         self.bank, self.prefix, self.layers, self.scratch = bank, prefix, layers, scratch
         assert layers[-1][2] == "none"
+        self.tc = {}                                  # layer index -> TcWeight (wide layers only)
+
+    def enable_tc(self):
+        """(Re)build the tensor-core weight shadows of the wide layers; call after the parameters were (re)loaded.
+        They are refreshed after every optimiser step of the owning bank (ParamBank.adam_step)."""
+        if not TC_ENABLED:
+            return
+        b, dev = self.bank, self.bank.device
+        b.tc_weights = [t for t in b.tc_weights if t not in self.tc.values()]
+        self.tc = {}
+        for i, (K, N, _) in enumerate(self.layers):
+            if K >= TC_MIN_K and K % 4 == 0 and N >= 16:
+                self.tc[i] = TcWeight(b.p(f"{self.prefix}.{2 * i}.weight"), K, N, dev, transposed_only=True)
+        b.tc_weights += list(self.tc.values())
 
     @staticmethod
     def specs(prefix, layers):
@@ -167,8 +183,8 @@ class DenseStack:
         acts = [x]
         for i, (K, N, act) in enumerate(self.layers):
             y = self.scratch.get(f"{self.prefix}{tag}.h{i}", M * N)[:M * N].view(M, N)
-            linear_fwd(acts[-1].data_ptr(), acts[-1].stride(0), self.bank.p(f"{self.prefix}.{2 * i}.weight"),
-                       self.bank.p(f"{self.prefix}.{2 * i}.bias"), M, K, N, ACT[act], y.data_ptr(), N)
+            dense_fwd(acts[-1].data_ptr(), acts[-1].stride(0), self.bank.p(f"{self.prefix}.{2 * i}.weight"),
+                      self.bank.p(f"{self.prefix}.{2 * i}.bias"), M, K, N, ACT[act], y.data_ptr(), N, self.tc.get(i))
             acts.append(y)
         return acts
 
@@ -223,7 +239,7 @@ class ParallelMLP:
 
     def enable_tc(self):
         """(Re)build the tensor-core weight shadows; call after the parameters were (re)loaded."""
-        if not TC_ENABLED:
+        if not (TC_ENABLED and TC_POLICY):
             return
         b, G, h, D, dev = self.bank, self.G, self.h, self.D, self.bank.device
         b.tc_weights = [t for t in b.tc_weights if t not in ([self.tc1] if self.tc1 else []) + (self.tc2 or [])]
@@ -458,6 +474,8 @@ class RndNetwork:
         for i in range(len(self.t_layers)):
             self.target_bank.view(f"target.{2 * i}.weight").fill_(0.01)
             self.target_bank.view(f"target.{2 * i}.bias").fill_(1.0)
+        self.predictor.enable_tc()
+        self.target.enable_tc()
 
     def load_state_dict(self, sd):
         t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).float()
@@ -465,6 +483,8 @@ class RndNetwork:
             for i in range(n):
                 bank.view(f"{name}.{2 * i}.weight").copy_(_to_in_major(t(sd[f"{name}.{2 * i}.weight"])))
                 bank.view(f"{name}.{2 * i}.bias").copy_(t(sd[f"{name}.{2 * i}.bias"]))
+        self.predictor.enable_tc()
+        self.target.enable_tc()
 
     def state_dict(self):
         sd = {}
@@ -569,6 +589,8 @@ class IntrinsicCuriosityModule:
         else:
             self.bank.view("action_encoder.weight").copy_(_to_in_major(t(sd["action_encoder.weight"])))
             self.bank.view("action_encoder.bias").copy_(t(sd["action_encoder.bias"]))
+        for st in (self.enc, self.fwd, self.inv):
+            st.enable_tc()
 
     def state_dict(self):
         sd = {}

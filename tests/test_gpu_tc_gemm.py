@@ -35,7 +35,7 @@ def _run(M, R, N, act, dgrad, seed=0):
 
 @pytest.mark.parametrize("M,R,N,act,dgrad", [(128, 32, 64, 0, 0), (128, 64, 64, 1, 0), (1000, 8, 128, 1, 0), (300, 64, 100, 2, 0),
                                              (131072, 64, 64, 1, 0), (131072, 64, 64, 1, 1), (257, 100, 16, 3, 1),
-                                             (64, 36, 40, 0, 0)])
+                                             (64, 36, 40, 0, 0), (4096, 3136, 512, 2, 0), (777, 28224, 256, 2, 0), (300, 1000, 128, 1, 1)])
 def test_tc_linear_matches_fp64(M, R, N, act, dgrad):
     C, ref, acc = _run(M, R, N, act, dgrad)
     assert torch.isfinite(C).all()
@@ -52,3 +52,34 @@ def test_tc_split_transposed():
     hi, lo = torch.empty_like(W), torch.empty_like(W)
     L.call("ppx_tc_split", W.data_ptr(), 70, 45, hi.data_ptr(), lo.data_ptr(), hiT.data_ptr(), loT.data_ptr(), L.stream())
     assert torch.equal(hi.t().contiguous(), hiT) and torch.equal(lo.t().contiguous(), loT) and torch.equal(hi + lo, W)
+
+
+def test_wide_bonus_net_forward_uses_tensor_cores_and_matches_fp64():
+    """RND bonus (models.py:261-267) on a wide observation: the first layers take the tcgen05 path (K >= 256);
+    result vs an fp64 torch evaluation of the same weights, and vs the SIMT fp32 kernels."""
+    import ppo_exploration_b200 as ppx
+    from ppo_exploration_b200 import models as PM
+    torch.manual_seed(0)
+    D, h, M = 1024, 128, 300
+    rnd = ppx.RndNetwork(D, hidden_size=h, device="cuda")
+    sd = {}
+    for name, layers in (("predictor", rnd.p_layers), ("target", rnd.t_layers)):
+        for i, (K, N, _) in enumerate(layers):
+            sd[f"{name}.{2 * i}.weight"] = torch.randn(N, K) / np.sqrt(K)
+            sd[f"{name}.{2 * i}.bias"] = 0.1 * torch.randn(N)
+    rnd.load_state_dict(sd)
+    assert 0 in rnd.predictor.tc and 0 in rnd.target.tc, "wide first layers must have tensor-core shadows"
+    obs = torch.randn(M, D)
+    got = rnd.int_reward(obs.cuda()).cpu().double()
+
+    def mlp(x, name, acts):
+        for i, a in enumerate(acts):
+            x = x @ sd[f"{name}.{2 * i}.weight"].double().t() + sd[f"{name}.{2 * i}.bias"].double()
+            x = {"l": F.leaky_relu, "e": F.elu, "n": lambda z: z}[a](x)
+        return x
+    x = obs.double()
+    want = (mlp(x, "predictor", "llen") - mlp(x, "target", "lln")).pow(2).squeeze(-1)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
+    rnd.predictor.tc, rnd.target.tc = {}, {}
+    simt = rnd.int_reward(obs.cuda()).cpu().double()
+    torch.testing.assert_close(got, simt, rtol=2e-5, atol=1e-6 * float(want.abs().max()))
