@@ -211,10 +211,11 @@ def run_ppx(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    np.random.seed(0); torch.manual_seed(0)
+    np.random.seed(rank); torch.manual_seed(0)          # per-rank shuffle stream, replicated weights
     env = ppx.SyntheticVecEnv(N, D, ppx.Box((A,)), seed=rank)
     B = T * N // N_MINIBATCH
     m = ppx.PPO(env=env, nstep=T, batch_size=B, hidden_size=HIDDEN, sim_hash=True, hash_bits=K_BITS, device=dev, **HP)
+    m.shard_shuffle = "local"                           # N>1: every rank shuffles its own rollout
     ro = m.rollout
     host = synth_rollout(100 + rank)
     pinned = {k: torch.as_tensor(v).pin_memory() for k, v in host.items()}
@@ -338,12 +339,20 @@ def run_ppx(args):
                                 "sample": det["sample"], "host": th,
                                 "split_s_per_pass": {k: det[k] for k in ("sim_hash_s", "gae_s", "train_s")}}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by captured CUDA graphs do not tear down cleanly (destroy_process_group
+        # blocks); everything is flushed and synchronised here, so leave without the destructor chain.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
+    # watchdog: a wedged collective must not burn the box -- dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("PPX_BENCH_WATCHDOG_S", "600")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

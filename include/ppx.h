@@ -117,6 +117,11 @@ int ppx_np_shuffle_draws32_stream(uint32_t* key624_host, int* pos_host, int64_t 
 int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int64_t* progress_host,
                                   int32_t* scratch_host, int64_t* out_host);
 
+/* Sharded minibatches: rec3 = {n, mean, M2} from the local {mean, std}; after an all-gather of the
+ * W records, out2 = {mean, std(ddof 1)} of the global minibatch (merged in rank order). */
+int ppx_moments_pack(const double* stats2, int64_t n, double* rec3, void* stream);
+int ppx_moments_merge(const double* recs, int W, double* out2, void* stream);
+
 /* ---------------------------------------------------------------- dense layers (fp32) ------- */
 /* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.
  * Strides (in elements) step X/W/bias/Y per batch entry; batch=1 ignores them.
@@ -215,6 +220,9 @@ int ppx_ppo_loss_head_final(const ppx_ppo_cfg* cfg_host, const float* actor_out,
                             const float* int_values, const float* old_int_values, const float* int_returns,
                             float* d_actor_out, float* d_log_std, double* losses_out, double* branch_out,
                             void* workspace, void* stream);
+/* finalize only (no value-head gradients): loss scalars, branch weights and d_log_std from GLOBAL sums[32]. */
+int ppx_ppo_loss_finalize(const ppx_ppo_cfg* cfg_host, const double* sums, const float* log_std, float* d_log_std,
+                          double* losses_out, double* branch_out, void* stream);
 /* The same computation split at its only global dependency, for sharded minibatches:
  * head   -> per-sample work + sums_out[32] (f64 partial sums of this rank);
  *           all-reduce sums_out across ranks (one 256-byte message), then

@@ -70,6 +70,9 @@ SIGNATURES = {
     "ppx_ppo_loss_workspace": (c_l, [c_l, c_i]),
     "ppx_ppo_loss_fwd_bwd": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 21),
     "ppx_ppo_loss_head_final": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 20),
+    "ppx_ppo_loss_finalize": (c_i, [C.POINTER(PpoCfg), c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ppx_moments_pack": (c_i, [c_p, c_l, c_p, c_p]),
+    "ppx_moments_merge": (c_i, [c_p, c_i, c_p, c_p]),
     "ppx_ppo_loss_head": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 18),
     "ppx_ppo_loss_finish": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 14),
     "ppx_mse_fwd_bwd": (c_i, [c_p, c_p, c_l, c_d, c_p, c_p, c_p, c_p]),

@@ -60,6 +60,12 @@ class BaseAlgorithm(object):
         self._sums = torch.zeros(32, dtype=torch.float64, device=self.device)
         self._branch = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.scale_batch_with_world = True     # sharded runs: batch_size is per rank (weak scaling)
+        # sharded minibatch composition: "global" = every rank draws the SAME permutation over the global
+        # [T, W*N] index space and keeps the rows it owns (bit-identical to one GPU holding all envs; host cost
+        # grows with W); "local" = every rank shuffles its own rollout with its own numpy stream (the reference's
+        # buffer semantics per rank; static shapes -> CUDA graphs, scales)
+        self.shard_shuffle = "global"
+        self._mrec = None
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
         self._graphs = {}
         self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
@@ -95,9 +101,7 @@ class BaseAlgorithm(object):
             iadv = bufs['int_advantages'][:B]
             L.call("ppx_mean_std", iadv.data_ptr(), B, self._stats.data_ptr() + 16, L.stream())
         if sharded:
-            self._stats[0:2].copy_(D.merge_mean_std(self._stats[0:2], B))
-            if dual:
-                self._stats[2:4].copy_(D.merge_mean_std(self._stats[2:4], B))
+            self._merge_stats(B, dual)
         d_actor = sc.get("d_actor", B * A)[:B * A].view(B, A)
         cfg = L.PpoCfg(B, int(B_total), A, int(self.discrete), int(dual), float(self.clip_range), float(self.ent_coef),
                        float(self.vf_coef), float(int_vf_coef), float(policy_weight))
@@ -107,18 +111,26 @@ class BaseAlgorithm(object):
                      g('old_log_probs'), adv.data_ptr(), self._stats.data_ptr(), outs[1].data_ptr(), g('old_values'),
                      g('returns'), g('int_advantages'), self._stats.data_ptr() + 16,
                      outs[2].data_ptr() if dual else None, g('int_values'), g('int_returns'), d_actor.data_ptr())
-        if not sharded and pol.mlp.fused():
-            # single GPU: head + partial sums + loss scalars / branch in ONE launch; the value-head gradients are
-            # evaluated inside the fused MLP backward from the branch weights
-            L.call("ppx_ppo_loss_head_final", *head_args, pol.bank.g("action_log_std"), losses_row,
-                   self._branch.data_ptr(), ws, L.stream())
+        if pol.mlp.fused():
+            # head + partial sums (+ loss scalars / branch when single-GPU) in ONE launch; the value-head gradients are
+            # evaluated inside the fused MLP backward from the branch weights.  Sharded: the 32 partial sums are
+            # all-reduced (256 bytes) before the finalize kernel so the max-of-means branch is the global one.
+            Bt = int(B_total) if B_total else B
+            if not sharded:
+                L.call("ppx_ppo_loss_head_final", *head_args, pol.bank.g("action_log_std"), losses_row,
+                       self._branch.data_ptr(), ws, L.stream())
+            else:
+                L.call("ppx_ppo_loss_head", *head_args, self._sums.data_ptr(), ws, L.stream())
+                D.all_reduce_sum_(self._sums)
+                L.call("ppx_ppo_loss_finalize", C.byref(cfg), self._sums.data_ptr(), pol.bank.p("action_log_std"),
+                       pol.bank.g("action_log_std"), losses_row, self._branch.data_ptr(), L.stream())
             vh = {1: (outs[1], bufs['old_values'][:B], bufs['returns'][:B], self._branch.data_ptr(),
                       float(policy_weight) * float(self.vf_coef))}
             if dual:
                 vh[2] = (outs[2], bufs['int_values'][:B], bufs['int_returns'][:B], self._branch.data_ptr() + 16,
                          float(int_vf_coef))
             pol.mlp.backward([d_actor, None] + ([None] if dual else []), value_heads=vh, clip_range=self.clip_range,
-                             B_total=B)
+                             B_total=Bt)
             return
         d_val = sc.get("d_val", B)[:B].view(B, 1)
         d_ival = sc.get("d_ival", B)[:B].view(B, 1)
@@ -131,10 +143,28 @@ class BaseAlgorithm(object):
                d_ival.data_ptr() if dual else None, losses_row, ws, L.stream())
         pol.mlp.backward([d_actor, d_val] + ([d_ival] if dual else []))
 
+    def _merge_stats(self, B, dual):
+        """Sharded minibatch: local {mean, std} -> global, through one all-gather of {n, mean, M2} records."""
+        W = D.world_size()
+        if self._mrec is None or self._mrec_all.shape[0] != W:
+            self._mrec = torch.zeros(6, dtype=torch.float64, device=self.device)
+            self._mrec_all = torch.zeros(W, 6, dtype=torch.float64, device=self.device)
+        L.call("ppx_moments_pack", self._stats.data_ptr(), B, self._mrec.data_ptr(), L.stream())
+        if dual:
+            L.call("ppx_moments_pack", self._stats.data_ptr() + 16, B, self._mrec.data_ptr() + 24, L.stream())
+        D.all_gather_into(self._mrec_all, self._mrec)
+        # records of one stream are strided by 6 doubles in the gathered buffer: merge from a compact copy
+        a = self._mrec_all[:, 0:3].contiguous()
+        L.call("ppx_moments_merge", a.data_ptr(), W, self._stats.data_ptr(), L.stream())
+        if dual:
+            b = self._mrec_all[:, 3:6].contiguous()
+            L.call("ppx_moments_merge", b.data_ptr(), W, self._stats.data_ptr() + 16, L.stream())
+
     def _graph_call(self, key, fn):
-        """Run fn() -- a fixed sequence of libppx launches on static buffers -- through a CUDA graph: eager the
-        first time a key is seen (allocations settle), captured the second time, replayed afterwards."""
-        if not self.use_cuda_graph or D.world_size() > 1:
+        """Run fn() -- a fixed sequence of libppx launches (and, when sharded with local shuffles, NCCL collectives)
+        on static buffers -- through a CUDA graph: eager the first time a key is seen (allocations settle),
+        captured the second time, replayed afterwards."""
+        if not self.use_cuda_graph or (D.world_size() > 1 and self.shard_shuffle != "local"):
             return fn()
         ent = self._graphs.get(key)
         if ent is None:
@@ -152,7 +182,7 @@ class BaseAlgorithm(object):
         L.extra_launches += ent[1]
 
     def _rng_script(self, ro, randn_per_minibatch=False):
-        W = D.world_size()
+        W = D.world_size() if self.shard_shuffle != "local" else 1
         total = ro.buffer_size * ro.n_envs * W
         Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
         n_mb = -(-total // Bg)
@@ -185,6 +215,9 @@ class BaseAlgorithm(object):
         keeps the rows of each global minibatch whose env it owns (owner-computes)."""
         W, r = D.world_size(), D.rank()
         T, N = ro.buffer_size, ro.n_envs
+        local = W > 1 and self.shard_shuffle == "local"
+        if local:
+            W_eff, W = W, 1                                     # per-rank shuffle: the single-GPU path + B_total
         total = T * N * W
         Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
         if W == 1:
@@ -196,7 +229,7 @@ class BaseAlgorithm(object):
             buf = self._perm_bufs[slot]
             for s in range(0, total, Bg):
                 sl = buf[s:s + Bg]
-                yield sl, sl.numel(), 0, (slot, s)
+                yield sl, sl.numel(), (sl.numel() * W_eff if local else 0), (slot, s)
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream())
             self._perm_free[slot] = done

@@ -70,8 +70,35 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
   }
 }
 
+// sharded minibatches: {mean, std(ddof 1)} of n local samples -> {n, mean, M2}; and the merge of W such records
+// (in rank order, Chan's parallel-variance formula) back to the {mean, std} of the global minibatch
+__global__ void moments_pack_kernel(const double* __restrict__ stats, double n, double* __restrict__ rec) {
+  if (threadIdx.x == 0) { rec[0] = n; rec[1] = stats[0]; rec[2] = stats[1] * stats[1] * (n - 1.0); }
+}
+__global__ void moments_merge_kernel(const double* __restrict__ recs, int W, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double tot = 0.0, wsum = 0.0;
+  for (int r = 0; r < W; ++r) { tot += recs[3 * r]; wsum += recs[3 * r] * recs[3 * r + 1]; }
+  const double mean = wsum / tot;
+  double M2 = 0.0;
+  for (int r = 0; r < W; ++r) { const double d = recs[3 * r + 1] - mean; M2 += recs[3 * r + 2] + recs[3 * r] * d * d; }
+  out[0] = mean;
+  out[1] = sqrt(M2 / (tot - 1.0));
+}
+
 }  // namespace
 }  // namespace ppx
+
+extern "C" int ppx_moments_pack(const double* stats2, int64_t n, double* rec3, void* stream) {
+  PPX_REQUIRE(stats2 && rec3 && n >= 1, "moments_pack: bad arguments");
+  ppx::moments_pack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats2, (double)n, rec3);
+  return ppx::after_launch("moments_pack");
+}
+extern "C" int ppx_moments_merge(const double* recs, int W, double* out2, void* stream) {
+  PPX_REQUIRE(recs && out2 && W >= 1, "moments_merge: bad arguments");
+  ppx::moments_merge_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(recs, W, out2);
+  return ppx::after_launch("moments_merge");
+}
 
 extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                                     int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream) {

@@ -385,6 +385,18 @@ extern "C" int ppx_ppo_loss_head_final(const ppx_ppo_cfg* c, const float* actor_
                      workspace, d_log_std, losses_out, branch_out, stream);
 }
 
+extern "C" int ppx_ppo_loss_finalize(const ppx_ppo_cfg* c, const double* sums, const float* log_std, float* d_log_std,
+                                     double* losses_out, double* branch_out, void* stream) {
+  int rc = check_cfg(c);
+  if (rc) return rc;
+  PPX_REQUIRE(sums && losses_out && branch_out, "ppo_loss_finalize: null pointer");
+  if (!c->discrete) PPX_REQUIRE(log_std && d_log_std, "ppo_loss_finalize: Box head needs log_std / d_log_std");
+  FinalArgs f{sums, log_std, d_log_std, losses_out, branch_out, total_rows(c), c->A, c->discrete, c->dual,
+              c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight};
+  finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f);
+  return after_launch("ppo_loss finalize");
+}
+
 extern "C" int ppx_ppo_loss_finish(const ppx_ppo_cfg* c, const double* sums, const float* log_std, const float* values,
                                    const float* old_values, const float* returns, const float* int_values,
                                    const float* old_int_values, const float* int_returns, float* d_log_std,

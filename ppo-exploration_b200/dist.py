@@ -28,6 +28,15 @@ def all_reduce_sum_(t):
     return t
 
 
+def all_gather_into(out, t):
+    """out [W, ...] <- t [...] from every rank (static buffers: capturable in a CUDA graph)."""
+    if world_size() == 1:
+        out[0].copy_(t)
+    else:
+        dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+    return out
+
+
 def all_gather_cat(t):
     """[n, ...] per rank -> [W, n, ...] (same n on every rank)."""
     W = world_size()
