@@ -196,6 +196,51 @@ class OpTimer:
         return agg
 
 
+def es_step_bench(torch, ppx, dev, world, rank, steps=20, warmup=5):
+    """ES-NSRA step at C5 (P=10 000 members, MLP 8-64-64-2 -> D=4736, noise table 2^28 f32, K=10, archive 10 000):
+    sample offsets -> theta + sigma*eps for this rank's P/W members -> all-gather fitness -> novelty k-NN ->
+    replicated update.  Strong scaling (the population is fixed).  Returns perturbations/s and ms/step."""
+    import torch.distributed as dist
+    P, M = 10000 - 10000 % world, 10000
+    np.random.seed(0)
+    es = ppx.EvolutionStrategy(obs_dim=8, n_actions=2, hidden_sizes=(64, 64), population_size=P, sigma=0.1,
+                               learning_rate=0.01, decay=0.9995, novelty_param=0.5, device=dev,
+                               noise_table_size=1 << 28, noise_seed=0)
+    es.noise_table()
+    g = torch.Generator(device=dev).manual_seed(1)
+    archive = torch.randn(M, 2, dtype=torch.float64, device=dev, generator=g)
+    queries = torch.randn(2, 2, dtype=torch.float64, device=dev, generator=g)
+    fit_local = torch.randn(P // world, dtype=torch.float64, device=dev, generator=g)
+
+    def step():
+        pop = es._get_population()                          # identical offsets on every rank (shared seed)
+        w = es.perturb_all(es.shard_population(pop))        # [P/W, D] f32: what the evaluators consume
+        r_all = es.gather_fitness(fit_local)
+        _, nov = es.novelty_batch(archive, queries)
+        es._update_weights(r_all, pop, novelty=float(nov[0].item()))
+        return w
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / steps
+    return {"metric": "ES perturbations/s", "value": P / (ms / 1e3), "unit": "perturbations/s", "ms_per_step": ms,
+            "scaling": "strong", "config": {"workload": "C5: ES-NSRA, P=%d, MLP 8-64-64-2 (D=4736), noise table 2^28 f32, "
+                                                        "K=10, archive 10000, z-score shaping" % P,
+                                            "alg_bytes_per_perturbation": 56832}}
+
+
 def run_ppx(args):
     import torch
     import torch.distributed as dist
@@ -332,6 +377,8 @@ def run_ppx(args):
                          "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
                          "fp32_frac": achieved / 74.4,
                          "ms_per_launch": tot_ms / cnt, "launches_per_step": cnt, "top_ops_ms_per_step": ops}}
+    es = es_step_bench(torch, ppx, dev, world, rank)
+    line["es"] = es
     if world == 1 and rank == 0:
         v, det = cpu_reference_pass(hash_envs=512, hash_steps=64, train_minibatches=8)
         th = host_threads()

@@ -187,47 +187,75 @@ es_apply_kernel(double* __restrict__ theta, const double* __restrict__ partial, 
 }
 
 // ---------------- novelty k-NN ----------------
+// Exact k-NN distance sums.  Stage 1: grid (splits, Q), one WARP per (query, archive slice): every lane keeps a
+// sorted top-K of the distances it saw, a K-round warp merge pops the slice's K smallest in ascending order into
+// cand[q][split][K].  Stage 2: one warp per query merges the splits*K candidates the same way and sums the S
+// smallest in ascending order (the order the reference's sorted kneighbors() output is summed in).  Few queries
+// (the reference asks for 2 per iteration) still spread over the whole machine through the archive split.
+// Distances use explicit __dmul_rn/__dadd_rn (no FMA contraction) -> bit-equal to the direct CPU distance.
 template <int KMAX>
-__global__ void __launch_bounds__(128)
-knn_kernel(const double* __restrict__ archive, int64_t M, const double* __restrict__ queries, int Q, int dim, int K,
-           double* __restrict__ sum_out, double* __restrict__ nov_out) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= Q) return;
-  const int lane = threadIdx.x & 31;
-  const double* qv = queries + (int64_t)q * dim;
-  double best[KMAX];
-#pragma unroll
-  for (int i = 0; i < KMAX; ++i) best[i] = INFINITY;
-  const int S = (int)min((int64_t)K, M);
-  for (int64_t m = lane; m < M; m += 32) {
-    const double* a = archive + m * dim;
-    double d2 = 0.0;
-    for (int d = 0; d < dim; ++d) {
-      const double diff = __dsub_rn(a[d], qv[d]);
-      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));                      // no FMA contraction: match the CPU distance
-    }
-    double v = __dsqrt_rn(d2);
-    if (v < best[KMAX - 1]) {
-#pragma unroll
-      for (int i = 0; i < KMAX; ++i) {                                 // sorted insert
-        if (v < best[i]) { const double t = best[i]; best[i] = v; v = t; }
-      }
-    }
-  }
-  // S rounds: pop the global minimum among the 32 sorted lists, summing in ascending order
-  double sum = 0.0;
-  for (int round = 0; round < S; ++round) {
+__device__ __forceinline__ void warp_pop_sorted(double (&best)[KMAX], int rounds, int lane, double* out /*[rounds] or null*/, double* sum) {
+  double acc = 0.0;
+  for (int round = 0; round < rounds; ++round) {
     double mn = best[0];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     const unsigned who = __ballot_sync(0xffffffffu, best[0] == mn);
-    sum = __dadd_rn(sum, mn);
+    acc = __dadd_rn(acc, mn);
+    if (out && lane == 0) out[round] = mn;
     if (lane == __ffs(who) - 1) {
 #pragma unroll
       for (int i = 0; i + 1 < KMAX; ++i) best[i] = best[i + 1];
       best[KMAX - 1] = INFINITY;
     }
   }
+  if (sum) *sum = acc;
+}
+
+template <int KMAX>
+__device__ __forceinline__ void sorted_insert(double (&best)[KMAX], double v) {
+  if (v < best[KMAX - 1]) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      if (v < best[i]) { const double t = best[i]; best[i] = v; v = t; }
+    }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(32)
+knn_slice_kernel(const double* __restrict__ archive, int64_t M, const double* __restrict__ queries, int dim, int K,
+                 int splits, double* __restrict__ cand) {
+  const int q = blockIdx.y, sp = blockIdx.x, lane = threadIdx.x;
+  const int64_t per = (M + splits - 1) / splits, m0 = sp * per, m1 = min(M, m0 + per);
+  const double* qv = queries + (int64_t)q * dim;
+  double best[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) best[i] = INFINITY;
+  for (int64_t m = m0 + lane; m < m1; m += 32) {
+    const double* a = archive + m * dim;
+    double d2 = 0.0;
+    for (int d = 0; d < dim; ++d) {
+      const double diff = __dsub_rn(a[d], qv[d]);
+      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));                      // no FMA contraction: match the CPU distance
+    }
+    sorted_insert<KMAX>(best, __dsqrt_rn(d2));
+  }
+  warp_pop_sorted<KMAX>(best, K, lane, cand + ((int64_t)q * splits + sp) * K, nullptr);   // INF-padded when the slice is short
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(32)
+knn_merge_kernel(const double* __restrict__ cand, int n_cand, int64_t M, int K, double* __restrict__ sum_out,
+                 double* __restrict__ nov_out) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  double best[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) best[i] = INFINITY;
+  for (int c = lane; c < n_cand; c += 32) sorted_insert<KMAX>(best, cand[(int64_t)q * n_cand + c]);
+  const int S = (int)min((int64_t)K, M);
+  double sum;
+  warp_pop_sorted<KMAX>(best, S, lane, nullptr, &sum);
   if (lane == 0) {
     if (sum_out) sum_out[q] = sum;
     if (nov_out) {
@@ -329,8 +357,31 @@ extern "C" int ppx_knn_novelty(const double* archive, int64_t M, const double* q
                                double* novelty_out, void* stream) {
   PPX_REQUIRE(archive && queries && M >= 1 && Q >= 1 && dim >= 1, "knn_novelty: bad arguments");
   PPX_REQUIRE(K >= 1 && K <= 32, "knn_novelty: K=%d (1..32)", K);
-  const unsigned grid = (unsigned)ceil_div(Q, 4);
-  if (K <= 16) knn_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>(archive, M, queries, Q, dim, K, sum_out, novelty_out);
-  else knn_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(archive, M, queries, Q, dim, K, sum_out, novelty_out);
+  // archive split: enough warps to fill the machine for few queries, >= 256 points per warp
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), ceil_div(8 * (int64_t)sm_count(), Q)));
+  splits = std::min(splits, 1024);
+  static double* cand = nullptr;                       // per-process scratch; calls are stream-ordered (one learner thread)
+  static size_t cand_cap = 0;
+  const size_t need = (size_t)Q * splits * K * sizeof(double);
+  if (need > cand_cap) {
+    PPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaFree(cand);
+    cand = nullptr; cand_cap = 0;
+    PPX_CUDA(cudaMalloc((void**)&cand, need));
+    cand_cap = need;
+  }
+  dim3 grid((unsigned)splits, (unsigned)Q);
+  PPX_REQUIRE(Q <= 65535, "knn_novelty: Q=%d exceeds grid.y; call in slices", Q);
+  if (K <= 16) {
+    knn_slice_kernel<16><<<grid, 32, 0, (cudaStream_t)stream>>>(archive, M, queries, dim, K, splits, cand);
+    int rc = after_launch("knn_novelty(slices)");
+    if (rc) return rc;
+    knn_merge_kernel<16><<<(unsigned)Q, 32, 0, (cudaStream_t)stream>>>(cand, splits * K, M, K, sum_out, novelty_out);
+  } else {
+    knn_slice_kernel<32><<<grid, 32, 0, (cudaStream_t)stream>>>(archive, M, queries, dim, K, splits, cand);
+    int rc = after_launch("knn_novelty(slices)");
+    if (rc) return rc;
+    knn_merge_kernel<32><<<(unsigned)Q, 32, 0, (cudaStream_t)stream>>>(cand, splits * K, M, K, sum_out, novelty_out);
+  }
   return after_launch("knn_novelty");
 }

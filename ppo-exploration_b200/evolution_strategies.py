@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import dist as D
 
 
 class EvolutionStrategy(object):
@@ -120,6 +121,28 @@ class EvolutionStrategy(object):
             out.append(flat[o:o + n].reshape(s))
             o += n
         return out
+
+    # ---- population sharding: members split across ranks, update replicated ----
+    def shard_population(self, population):
+        """The contiguous slice of `population` (offsets [P] or dense eps [P,D]) this rank perturbs and evaluates.
+        Every rank must hold the same `population` (same noise seed -> `_get_population` draws identical offsets)."""
+        W, r = D.world_size(), D.rank()
+        P = population.shape[0]
+        if P % W:
+            raise ValueError(f"population size {P} must be a multiple of the world size {W}")
+        return population[r * (P // W):(r + 1) * (P // W)]
+
+    def gather_fitness(self, local_rewards):
+        """all-gather of the per-rank fitness slices -> [P] f64 in member order on every rank; each rank then applies
+        the identical `_update_weights` from the replicated noise table (no parameter traffic)."""
+        r = torch.as_tensor(np.asarray(local_rewards, dtype=np.float64)).to(self.device) \
+            if not isinstance(local_rewards, torch.Tensor) else local_rewards.to(self.device, torch.float64)
+        W = D.world_size()
+        if W == 1:
+            return r
+        out = torch.empty(W, r.numel(), dtype=torch.float64, device=self.device)
+        D.all_gather_into(out, r)
+        return out.reshape(-1)
 
     # ---- update ----
     def _update_weights(self, rewards, population, novelty=None):
