@@ -30,6 +30,8 @@ T, N, D, A, K_BITS = 256, 2048, 8, 2, 64
 HP = dict(lr=3e-4, gamma=0.999, gae_lam=0.95, vf_coef=1, max_grad_norm=5, n_epochs=10, clip_range=0.2, ent_coef=0.0)
 HIDDEN = 64
 N_MINIBATCH = 4
+# DRAM bytes per launch of the fused MLP kernels at the C2 minibatch, from the committed ncu captures
+NCU_TRAFFIC = {"ppx_mlp3_bwd": 144.0e6, "ppx_mlp3_fwd": 81.9e6}
 WORKLOAD = ("C2: PPO+SimHash, obs 8, Box(2), k=64, 2048 envs x 256 steps per GPU, swimmer_ppo hparams, "
             "4 minibatches/epoch x 10 epochs")
 
@@ -366,14 +368,16 @@ def run_ppx(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed every step (256 MiB memset inside the timed region)",
                        "shuffle": "np.random.permutation on the host each epoch (bit-exact reference stream), inside the timed region",
-                       "global_minibatch": B * world, "cuda_graph": "per-minibatch launch sequence replayed as a CUDA graph (N=1)"},
+                       "global_minibatch": B * world, "cuda_graph": "per-minibatch launch sequence (incl. the NCCL collectives when N>1) replayed as a CUDA graph",
+                       "shard_shuffle": "local (per-rank shuffle stream)" if world > 1 else "n/a (1 GPU)"},
             "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d + perm_bytes // world),
                     "d2h_bytes_per_step": int(HP["n_epochs"] * N_MINIBATCH * 64), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": f"{op} M={M_} K/D={K_} N/H={N_} batch/G={b_}",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                         "traffic": NCU_TRAFFIC.get(op), "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_mlp3_r01b.md)" if op in NCU_TRAFFIC else None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                          "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
                          "fp32_frac": achieved / 74.4,
                          "ms_per_launch": tot_ms / cnt, "launches_per_step": cnt, "top_ops_ms_per_step": ops}}
