@@ -221,8 +221,15 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
   __shared__ double s_sum[kPart];
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5, nblocks = gridDim.x;
   double acc = 0.0;
-#pragma unroll 4
-  for (int k = ph; k < nblocks; k += 8) acc += __ldcg(p.partials + (int64_t)k * kPart + lane);
+  {
+    int k = ph;
+    for (; k + 24 < nblocks; k += 32) {                      // 4 independent loads in flight, summed in a fixed order
+      const double v0 = __ldcg(p.partials + (int64_t)k * kPart + lane), v1 = __ldcg(p.partials + (int64_t)(k + 8) * kPart + lane);
+      const double v2 = __ldcg(p.partials + (int64_t)(k + 16) * kPart + lane), v3 = __ldcg(p.partials + (int64_t)(k + 24) * kPart + lane);
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; k < nblocks; k += 8) acc += __ldcg(p.partials + (int64_t)k * kPart + lane);
+  }
   s_p[ph][lane] = acc;
   __syncthreads();
   if (ph == 0) {
@@ -298,7 +305,7 @@ __global__ void accum_loss_kernel(const double* __restrict__ partials, int n, do
 
 int grid_for(int64_t n) {
   int64_t g = ceil_div(n, 256);
-  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
+  const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 2);   // few partials: the last-CTA tail reads them all
   return (int)std::max<int64_t>(1, std::min(g, cap));
 }
 
