@@ -326,11 +326,11 @@ def run_ppx(args):
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "launches": L.launch_count()}))
         return
+    clocks = ClockSampler(local_rank)                   # sampled over warm-up + timed region (same load; nvidia-smi
+    clocks.start()                                      # needs a few hundred ms to produce its first line)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     l0 = L.launch_count()
     ms = timed(step_resident, args.steps)
     launches = L.launch_count() - l0
@@ -381,6 +381,28 @@ def run_ppx(args):
                          "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
                          "fp32_frac": achieved / 74.4,
                          "ms_per_launch": tot_ms / cnt, "launches_per_step": cnt, "top_ops_ms_per_step": ops}}
+    if os.environ.get("PPX_BENCH_TRACE") == "1":        # diagnosis: per-rank host timeline of one more pass
+        from ppo_exploration_b200 import buffer as BUF
+        marks, orig_next = [], BUF.HostRngStream.next
+        def next_(self):
+            t0 = time.perf_counter(); v = orig_next(self); marks.append((t0, time.perf_counter())); return v
+        BUF.HostRngStream.next = next_
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter(); flush.zero_(); ro.rewards.copy_(raw_rewards); bonus_and_gae(); torch.cuda.synchronize()
+        t1 = time.perf_counter(); m.train(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        BUF.HostRngStream.next = orig_next
+        gs = [v[0] for k, v in m._graphs.items() if isinstance(v, tuple)]
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            for gph in gs:
+                gph.replay()
+        eb.record(); torch.cuda.synchronize()
+        print(f"[trace rank {rank}] bonus+gae {1e3 * (t1 - t0):.2f} ms, train {1e3 * (t2 - t1):.2f} ms, 40 graphs back-to-back "
+              f"{ea.elapsed_time(eb):.2f} ms, rng waits " + " ".join(f"{1e3 * (b - a):.2f}@{1e3 * (a - t1):.1f}" for a, b in marks),
+              file=sys.stderr, flush=True)
     es = es_step_bench(torch, ppx, dev, world, rank)
     line["es"] = es
     if world == 1 and rank == 0:
