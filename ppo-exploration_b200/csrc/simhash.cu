@@ -8,9 +8,11 @@
 // wrong envs.  Two launches, no inter-CTA ordering:
 //   A. (parallel over observations)  codes: bit b = (A[b,:] . obs[i,:] > 0), f64 dot (buffer.py:194), plus a
 //      16-bit BUCKET id = hash(code) % NB.  A is staged in shared memory, two observations per thread.
+//   P. (stable partition by bucket, 3 small launches)  tiles of 4096 elements sort (bucket, local index) keys in
+//      shared memory and emit per-tile bucket counts; an exclusive scan over tiles / buckets turns them into
+//      offsets; the tiles scatter their element indices into one list per bucket, in index order.
 //   B. (one CTA per bucket)  a bucket OWNS its codes, so everything order-dependent happens inside one CTA:
-//      the CTA streams the bucket ids in index order, compacts the indices of its own elements (a stable
-//      block scan keeps them in index order) into batches of <= 4096, and per batch
+//      the CTA walks its list (index order) in batches of <= 4096, and per batch
 //        1. bitonic sort of (code, position) in shared memory -> rank among equal codes in index order and
 //           one representative (the run tail) that knows the run length m
 //        2. representatives find / claim their slot (linear probing, 64-bit atomicCAS: other buckets claim
@@ -31,6 +33,10 @@ struct ppx_count_table {
   uint64_t used_bound;   // host-side upper bound of keys in use (avoids a sync per call)
   uint64_t* scratch_codes;   // [scratch_n] codes of the launch in flight
   uint16_t* scratch_bucket;  // [scratch_n] bucket ids
+  uint32_t* scratch_sorted;  // [scratch_n] per-tile sorted (bucket << 12 | local index) keys
+  uint32_t* scratch_list;    // [scratch_n] element indices grouped by bucket, index order inside a bucket
+  uint32_t* scratch_hist;    // [tiles * nb] per-tile bucket counts -> exclusive offsets over tiles
+  uint32_t* scratch_bstart;  // [2 * nb + 2] bucket totals | bucket starts
   int64_t scratch_n;
 };
 
@@ -41,7 +47,7 @@ constexpr uint64_t kEmpty = ~0ull;
 constexpr int CAP = 4096;         // elements per sorted batch
 constexpr int CT = 1024;          // threads per bucket CTA (4 elements each)
 constexpr int64_t LMAX = 1 << 20; // observations per launch
-constexpr int TARGET = 3072;      // expected elements per bucket
+constexpr int TARGET = 1536;      // expected elements per bucket (sorted as a 2048-wide bitonic network)
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {     // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -253,61 +259,170 @@ __device__ void process_batch(BucketSmem& S, int m, uint64_t* __restrict__ keys,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CT)
-bucket_update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap, uint32_t* ctrl,
-                     const uint64_t* __restrict__ codes, const uint16_t* __restrict__ bucket, int n, int64_t e0, double beta,
-                     void* rewards, int rewards_f64, uint32_t* __restrict__ counts_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  BucketSmem& S = *reinterpret_cast<BucketSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint16_t mine = (uint16_t)blockIdx.x;
-  int fill = 0;
-  // stream the bucket ids in index order, CAP elements per step (4 per thread), stable compaction of the matches
-  for (int b0 = 0; b0 < n; b0 += CAP) {
-    const int i0 = b0 + 4 * tid;
-    bool mt[4];
-    if (i0 + 3 < n) {
-      const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(bucket + i0));
-      mt[0] = v.x == mine; mt[1] = v.y == mine; mt[2] = v.z == mine; mt[3] = v.w == mine;
-    } else {
+constexpr int TP = 4096;          // elements per partition tile
+
+// block-wide inclusive max-scan of one int per thread (1024 threads); `warp_buf` is 32 ints of shared memory
+__device__ __forceinline__ int block_prefix_max_excl(int v, int* warp_buf) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) mt[q] = (i0 + q < n) && (__ldg(bucket + i0 + q) == mine);
-    }
-    const int cnt = (int)mt[0] + (int)mt[1] + (int)mt[2] + (int)mt[3];
-    int incl = cnt;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl = max(incl, o);
+  }
+  if (lane == 31) warp_buf[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int x = warp_buf[lane];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
+      const int o = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x = max(x, o);
     }
-    if (lane == 31) S.warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      int x = S.warp[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, x, d);
-        if (lane >= d) x += o;
-      }
-      S.warp[lane] = x;
-      if (lane == 31) S.total = x;
-    }
-    __syncthreads();
-    const int total = S.total;
-    int excl = incl - cnt + (wid > 0 ? S.warp[wid - 1] : 0);
-    __syncthreads();                                         // S.warp / S.total are reused below and next step
-    if (total == 0) continue;
-    if (fill + total > CAP) {                                // batch full: settle it before appending (index order)
-      process_batch(S, fill, keys, counts, cap, ctrl, codes, e0, beta, rewards, rewards_f64, counts_out);
-      fill = 0;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (mt[q]) S.elem[fill + excl++] = (uint32_t)(i0 + q);
-    fill += total;
-    __syncthreads();
+    warp_buf[lane] = x;
   }
-  if (fill > 0) process_batch(S, fill, keys, counts, cap, ctrl, codes, e0, beta, rewards, rewards_f64, counts_out);
+  __syncthreads();
+  int before = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) before = 0;
+  if (wid > 0) before = max(before, warp_buf[wid - 1]);
+  __syncthreads();
+  return before;                                              // max over all EARLIER threads (0 if none)
+}
+
+// P1: sort the tile's (bucket, local index) keys; per-tile bucket counts
+__global__ void __launch_bounds__(CT)
+tile_sort_kernel(const uint16_t* __restrict__ bucket, int n, uint32_t nb, uint32_t* __restrict__ sorted, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_key[TP];
+  const int tid = threadIdx.x, tile = blockIdx.x, e0 = tile * TP;
+  for (uint32_t b = tid; b < nb; b += CT) hist[(size_t)tile * nb + b] = 0u;
+#pragma unroll
+  for (int q = 0; q < TP / CT; ++q) {
+    const int j = tid + q * CT;
+    s_key[j] = (e0 + j < n) ? (((uint32_t)__ldg(bucket + e0 + j) << 12) | (uint32_t)j) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= TP; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = tid; t < TP / 2; t += CT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = (i & kk) == 0;
+        const uint32_t a = s_key[i], c = s_key[l];
+        if ((a > c) == up) { s_key[i] = c; s_key[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const int nv = min(TP, n - e0);
+#pragma unroll
+  for (int q = 0; q < TP / CT; ++q) {
+    const int p = tid + q * CT;
+    const uint32_t k = s_key[p];
+    sorted[(size_t)e0 + p] = k;
+    if (p < nv) {
+      const uint32_t b = k >> 12;
+      const bool tail = (p == nv - 1) || ((s_key[p + 1] >> 12) != b);
+      if (tail) {                                            // run head = lower bound of (b << 12) in the sorted keys
+        int lo = 0, hi = p;
+        const uint32_t key0 = b << 12;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < key0) lo = mid + 1; else hi = mid; }
+        hist[(size_t)tile * nb + b] = (uint32_t)(p - lo + 1);
+      }
+    }
+  }
+}
+
+// P2: per bucket, exclusive scan of the tile counts (in place) and the bucket total; the last CTA turns the totals
+// into bucket starts.  tiles <= 256 (LMAX / TP).
+__device__ unsigned int g_part_ticket = 0;
+__global__ void __launch_bounds__(256)
+bucket_offsets_kernel(uint32_t* __restrict__ hist, int tiles, uint32_t nb, uint32_t* __restrict__ btot /*[nb]*/,
+                      uint32_t* __restrict__ bstart /*[nb+1]*/) {
+  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_scan[1024];
+  const uint32_t b = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const uint32_t c = t < tiles ? hist[(size_t)t * nb + b] : 0u;
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_w[wid] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < wid; ++w) base += s_w[w];
+  if (t < tiles) hist[(size_t)t * nb + b] = base + incl - c;
+  if (t == 255) btot[b] = base + incl;
+  if (!last_block_done(&g_part_ticket)) return;
+  // exclusive scan of the nb totals (nb <= 1024 checked on the host), 4 per thread
+  uint32_t run = 0;
+  uint32_t v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const uint32_t i = (uint32_t)t * 4 + q; v[q] = i < nb ? __ldcg(btot + i) : 0u; run += v[q]; }
+  s_scan[t] = run;
+  __syncthreads();
+  if (t == 0) { uint32_t acc = 0; for (int i = 0; i < 256; ++i) { const uint32_t x = s_scan[i]; s_scan[i] = acc; acc += x; } }
+  __syncthreads();
+  uint32_t acc = s_scan[t];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const uint32_t i = (uint32_t)t * 4 + q; if (i <= nb) bstart[i] = acc; acc += v[q]; }
+}
+
+// P3: scatter the tile's element indices to their bucket lists (stable: tile order, then index order)
+__global__ void __launch_bounds__(CT)
+tile_scatter_kernel(const uint32_t* __restrict__ sorted, int n, uint32_t nb, const uint32_t* __restrict__ tile_off,
+                    const uint32_t* __restrict__ bstart, uint32_t* __restrict__ list) {
+  __shared__ int s_warp[32];
+  __shared__ uint32_t s_prev[CT];
+  const int tid = threadIdx.x, tile = blockIdx.x, e0 = tile * TP;
+  const int nv = min(TP, n - e0);
+  // thread owns 4 CONSECUTIVE sorted positions
+  const int p0 = 4 * tid;
+  uint32_t k[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) k[q] = sorted[(size_t)e0 + p0 + q];
+  s_prev[tid] = k[3];
+  __syncthreads();
+  const uint32_t kprev = tid > 0 ? s_prev[tid - 1] : 0xFFFFFFFFu;
+  bool head[4];
+  int run = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t before = q == 0 ? kprev : k[q - 1];
+    head[q] = (p0 + q < nv) && (p0 + q == 0 || (before >> 12) != (k[q] >> 12));
+    if (head[q]) run = p0 + q;
+  }
+  int before = block_prefix_max_excl(run, s_warp);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int p = p0 + q;
+    if (head[q]) before = p;
+    if (p < nv) {
+      const uint32_t b = k[q] >> 12;
+      list[bstart[b] + tile_off[(size_t)tile * nb + b] + (uint32_t)(p - before)] = (uint32_t)e0 + (k[q] & 0xFFFu);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CT)
+bucket_update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap, uint32_t* ctrl,
+                     const uint64_t* __restrict__ codes, const uint32_t* __restrict__ list, const uint32_t* __restrict__ bstart,
+                     uint32_t n_direct, int64_t e0, double beta, void* rewards, int rewards_f64,
+                     uint32_t* __restrict__ counts_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BucketSmem& S = *reinterpret_cast<BucketSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  // list == nullptr: a single bucket holding elements 0..n_direct-1 (small calls skip the partition)
+  const uint32_t lo = list ? bstart[blockIdx.x] : 0u, hi = list ? bstart[blockIdx.x + 1] : n_direct;
+  for (uint32_t b0 = lo; b0 < hi; b0 += CAP) {               // batches of one bucket run in index order
+    const int m = (int)min((uint32_t)CAP, hi - b0);
+    for (int j = tid; j < m; j += CT) S.elem[j] = list ? __ldg(list + b0 + j) : b0 + (uint32_t)j;
+    __syncthreads();
+    process_batch(S, m, keys, counts, cap, ctrl, codes, e0, beta, rewards, rewards_f64, counts_out);
+  }
 }
 
 __global__ void bonus_kernel(const uint32_t* __restrict__ counts, int64_t n, double beta, void* rewards, int f64) {
@@ -388,10 +503,17 @@ int reserve(ppx_count_table* t, int64_t incoming, cudaStream_t st) {
 
 int ensure_scratch(ppx_count_table* t, int64_t n) {
   if (t->scratch_n >= n) return PPX_OK;
-  cudaFree(t->scratch_codes); cudaFree(t->scratch_bucket);
-  t->scratch_codes = nullptr; t->scratch_bucket = nullptr; t->scratch_n = 0;
+  cudaFree(t->scratch_codes); cudaFree(t->scratch_bucket); cudaFree(t->scratch_sorted); cudaFree(t->scratch_list);
+  cudaFree(t->scratch_hist); cudaFree(t->scratch_bstart);
+  t->scratch_codes = nullptr; t->scratch_bucket = nullptr; t->scratch_sorted = nullptr; t->scratch_list = nullptr;
+  t->scratch_hist = nullptr; t->scratch_bstart = nullptr; t->scratch_n = 0;
+  const int64_t tiles = ceil_div(n, TP), nbmax = std::max<int64_t>(1, ceil_div(n, TARGET));
   PPX_CUDA(cudaMalloc((void**)&t->scratch_codes, (size_t)n * sizeof(uint64_t)));
   PPX_CUDA(cudaMalloc((void**)&t->scratch_bucket, (size_t)(n + 8) * sizeof(uint16_t)));
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_sorted, (size_t)tiles * TP * sizeof(uint32_t)));
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_list, (size_t)n * sizeof(uint32_t)));
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_hist, (size_t)tiles * nbmax * sizeof(uint32_t)));
+  PPX_CUDA(cudaMalloc((void**)&t->scratch_bstart, (size_t)(2 * nbmax + 2) * sizeof(uint32_t)));
   t->scratch_n = n;
   return PPX_OK;
 }
@@ -418,20 +540,35 @@ int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int
   }
   for (int64_t e0 = 0; e0 < n; e0 += LMAX) {                  // stream-ordered launches keep the index order
     const int64_t nl = std::min<int64_t>(LMAX, n - e0);
-    const uint32_t nb = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, TARGET), 65535));
+    // <= 1024 buckets: one-CTA scan of the totals; a call that fits one sorted batch needs no partition at all
+    const uint32_t nb = nl <= CAP ? 1u : (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, TARGET), 1024));
     const uint64_t* codes = codes_in ? codes_in + e0 : (codes_out ? codes_out + e0 : t->scratch_codes);
+    const size_t sz = rewards_f64 ? sizeof(double) : sizeof(float);
+    void* rew = rewards ? (char*)rewards + e0 * sz : nullptr;
+    uint32_t* cnt = counts_out ? counts_out + e0 : nullptr;
     if (obs) {
-      rc = launch_codes(A, obs + e0 * D, k, D, nl, const_cast<uint64_t*>(codes), t->scratch_bucket, nb, st);
+      rc = launch_codes(A, obs + e0 * D, k, D, nl, const_cast<uint64_t*>(codes), nb > 1 ? t->scratch_bucket : nullptr, nb, st);
       if (rc) return rc;
-    } else {
+    } else if (nb > 1) {
       bucket_ids_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(codes, nl, t->scratch_bucket, nb);
       rc = after_launch("simhash bucket ids");
       if (rc) return rc;
     }
-    const size_t sz = rewards_f64 ? sizeof(double) : sizeof(float);
-    bucket_update_kernel<<<nb, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, t->scratch_bucket,
-                                                            (int)nl, 0, beta, rewards ? (char*)rewards + e0 * sz : nullptr,
-                                                            rewards_f64, counts_out ? counts_out + e0 : nullptr);
+    if (nb == 1) {                                            // one bucket: no partition, elements in index order
+      bucket_update_kernel<<<1, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, nullptr, nullptr,
+                                                             (uint32_t)nl, 0, beta, rew, rewards_f64, cnt);
+    } else {
+      const int tiles = (int)ceil_div(nl, TP);
+      uint32_t* btot = t->scratch_bstart;
+      uint32_t* bstart = t->scratch_bstart + nb;
+      tile_sort_kernel<<<tiles, CT, 0, st>>>(t->scratch_bucket, (int)nl, nb, t->scratch_sorted, t->scratch_hist);
+      bucket_offsets_kernel<<<nb, 256, 0, st>>>(t->scratch_hist, tiles, nb, btot, bstart);
+      tile_scatter_kernel<<<tiles, CT, 0, st>>>(t->scratch_sorted, (int)nl, nb, t->scratch_hist, bstart, t->scratch_list);
+      rc = after_launch("simhash partition", 3);
+      if (rc) return rc;
+      bucket_update_kernel<<<nb, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, t->scratch_list,
+                                                              bstart, 0u, 0, beta, rew, rewards_f64, cnt);
+    }
     rc = after_launch("simhash update");
     if (rc) return rc;
   }
@@ -467,6 +604,7 @@ extern "C" int ppx_count_table_create(uint64_t capacity, ppx_count_table** out) 
 extern "C" int ppx_count_table_destroy(ppx_count_table* t) {
   if (!t) return PPX_OK;
   cudaFree(t->keys); cudaFree(t->counts); cudaFree(t->ctrl); cudaFree(t->scratch_codes); cudaFree(t->scratch_bucket);
+  cudaFree(t->scratch_sorted); cudaFree(t->scratch_list); cudaFree(t->scratch_hist); cudaFree(t->scratch_bstart);
   delete t;
   return PPX_OK;
 }
