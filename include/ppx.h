@@ -122,6 +122,26 @@ int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int6
 int ppx_moments_pack(const double* stats2, int64_t n, double* rec3, void* stream);
 int ppx_moments_merge(const double* recs, int W, double* out2, void* stream);
 
+/* ---------------------------------------------------------------- NVLink peer-memory exchanges ---- */
+/* The three global points of the sharded PPO minibatch as ONE kernel each over symmetric peer memory
+ * (p2p.cu): barrier (release store per peer + acquire polls) -> read the W peers' payloads in rank order -> consume.
+ * peer_* are HOST arrays of W device pointers (rank r's payload / flag array of this channel, >= W uint32, zeroed
+ * before first use); seq_dev / status_dev are local device words (sequence number; != 0 after a 4 s barrier timeout).
+ * Slot-reuse rule: between two uses of the same payload slot every rank must pass two other barriers. */
+int64_t ppx_p2p_max_params(void);
+/* merged {mean, std(ddof 1)} per stream from the ranks' {n, mean, M2} records (ppx_moments_pack), nstreams in {1,2} */
+int ppx_p2p_moments_merge(const void* const* peer_recs_host, void* const* peer_flags_host, int W, int rank, uint32_t* seq_dev,
+                          uint32_t* status_dev, int nstreams, double* stats_out, void* stream);
+/* sums_out[32] = sum over ranks of the loss partial sums written by ppx_ppo_loss_head; then ppx_ppo_loss_finalize */
+int ppx_p2p_sums_allreduce(const void* const* peer_sums_host, void* const* peer_flags_host, int W, int rank, uint32_t* seq_dev,
+                           uint32_t* status_dev, double* sums_out, void* stream);
+/* gradient all-reduce + clip_grad_norm_ + Adam in one kernel (n <= ppx_p2p_max_params()): replaces the NCCL
+ * all-reduce + ppx_clip_adam of algorithms.py:243-244 on replicated weights; every replica computes the identical sum. */
+int ppx_p2p_clip_adam(float* params, const void* const* peer_grads_host, void* const* peer_flags_host, int W, int rank,
+                      uint32_t* seq_dev, uint32_t* status_dev, float* exp_avg, float* exp_avg_sq, int64_t n, double max_norm,
+                      int64_t n_clip, double lr, double beta1, double beta2, double eps, int64_t* step_dev, double* norm_out,
+                      float* grad_sum_out, void* stream);
+
 /* ---------------------------------------------------------------- dense layers (fp32) ------- */
 /* Y[z] = act(X[z] @ W[z] + bias[z]) for z < batch.  X: [M,K] ld=ldx, W: [K,N] contiguous, Y ld=ldy.
  * Strides (in elements) step X/W/bias/Y per batch entry; batch=1 ignores them.

@@ -66,6 +66,7 @@ class BaseAlgorithm(object):
         # buffer semantics per rank; static shapes -> CUDA graphs, scales)
         self.shard_shuffle = "global"
         self._mrec = None
+        self._px = False                       # PeerExchange (NVLink peer-memory kernels) | None; False = not probed yet
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
         self._graphs = {}
         self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
@@ -120,9 +121,16 @@ class BaseAlgorithm(object):
                 L.call("ppx_ppo_loss_head_final", *head_args, pol.bank.g("action_log_std"), losses_row,
                        self._branch.data_ptr(), ws, L.stream())
             else:
+                px = self._peer_exchange()
                 L.call("ppx_ppo_loss_head", *head_args, self._sums.data_ptr(), ws, L.stream())
-                D.all_reduce_sum_(self._sums)
-                L.call("ppx_ppo_loss_finalize", C.byref(cfg), self._sums.data_ptr(), pol.bank.p("action_log_std"),
+                if px is not None:
+                    L.call("ppx_p2p_sums_allreduce", px.peer_sums, px.peer_flags[1], px.W, px.rank, px.seq[1], px.status_ptr,
+                           self._sums_global.data_ptr(), L.stream())
+                    gsums = self._sums_global
+                else:
+                    D.all_reduce_sum_(self._sums)
+                    gsums = self._sums
+                L.call("ppx_ppo_loss_finalize", C.byref(cfg), gsums.data_ptr(), pol.bank.p("action_log_std"),
                        pol.bank.g("action_log_std"), losses_row, self._branch.data_ptr(), L.stream())
             vh = {1: (outs[1], bufs['old_values'][:B], bufs['returns'][:B], self._branch.data_ptr(),
                       float(policy_weight) * float(self.vf_coef))}
@@ -143,9 +151,34 @@ class BaseAlgorithm(object):
                d_ival.data_ptr() if dual else None, losses_row, ws, L.stream())
         pol.mlp.backward([d_actor, d_val] + ([d_ival] if dual else []))
 
+    def _peer_exchange(self):
+        """Lazily move the policy bank's gradient vector, the loss partial sums and the moment records into symmetric
+        peer memory so the three per-minibatch exchanges run as ppx kernels over NVLink (p2p.cu) instead of NCCL."""
+        if self._px is False:
+            self._px = None
+            if D.world_size() > 1 and self.policy.mlp.fused():
+                bank = self.policy.bank
+                px = D.peer_exchange_or_none(bank.size, self.device, L.call("ppx_p2p_max_params"))
+                if px is not None:
+                    px.grad.copy_(bank.grad)
+                    bank.grad = px.grad                         # kernels now write the local gradient into peer-visible memory
+                    self.policy.mlp._fa = None                  # cached gradient pointers are stale
+                    self._sums = px.sums[:32]
+                    self._sums_global = torch.zeros(32, dtype=torch.float64, device=self.device)
+                    self._px = px
+        return self._px
+
     def _merge_stats(self, B, dual):
-        """Sharded minibatch: local {mean, std} -> global, through one all-gather of {n, mean, M2} records."""
+        """Sharded minibatch: local {mean, std} -> global, through one exchange of {n, mean, M2} records."""
         W = D.world_size()
+        px = self._peer_exchange()
+        if px is not None:
+            L.call("ppx_moments_pack", self._stats.data_ptr(), B, px.rec.data_ptr(), L.stream())
+            if dual:
+                L.call("ppx_moments_pack", self._stats.data_ptr() + 16, B, px.rec.data_ptr() + 24, L.stream())
+            L.call("ppx_p2p_moments_merge", px.peer_rec, px.peer_flags[0], W, px.rank, px.seq[0], px.status_ptr,
+                   2 if dual else 1, self._stats.data_ptr(), L.stream())
+            return
         if self._mrec is None or self._mrec_all.shape[0] != W:
             self._mrec = torch.zeros(6, dtype=torch.float64, device=self.device)
             self._mrec_all = torch.zeros(W, 6, dtype=torch.float64, device=self.device)
@@ -247,8 +280,26 @@ class BaseAlgorithm(object):
         if D.world_size() > 1:
             D.all_reduce_sum_(bank.grad)
 
+    def _policy_optim_step(self):
+        """Gradient exchange + clip + Adam for the policy bank.  Sharded with peer memory: ONE kernel reads every rank's
+        gradient over NVLink, sums in rank order, clips and applies Adam (weights stay bit-identical replicas)."""
+        bank = self.policy.bank
+        px = self._peer_exchange() if D.world_size() > 1 else None
+        if px is not None:
+            n_clip = bank.size if self.max_grad_norm > 0 else 0
+            L.call("ppx_p2p_clip_adam", bank.flat.data_ptr(), px.peer_grad, px.peer_flags[2], px.W, px.rank, px.seq[2],
+                   px.status_ptr, bank.exp_avg.data_ptr(), bank.exp_avg_sq.data_ptr(), bank.size, float(self.max_grad_norm),
+                   n_clip, float(self.lr), 0.9, 0.999, 1e-8, bank.step_dev.data_ptr(), bank.norm_dev.data_ptr(), None,
+                   L.stream())
+            bank.refresh_tc()
+            return
+        self._sync_grads(bank)
+        bank.adam_step(self.lr, self.max_grad_norm)
+
     def _finish_train(self, losses_dev, keys):
         losses = losses_dev.cpu().numpy()                         # the only D2H sync of train()
+        if self._px and int(self._px.status.item()) != 0:
+            raise RuntimeError("ppx: a peer-memory barrier timed out (a rank fell out of the sharded update)")
         self.last_losses = losses
         for i, k in enumerate(keys):
             self._record(k, float(np.mean(losses[:, i])))
@@ -327,8 +378,7 @@ class PPO(BaseAlgorithm):
                 def fn(sl=sl, b=b, bt=bt):
                     ro.gather_into(sl, bufs)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt)
-                    self._sync_grads(self.policy.bank)
-                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)
+                    self._policy_optim_step()
                 self._graph_call(("ppo", off, b, bt), fn)
                 losses[step].copy_(self._loss_row)
                 step += 1
@@ -431,8 +481,7 @@ class PPO_RND(BaseAlgorithm):
                     ro.gather_into(sl, bufs)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
                                       B_total=bt)
-                    self._sync_grads(self.policy.bank)
-                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)
+                    self._policy_optim_step()
                 self._graph_call(("rnd_policy", off, b, bt), fn)
                 losses[step].copy_(self._loss_row)
                 if rng.next() < 0.25:                               # algorithms.py:468, same host RNG stream

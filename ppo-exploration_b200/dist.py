@@ -78,3 +78,55 @@ def interleave_env_shards(x):
     """[W, T, n_local, ...] gathered per-rank blocks -> [T, W*n_local, ...] in global env order."""
     W, T, n = x.shape[:3]
     return x.transpose(0, 1).reshape(T, W * n, *x.shape[3:])
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) scratch of one sharded learner: the policy gradient vector, the loss partial sums, the
+    advantage-moment records and three barrier channels, visible to every rank over NVLink (p2p.cu).  The allocation and
+    handle exchange use torch.distributed._symmetric_memory; the kernels are ppx's own."""
+    FLAGS, SEQ, STATUS, REC, SUMS, GRAD = 0, 256, 272, 512, 1024, 4096       # byte offsets
+    MAXW = 16
+
+    def __init__(self, n_params, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        W, r = world_size(), rank()
+        assert 2 <= W <= self.MAXW
+        words = self.GRAD // 4 + (int(n_params) + 3) // 4 * 4
+        self.buf = symm_mem.empty(words, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        group = dist.group.WORLD
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()                                   # every rank's flags are zero before anyone signals
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        arr = lambda off: (C.c_void_p * W)(*[b + off for b in base])
+        self.W, self.rank = W, r
+        self.peer_grad, self.peer_sums, self.peer_rec = arr(self.GRAD), arr(self.SUMS), arr(self.REC)
+        self.peer_flags = [arr(self.FLAGS + 64 * ch) for ch in range(3)]     # 16 uint32 per channel
+        w = lambda off, n: self.buf[off // 4: off // 4 + n]
+        self.grad = w(self.GRAD, int(n_params))
+        self.sums = w(self.SUMS, 64).view(torch.float64)
+        self.rec = w(self.REC, 12).view(torch.float64)
+        self.seq = [self.buf.data_ptr() + self.SEQ + 4 * ch for ch in range(3)]
+        self.status_ptr = self.buf.data_ptr() + self.STATUS
+        self.status = w(self.STATUS, 1).view(torch.int32)
+
+
+def peer_exchange_or_none(n_params, device, max_params):
+    """A PeerExchange when every rank can build one (NVLink P2P, symmetric memory, bank small enough), else None --
+    decided collectively so all ranks take the same path."""
+    import os
+    ok, px = 1, None
+    if world_size() < 2 or world_size() > PeerExchange.MAXW or os.environ.get("PPX_P2P", "1") == "0" or n_params > max_params \
+            or not torch.cuda.is_available():
+        ok = 0
+    if ok:
+        try:
+            px = PeerExchange(n_params, device)
+        except Exception:                                     # no P2P / symmetric memory on this box
+            ok, px = 0, None
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    if world_size() > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return px if int(flag.item()) == 1 else None
