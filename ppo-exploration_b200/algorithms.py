@@ -24,7 +24,7 @@ import torch
 
 from . import _lib as L
 from . import dist as D
-from .buffer import RolloutStorage, IntrinsicStorage, HostRngStream, _dev
+from .buffer import RolloutStorage, IntrinsicStorage, HostRngStream, rng_states_equal, _dev
 from .models import Policy, RndNetwork, IntrinsicCuriosityModule, ActionConverter, _Scratch
 from .util import RunningMeanStd, normalize_obs
 
@@ -66,11 +66,18 @@ class BaseAlgorithm(object):
         # buffer semantics per rank; static shapes -> CUDA graphs, scales)
         self.shard_shuffle = "global"
         self._mrec = None
+        self._spec = None                      # (HostRngStream, rng snapshot) pre-drawn for the next train() call
+        self.speculative_shuffle = True
         self._px = False                       # PeerExchange (NVLink peer-memory kernels) | None; False = not probed yet
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
         self._graphs = {}
         self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._perm_bufs, self._perm_ready, self._perm_free, self._copy_stream = None, [None, None], [None, None], None
+
+    def __del__(self):
+        sp = getattr(self, "_spec", None)
+        if sp is not None:
+            sp[0].cancel()
 
     # ---- shared pieces of the fused update --------------------------------------------------
     def _record(self, key, value):
@@ -225,6 +232,27 @@ class BaseAlgorithm(object):
             script += [('randn',)] * (n_mb if randn_per_minibatch else 0)
         return script
 
+    def _rng_open(self, script):
+        """The RNG stream of this train() call.  If the stream started speculatively at the end of the previous call was
+        seeded with exactly the state np.random is in now (nobody drew in between) and has the same script, its
+        permutations are already waiting; otherwise it is dropped and a fresh stream starts from the current state.
+        Either way the draws are those the reference would make from this state."""
+        cur = np.random.get_state()
+        sp, self._spec = self._spec, None
+        if sp is not None:
+            stream, snapshot = sp
+            if stream.script == list(script) and rng_states_equal(cur, snapshot) and stream.err is None:
+                return stream
+            stream.cancel()
+        return HostRngStream(script, state=cur)
+
+    def _rng_close(self, rng, speculate=True):
+        """Commit the consumed draws to the global numpy RNG and pre-draw the next call's stream from there."""
+        final = rng.final_state()
+        np.random.set_state(final)
+        if speculate and self.speculative_shuffle:
+            self._spec = (HostRngStream(rng.script, state=final), final)
+
     def _perm_prefetch(self, rng, total, slot):
         """Upload the next epoch's permutation on a side stream into one of two static device buffers, so the
         4 MB H2D copy overlaps the previous epoch's kernels instead of sitting in the compute stream."""
@@ -371,7 +399,7 @@ class PPO(BaseAlgorithm):
         losses = torch.zeros(self.n_epochs * n_mb, 8, dtype=torch.float64, device=self.device)
         bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
         step = 0
-        rng = HostRngStream(self._rng_script(ro))
+        rng = self._rng_open(self._rng_script(ro))
         self._perm_ready = [None, None]
         for ep in range(self.n_epochs):
             for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
@@ -383,6 +411,7 @@ class PPO(BaseAlgorithm):
                 losses[step].copy_(self._loss_row)
                 step += 1
         ro.generator_ready = True
+        self._rng_close(rng)
         self._finish_train(losses[:step], ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
                                            "train/entropy_loss"))
 
@@ -473,7 +502,7 @@ class PPO_RND(BaseAlgorithm):
         bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
         step = 0
         self.rnd_trained_steps = 0
-        rng = HostRngStream(self._rng_script(ro, randn_per_minibatch=True))
+        rng = self._rng_open(self._rng_script(ro, randn_per_minibatch=True))
         self._perm_ready = [None, None]
         for ep in range(self.n_epochs):
             for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
@@ -489,6 +518,7 @@ class PPO_RND(BaseAlgorithm):
                     self.rnd_trained_steps += 1
                 step += 1
         ro.generator_ready = True
+        self._rng_close(rng)
         self._finish_train(losses[:step], ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
                                            "train/entropy_loss", "train/intrinsic_loss"))
 
@@ -560,7 +590,7 @@ class PPO_ICM(BaseAlgorithm):
         icm_losses = torch.zeros(self.n_epochs * n_mb, dtype=torch.float64, device=self.device)
         bufs = ro._minibatch_buffers(B)
         step = 0
-        rng = HostRngStream(self._rng_script(ro))
+        rng = self._rng_open(self._rng_script(ro))
         icm_row = torch.zeros(1, dtype=torch.float64, device=self.device) if not hasattr(self, "_icm_row") else self._icm_row
         self._icm_row = icm_row
         self._perm_ready = [None, None]
@@ -578,6 +608,7 @@ class PPO_ICM(BaseAlgorithm):
                 icm_losses[step:step + 1].copy_(icm_row)
                 step += 1
         ro.generator_ready = True
+        self._rng_close(rng)
         losses[:, 5] = icm_losses
         losses[:, 0] += icm_losses                                  # total = pw*(...) + icm_loss (:692)
         keys = ("train/total_loss", "train/policy_gradient_loss", "train/value_loss", "train/entropy_loss")

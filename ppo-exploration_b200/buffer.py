@@ -14,10 +14,12 @@ Deliberate differences (documented in DESIGN.md):
 The shuffle indices come from the same `np.random.permutation(T*N)` draw as the reference
 (buffer.py:239), so a seeded run visits identical minibatches.
 """
+import atexit
 import ctypes as C
 import os
 import queue
 import threading
+import weakref
 from collections import namedtuple
 
 import numpy as np
@@ -45,18 +47,49 @@ def np_permutation(n):
     return out
 
 
+_live_streams = weakref.WeakSet()
+
+
+def _stop_streams_at_exit():
+    """Worker threads must not be inside torch / CUDA calls while the interpreter finalises."""
+    for st in list(_live_streams):
+        st.cancel()
+    for st in list(_live_streams):
+        st.t1.join(timeout=2.0)
+        st.t2.join(timeout=2.0)
+
+
+atexit.register(_stop_streams_at_exit)
+
+
+def rng_states_equal(a, b):
+    """Equality of two np.random.get_state() tuples (legacy MT19937)."""
+    return (a[0] == b[0] and int(a[2]) == int(b[2]) and int(a[3]) == int(b[3]) and float(a[4]) == float(b[4])
+            and np.array_equal(a[1], b[1]))
+
+
 class HostRngStream:
-    """Replays a fixed script of draws from the GLOBAL numpy RNG in worker threads, in order, so the host
-    shuffle (buffer.py:239) and RND's per-minibatch randn() (algorithms.py:468) overlap the GPU work while
-    consuming exactly the reference's random stream.  script items: ('perm', n) | ('randn',).
+    """Replays a fixed script of draws of the numpy legacy RNG in worker threads, in order, so the host shuffle
+    (buffer.py:239) and RND's per-minibatch randn() (algorithms.py:468) overlap the GPU work while consuming exactly
+    the reference's random stream.  script items: ('perm', n) | ('randn',).
 
-    Two pipelined stages (both release the GIL inside libppx): stage 1 owns the RNG -- it draws the
-    Fisher-Yates partner sequence of each permutation (RNG-bound) and the scalar randn()s; stage 2 applies
-    the swaps into a pinned buffer (memory-bound) while stage 1 already works on the next epoch."""
+    The stream works on a PRIVATE RandomState seeded with `state` (default: a snapshot of the global np.random state)
+    and never touches the global one; the caller commits `final_state()` with np.random.set_state once the script has
+    been consumed.  That makes a stream safe to start speculatively (before the caller knows it will be needed) and to
+    cancel.  Two pipelined stages (both release the GIL inside libppx): stage 1 owns the RNG -- it draws the
+    Fisher-Yates partner sequence of each permutation and the scalar randn()s; stage 2 applies the swaps into a pinned
+    buffer, running behind stage 1's published progress inside the SAME permutation.  At most `ahead` finished items
+    wait in the output queue (the workers then sleep)."""
 
-    def __init__(self, script):
-        self.q, self.mid = queue.Queue(), queue.Queue(maxsize=2)
+    def __init__(self, script, state=None, ahead=3):
+        self.script = list(script)
+        self.q, self.mid = queue.Queue(maxsize=max(1, int(ahead))), queue.Queue(maxsize=2)
         self.err = None
+        self.cancelled = False
+        self._final = None
+        self.rs = np.random.RandomState()
+        self.rs.set_state(np.random.get_state() if state is None else state)
+        script = self.script
         if os.environ.get("PPX_DIAG_REUSE_PERM") == "1":        # diagnosis only: isolates the host shuffle cost
             seen, sc = False, []
             for op in script:
@@ -67,15 +100,27 @@ class HostRngStream:
         self._scratch32 = None
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
         self.t2 = threading.Thread(target=self._apply, daemon=True)
+        _live_streams.add(self)
         self.t1.start()
         self.t2.start()
+
+    def _put(self, qq, item):
+        while not self.cancelled:
+            try:
+                qq.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def _draw(self, script):
         try:
             for op in script:
+                if self.cancelled:
+                    break
                 if op[0] == 'perm':
                     n = int(op[1])
-                    st = np.random.get_state()
+                    st = self.rs.get_state()
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
                     small = n <= 0x7fffffff
@@ -86,7 +131,8 @@ class HostRngStream:
                     if small:
                         # streaming: hand the buffer to stage 2 first, it runs behind the published progress counter
                         prog[0] = 0
-                        self.mid.put(('perm', j, n, prog))
+                        if not self._put(self.mid, ('perm', j, n, prog)):
+                            break
                         try:
                             L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, j.ctypes.data,
                                    prog.ctypes.data)
@@ -95,20 +141,28 @@ class HostRngStream:
                             raise
                     else:
                         L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
-                        self.mid.put(('perm', j, n, None))
-                    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+                        if not self._put(self.mid, ('perm', j, n, None)):
+                            break
+                    self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
                 elif op[0] == 'reuse':
-                    self.mid.put(('reuse',))
+                    if not self._put(self.mid, ('reuse',)):
+                        break
                 else:
-                    self.mid.put(('val', float(np.random.randn())))
+                    if not self._put(self.mid, ('val', float(self.rs.randn()))):
+                        break
+            else:
+                self._final = self.rs.get_state()
         except Exception as e:
             self.err = e
-        self.mid.put(None)
+        self._put(self.mid, None)
 
     def _apply(self):
         try:
-            while True:
-                item = self.mid.get()
+            while not self.cancelled:
+                try:
+                    item = self.mid.get(timeout=0.05)
+                except queue.Empty:
+                    continue
                 if item is None:
                     break
                 if item[0] == 'perm':
@@ -122,20 +176,34 @@ class HostRngStream:
                     else:
                         L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
                     self._last = out
-                    self.q.put(out)
+                    if not self._put(self.q, out):
+                        break
                 elif item[0] == 'reuse':
-                    self.q.put(self._last)
+                    if not self._put(self.q, self._last):
+                        break
                 else:
-                    self.q.put(item[1])
+                    if not self._put(self.q, item[1]):
+                        break
         except Exception as e:
             self.err = e
-        self.q.put(None)
+        self._put(self.q, None)
 
     def next(self):
         v = self.q.get()
         if v is None:
             raise self.err if self.err is not None else RuntimeError("HostRngStream: script exhausted")
         return v
+
+    def final_state(self):
+        """RNG state after the whole script (blocks until stage 1 has drawn everything)."""
+        self.t1.join()
+        if self.err is not None:
+            raise self.err
+        return self._final
+
+    def cancel(self):
+        """Abandon the stream (a speculative stream whose snapshot no longer matches the global RNG)."""
+        self.cancelled = True
 
     def drain(self):
         self.t1.join()

@@ -112,4 +112,25 @@ def test_host_permutation_is_bit_exact_numpy_replay():
         g = s.next()
         assert np.array_equal(g.numpy(), w) if isinstance(w, np.ndarray) else g == w
     s.drain()
+    np.random.set_state(s.final_state())                    # the stream works on a private copy; the caller commits
     assert np.random.randn() == tail
+
+
+def test_speculative_rng_stream_is_exact_and_cancellable():
+    """A stream pre-drawn from a snapshot gives the reference's permutations when the global state still equals the
+    snapshot; after a foreign draw the snapshot no longer matches (the learner then drops the stream)."""
+    from ppo_exploration_b200.buffer import HostRngStream, rng_states_equal
+    np.random.seed(11)
+    snap = np.random.get_state()
+    spec = HostRngStream([('perm', 5000)] * 4, state=snap, ahead=2)      # runs ahead while "the GPU is busy"
+    assert rng_states_equal(np.random.get_state(), snap)                 # global stream untouched
+    want = [np.random.permutation(5000) for _ in range(4)]
+    for w in want:
+        assert np.array_equal(spec.next().numpy(), w)
+    assert rng_states_equal(spec.final_state(), np.random.get_state())
+    snap2 = np.random.get_state()
+    spec2 = HostRngStream([('perm', 5000)] * 4, state=snap2, ahead=2)
+    np.random.randn()                                                    # somebody else draws
+    assert not rng_states_equal(np.random.get_state(), snap2)
+    spec2.cancel()
+    spec2.drain()
