@@ -55,6 +55,16 @@ struct RedP {
 
 __host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
 
+// tanh(x) = 1 - 2 / (1 + e^{2x}) with ex2.approx / rcp.approx: 5 instructions instead of ~17 for tanhf, ABSOLUTE
+// error <= ~2e-7 on [-1, 1] outputs (the hidden activations enter the next layer as absolute values; measured against
+// the fp64 reference in tests/test_gpu_mlp_fused.py).  Saturates correctly: e -> inf gives 1, e -> 0 gives -1.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+
 // acc[i][q*4+c] += a_i * b[q].c  for one k
 template <int CQ>
 __device__ __forceinline__ void outer(float (&acc)[8][CQ * 4], const float (&a)[8], const float4 (&b)[CQ]) {
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_fwd_kernel(FwdP p) {
       const int r = ty * 8 + i;
 #pragma unroll
       for (int q = 0; q < CQ; ++q) {
-        const float4 v = make_float4(tanhf(acc[i][q * 4]), tanhf(acc[i][q * 4 + 1]), tanhf(acc[i][q * 4 + 2]), tanhf(acc[i][q * 4 + 3]));
+        const float4 v = make_float4(tanh_fast(acc[i][q * 4]), tanh_fast(acc[i][q * 4 + 1]), tanh_fast(acc[i][q * 4 + 2]), tanh_fast(acc[i][q * 4 + 3]));
         *reinterpret_cast<float4*>(&As[r * H + q * 64 + tx * 4]) = v;
         if (m0 + r < p.M) *reinterpret_cast<float4*>(&p.H1[(size_t)(m0 + r) * p.ldh + g * H + q * 64 + tx * 4]) = v;
       }
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_fwd_kernel(FwdP p) {
         float po[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int q = 0; q < CQ; ++q) {
-          const float4 v = make_float4(tanhf(acc[i][q * 4]), tanhf(acc[i][q * 4 + 1]), tanhf(acc[i][q * 4 + 2]), tanhf(acc[i][q * 4 + 3]));
+          const float4 v = make_float4(tanh_fast(acc[i][q * 4]), tanh_fast(acc[i][q * 4 + 1]), tanh_fast(acc[i][q * 4 + 2]), tanh_fast(acc[i][q * 4 + 3]));
           if (m0 + r < p.M) *reinterpret_cast<float4*>(&p.H2[(size_t)(m0 + r) * p.ldh + g * H + q * 64 + tx * 4]) = v;
           const float* w = &W3s[(q * 64 + tx * 4) * o];
 #pragma unroll
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_fwd_kernel(FwdP p) {
       const int r = ty * 8 + i;
 #pragma unroll
       for (int q = 0; q < CQ; ++q) {
-        const float4 v = make_float4(tanhf(acc[i][q * 4]), tanhf(acc[i][q * 4 + 1]), tanhf(acc[i][q * 4 + 2]), tanhf(acc[i][q * 4 + 3]));
+        const float4 v = make_float4(tanh_fast(acc[i][q * 4]), tanh_fast(acc[i][q * 4 + 1]), tanh_fast(acc[i][q * 4 + 2]), tanh_fast(acc[i][q * 4 + 3]));
         *reinterpret_cast<float4*>(&As[r * H + q * 64 + tx * 4]) = v;
         if (m0 + r < p.M) *reinterpret_cast<float4*>(&p.H2[(size_t)(m0 + r) * p.ldh + g * H + q * 64 + tx * 4]) = v;
       }

@@ -53,9 +53,11 @@ def test_simhash_f64_rewards():
     assert r.dtype == np.float64 and np.array_equal(r, g["rew_out"])
 
 
-@pytest.mark.parametrize("n,k,D,calls", [(5000, 8, 3, 3), (2048, 4, 2, 2), (2049, 6, 2, 1), (1, 16, 5, 4), (20000, 64, 8, 2)])
+@pytest.mark.parametrize("n,k,D,calls", [(5000, 8, 3, 3), (2048, 4, 2, 2), (2049, 6, 2, 1), (1, 16, 5, 4), (20000, 64, 8, 2),
+                                          (4096, 5, 2, 2), (4097, 12, 3, 2), (50000, 3, 2, 2), (1200000, 10, 4, 1)])
 def test_count_update_heavy_collisions_vs_oracle(n, k, D, calls):
-    """Many duplicates inside a chunk, across chunks and across calls; table grows from 1024 slots."""
+    """Many duplicates inside a batch, across partition tiles / buckets / launches (n > 2^20) and across calls; skewed
+    buckets (8 distinct codes over 50 000 elements) run as sequential batches of one CTA; table grows from 1024 slots."""
     rs = np.random.RandomState(n + k)
     buf = _buf(k, D, n)
     table = {}
