@@ -219,7 +219,7 @@ def es_step_bench(torch, ppx, dev, world, rank, steps=20, warmup=5):
         w = es.perturb_all(es.shard_population(pop))        # [P/W, D] f32: what the evaluators consume
         r_all = es.gather_fitness(fit_local)
         _, nov = es.novelty_batch(archive, queries)
-        es._update_weights(r_all, pop, novelty=float(nov[0].item()))
+        es._update_weights(r_all, pop, novelty=nov[0:1])      # novelty stays on the device
         return w
 
     for _ in range(warmup):

@@ -148,7 +148,7 @@ def bench_es(rows, iters):
     ms, mn = timed(fnp, iters)
     report(rows, "es_perturb", f"P={P} D={D} f32 out", P * D * 8, 0, ms, mn)
     ms, mn = timed(lambda: es._update_weights(r, off, 0.5), iters)
-    report(rows, "es_update", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=4, note="stats + coef + gemv + apply")
+    report(rows, "es_update", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=3, note="stats+coef, gemv, apply")
     es.fitness_shaping = "centered_rank"
     ms, mn = timed(lambda: es._update_weights(r, off, 0.5), iters)
     report(rows, "es_update(rank)", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=5)

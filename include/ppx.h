@@ -318,7 +318,8 @@ int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offse
  * not in the reference).  All scalars state lives on device: lr_inout[1]; status_out[0]=1 if skipped. */
 int64_t ppx_es_update_workspace(int P, int D);
 int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int D,
-                  double sigma, double novelty_param, double novelty, int use_novelty, int rank_mode,
+                  double sigma, double novelty_param, double novelty, const double* novelty_dev /* overrides `novelty` when
+                  non-NULL: the k-NN result stays on the device, no host round trip */, int use_novelty, int rank_mode,
                   double decay, double* lr_inout, int* status_out, void* workspace, void* stream);
 /* centred ranks: rank_out[p] = #{q: r_q < r_p or (r_q == r_p and q < p)}, centred_out = rank/(P-1) - 0.5 */
 int ppx_rank_center(const double* r, int P, int64_t* rank_out, double* centred_out, void* stream);

@@ -131,15 +131,41 @@ rank_kernel(const double* __restrict__ r, int P, int64_t* __restrict__ rank_out,
 // coef[p] = f * shaped fitness (0 everywhere when the update is skipped)
 __global__ void __launch_bounds__(256)
 es_coef_kernel(const double* __restrict__ r, const double* __restrict__ centred, int P, const double* __restrict__ stats,
-               const double* __restrict__ lr, double sigma, double nw, double novelty, int use_novelty, int rank_mode,
-               double* __restrict__ coef) {
+               const double* __restrict__ lr, double sigma, double nw, double novelty, const double* __restrict__ novelty_dev,
+               int use_novelty, int rank_mode, double* __restrict__ coef) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   if (stats[2] != 0.0) { coef[p] = 0.0; return; }
+  if (novelty_dev) novelty = *novelty_dev;
   const double f = *lr / ((double)P * sigma);                          // update_factor, :230
   double z = rank_mode ? centred[p] : (r[p] - stats[0]) / stats[1];   // :227
   if (use_novelty) z = ((1.0 - nw) * z + nw * novelty) / 2.0;          // :235
   coef[p] = f * z;
+}
+
+// z-score path in ONE launch: mean / std (ddof 0) / skip flag, then the coefficients of all P members
+__global__ void __launch_bounds__(1024)
+es_stats_coef_kernel(const double* __restrict__ r, int P, double* stats, int* status, const double* __restrict__ lr, double sigma,
+                     double nw, double novelty, const double* __restrict__ novelty_dev, int use_novelty, double* __restrict__ coef) {
+  __shared__ double s_red[32];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a += r[i];
+  const double mean = block_sum(a, s_red) / (double)P;
+  a = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { const double d = r[i] - mean; a += d * d; }
+  const double sd = sqrt(block_sum(a, s_red) / (double)P);
+  const bool skip = (sd == 0.0);
+  if (threadIdx.x == 0) {
+    stats[0] = mean; stats[1] = sd; stats[2] = skip ? 1.0 : 0.0;
+    if (status) *status = skip ? 1 : 0;
+  }
+  if (novelty_dev) novelty = *novelty_dev;
+  const double f = *lr / ((double)P * sigma);
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    double z = (r[p] - mean) / sd;
+    if (use_novelty) z = ((1.0 - nw) * z + nw * novelty) / 2.0;
+    coef[p] = skip ? 0.0 : f * z;
+  }
 }
 
 template <bool VEC>
@@ -311,8 +337,8 @@ extern "C" int64_t ppx_es_update_workspace(int P, int D) {
 }
 
 extern "C" int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int D,
-                             double sigma, double novelty_param, double novelty, int use_novelty, int rank_mode, double decay,
-                             double* lr_inout, int* status_out, void* workspace, void* stream) {
+                             double sigma, double novelty_param, double novelty, const double* novelty_dev, int use_novelty,
+                             int rank_mode, double decay, double* lr_inout, int* status_out, void* workspace, void* stream) {
   PPX_REQUIRE(theta && noise && rewards && lr_inout && workspace, "es_update: null pointer");
   PPX_REQUIRE(P >= 2 && D >= 1 && sigma != 0.0, "es_update: P=%d D=%d sigma=%g", P, D, sigma);
   cudaStream_t st = (cudaStream_t)stream;
@@ -320,17 +346,22 @@ extern "C" int ppx_es_update(double* theta, const float* noise, const int64_t* o
   double* coef = stats + 8;
   double* centred = coef + P;
   double* partial = centred + P;
-  es_stats_kernel<<<1, 1024, 0, st>>>(rewards, P, rank_mode, stats, status_out);
-  int rc = after_launch("es_update(stats)");
-  if (rc) return rc;
+  int rc;
   if (rank_mode) {
+    es_stats_kernel<<<1, 1024, 0, st>>>(rewards, P, rank_mode, stats, status_out);
+    rc = after_launch("es_update(stats)");
+    if (rc) return rc;
     rank_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(rewards, P, nullptr, centred);
     rc = after_launch("es_update(rank)");
     if (rc) return rc;
+    es_coef_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(rewards, centred, P, stats, lr_inout, sigma, novelty_param, novelty,
+                                                               novelty_dev, use_novelty, rank_mode, coef);
+    rc = after_launch("es_update(coef)");
+  } else {
+    es_stats_coef_kernel<<<1, 1024, 0, st>>>(rewards, P, stats, status_out, lr_inout, sigma, novelty_param, novelty, novelty_dev,
+                                             use_novelty, coef);
+    rc = after_launch("es_update(stats+coef)");
   }
-  es_coef_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(rewards, centred, P, stats, lr_inout, sigma, novelty_param, novelty,
-                                                             use_novelty, rank_mode, coef);
-  rc = after_launch("es_update(coef)");
   if (rc) return rc;
   const int splits = gemv_splits(P, D);
   const int p_chunk = (int)ceil_div(P, splits);

@@ -146,7 +146,9 @@ class EvolutionStrategy(object):
 
     # ---- update ----
     def _update_weights(self, rewards, population, novelty=None):
-        """:217-239.  Asynchronous; `self.update_skipped` reads back the std==0 flag."""
+        """:217-239.  Asynchronous; `self.update_skipped` reads back the std==0 flag.  `novelty` may be a python float
+        (as in the reference) or a 1-element f64 CUDA tensor (e.g. `novelty_batch(...)[1][m:m+1]`), which keeps the
+        k-NN result on the device -- no host round trip in the step."""
         noise, off = self._as_eps(population)
         P = off.numel() if off is not None else noise.shape[0]
         r = torch.as_tensor(np.asarray(rewards, dtype=np.float64)).to(self.device) if not isinstance(rewards, torch.Tensor) \
@@ -154,9 +156,13 @@ class EvolutionStrategy(object):
         need = L.call("ppx_es_update_workspace", P, self.D)
         if self._ws is None or self._ws.numel() * 8 < need:
             self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=self.device)
+        nov_dev = None
+        if isinstance(novelty, torch.Tensor):
+            nov_dev = novelty.to(self.device, torch.float64).reshape(-1)[:1].contiguous()
         L.call("ppx_es_update", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
                r.data_ptr(), P, self.D, float(self.SIGMA), float(self.novelty_param),
-               float(novelty) if novelty is not None else 0.0, int(novelty is not None),
+               float(novelty) if (novelty is not None and nov_dev is None) else 0.0,
+               nov_dev.data_ptr() if nov_dev is not None else None, int(novelty is not None),
                int(self.fitness_shaping == "centered_rank"), float(self.decay), self._lr.data_ptr(),
                self._status.data_ptr(), self._ws.data_ptr(), L.stream())
 
