@@ -23,6 +23,7 @@ from ppo_exploration_b200 import _lib as L  # noqa: E402
 from ppo_exploration_b200 import models as PM  # noqa: E402
 
 DEV = "cuda"
+LARGE_ONLY = os.environ.get("PPX_KERNELS_LARGE_ONLY") == "1"        # profiling runs: only the bandwidth-sized shapes
 PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 HBM = PEAKS.get("hbm_gbs", 6650.0)
 TF = PEAKS.get("bf16_tflops", 1590.0)
@@ -60,7 +61,7 @@ def report(rows, name, shape, bytes_, flops, ms, ms_min, launches=1, note=""):
 
 
 def bench_gae(rows, iters):
-    for T, N, dual in ((256, 2048, False), (256, 131072, False), (128, 128, True), (128, 131072, True)):
+    for T, N, dual in ((256, 2048, False), (256, 131072, False), (128, 128, True), (128, 131072, True))[(1 if LARGE_ONLY else 0)::(2 if LARGE_ONLY else 1)]:
         o, a = ppx.Box((4,)), ppx.Box((1,))
         cls = ppx.IntrinsicStorage if dual else ppx.RolloutStorage
         buf = cls(T, N, o, a)
@@ -76,7 +77,7 @@ def bench_gae(rows, iters):
 
 
 def bench_simhash(rows, iters):
-    for n, D, k in ((2048, 8, 64), (524288, 8, 64), (8 << 20, 8, 64)):
+    for n, D, k in ((2048, 8, 64), (524288, 8, 64), (8 << 20, 8, 64))[(1 if LARGE_ONLY else 0):(2 if LARGE_ONLY else 3)]:
         np.random.seed(0)
         buf = ppx.RolloutStorage(1, 1, ppx.Box((D,)), ppx.Box((1,)), sim_hash=True, hash_bits=k, table_capacity=1 << 25)
         obs = torch.randn(n, D, device=DEV)
@@ -92,7 +93,7 @@ def bench_simhash(rows, iters):
 
 
 def bench_gather(rows, iters):
-    for T, N, D, A, B in ((256, 2048, 8, 2, 131072), (256, 2048, 8, 2, 524288), (128, 128, 28224, 1, 4096)):
+    for T, N, D, A, B in ((256, 2048, 8, 2, 131072), (256, 2048, 8, 2, 524288), (128, 128, 28224, 1, 4096))[(1 if LARGE_ONLY else 0):]:
         buf = ppx.RolloutStorage(T, N, ppx.Box((D,)), ppx.Box((A,)))
         buf.observations.normal_()
         idx = torch.randperm(T * N, device=DEV)[:B].contiguous()
@@ -104,7 +105,7 @@ def bench_gather(rows, iters):
 
 
 def bench_loss(rows, iters):
-    for B, A, disc in ((131072, 2, 0), (4 << 20, 2, 0), (131072, 18, 1), (4 << 20, 1, 0)):
+    for B, A, disc in ((131072, 2, 0), (4 << 20, 2, 0), (131072, 18, 1), (4 << 20, 1, 0))[(1 if LARGE_ONLY else 0):(2 if LARGE_ONLY else 4)]:
         f = lambda *s: torch.randn(*s, device=DEV)
         actor, lstd = f(B, A), torch.zeros(A, device=DEV)
         actions = (torch.randint(0, A, (B,), device=DEV).double() if disc else f(B, A).double())
@@ -127,7 +128,7 @@ def bench_loss(rows, iters):
 
 
 def bench_adam(rows, iters):
-    for n in (9732, 16 << 20):
+    for n in (9732, 16 << 20)[(1 if LARGE_ONLY else 0):]:
         bank = PM.ParamBank([("w", (n,))], torch.device(DEV))
         bank.flat.normal_(); bank.grad.normal_()
         ms, mn = timed(lambda: bank.adam_step(3e-4, 5.0), iters)

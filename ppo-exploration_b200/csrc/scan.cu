@@ -163,7 +163,7 @@ gae_seq_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
   float nv = last_value[n];
   double nnt = 1.0 - (double)last_done[n];
   float niv = DUAL ? last_int_value[n] : 0.f;
-#pragma unroll 8
+#pragma unroll 16
   for (int t = T - 1; t >= 0; --t) {
     const size_t g = (size_t)t * N + n;
     const float r = ld_stream(rewards + g), v = ld_stream(values + g);
