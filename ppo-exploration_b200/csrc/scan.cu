@@ -163,26 +163,39 @@ gae_seq_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
   float nv = last_value[n];
   double nnt = 1.0 - (double)last_done[n];
   float niv = DUAL ? last_int_value[n] : 0.f;
-#pragma unroll 16
-  for (int t = T - 1; t >= 0; --t) {
-    const size_t g = (size_t)t * N + n;
-    const float r = ld_stream(rewards + g), v = ld_stream(values + g);
-    const uint8_t m = masks[g];
-    const float gv = __fmul_rn(g32, nv);
-    const double delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn((double)gv, nnt)), (double)v);
-    carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nnt), carry));
-    const float a = (float)carry;
-    adv[g] = a;
-    ret[g] = __fadd_rn(a, v);
-    nv = v;
-    nnt = 1.0 - (double)m;
-    if (DUAL) {
-      const float ir = ld_stream(int_rewards + g), iv = ld_stream(int_values + g);
-      const float idelta = __fsub_rn(__fadd_rn(ir, __fmul_rn(gi32, niv)), iv);
-      icarry = __fadd_rn(idelta, __fmul_rn(gil32, icarry));
-      iadv[g] = icarry;
-      iret[g] = __fadd_rn(icarry, iv);
-      niv = iv;
+  constexpr int U = 8;                                        // rows fetched ahead of the dependent chain
+  for (int t1 = T; t1 > 0; t1 -= U) {
+    float r[U], v[U], ir[U], iv[U];
+    uint8_t m[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                             // independent loads: U x (3 | 5) in flight per thread
+      const int t = t1 - 1 - u;
+      if (t >= 0) {
+        const size_t g = (size_t)t * N + n;
+        r[u] = __ldcs(rewards + g); v[u] = __ldcs(values + g); m[u] = __ldcs(masks + g);
+        if (DUAL) { ir[u] = __ldcs(int_rewards + g); iv[u] = __ldcs(int_values + g); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t1 - 1 - u;
+      if (t < 0) break;
+      const size_t g = (size_t)t * N + n;
+      const float gv = __fmul_rn(g32, nv);
+      const double delta = __dsub_rn(__dadd_rn((double)r[u], __dmul_rn((double)gv, nnt)), (double)v[u]);
+      carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nnt), carry));
+      const float a = (float)carry;
+      __stcs(adv + g, a);
+      __stcs(ret + g, __fadd_rn(a, v[u]));
+      nv = v[u];
+      nnt = 1.0 - (double)m[u];
+      if (DUAL) {
+        const float idelta = __fsub_rn(__fadd_rn(ir[u], __fmul_rn(gi32, niv)), iv[u]);
+        icarry = __fadd_rn(idelta, __fmul_rn(gil32, icarry));
+        __stcs(iadv + g, icarry);
+        __stcs(iret + g, __fadd_rn(icarry, iv[u]));
+        niv = iv[u];
+      }
     }
   }
 }
