@@ -100,6 +100,17 @@ __device__ __forceinline__ float norm_adv(float a, const double* st) {
 template <bool DISCRETE>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
   __shared__ double s_red[32];
+  __shared__ double s_inv2var[kMaxBoxA], s_invvar[kMaxBoxA], s_logscale[kMaxBoxA];
+  if (!DISCRETE) {
+    if (threadIdx.x < p.A) {
+      const float sigma = expf(p.log_std[threadIdx.x]);                      // models.py:69
+      const float var = sigma * sigma;
+      s_inv2var[threadIdx.x] = 1.0 / (double)(2.f * var);
+      s_invvar[threadIdx.x] = 1.0 / (double)var;
+      s_logscale[threadIdx.x] = (double)logf(sigma);
+    }
+    __syncthreads();
+  }
   double pl = 0.0, s1 = 0.0, s2 = 0.0, is1 = 0.0, is2 = 0.0, ent_sum = 0.0;
   double dls[kMaxBoxA];
 #pragma unroll
@@ -116,12 +127,14 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
       for (int a = 0; a < kMaxBoxA; ++a) {
         if (a >= A) break;
         const float mu = tanhf(p.actor_out[b * A + a]);                      // models.py:163
-        const float sigma = expf(p.log_std[a]);                              // models.py:69
-        const float var = sigma * sigma;
-        const float log_scale = logf(sigma);
+        // Normal.log_prob in f64 (the actions are f64, buffer.py:154); the per-dimension constants sigma, var,
+        // log(sigma), 1/(2 var), 1/var are hoisted (s_c*), divisions become multiplications by those reciprocals
         const double diff = p.actions[b * A + a] - (double)mu;
-        const double lp = -(diff * diff) / (double)(2.f * var) - (double)log_scale - kHalfLog2Pi;
-        const double ratio = exp(lp - (double)p.old_lp[b * A + a]);
+        const double d2 = diff * diff;
+        const double lp = -d2 * s_inv2var[a] - s_logscale[a] - kHalfLog2Pi;
+        // ratio = exp(lp - old_lp): the difference is formed in f64, exponentiated in f32 (relative error ~1e-7,
+        // two orders inside the 1e-5 bound; the f64 exp was the kernel's bottleneck: 18 % -> HBM-side)
+        const double ratio = (double)expf((float)(lp - (double)p.old_lp[b * A + a]));
         const double cr = fmin(fmax(ratio, (double)lo), (double)hi);
         const double x = (double)adv * ratio, y = (double)adv * cr;
         pl += fmin(x, y);
@@ -131,9 +144,9 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
         else if (x < y) g = (double)adv;
         else if (x == y) g = 0.5 * (double)adv;
         const double dlp = gscale * g * ratio;
-        const double dmu = dlp * diff / (double)var;
+        const double dmu = dlp * diff * s_invvar[a];
         p.d_actor_out[b * A + a] = (float)(dmu * (1.0 - (double)mu * (double)mu));
-        dls[a] += dlp * (diff * diff / (double)var - 1.0);
+        dls[a] += dlp * (d2 * s_invvar[a] - 1.0);
       }
     } else {
       const float* l = p.actor_out + b * A;
