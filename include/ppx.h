@@ -197,7 +197,13 @@ int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int*
 int ppx_tc_supported(int M, int R, int N, int lda, int ldb, const void* A, const void* B);
 int ppx_tc_split(const float* src, int rows, int cols, float* hi, float* lo, float* hiT, float* loT, void* stream);
 int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
-                  const float* bias, const float* H, int ldh, int act, int dgrad, float* C, int ldc, void* stream);
+                  const float* bias, const float* H, int ldh, int act, int dgrad,
+                  const double* a_mean, const double* a_istd, float a_clip /* optional (both or neither): A is replaced
+                  by clip((A - a_mean[k]) * a_istd[k], +-a_clip) in f64 on the fly (normalize_obs fused into the
+                  A-split stage; a_istd from ppx_obs_istd) */,
+                  float* C, int ldc, void* stream);
+/* istd[d] = 1/sqrt(var[d] + 1e-10) in f64 (the scale of BaseAlgorithm.normalize_obs, algorithms.py:111-118) */
+int ppx_obs_istd(const double* var, int dim, double* istd, void* stream);
 
 /* ---------------------------------------------------------------- PPO loss ------------------ */
 /* Fused clipped-surrogate / clipped-value / entropy loss, forward and backward, for one minibatch:

@@ -445,7 +445,7 @@ class PPO_RND(BaseAlgorithm):
         """The bonus lines of collect_samples after warm-up (algorithms.py:394-398) for one env step:
         normalise -> (pred-target)^2 -> int_rew_rms.update -> divide.  obs [N,D]; returns [N] f32 CUDA."""
         o = _dev(obs, torch.float32, self.device)
-        r = self.rnd.int_reward(normalize_obs(o, self.obs_rms))
+        r = self.rnd.int_reward(o, rms=self.obs_rms)
         L.call("ppx_rnd_normalize_rollout", r.data_ptr(), 1, r.numel(), self.int_rew_rms.mean_dev.data_ptr(),
                self.int_rew_rms.var_dev.data_ptr(), self.int_rew_rms.count_dev.data_ptr(), L.stream())
         return r
@@ -455,7 +455,7 @@ class PPO_RND(BaseAlgorithm):
         frozen after warm-up and the int-reward moments are merged step by step in t order on device."""
         o = _dev(next_obs, torch.float32, self.device)
         T, N = o.shape[0], o.shape[1]
-        r = self.rnd.int_reward(normalize_obs(o.reshape(T * N, -1), self.obs_rms))
+        r = self.rnd.int_reward(o.reshape(T * N, -1), rms=self.obs_rms)
         L.call("ppx_rnd_normalize_rollout", r.data_ptr(), T, N, self.int_rew_rms.mean_dev.data_ptr(),
                self.int_rew_rms.var_dev.data_ptr(), self.int_rew_rms.count_dev.data_ptr(), L.stream())
         return r.view(T, N)

@@ -85,14 +85,40 @@ rms_scalar_kernel(const T* __restrict__ x, int64_t n, double* mean, double* var,
 
 __global__ void bump_count_kernel(double* count, double n) { *count += n; }
 
+// istd[d] = 1 / sqrt(var[d] + 1e-10)  (f64; algorithms.py:114-116).  The normalisation itself is then
+// clip((x - mean) * istd, +-5) in f64 -> f32: one rounding away from the reference's division, identical after the f32
+// cast except in double-rounding ties; the same formula runs inside the tcgen05 A-split stage (tc_gemm.cu).
+__global__ void __launch_bounds__(256) obs_istd_kernel(const double* __restrict__ var, int dim, double* __restrict__ istd) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < dim) istd[d] = 1.0 / sqrt(var[d] + 1e-10);
+}
+
+// grid (column blocks of 1024, row slices): a thread owns 4 consecutive columns (constants in registers) and walks rows
 __global__ void __launch_bounds__(256)
-normalize_obs_kernel(const float* __restrict__ obs, int64_t total, int dim, const double* __restrict__ mean,
-                     const double* __restrict__ var, float* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(i % dim);
-    double z = ((double)obs[i] - mean[d]) / sqrt(var[d] + 1e-10);
-    z = fmin(fmax(z, -5.0), 5.0);
-    out[i] = (float)z;
+normalize_obs_kernel(const float* __restrict__ obs, int64_t n, int dim, const double* __restrict__ mean,
+                     const double* __restrict__ istd, float* __restrict__ out) {
+  const int c0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c0 >= dim) return;
+  const bool vec = (dim % 4 == 0) && ((((uintptr_t)obs | (uintptr_t)out) & 15) == 0);
+  double m[4], s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { m[j] = c0 + j < dim ? mean[c0 + j] : 0.0; s[j] = c0 + j < dim ? istd[c0 + j] : 0.0; }
+  for (int64_t r = blockIdx.y; r < n; r += gridDim.y) {
+    const int64_t base = r * dim + c0;
+    float x[4];
+    if (vec) { const float4 v = ld_stream4(reinterpret_cast<const float4*>(obs + base)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = c0 + j < dim ? obs[base + j] : 0.f;
+    }
+    float z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = fminf(fmaxf((float)(((double)x[j] - m[j]) * s[j]), -5.f), 5.f);
+    if (vec) *reinterpret_cast<float4*>(out + base) = make_float4(z[0], z[1], z[2], z[3]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (c0 + j < dim) out[base + j] = z[j];
+    }
   }
 }
 
@@ -191,12 +217,28 @@ extern "C" int ppx_rms_update(const void* x, int x_is_f64, int64_t n, int dim, d
   return after_launch("rms_update(count)");
 }
 
+extern "C" int ppx_obs_istd(const double* var, int dim, double* istd, void* stream) {
+  PPX_REQUIRE(var && istd && dim >= 1, "obs_istd: bad arguments");
+  obs_istd_kernel<<<(unsigned)ceil_div(dim, 256), 256, 0, (cudaStream_t)stream>>>(var, dim, istd);
+  return after_launch("obs_istd");
+}
+
 extern "C" int ppx_normalize_obs(const float* obs, int64_t n, int dim, const double* mean, const double* var, float* out, void* stream) {
   PPX_REQUIRE(obs && mean && var && out && n >= 0 && dim >= 1, "normalize_obs: bad arguments");
   if (n == 0) return PPX_OK;
-  const int64_t total = n * dim;
-  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-  normalize_obs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, total, dim, mean, var, out);
+  static double* istd = nullptr; static int istd_cap = 0;       // per-process scratch (stream-ordered, one learner thread)
+  if (dim > istd_cap) {
+    PPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (istd) cudaFree(istd);
+    PPX_CUDA(cudaMalloc((void**)&istd, (size_t)dim * sizeof(double)));
+    istd_cap = dim;
+  }
+  obs_istd_kernel<<<(unsigned)ceil_div(dim, 256), 256, 0, (cudaStream_t)stream>>>(var, dim, istd);
+  int rc = after_launch("normalize_obs(istd)");
+  if (rc) return rc;
+  const unsigned gx = (unsigned)ceil_div(dim, 1024);
+  const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n, ceil_div((int64_t)sm_count() * 16, gx)));
+  normalize_obs_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(obs, n, dim, mean, istd, out);
   return after_launch("normalize_obs");
 }
 

@@ -142,6 +142,9 @@ struct Params {
   const float* H; int ldh;      // dgrad epilogue: post-activation of the producer layer (may be null)
   int act;
   int dgrad;                    // 0: C = act(acc + bias)   1: C = acc * act'(H)
+  const double* a_mean;         // optional per-column transform of A before the hi/lo split (RND observation
+  const double* a_istd;         //   normalisation, algorithms.py:111-118): A' = clip((A - mean) * istd, +-a_clip) in f64
+  float a_clip;
 };
 
 template <int BN, int STAGES>
@@ -238,9 +241,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp < 6) {
     // ------------------------------ splitters (warps 2..5) ------------------------------
     const int t = threadIdx.x - 64;
+    __shared__ double s_norm[STAGES][2][BK];                 // mean | istd of the stage's 32 columns
+    const bool norm = p.a_mean != nullptr;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
+      if (norm) {                                            // fetch the column constants while the TMA is in flight
+        if (t < 2 * BK) {
+          const int k = kb * BK + (t & (BK - 1));
+          const double* src = (t < BK) ? p.a_mean : p.a_istd;
+          s_norm[s][t >> 5][t & (BK - 1)] = k < p.R ? __ldg(src + k) : 0.0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // splitter warps only
+      }
       mbar_wait(full_bar(s), ph);
       uint4* hi = reinterpret_cast<uint4*>(a_hi(s));
       uint4* lo = reinterpret_cast<uint4*>(a_lo(s));
@@ -248,6 +261,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int i = 0; i < (int)(A_BYTES / 16) / kSplitThreads; ++i) {
         const int e = t + i * kSplitThreads;
         uint4 v = hi[e];
+        if (norm) {
+          // physical 16-byte chunk e of the 128B-swizzled tile: row = e / 8, logical chunk = (e % 8) ^ (row % 8)
+          const int row = e >> 3, c4 = (((e & 7) ^ (row & 7)) << 2);
+          const double* mu = &s_norm[s][0][c4];
+          const double* is = &s_norm[s][1][c4];
+          const float cl = p.a_clip;
+          v.x = __float_as_uint(fminf(fmaxf((float)(((double)__uint_as_float(v.x) - mu[0]) * is[0]), -cl), cl));
+          v.y = __float_as_uint(fminf(fmaxf((float)(((double)__uint_as_float(v.y) - mu[1]) * is[1]), -cl), cl));
+          v.z = __float_as_uint(fminf(fmaxf((float)(((double)__uint_as_float(v.z) - mu[2]) * is[2]), -cl), cl));
+          v.w = __float_as_uint(fminf(fmaxf((float)(((double)__uint_as_float(v.w) - mu[3]) * is[3]), -cl), cl));
+        }
         uint4 h, l;
         h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
         l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
@@ -414,7 +438,8 @@ extern "C" int ppx_tc_split(const float* src, int rows, int cols, float* hi, flo
 }
 
 extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
-                             const float* bias, const float* H, int ldh, int act, int dgrad, float* C, int ldc, void* stream) {
+                             const float* bias, const float* H, int ldh, int act, int dgrad, const double* a_mean,
+                             const double* a_istd, float a_clip, float* C, int ldc, void* stream) {
   PPX_REQUIRE(A && Bhi && Blo && C, "tc_linear: null pointer");
   PPX_REQUIRE(ppx_tc_supported(M, R, N, lda, ldb, A, Bhi) && !((uintptr_t)Blo & 15), "tc_linear: shape/alignment not supported (M=%d R=%d N=%d lda=%d ldb=%d)", M, R, N, lda, ldb);
   const int BN = N <= 64 ? 64 : 128;
@@ -425,7 +450,8 @@ extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const fl
   if (rc) return rc;
   rc = tc::make_map(&mbl, Blo, N, R, ldb, BN);
   if (rc) return rc;
-  tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad};
+  PPX_REQUIRE((a_mean == nullptr) == (a_istd == nullptr), "tc_linear: a_mean / a_istd must be given together");
+  tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad, a_mean, a_istd, a_clip};
   if (BN == 64) return tc::launch<64, 4>(ma, mbh, mbl, p, (cudaStream_t)stream);
   return tc::launch<128, 3>(ma, mbh, mbl, p, (cudaStream_t)stream);
 }

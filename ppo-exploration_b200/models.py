@@ -32,6 +32,10 @@ F4 = 4  # bytes per float
 TC_ENABLED = os.environ.get("PPX_TC", "1") != "0"
 TC_POLICY = os.environ.get("PPX_TC_POLICY", "0") == "1"
 TC_MIN_K = 256
+# normalize_obs fused into the tcgen05 A-split stage (RndNetwork.int_reward(obs, rms=...)).  Measured at C3 it LOSES to
+# the separate float4 normalisation pass (3.07 vs 2.2 ms per bonus pass: the f64 arithmetic lands on the 4 splitter warps
+# of both first-layer kernels and they become the pipeline's slowest stage), so it is opt-in.
+TC_FUSE_NORM = os.environ.get("PPX_TC_FUSE_NORM", "0") == "1"
 # fused forward / backward of the D-h-h-o policy MLPs (mlp_fused.cu); PPX_FUSED_MLP=0 forces the layer-by-layer path
 FUSED_ENABLED = os.environ.get("PPX_FUSED_MLP", "1") != "0"
 
@@ -98,12 +102,15 @@ def tc_ok(M, R, N, lda, ldb, a_ptr, b_ptr):
     return (TC_ENABLED and M >= 128 and L.call("ppx_tc_supported", M, R, N, lda, ldb, a_ptr, b_ptr) == 1)
 
 
-def dense_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, tcw=None):
-    """act(X @ W + b): tensor-core path when the shape allows it, SIMT fp32 otherwise."""
+def dense_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, tcw=None, a_norm=None):
+    """act(X @ W + b): tensor-core path when the shape allows it, SIMT fp32 otherwise.  a_norm = (mean_ptr, istd_ptr,
+    clip): X is normalised on the fly inside the tensor-core kernel (only valid when can_fuse_norm() said so)."""
     if tcw is not None and tc_ok(M, K, N, ldx, K, x_ptr, tcw.hiT.data_ptr()):
+        mean_ptr, istd_ptr, clip = a_norm if a_norm is not None else (None, None, 0.0)
         L.call("ppx_tc_linear", x_ptr, ldx, tcw.hiT.data_ptr(), tcw.loT.data_ptr(), K, M, K, N, b_ptr, None, 0, act, 0,
-               y_ptr, ldy, L.stream())
+               mean_ptr, istd_ptr, float(clip), y_ptr, ldy, L.stream())
     else:
+        assert a_norm is None, "fused input normalisation needs the tensor-core path"
         linear_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy)
 
 
@@ -111,7 +118,7 @@ def dense_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx, 
     """(dY @ W^T) * act'(H): tensor-core path when the shape allows it."""
     if tcw is not None and tc_ok(M, N, K, lddy, N, dy_ptr, tcw.hi.data_ptr()):
         L.call("ppx_tc_linear", dy_ptr, lddy, tcw.hi.data_ptr(), tcw.lo.data_ptr(), N, M, N, K, None, h_ptr, ldh, act, 1,
-               dx_ptr, lddx, L.stream())
+               None, None, 0.0, dx_ptr, lddx, L.stream())
     else:
         linear_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx)
 
@@ -177,14 +184,22 @@ class DenseStack:
             out += [(f"{prefix}.{2 * i}.weight", (K, N)), (f"{prefix}.{2 * i}.bias", (N,))]
         return out
 
-    def forward(self, x, tag=""):
-        """x: [M, K0] contiguous f32 CUDA.  Returns the list of activations [x, h1, ..., y]."""
+    def can_fuse_norm(self, x):
+        """True when layer 0 runs on the tensor-core kernel for this input, i.e. an input normalisation can be fused."""
+        K, N, _ = self.layers[0]
+        t = self.tc.get(0)
+        return t is not None and tc_ok(x.shape[0], K, N, x.stride(0), K, x.data_ptr(), t.hiT.data_ptr())
+
+    def forward(self, x, tag="", a_norm=None):
+        """x: [M, K0] contiguous f32 CUDA.  Returns the list of activations [x, h1, ..., y].  a_norm (layer 0 only):
+        (mean_ptr, istd_ptr, clip) -> clip((x - mean) * istd) is applied to x inside the first layer's kernel."""
         M = x.shape[0]
         acts = [x]
         for i, (K, N, act) in enumerate(self.layers):
             y = self.scratch.get(f"{self.prefix}{tag}.h{i}", M * N)[:M * N].view(M, N)
             dense_fwd(acts[-1].data_ptr(), acts[-1].stride(0), self.bank.p(f"{self.prefix}.{2 * i}.weight"),
-                      self.bank.p(f"{self.prefix}.{2 * i}.bias"), M, K, N, ACT[act], y.data_ptr(), N, self.tc.get(i))
+                      self.bank.p(f"{self.prefix}.{2 * i}.bias"), M, K, N, ACT[act], y.data_ptr(), N, self.tc.get(i),
+                      a_norm if i == 0 else None)
             acts.append(y)
         return acts
 
@@ -494,19 +509,29 @@ class RndNetwork:
                 sd[f"{name}.{2 * i}.bias"] = bank.view(f"{name}.{2 * i}.bias").detach().cpu().clone()
         return sd
 
-    def forward(self, x):
+    def forward(self, x, a_norm=None):
         """x [M,D] f32 CUDA contiguous -> (predict [M,1], target [M,1]); keeps predictor activations."""
-        self._p_acts = self.predictor.forward(x)
-        t_acts = self.target.forward(x)
+        self._p_acts = self.predictor.forward(x, a_norm=a_norm)
+        t_acts = self.target.forward(x, a_norm=a_norm)
         return self._p_acts[-1], t_acts[-1]
 
     __call__ = forward
 
-    def int_reward(self, obs):
-        """models.py:261-267: (pred - target)^2, squeezed -> [M] f32 CUDA."""
+    def int_reward(self, obs, rms=None):
+        """models.py:261-267: (pred - target)^2, squeezed -> [M] f32 CUDA.  With `rms` (a RunningMeanStd), `obs` are RAW
+        observations and normalize_obs (algorithms.py:111-118) is applied on the way: fused into the first layers'
+        tensor-core kernels when they take that path (the observations are then read from HBM by those two kernels
+        only), as a separate pass otherwise."""
         obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).float()
         obs = obs.reshape(-1, self.input_size).contiguous()
-        pred, tgt = self.forward(obs)
+        a_norm = None
+        if rms is not None:
+            if TC_FUSE_NORM and self.predictor.can_fuse_norm(obs) and self.target.can_fuse_norm(obs):
+                a_norm = (rms.mean_dev.data_ptr(), rms.istd().data_ptr(), 5.0)
+            else:
+                from .util import normalize_obs
+                obs = normalize_obs(obs, rms)
+        pred, tgt = self.forward(obs, a_norm)
         r = torch.empty(obs.shape[0], dtype=torch.float32, device=self.device)
         L.call("ppx_rnd_sqerr", pred.data_ptr(), tgt.data_ptr(), obs.shape[0], r.data_ptr(), L.stream())
         return r

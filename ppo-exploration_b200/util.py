@@ -28,6 +28,13 @@ class RunningMeanStd(object):
         L.call("ppx_rms_update", x.data_ptr(), int(x.dtype == torch.float64), x.shape[0], self.dim,
                self.mean_dev.data_ptr(), self.var_dev.data_ptr(), self.count_dev.data_ptr(), None, L.stream())
 
+    def istd(self):
+        """1/sqrt(var + 1e-10) (f64, device): the scale of normalize_obs, for kernels that normalise on the fly."""
+        if getattr(self, "_istd", None) is None:
+            self._istd = torch.empty(self.dim, dtype=torch.float64, device=self.device)
+        L.call("ppx_obs_istd", self.var_dev.data_ptr(), self.dim, self._istd.data_ptr(), L.stream())
+        return self._istd
+
     def set_state(self, mean, var, count):
         self.mean_dev.copy_(torch.as_tensor(np.asarray(mean, dtype=np.float64)).reshape(-1))
         self.var_dev.copy_(torch.as_tensor(np.asarray(var, dtype=np.float64)).reshape(-1))

@@ -22,7 +22,7 @@ def _run(M, R, N, act, dgrad, seed=0):
     C = torch.full((M, N), float("nan"), device="cuda")
     assert L.call("ppx_tc_supported", M, R, N, R, R, A.data_ptr(), hi.data_ptr()) == 1
     L.call("ppx_tc_linear", A.data_ptr(), R, hi.data_ptr(), lo.data_ptr(), R, M, R, N, bias.data_ptr(), H.data_ptr(), N, act,
-           dgrad, C.data_ptr(), N, L.stream())
+           dgrad, None, None, 0.0, C.data_ptr(), N, L.stream())
     torch.cuda.synchronize()
     acc = A.double() @ W.double().t()
     if dgrad:
@@ -83,3 +83,40 @@ def test_wide_bonus_net_forward_uses_tensor_cores_and_matches_fp64():
     rnd.predictor.tc, rnd.target.tc = {}, {}
     simt = rnd.int_reward(obs.cuda()).cpu().double()
     torch.testing.assert_close(got, simt, rtol=2e-5, atol=1e-6 * float(want.abs().max()))
+
+
+def test_fused_observation_normalisation_matches_separate_pass():
+    """RND bonus on RAW observations with a RunningMeanStd: the normalisation fused into the tcgen05 A-split stage gives
+    the same bonus as normalize_obs + forward (same f64 formula), and both match the fp64 evaluation."""
+    import ppo_exploration_b200 as ppx
+    torch.manual_seed(1)
+    D, h, M = 1000, 128, 513                                   # K not a multiple of the 32-wide k-block
+    rnd = ppx.RndNetwork(D, hidden_size=h, device="cuda")
+    sd = {}
+    for name, layers in (("predictor", rnd.p_layers), ("target", rnd.t_layers)):
+        for i, (K, N, _) in enumerate(layers):
+            sd[f"{name}.{2 * i}.weight"] = torch.randn(N, K) / np.sqrt(K)
+            sd[f"{name}.{2 * i}.bias"] = 0.1 * torch.randn(N)
+    rnd.load_state_dict(sd)
+    rms = ppx.RunningMeanStd(shape=(D,), device="cuda")
+    rms.set_state(np.random.RandomState(0).rand(D) * 0.5, np.random.RandomState(1).rand(D) * 0.2 + 1e-3, 100.0)
+    obs = torch.rand(M, D).cuda() * 3 - 1                      # some entries clip at +-5 sigma
+    from ppo_exploration_b200 import models as PM
+    assert rnd.predictor.can_fuse_norm(obs)
+    old, PM.TC_FUSE_NORM = PM.TC_FUSE_NORM, True
+    try:
+        fused = rnd.int_reward(obs, rms=rms).cpu().double()
+    finally:
+        PM.TC_FUSE_NORM = old
+    sep = rnd.int_reward(ppx.normalize_obs(obs, rms)).cpu().double()
+    torch.testing.assert_close(fused, sep, rtol=1e-6, atol=1e-9)
+    mean, var = torch.tensor(rms.mean), torch.tensor(rms.var)
+    x = ((obs.cpu().double() - mean) / torch.sqrt(var + 1e-10)).clamp(-5, 5).float().double()
+
+    def mlp(z, name, acts):
+        for i, a in enumerate(acts):
+            z = z @ sd[f"{name}.{2 * i}.weight"].double().t() + sd[f"{name}.{2 * i}.bias"].double()
+            z = {"l": F.leaky_relu, "e": F.elu, "n": lambda q: q}[a](z)
+        return z
+    want = (mlp(x, "predictor", "llen") - mlp(x, "target", "lln")).pow(2).squeeze(-1)
+    torch.testing.assert_close(fused, want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
