@@ -253,14 +253,20 @@ class ParallelMLP:
         self._fa = None
 
     def enable_tc(self):
-        """(Re)build the tensor-core weight shadows; call after the parameters were (re)loaded."""
-        if not (TC_ENABLED and TC_POLICY):
+        """(Re)build the tensor-core weight shadows; call after the parameters were (re)loaded.  The first layer takes
+        the tcgen05 path when it is wide (Atari-shaped flat input, D >= TC_MIN_K); the h x h second layers only with
+        PPX_TC_POLICY=1 (slower than SIMT at these widths)."""
+        if not TC_ENABLED:
             return
         b, G, h, D, dev = self.bank, self.G, self.h, self.D, self.bank.device
         b.tc_weights = [t for t in b.tc_weights if t not in ([self.tc1] if self.tc1 else []) + (self.tc2 or [])]
-        self.tc1 = TcWeight(b.p("W1"), D, G * h, dev)
-        self.tc2 = [TcWeight(b.p("W2", g * h * h), h, h, dev) for g in range(G)]
-        b.tc_weights += [self.tc1] + self.tc2
+        self.tc1 = self.tc2 = None
+        if TC_POLICY or (D >= TC_MIN_K and D % 4 == 0):
+            self.tc1 = TcWeight(b.p("W1"), D, G * h, dev, transposed_only=not TC_POLICY)
+            b.tc_weights.append(self.tc1)
+        if TC_POLICY:
+            self.tc2 = [TcWeight(b.p("W2", g * h * h), h, h, dev) for g in range(G)]
+            b.tc_weights += self.tc2
 
     @staticmethod
     def specs(names, D, h, outs):

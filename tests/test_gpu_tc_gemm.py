@@ -120,3 +120,28 @@ def test_fused_observation_normalisation_matches_separate_pass():
         return z
     want = (mlp(x, "predictor", "llen") - mlp(x, "target", "lln")).pow(2).squeeze(-1)
     torch.testing.assert_close(fused, want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
+
+
+def test_wide_policy_first_layer_on_tensor_cores():
+    """Atari-shaped flat observations (D >= 256): the policy MLPs' shared first layer runs on tcgen05; outputs and
+    gradients still match torch autograd."""
+    import ppo_exploration_b200 as ppx
+    torch.manual_seed(2)
+    D, h, M = 1024, 64, 384
+    env = ppx.SyntheticVecEnv(4, D, ppx.Discrete(6), seed=0)
+    pol = ppx.models.Policy(env, h, intrinsic_model=True, device="cuda")
+    assert pol.mlp.tc1 is not None and not pol.mlp.fused()
+    x = torch.randn(M, D)
+    outs = pol.forward_raw(x.cuda())
+    sd = pol.state_dict()
+    d_outs = [torch.randn(M, o) / M for o in pol.outs]
+    pol.mlp.backward([d.cuda().contiguous() for d in d_outs])
+    got = pol.state_dict(grad=True)
+    for gi, (name, o) in enumerate(zip(pol.names, pol.outs)):
+        seq = torch.nn.Sequential(torch.nn.Linear(D, h), torch.nn.Tanh(), torch.nn.Linear(h, h), torch.nn.Tanh(), torch.nn.Linear(h, o))
+        seq.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")})
+        y = seq(x)
+        torch.testing.assert_close(outs[gi].cpu(), y.detach(), rtol=1e-5, atol=2e-5 * max(1.0, float(y.abs().max())))
+        y.backward(d_outs[gi])
+        for k, prm in seq.named_parameters():
+            torch.testing.assert_close(got[f"{name}.{k}"], prm.grad, rtol=1e-5, atol=2e-5 * max(1.0, float(prm.grad.abs().max())))
