@@ -252,7 +252,48 @@ def bench_bonus(rows, iters):
                note=f"{tag}; encoder(s), encoder(s'), forward model, clamp(mse); {M / ms * 1e3:.0f} transitions/s")
 
 
-ALL = {"bonus": bench_bonus, "mlp3": bench_mlp3, "tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
+def bench_configs(rows, iters):
+    """Whole learner passes at the Atari-shaped configs (BASELINE configs[2], [3]) with synthetic rollouts:
+    C3 = PPO_RND, 128 envs x 128 steps, flattened 84x84x4 frames (D=28224), dual-head GAE (gamma .999 / .99), h=128;
+    C4 = PPO_ICM, 32 envs x 128 steps per GPU, D=3136 features, h=f=512, Discrete(18)."""
+    for name in ("C3", "C4"):
+        np.random.seed(0); torch.manual_seed(0)
+        if name == "C3":
+            T, N, D, space = 128, 128, 28224, ppx.Discrete(18)
+            env = ppx.SyntheticVecEnv(N, D, space, seed=0)
+            m = ppx.PPO_RND(env=env, nstep=T, batch_size=4096, n_epochs=4, gamma=0.999, int_gamma=0.99, hidden_size=128,
+                            int_hidden_size=128, device=DEV)
+        else:
+            T, N, D, space = 128, 32, 3136, ppx.Discrete(18)
+            env = ppx.SyntheticVecEnv(N, D, space, seed=0)
+            m = ppx.PPO_ICM(env=env, nstep=T, batch_size=1024, n_epochs=4, hidden_size=128, int_hidden_size=512, device=DEV)
+        ro = m.rollout
+        g = torch.Generator(device=DEV).manual_seed(0)
+        ro.observations.copy_(torch.rand(T, N, D, device=DEV, generator=g))
+        ro.actions.copy_(torch.randint(0, 18, (T, N, 1), device=DEV, generator=g).double())
+        for nm in ("rewards", "values", "action_log_probs") + (("int_values",) if name == "C3" else ()):
+            getattr(ro, nm).copy_(torch.randn(getattr(ro, nm).shape, device=DEV, generator=g) * (0.1 if nm == "action_log_probs" else 1.0) - (2.9 if nm == "action_log_probs" else 0.0))
+        ro.masks.copy_((torch.rand(T, N, device=DEV, generator=g) < 0.02).to(torch.uint8))
+        ro.pos, ro.full = T, True
+        lv = torch.randn(N, device=DEV)
+        next_obs = torch.rand(T, N, D, device=DEV, generator=g)
+
+        def one_pass():
+            if name == "C3":
+                ro.int_rewards.copy_(m.rnd_bonus_rollout(next_obs))
+                ro.compute_returns_and_advantages(lv, lv, ro.masks[-1])
+            else:
+                ro.compute_returns_and_advantages(lv, ro.masks[-1])
+            m.train()
+        ms, mn = timed(one_pass, max(3, iters // 4), warm=3)
+        report(rows, f"{name}_learner_pass", f"T={T} N={N} D={D}", 0, 0, ms, mn, launches=0,
+               note=f"{T * N / ms * 1e3:.0f} transitions/s ({'RND bonus over the rollout + dual GAE + ' if name == 'C3' else 'GAE + '}"
+                    f"{m.n_epochs} epochs x {-(-T * N // m.batch_size)} minibatches of {m.batch_size})")
+        del m, ro, next_obs
+        torch.cuda.empty_cache()
+
+
+ALL = {"configs": bench_configs, "bonus": bench_bonus, "mlp3": bench_mlp3, "tc": bench_tc, "gae": bench_gae, "simhash": bench_simhash, "gather": bench_gather, "loss": bench_loss, "adam": bench_adam,
        "es": bench_es, "linear": bench_linear}
 
 

@@ -202,6 +202,13 @@ int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, i
                   by clip((A - a_mean[k]) * a_istd[k], +-a_clip) in f64 on the fly (normalize_obs fused into the
                   A-split stage; a_istd from ppx_obs_istd) */,
                   float* C, int ldc, void* stream);
+/* Weight gradient of a wide layer on the tensor cores: dW [K,N] = X^T . dY over M samples, dbias = colsum(dY)
+ * (dbias may be NULL).  X is transposed and dY split/transposed into `workspace` (>= ppx_tc_wgrad_workspace floats),
+ * then the 3xTF32 kernel runs with the samples as the reduction dimension.  M % 4 == 0, M >= 256, K >= 128, N >= 16. */
+int64_t ppx_tc_wgrad_workspace(int M, int K, int N);
+int ppx_tc_wgrad_supported(int M, int K, int N, const void* X, const void* dY);
+int ppx_tc_wgrad(const float* X, int ldx, const float* dY, int lddy, int M, int K, int N, float* dW, float* dbias,
+                 float* workspace, void* stream);
 /* istd[d] = 1/sqrt(var[d] + 1e-10) in f64 (the scale of BaseAlgorithm.normalize_obs, algorithms.py:111-118) */
 int ppx_obs_istd(const double* var, int dim, double* istd, void* stream);
 

@@ -72,6 +72,9 @@ SIGNATURES = {
     "ppx_tc_split": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "ppx_tc_linear": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, C.c_float, c_p, c_i, c_p]),
     "ppx_obs_istd": (c_i, [c_p, c_i, c_p, c_p]),
+    "ppx_tc_wgrad_workspace": (c_l, [c_i, c_i, c_i]),
+    "ppx_tc_wgrad_supported": (c_i, [c_i, c_i, c_i, c_p, c_p]),
+    "ppx_tc_wgrad": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ppx_ppo_loss_workspace": (c_l, [c_l, c_i]),
     "ppx_ppo_loss_fwd_bwd": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 21),
     "ppx_ppo_loss_head_final": (c_i, [C.POINTER(PpoCfg)] + [c_p] * 20),
@@ -97,7 +100,7 @@ SIGNATURES = {
     "ppx_rank_center": (c_i, [c_p, c_i, c_p, c_p, c_p]),
     "ppx_knn_novelty": (c_i, [c_p, c_l, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
 }
-_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n not in ("ppx_version", "ppx_tc_supported", "ppx_mlp3_supported")}
+_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n not in ("ppx_version", "ppx_tc_supported", "ppx_mlp3_supported", "ppx_tc_wgrad_supported")}
 
 _lib = None
 

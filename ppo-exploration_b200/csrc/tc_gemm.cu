@@ -345,34 +345,57 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-// hi/lo split of a matrix, optionally transposed: src [rows, cols] -> hi/lo [rows, cols] and/or hiT/loT [cols, rows]
+// hi/lo split of a matrix, optionally transposed: src [rows, cols] (row pitch ld) -> hi/lo [rows, cols] and/or
+// hiT/loT [cols, rows]; rawT [cols, rows] = plain transpose (the on-the-fly-split A operand of the wgrad GEMM)
 __global__ void __launch_bounds__(256)
-split_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo,
-             float* __restrict__ hiT, float* __restrict__ loT) {
+split_kernel(const float* __restrict__ src, int ld, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo,
+             float* __restrict__ hiT, float* __restrict__ loT, float* __restrict__ rawT) {
   __shared__ float th[32][33], tl[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i;
     float h = 0.f, l = 0.f;
     if (r < rows && c < cols) {
-      const float v = src[(size_t)r * cols + c];
-      h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-      l = v - h;
-      if (hi) { hi[(size_t)r * cols + c] = h; lo[(size_t)r * cols + c] = l; }
+      const float v = src[(size_t)r * ld + c];
+      if (rawT) { h = v; }
+      else {
+        h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        l = v - h;
+        if (hi) { hi[(size_t)r * cols + c] = h; lo[(size_t)r * cols + c] = l; }
+      }
     }
     th[i][threadIdx.x] = h;
     tl[i][threadIdx.x] = l;
   }
   __syncthreads();
-  if (hiT) {
+  if (hiT || rawT) {
     const int rr = r0 + threadIdx.x;                         // transposed: output row = source column
     for (int i = threadIdx.y; i < 32; i += 8) {
       const int cc = blockIdx.x * 32 + i;
       if (rr < rows && cc < cols) {
-        hiT[(size_t)cc * rows + rr] = th[threadIdx.x][i];
-        loT[(size_t)cc * rows + rr] = tl[threadIdx.x][i];
+        if (rawT) rawT[(size_t)cc * rows + rr] = th[threadIdx.x][i];
+        else {
+          hiT[(size_t)cc * rows + rr] = th[threadIdx.x][i];
+          loT[(size_t)cc * rows + rr] = tl[threadIdx.x][i];
+        }
       }
     }
+  }
+}
+
+// out[c] = sum over rows of src[r, c], fixed order: block = 32 columns x 8 row slices, slices combined 0..7
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float sl[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = slice; r < rows; r += 8) s += src[(size_t)r * ld + c];
+  sl[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && c < cols) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += sl[q][threadIdx.x & 31];
+    out[c] = s;
   }
 }
 
@@ -433,7 +456,7 @@ extern "C" int ppx_tc_supported(int M, int R, int N, int lda, int ldb, const voi
 extern "C" int ppx_tc_split(const float* src, int rows, int cols, float* hi, float* lo, float* hiT, float* loT, void* stream) {
   PPX_REQUIRE(src && rows > 0 && cols > 0 && ((hi && lo) || (hiT && loT)), "tc_split: bad arguments");
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
-  tc::split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, rows, cols, hi, lo, hiT, loT);
+  tc::split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, cols, rows, cols, hi, lo, hiT, loT, nullptr);
   return after_launch("tc_split");
 }
 
@@ -454,4 +477,35 @@ extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const fl
   tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad, a_mean, a_istd, a_clip};
   if (BN == 64) return tc::launch<64, 4>(ma, mbh, mbl, p, (cudaStream_t)stream);
   return tc::launch<128, 3>(ma, mbh, mbl, p, (cudaStream_t)stream);
+}
+
+// Weight gradient of a wide layer on the tensor cores:  dW [K,N] = X^T [K,M] . dY [M,N]  (+ dbias = colsum dY).
+// The reduction runs over the M samples, so both operands are needed K-major in M: X is transposed once
+// (Xt [K,M], split hi/lo on the fly as the A operand), dY is split and transposed (hiT/loT [N,M], the B operand), and
+// the same 3xTF32 kernel as the forward produces dW row-major [K,N] -- the in-major weight layout.
+extern "C" int64_t ppx_tc_wgrad_workspace(int M, int K, int N) { return (int64_t)M * K + 2 * (int64_t)M * N; }
+
+extern "C" int ppx_tc_wgrad_supported(int M, int K, int N, const void* X, const void* dY) {
+  return (M >= 256 && M % 4 == 0 && K >= 128 && N >= 16 && X && dY) ? 1 : 0;
+}
+
+extern "C" int ppx_tc_wgrad(const float* X, int ldx, const float* dY, int lddy, int M, int K, int N, float* dW, float* dbias,
+                            float* workspace, void* stream) {
+  PPX_REQUIRE(X && dY && dW && workspace && ldx >= K && lddy >= N, "tc_wgrad: bad arguments");
+  PPX_REQUIRE(ppx_tc_wgrad_supported(M, K, N, X, dY) && (((uintptr_t)workspace | (uintptr_t)dW) & 15) == 0, "tc_wgrad: shape/alignment not supported (M=%d K=%d N=%d)", M, K, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Xt = workspace;
+  float* dYhiT = Xt + (size_t)M * K;
+  float* dYloT = dYhiT + (size_t)M * N;
+  dim3 block(32, 8);
+  tc::split_kernel<<<dim3((unsigned)ceil_div(K, 32), (unsigned)ceil_div(M, 32)), block, 0, st>>>(X, ldx, M, K, nullptr, nullptr, nullptr, nullptr, Xt);
+  tc::split_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32)), block, 0, st>>>(dY, lddy, M, N, nullptr, nullptr, dYhiT, dYloT, nullptr);
+  int rc = after_launch("tc_wgrad(transpose/split)", 2);
+  if (rc) return rc;
+  if (dbias) {
+    tc::colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(dY, lddy, M, N, dbias);
+    rc = after_launch("tc_wgrad(colsum)");
+    if (rc) return rc;
+  }
+  return ppx_tc_linear(Xt, M, dYhiT, dYloT, M, K, M, N, nullptr, nullptr, 0, PPX_ACT_NONE, 0, nullptr, nullptr, 0.f, dW, N, stream);
 }

@@ -147,6 +147,12 @@ def linear_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx,
 
 
 def linear_bwd_weight(scratch, x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, batch=1, sx=0, sdy=0, sdw=0, sdb=0):
+    if (TC_ENABLED and batch == 1 and K >= TC_MIN_K and dw_ptr % 16 == 0
+            and L.call("ppx_tc_wgrad_supported", M, K, N, x_ptr, dy_ptr) == 1):
+        # wide layer: samples as the reduction dimension of the tcgen05 3xTF32 kernel (tc_gemm.cu)
+        ws = scratch.get("tc_wgrad_ws", L.call("ppx_tc_wgrad_workspace", M, K, N))
+        L.call("ppx_tc_wgrad", x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, ws.data_ptr(), L.stream())
+        return
     need = L.call("ppx_linear_bwd_weight_workspace", M, K, N, batch)
     ws = scratch.get("wgrad_ws", need)
     L.call("ppx_linear_bwd_weight", x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, ws.data_ptr(), batch, sx, sdy,

@@ -145,3 +145,24 @@ def test_wide_policy_first_layer_on_tensor_cores():
         y.backward(d_outs[gi])
         for k, prm in seq.named_parameters():
             torch.testing.assert_close(got[f"{name}.{k}"], prm.grad, rtol=1e-5, atol=2e-5 * max(1.0, float(prm.grad.abs().max())))
+
+
+@pytest.mark.parametrize("M,K,N,ldx_pad", [(4096, 3136, 512, 0), (1024, 1000, 100, 8), (256, 28224, 128, 0)])
+def test_tc_wgrad_matches_fp64(M, K, N, ldx_pad):
+    """dW = X^T dY and dbias = colsum(dY) through the tensor-core path (samples = reduction dimension) vs fp64."""
+    from ppo_exploration_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    Xfull = torch.randn(M, K + ldx_pad, device="cuda", generator=g)
+    X = Xfull[:, :K]
+    dY = torch.randn(M, N, device="cuda", generator=g) / M
+    assert L.call("ppx_tc_wgrad_supported", M, K, N, X.data_ptr(), dY.data_ptr()) == 1
+    ws = torch.empty(L.call("ppx_tc_wgrad_workspace", M, K, N), device="cuda")
+    dW = torch.full((K, N), float("nan"), device="cuda")
+    db = torch.full((N,), float("nan"), device="cuda")
+    L.call("ppx_tc_wgrad", X.data_ptr(), K + ldx_pad, dY.data_ptr(), N, M, K, N, dW.data_ptr(), db.data_ptr(), ws.data_ptr(), L.stream())
+    torch.cuda.synchronize()
+    want = X.double().t() @ dY.double()
+    scale = float(want.abs().max())
+    assert float((dW.double() - want).abs().max()) <= 4e-6 * max(scale, 1e-3)
+    wb = dY.double().sum(0)
+    assert float((db.double() - wb).abs().max()) <= 1e-5 * max(float(wb.abs().max()), 1e-3)
