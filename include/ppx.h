@@ -93,6 +93,12 @@ int ppx_count_table_dump(ppx_count_table* t, uint64_t* keys_dev, uint32_t* count
 #define PPX_MAX_GATHER 12
 int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                          int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream);
+/* Same gather, and on the way {mean, unbiased std} (f64, device) of up to two gathered f32 [B] fields -- the
+ * advantage normalisation statistics of algorithms.py:219 / :431-434 -- finished by the field's last CTA in a fixed
+ * order: stat_outs_host[k] receives 2 doubles for array index stat_fields_host[k]. */
+int ppx_gather_minibatch_stats(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
+                               int n_arrays, const int64_t* idx, int64_t B, int T, int N, const int* stat_fields_host,
+                               double* const* stat_outs_host, int n_stats, void* stream);
 /* mean and unbiased std of a contiguous f32 vector, accumulated in f64 (advantages.mean()/.std(),
  * algorithms.py:219).  out[0]=mean, out[1]=std(ddof=1). */
 int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "ppx_count_table_size": (c_i, [c_p, C.POINTER(c_u)]),
     "ppx_count_table_dump": (c_i, [c_p, c_p, c_p, c_u, C.POINTER(c_u)]),
     "ppx_gather_minibatch": (c_i, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_p, c_l, c_i, c_i, c_p]),
+    "ppx_gather_minibatch_stats": (c_i, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_p, c_l, c_i, c_i, C.POINTER(c_i),
+                                         C.POINTER(c_p), c_i, c_p]),
     "ppx_mean_std": (c_i, [c_p, c_l, c_p, c_p]),
     "ppx_np_permutation": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),
     "ppx_np_shuffle_draws": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),

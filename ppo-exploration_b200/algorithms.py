@@ -94,7 +94,13 @@ class BaseAlgorithm(object):
     def _loss_workspace(self):
         return self._scratch.get("ppo_loss_ws", L.call("ppx_ppo_loss_workspace", 0, 0) // 8 + 1, torch.float64)
 
-    def _policy_step(self, bufs, B, losses_row, dual=False, policy_weight=1.0, int_vf_coef=0.0, B_total=0):
+    def _gather_with_stats(self, ro, sl, bufs, dual=False):
+        """Minibatch gather; the advantage moments (algorithms.py:219, :431-434) come out of the same launch."""
+        stats = [('advantages', self._stats.data_ptr())] + ([('int_advantages', self._stats.data_ptr() + 16)] if dual else [])
+        ro.gather_into(sl, bufs, stats=stats if sl.numel() >= 2 else None)
+        return sl.numel() >= 2
+
+    def _policy_step(self, bufs, B, losses_row, dual=False, policy_weight=1.0, int_vf_coef=0.0, B_total=0, stats_ready=False):
         """One minibatch: forward, fused loss fwd+bwd, backward.  Gradients land in policy.bank.grad.
         Sharded runs (B_total = rows of the global minibatch) exchange only the advantage moments and the
         32 loss partial sums; the caller all-reduces the flat gradient."""
@@ -104,10 +110,11 @@ class BaseAlgorithm(object):
         outs = pol.forward_raw(obs)
         adv = bufs['advantages'][:B]
         sharded = D.world_size() > 1
-        L.call("ppx_mean_std", adv.data_ptr(), B, self._stats.data_ptr(), L.stream())
-        if dual:
-            iadv = bufs['int_advantages'][:B]
-            L.call("ppx_mean_std", iadv.data_ptr(), B, self._stats.data_ptr() + 16, L.stream())
+        if not stats_ready:
+            L.call("ppx_mean_std", adv.data_ptr(), B, self._stats.data_ptr(), L.stream())
+            if dual:
+                iadv = bufs['int_advantages'][:B]
+                L.call("ppx_mean_std", iadv.data_ptr(), B, self._stats.data_ptr() + 16, L.stream())
         if sharded:
             self._merge_stats(B, dual)
         d_actor = sc.get("d_actor", B * A)[:B * A].view(B, A)
@@ -404,8 +411,8 @@ class PPO(BaseAlgorithm):
         for ep in range(self.n_epochs):
             for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b, bt=bt):
-                    ro.gather_into(sl, bufs)
-                    self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt)
+                    ok = self._gather_with_stats(ro, sl, bufs)
+                    self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt, stats_ready=ok)
                     self._policy_optim_step()
                 self._graph_call(("ppo", off, b, bt), fn)
                 losses[step].copy_(self._loss_row)
@@ -507,9 +514,9 @@ class PPO_RND(BaseAlgorithm):
         for ep in range(self.n_epochs):
             for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b, bt=bt):
-                    ro.gather_into(sl, bufs)
+                    ok = self._gather_with_stats(ro, sl, bufs, dual=True)
                     self._policy_step(bufs, b, self._loss_row.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
-                                      B_total=bt)
+                                      B_total=bt, stats_ready=ok)
                     self._policy_optim_step()
                 self._graph_call(("rnd_policy", off, b, bt), fn)
                 losses[step].copy_(self._loss_row)
@@ -597,8 +604,9 @@ class PPO_ICM(BaseAlgorithm):
         for ep in range(self.n_epochs):
             for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
                 def fn(sl=sl, b=b):
-                    ro.gather_into(sl, bufs)
-                    self._policy_step(bufs, b, self._loss_row.data_ptr(), policy_weight=float(self.policy_weight))
+                    ok = self._gather_with_stats(ro, sl, bufs)
+                    self._policy_step(bufs, b, self._loss_row.data_ptr(), policy_weight=float(self.policy_weight),
+                                      stats_ready=ok)
                     icm_row.zero_()
                     self.intrinsic_module.train_step(bufs['observations'][:b], bufs['actions'][:b], self.beta, icm_row)
                     self.policy.bank.adam_step(self.lr, self.max_grad_norm)     # only policy grads are clipped (:697)

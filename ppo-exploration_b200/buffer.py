@@ -426,8 +426,10 @@ class RolloutStorage(BaseBuffer):
             self._mb[key] = bufs
         return self._mb[key]
 
-    def gather_into(self, idx_dev, bufs):
-        """One fused launch: every RolloutSample field for the flat indices `idx_dev` (int64, CUDA)."""
+    def gather_into(self, idx_dev, bufs, stats=None):
+        """One fused launch: every RolloutSample field for the flat indices `idx_dev` (int64, CUDA).  stats: optional list
+        of (field, device pointer to 2 doubles) -- {mean, unbiased std} of that gathered f32 [B] field (the advantage
+        normalisation statistics) computed by the same launch."""
         B = idx_dev.numel()
         n = len(self._fields)
         srcs = (C.c_void_p * n)()
@@ -438,6 +440,13 @@ class RolloutStorage(BaseBuffer):
             srcs[i] = s.data_ptr()
             dsts[i] = bufs[field].data_ptr()
             rb[i] = int(s[0, 0].numel() * s.element_size()) if s.dim() > 2 else s.element_size()
+        if stats:
+            names = [f for f, _ in self._fields]
+            sf = (C.c_int * len(stats))(*[names.index(f) for f, _ in stats])
+            so = (C.c_void_p * len(stats))(*[p for _, p in stats])
+            L.call("ppx_gather_minibatch_stats", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, self.n_envs,
+                   sf, so, len(stats), L.stream())
+            return
         L.call("ppx_gather_minibatch", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, self.n_envs,
                L.stream())
 

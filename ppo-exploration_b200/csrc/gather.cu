@@ -15,7 +15,14 @@ struct GatherArgs {
   char* dst[PPX_MAX_GATHER];
   int row_bytes[PPX_MAX_GATHER];
   int vec16[PPX_MAX_GATHER];
+  // optional: {mean, unbiased std} of up to two gathered f32 [B] fields (the advantages, algorithms.py:219 / :431-434),
+  // computed on the way so the minibatch needs no separate moments launch
+  int stat_field[2];
+  double* stat_out[2];
+  double* stat_part;             // [2][kStatMax][2]
+  unsigned int* stat_ticket;     // [2]
 };
+constexpr int kStatMax = 4096;
 
 template <typename V>
 __device__ __forceinline__ void gather_rows(const char* __restrict__ src, char* __restrict__ dst, int row_bytes,
@@ -31,9 +38,51 @@ __device__ __forceinline__ void gather_rows(const char* __restrict__ src, char* 
   }
 }
 
+// one f32 per row + running (sum, sum of squares) in f64; the last CTA of the field finishes the moments in a fixed order
+__device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot, const int64_t* __restrict__ idx, int64_t B,
+                                         int T, int N) {
+  __shared__ double s_red[32];
+  __shared__ bool s_last;
+  const float* src = reinterpret_cast<const float*>(args.src[a]);
+  float* dst = reinterpret_cast<float*>(args.dst[a]);
+  double s = 0.0, q = 0.0;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = __ldg(idx + b);
+    const float v = __ldg(src + (i % T) * N + i / T);
+    dst[b] = v;
+    s += (double)v;
+    q += (double)v * (double)v;
+  }
+  s = block_sum(s, s_red);
+  q = block_sum(q, s_red);
+  double* part = args.stat_part + (size_t)slot * kStatMax * 2;
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = q; }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(args.stat_ticket + slot, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) args.stat_ticket[slot] = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  s = 0.0; q = 0.0;
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) { s += __ldcg(part + 2 * k); q += __ldcg(part + 2 * k + 1); }
+  s = block_sum(s, s_red);
+  q = block_sum(q, s_red);
+  if (threadIdx.x == 0) {
+    const double mean = s / (double)B;
+    args.stat_out[slot][0] = mean;
+    args.stat_out[slot][1] = sqrt(fmax(q - s * mean, 0.0) / (double)(B - 1));     // unbiased, like torch.Tensor.std()
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gather_kernel(GatherArgs args, const int64_t* __restrict__ idx, int64_t B, int T, int N) {
   const int a = blockIdx.y;
+  if (a == args.stat_field[0]) { gather_scalar_with_stats(args, a, 0, idx, B, T, N); return; }
+  if (a == args.stat_field[1]) { gather_scalar_with_stats(args, a, 1, idx, B, T, N); return; }
   if (args.vec16[a]) gather_rows<int4>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N);
   else gather_rows<int>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N);
 }
@@ -100,11 +149,13 @@ extern "C" int ppx_moments_merge(const double* recs, int W, double* out2, void* 
   return ppx::after_launch("moments_merge");
 }
 
-extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
-                                    int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream) {
+namespace {
+int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host, int n_arrays, const int64_t* idx,
+                int64_t B, int T, int N, const int* stat_fields, double* const* stat_outs, int n_stats, void* stream) {
   PPX_REQUIRE(srcs_host && dsts_host && row_bytes_host && idx, "gather_minibatch: null pointer");
   PPX_REQUIRE(n_arrays >= 1 && n_arrays <= PPX_MAX_GATHER, "gather_minibatch: n_arrays=%d (1..%d)", n_arrays, PPX_MAX_GATHER);
   PPX_REQUIRE(B >= 0 && T > 0 && N > 0, "gather_minibatch: B=%lld T=%d N=%d", (long long)B, T, N);
+  PPX_REQUIRE(n_stats >= 0 && n_stats <= 2, "gather_minibatch: at most two statistics fields");
   if (B == 0) return PPX_OK;
   ppx::GatherArgs args;
   int64_t max_words = 0;
@@ -118,12 +169,45 @@ extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* d
     const int64_t words = B * (row_bytes_host[a] / (args.vec16[a] ? 16 : 4));
     if (words > max_words) max_words = words;
   }
+  args.stat_field[0] = args.stat_field[1] = -1;
+  args.stat_out[0] = args.stat_out[1] = nullptr;
+  args.stat_part = nullptr; args.stat_ticket = nullptr;
   int64_t gx = ppx::ceil_div(max_words, 256);
   const int64_t cap = (int64_t)ppx::sm_count() * 16;
   if (gx > cap) gx = cap;
+  if (n_stats > 0) {
+    static double* part = nullptr;                       // per-process scratch; calls are stream-ordered (one learner thread)
+    static unsigned int* ticket = nullptr;
+    if (!part) {
+      PPX_CUDA(cudaMalloc((void**)&part, 2 * ppx::kStatMax * 2 * sizeof(double)));
+      PPX_CUDA(cudaMalloc((void**)&ticket, 2 * sizeof(unsigned int)));
+      PPX_CUDA(cudaMemset(ticket, 0, 2 * sizeof(unsigned int)));
+    }
+    PPX_REQUIRE(B >= 2, "gather_minibatch: statistics need B >= 2");
+    for (int k = 0; k < n_stats; ++k) {
+      PPX_REQUIRE(stat_fields && stat_outs && stat_fields[k] >= 0 && stat_fields[k] < n_arrays && stat_outs[k] &&
+                  row_bytes_host[stat_fields[k]] == 4, "gather_minibatch: statistics field %d must be an f32 [B] field", k);
+      args.stat_field[k] = stat_fields[k];
+      args.stat_out[k] = stat_outs[k];
+    }
+    args.stat_part = part; args.stat_ticket = ticket;
+    if (gx > ppx::kStatMax) gx = ppx::kStatMax;
+  }
   dim3 grid((unsigned)gx, (unsigned)n_arrays);
   ppx::gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(args, idx, B, T, N);
   return ppx::after_launch("gather_minibatch");
+}
+}  // namespace
+
+extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
+                                    int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream) {
+  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int ppx_gather_minibatch_stats(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
+                                          int n_arrays, const int64_t* idx, int64_t B, int T, int N, const int* stat_fields_host,
+                                          double* const* stat_outs_host, int n_stats, void* stream) {
+  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, stat_fields_host, stat_outs_host, n_stats, stream);
 }
 
 extern "C" int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream) {
