@@ -192,7 +192,10 @@ int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int*
                  const float* const* W3_host, const float* H1, const float* H2, const float* const* dOut_host,
                  const ppx_value_head* value_heads_host /* G entries or NULL */, float clip_range, int64_t B_total,
                  float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
-                 float* workspace, void* stream);
+                 float* workspace, double* sumsq_partials /* optional, ppx_mlp3_sumsq_partials() doubles: per-block sums of
+                 squares of the final MLP gradients for ppx_clip_adam_pre; step_dev is then bumped here */,
+                 int64_t* step_dev, void* stream);
+int ppx_mlp3_sumsq_partials(int D, int H, int G, const int* outs_host);
 
 /* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
 /* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma
@@ -296,6 +299,12 @@ int ppx_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_
                   double lr, double beta1, double beta2, double eps, int64_t step,
                   int64_t* step_dev /* NULL, or device counter of steps done: incremented, then used (graph replay) */,
                   double* norm_out, void* workspace /* >= 4096 doubles */, void* stream);
+/* Same update when the sum of squares of (most of) the gradient was already produced by the kernel that wrote it
+ * (ppx_mlp3_bwd): the clip norm is sqrt(sum(sumsq_partials) + sum(extra_grads^2)); the whole vector is clipped;
+ * *step_dev must already hold the NEW step number. */
+int ppx_clip_adam_pre(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double max_norm,
+                      double lr, double beta1, double beta2, double eps, const int64_t* step_dev, double* norm_out,
+                      const double* sumsq_partials, int n_partials, const float* extra_grads, int n_extra, void* stream);
 
 /* ---------------------------------------------------------------- bonus-net epilogues ------- */
 /* RunningMeanStd.update (util.py:20-44), f64 moments on device: state = {mean[dim], var[dim], count}.

@@ -151,9 +151,12 @@ class BaseAlgorithm(object):
             if dual:
                 vh[2] = (outs[2], bufs['int_values'][:B], bufs['int_returns'][:B], self._branch.data_ptr() + 16,
                          float(int_vf_coef))
+            # single GPU with clipping: the reduce kernel also leaves the clip_grad_norm_ partials (no sumsq launch)
+            self._pre_sumsq = (not sharded) and self.max_grad_norm > 0
             pol.mlp.backward([d_actor, None] + ([None] if dual else []), value_heads=vh, clip_range=self.clip_range,
-                             B_total=Bt)
+                             B_total=Bt, with_sumsq=self._pre_sumsq)
             return
+        self._pre_sumsq = False
         d_val = sc.get("d_val", B)[:B].view(B, 1)
         d_ival = sc.get("d_ival", B)[:B].view(B, 1)
         L.call("ppx_ppo_loss_head", *head_args, self._sums.data_ptr(), ws, L.stream())
@@ -327,6 +330,10 @@ class BaseAlgorithm(object):
                    n_clip, float(self.lr), 0.9, 0.999, 1e-8, bank.step_dev.data_ptr(), bank.norm_dev.data_ptr(), None,
                    L.stream())
             bank.refresh_tc()
+            return
+        if getattr(self, "_pre_sumsq", False):
+            ss, n_ss = self.policy.mlp.sumsq
+            bank.adam_step_pre(self.lr, self.max_grad_norm, ss, n_ss, extra_name="action_log_std")
             return
         self._sync_grads(bank)
         bank.adam_step(self.lr, self.max_grad_norm)
@@ -609,7 +616,7 @@ class PPO_ICM(BaseAlgorithm):
                                       stats_ready=ok)
                     icm_row.zero_()
                     self.intrinsic_module.train_step(bufs['observations'][:b], bufs['actions'][:b], self.beta, icm_row)
-                    self.policy.bank.adam_step(self.lr, self.max_grad_norm)     # only policy grads are clipped (:697)
+                    self._policy_optim_step()                                   # only policy grads are clipped (:697)
                     self.intrinsic_module.bank.adam_step(self.int_lr, 0.0)
                 self._graph_call(("icm", off, b), fn)
                 losses[step].copy_(self._loss_row)

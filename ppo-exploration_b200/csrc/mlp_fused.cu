@@ -51,6 +51,8 @@ struct RedP {
   const float* ws2; const float* wsr; int n2, nr, RS;      // partial counts per net
   int D, G;
   float* dW1; float* db1; float* dW2; float* db2; float* dW3[MAXG]; float* db3[MAXG]; int o[MAXG];
+  double* sumsq;             // optional [G * gridDim.x]: per-block sum of squares of the final gradients (clip_grad_norm_)
+  int64_t* step_dev;         // optional: optimiser step counter, bumped here when the sumsq launch is skipped
 };
 
 __host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
@@ -531,9 +533,20 @@ __global__ void __launch_bounds__(256) mlp3_reduce_kernel(RedP p) {
   }
   sl[slice][el] = s;
   __syncthreads();
-  if (slice != 0 || e >= H * H + R) return;
+  if (slice != 0) return;
+  const bool live = e < H * H + R;
+  if (live) {
 #pragma unroll
-  for (int q = 1; q < 8; ++q) s += sl[q][el];
+    for (int q = 1; q < 8; ++q) s += sl[q][el];
+  } else {
+    s = 0.f;
+  }
+  if (p.sumsq) {                                              // first warp: fixed-order sum of squares of this block's 32 gradients
+    const double ss = warp_sum((double)s * (double)s);
+    if (el == 0) p.sumsq[(size_t)g * gridDim.x + blockIdx.x] = ss;
+    if (p.step_dev && el == 0 && blockIdx.x == 0 && g == 0) *p.step_dev += 1;
+  }
+  if (!live) return;
   if (e < H * H) { p.dW2[(size_t)g * H * H + e] = s; return; }
   const int r = e - H * H;
   if (r < D * H) p.dW1[(size_t)(r / H) * (p.G * H) + g * H + r % H] = s;
@@ -626,6 +639,12 @@ int bwd_grid(int M, int H, int G) {
 }
 }  // namespace
 
+extern "C" int ppx_mlp3_sumsq_partials(int D, int H, int G, const int* outs) {
+  mf::Shape s;
+  if (!outs || !mf::shape_ok(D, H, G, outs, &s)) return -1;
+  return G * (int)ceil_div(H * H + mf::rest_size(H, D, s.omax), 32);
+}
+
 extern "C" int64_t ppx_mlp3_bwd_workspace(int M, int D, int H, int G, const int* outs) {
   mf::Shape s;
   if (!outs || !mf::shape_ok(D, H, G, outs, &s)) return -1;
@@ -637,7 +656,7 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
                             const float* const* W3, const float* H1, const float* H2, const float* const* dOut,
                             const ppx_value_head* vh, float clip_range, int64_t B_total,
                             float* dW1, float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3,
-                            float* workspace, void* stream) {
+                            float* workspace, double* sumsq_partials, int64_t* step_dev, void* stream) {
   mf::Shape s;
   PPX_REQUIRE(X && outs && W2 && W3 && H1 && H2 && dOut && dW1 && db1 && dW2 && db2 && dW3 && db3 && workspace, "mlp3_bwd: null pointer");
   PPX_REQUIRE(mf::shape_ok(D, H, G, outs, &s), "mlp3_bwd: unsupported shape D=%d H=%d G=%d", D, H, G);
@@ -676,7 +695,7 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
   if (rc) return rc;
   mf::RedP r{};
   r.ws2 = p.ws2; r.wsr = p.wsr; r.n2 = n; r.nr = n; r.RS = s.RS; r.D = D; r.G = G;
-  r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2;
+  r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2; r.sumsq = sumsq_partials; r.step_dev = sumsq_partials ? step_dev : nullptr;
   for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
   dim3 rgrid((unsigned)ceil_div(H * H + mf::rest_size(H, D, s.omax), 32), (unsigned)G);
   if (H == 64) mf::mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
             const double* __restrict__ partials, int n_partials, float max_norm, int64_t n_clip, float w1 /*1-beta1*/,
             double beta1, double beta2d, double lr, float beta2, float w2 /*1-beta2*/, float step_size, float bc2_sqrt,
-            float eps, const int64_t* __restrict__ step_dev, double* norm_out) {
+            float eps, const int64_t* __restrict__ step_dev, double* norm_out, const float* __restrict__ extra, int n_extra) {
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     if (step_dev) {                                          // device-resident step counter (CUDA-graph replay)
@@ -48,6 +48,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     if (n_partials > 0) {
       double s = 0.0;
       for (int k = 0; k < n_partials; ++k) s += partials[k];
+      for (int k = 0; k < n_extra; ++k) s += (double)extra[k] * (double)extra[k];   // gradients not covered by the partials
       const float norm = (float)sqrt(s);
       coef = fminf(max_norm / (norm + 1e-6f), 1.f);          // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
       if (blockIdx.x == 0 && norm_out) *norm_out = sqrt(s);
@@ -123,6 +124,19 @@ extern "C" int ppx_clip_adam(float* params, const float* grads, float* exp_avg, 
   const int grid = (int)std::min<int64_t>(ceil_div(n, 2048), (int64_t)sm_count() * 8);
   adam_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, n_partials, (float)max_norm, n_clip,
                                     (float)(1.0 - beta1), beta1, beta2, lr, (float)beta2, (float)(1.0 - beta2),
-                                    (float)(lr / bc1), (float)sqrt(bc2), (float)eps, step_dev, norm_out);
+                                    (float)(lr / bc1), (float)sqrt(bc2), (float)eps, step_dev, norm_out, nullptr, 0);
   return after_launch("clip_adam");
+}
+
+extern "C" int ppx_clip_adam_pre(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double max_norm,
+                                 double lr, double beta1, double beta2, double eps, const int64_t* step_dev, double* norm_out,
+                                 const double* sumsq_partials, int n_partials, const float* extra_grads, int n_extra, void* stream) {
+  using namespace ppx;
+  PPX_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_dev && sumsq_partials, "clip_adam_pre: null pointer");
+  PPX_REQUIRE(n >= 1 && max_norm > 0.0 && n_partials >= 1 && n_extra >= 0 && (n_extra == 0 || extra_grads), "clip_adam_pre: bad arguments");
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 2048), (int64_t)sm_count() * 8);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, sumsq_partials, n_partials, (float)max_norm, n,
+                                                     (float)(1.0 - beta1), beta1, beta2, lr, (float)beta2, (float)(1.0 - beta2), 0.f, 0.f,
+                                                     (float)eps, step_dev, norm_out, extra_grads, n_extra);
+  return after_launch("clip_adam(pre)");
 }

@@ -73,6 +73,14 @@ class ParamBank:
     def g(self, name, extra=0):
         return self.grad.data_ptr() + (self.offsets[name] + extra) * F4
 
+    def adam_step_pre(self, lr, max_norm, sumsq, n_partials, extra_name=None, betas=(0.9, 0.999), eps=1e-8):
+        """clip + Adam when the producer of the gradients already left sum-of-squares partials (and bumped the step)."""
+        ex_ptr, ex_n = (self.g(extra_name), int(np.prod(self.shapes[extra_name]))) if extra_name else (None, 0)
+        L.call("ppx_clip_adam_pre", self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+               self.exp_avg_sq.data_ptr(), self.size, float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
+               self.step_dev.data_ptr(), self.norm_dev.data_ptr(), sumsq.data_ptr(), int(n_partials), ex_ptr, ex_n, L.stream())
+        self.refresh_tc()
+
     def adam_step(self, lr, max_norm=0.0, betas=(0.9, 0.999), eps=1e-8):
         """clip_grad_norm_(max_norm) over the whole bank + Adam (device-side step counter)."""
         L.call("ppx_clip_adam", self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
@@ -326,7 +334,7 @@ class ParallelMLP:
     def fused(self):
         return self._fused_args()["ok"]
 
-    def backward(self, d_outs, value_heads=None, clip_range=0.0, B_total=0):
+    def backward(self, d_outs, value_heads=None, clip_range=0.0, B_total=0, with_sumsq=False):
         """d_outs[g]: [M, out_g] contiguous (None for a net listed in `value_heads`).  Fills bank.grad for every
         MLP parameter.  value_heads (fused path only): {g_index: (values, old_values, returns, branch_ptr, scale)}
         -- the clipped-value-loss gradient of that head is evaluated inside the backward kernel."""
@@ -341,9 +349,15 @@ class ParallelMLP:
                 for gi, (v, ov, R, br, scale) in value_heads.items():
                     vh[gi] = L.ValueHead(v.data_ptr(), ov.data_ptr(), R.data_ptr(), br, float(scale))
             dptr = (C.c_void_p * G)(*[(d.data_ptr() if d is not None else None) for d in d_outs])
+            ss = None
+            if with_sumsq:                                      # clip_grad_norm_ partials come out of the reduce kernel
+                n_ss = L.call("ppx_mlp3_sumsq_partials", D, h, G, fa["outs"])
+                ss = sc.get("pmlp.sumsq", n_ss, torch.float64)
+                self.sumsq = (ss, n_ss)
             L.call("ppx_mlp3_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
                    H2.data_ptr(), dptr, vh, float(clip_range), int(B_total), b.g("W1"), b.g("b1"), b.g("W2"),
-                   b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), L.stream())
+                   b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), ss.data_ptr() if ss is not None else None,
+                   b.step_dev.data_ptr() if ss is not None else None, L.stream())
             return
         assert not value_heads, "value_heads needs the fused MLP path"
         dP2 = sc.get("pmlp.dP2", M * G * h)[:M * G * h].view(M, G * h)
