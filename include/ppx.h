@@ -197,6 +197,25 @@ int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int*
                  int64_t* step_dev, void* stream);
 int ppx_mlp3_sumsq_partials(int D, int H, int G, const int* outs_host);
 
+/* Tensor-core variant of the same pair for H = 64, D <= 32, o_g <= 4, G <= 4 (ppx_mlp3_tc_supported): the two
+ * 64x64 GEMMs of each pass run as tcgen05.mma kind::tf32 in three hi/lo passes (fp32-equivalent), operands are
+ * written by the elementwise threads straight into swizzled shared-memory images, accumulators live in TMEM.
+ * Same arguments and results as ppx_mlp3_fwd / ppx_mlp3_bwd except that H1t / H2t are OPAQUE activation
+ * workspaces of ppx_mlp3_tc_act_elems(M, H, G) floats each (tile-transposed layout private to this pair), and the
+ * backward workspace size comes from ppx_mlp3_tc_bwd_workspace.  The gradient partial sums go through the same
+ * fixed-order reduce as ppx_mlp3_bwd (deterministic; sumsq_partials has ppx_mlp3_sumsq_partials() entries). */
+int ppx_mlp3_tc_supported(int D, int H, int G, const int* outs_host);
+int64_t ppx_mlp3_tc_act_elems(int M, int H, int G);
+int ppx_mlp3_tc_fwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W1,
+                    const float* b1, const float* W2, const float* b2, const float* const* W3_host,
+                    const float* const* b3_host, float* H1t, float* H2t, float* const* out_host, void* stream);
+int64_t ppx_mlp3_tc_bwd_workspace(int M, int D, int H, int G, const int* outs_host);
+int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W2,
+                    const float* const* W3_host, const float* H1t, const float* H2t, const float* const* dOut_host,
+                    const ppx_value_head* value_heads_host, float clip_range, int64_t B_total,
+                    float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
+                    float* workspace, double* sumsq_partials, int64_t* step_dev, void* stream);
+
 /* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
 /* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma
  * kind::tf32 and a 3-pass hi/lo split (fp32-equivalent, error ~2^-21), TMA-fed, TMEM accumulators.

@@ -595,6 +595,22 @@ inline int grid_x(int M, int G, int per_sm) {
   return std::max(1, std::min(nTiles, slots));
 }
 
+// fixed-order sum of the per-CTA partials of a backward kernel (this file's or mlp_tc.cu's) into the gradient tensors
+int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, const float* wsr, int n, int RS, float* dW1,
+                       float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3, double* sumsq,
+                       int64_t* step_dev, cudaStream_t st) {
+  int omax = 0;
+  for (int g = 0; g < G; ++g) omax = std::max(omax, outs[g]);
+  RedP r{};
+  r.ws2 = ws2; r.wsr = wsr; r.n2 = n; r.nr = n; r.RS = RS; r.D = D; r.G = G;
+  r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2; r.sumsq = sumsq; r.step_dev = step_dev;
+  for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
+  dim3 rgrid((unsigned)ceil_div(H * H + rest_size(H, D, omax), 32), (unsigned)G);
+  if (H == 64) mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
+  else mlp3_reduce_kernel<128><<<rgrid, 256, 0, st>>>(r);
+  return after_launch("mlp3_reduce");
+}
+
 }  // namespace mf
 }  // namespace ppx
 
@@ -693,12 +709,6 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
   }
   int rc = after_launch("mlp3_bwd");
   if (rc) return rc;
-  mf::RedP r{};
-  r.ws2 = p.ws2; r.wsr = p.wsr; r.n2 = n; r.nr = n; r.RS = s.RS; r.D = D; r.G = G;
-  r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2; r.sumsq = sumsq_partials; r.step_dev = sumsq_partials ? step_dev : nullptr;
-  for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
-  dim3 rgrid((unsigned)ceil_div(H * H + mf::rest_size(H, D, s.omax), 32), (unsigned)G);
-  if (H == 64) mf::mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
-  else mf::mlp3_reduce_kernel<128><<<rgrid, 256, 0, st>>>(r);
-  return after_launch("mlp3_reduce");
+  return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, s.RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
+                                sumsq_partials ? step_dev : nullptr, st);
 }

@@ -1,0 +1,616 @@
+// Policy MLPs on the Blackwell tensor cores: forward and backward of G independent  D -> 64 -> 64 -> o_g  tanh MLPs
+// (actor | critic | int_critic of models.py:137-213) with the two 64x64 GEMMs of every pass on tcgen05.mma kind::tf32
+// in fp32-equivalent precision (3xTF32: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, the lo.lo term ~2^-22 dropped).
+//
+// The SIMT kernels of mlp_fused.cu spend ~90 % of their instructions on the FMAs of those GEMMs.  Here a thread owns
+// (sample s, 32 hidden columns) -- the tcgen05.ld 32x32b register layout -- and only does the elementwise work (first
+// layer with K = D <= 32, tanh, hi/lo split, head layer, thin reductions); the GEMM operands are written by the same
+// threads straight into 128-byte-swizzled K-major shared-memory images and the accumulators live in TMEM.
+//   * kind::tf32 truncates its operands, so the RAW fp32 image is the "hi" operand; only lo = x - trunc(x) is extra
+//     (tools/umma_probe.cu: identical results with and without the explicit mask).
+//   * MN-major tf32 operands need the 32-byte-atom swizzle and cannot share an image with a K-major use of the same
+//     data, so the weight-gradient GEMM (reduction over the samples) gets TRANSPOSED images, written with
+//     conflict-free scalar stores (lanes = consecutive samples = consecutive words of a 128-byte row).
+//   * the saved activations are private to this pair of kernels and are kept TRANSPOSED per tile in HBM
+//     (Ht [G][tile][64][128]): both kernels then read/write them with fully coalesced 128-byte warp accesses.
+//   * the tensor core's fp32 accumulator truncates on every MMA; small terms are accumulated first and dW2 is drained
+//     into fp32 registers after every tile (48 MMAs), so the drift stays ~1e-6 (tests/test_gpu_mlp_tc.py).
+// Forward: 2 CTAs/SM (96 KB of images each) so one CTA's MMA + epilogue overlaps the other's first layer.
+// Backward: 1 CTA/SM (198 KB); GEMM 2 (dP1 = dP2 W2^T) runs under the H1^T image writes and the dW3/db2 sums,
+// GEMM 1 (dW2 += H1^T dP2) under the dW1/db1 sums and the next tile's loads.  Partials leave in the same format as
+// mlp_fused.cu's backward and go through the same fixed-order reduce kernel (deterministic, no float atomics).
+//
+// Replaces, for H = 64, the nn.Linear/Tanh stacks + autograd of Policy.evaluate inside train()
+// (models.py:52-73, 101-124; algorithms.py:213, 242, 425, 464, 665, 696).
+#include "tc_common.cuh"
+
+namespace ppx {
+namespace mf {
+// defined in mlp_fused.cu: fixed-order sum of the per-CTA partials (+ optional clip_grad_norm_ partial sums)
+int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, const float* wsr, int n, int RS, float* dW1,
+                       float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3, double* sumsq,
+                       int64_t* step_dev, cudaStream_t st);
+}  // namespace mf
+
+namespace mt {
+using namespace tc;
+
+constexpr int H = 64, TM = 128, NT = 256, MAXG = 4, MAXO = 4, MAXD = 32;
+__host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
+
+__device__ __forceinline__ float tanh_fast(float x) {   // same 5-instruction form as mlp_fused.cu (abs error <= 2e-7)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+struct FwdP {
+  const float* X; int ldx; int M, D, G, nTiles;
+  const float* W1; const float* b1; const float* W2; const float* b2;     // W1 [D, G*H], b1 [G*H], W2 [G,H,H] in-major, b2 [G,H]
+  const float* W3[MAXG]; const float* b3[MAXG]; int o[MAXG];
+  float* H1t; float* H2t;                                                  // [G][nTiles][H][TM]
+  float* out[MAXG];
+};
+
+// row `row` of X (zero beyond M / D) into registers
+template <int DP>
+__device__ __forceinline__ void load_x_row(const float* __restrict__ X, int ldx, int D, bool live, float (&x)[DP]) {
+  const bool vec = ((ldx & 3) == 0) && ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < DP; k += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && k < D) v = __ldg(reinterpret_cast<const float4*>(X + k));
+      x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < DP; ++k) x[k] = (live && k < D) ? __ldg(X + k) : 0.f;
+  }
+}
+
+// one thread: v[32] = 32 consecutive columns (c0..c0+31, block kb = c0/32) of row s -> raw and lo K-major images
+__device__ __forceinline__ void store_row_images(uint8_t* raw, uint8_t* lo, int s, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t off = (uint32_t)(s * 128 + ((j ^ (s & 7)) << 4));
+    *reinterpret_cast<float4*>(raw + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<float4*>(lo + off) = make_float4(lo_of(v[4 * j]), lo_of(v[4 * j + 1]), lo_of(v[4 * j + 2]), lo_of(v[4 * j + 3]));
+  }
+}
+// one thread: v[32] = elements (row r0+c, column s) of a transposed image with 64-row k-blocks (block = s/32)
+__device__ __forceinline__ void store_col_images(uint8_t* raw, uint8_t* lo, int r0, int s, const float (&v)[32]) {
+  const int kb = s >> 5, l = s & 31;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const int r = r0 + c;
+    const uint32_t off = (uint32_t)(kb * 8192 + r * 128 + ((((l >> 2) ^ (r & 7)) << 4) | ((l & 3) << 2)));
+    *reinterpret_cast<float*>(raw + off) = v[c];
+    *reinterpret_cast<float*>(lo + off) = lo_of(v[c]);
+  }
+}
+
+// W [64][64] row-major (global) -> K-major image of B[n][k] = W[n][k] (transpose = false) or W[k][n] (transpose = true)
+__device__ __forceinline__ void stage_weight(uint8_t* raw, uint8_t* lo, const float* __restrict__ W, bool transpose, int tid) {
+  for (int e = tid; e < H * H; e += NT) {
+    const int a = e >> 6, b = e & 63;                 // W[a][b]
+    const float w = __ldg(W + e);
+    const int n = transpose ? b : a, k = transpose ? a : b;
+    const uint32_t off = (uint32_t)((k >> 5) * 8192) + sw128_off(n, k & 31);
+    *reinterpret_cast<float*>(raw + off) = w;
+    *reinterpret_cast<float*>(lo + off) = lo_of(w);
+  }
+}
+
+// 3xTF32 product of two K-major image pairs: D[128 x 64] (+)= A . B^T over `ksteps` k-steps of 8.
+// Blocks of 32 k are a_kb / b_kb bytes apart.  Small terms first, then the hi.hi pass.
+__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t a_kb, uint32_t b_raw,
+                                             uint32_t b_lo, uint32_t b_kb, int ksteps) {
+  constexpr uint32_t idesc = make_idesc(64);
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t oa = (ks >> 2) * a_kb + (ks & 3) * 32, ob = (ks >> 2) * b_kb + (ks & 3) * 32;
+    umma_tf32(tacc, make_desc(a_lo + oa), make_desc(b_raw + ob), idesc, ks ? 1u : 0u);
+    umma_tf32(tacc, make_desc(a_raw + oa), make_desc(b_lo + ob), idesc, 1u);
+  }
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t oa = (ks >> 2) * a_kb + (ks & 3) * 32, ob = (ks >> 2) * b_kb + (ks & 3) * 32;
+    umma_tf32(tacc, make_desc(a_raw + oa), make_desc(b_raw + ob), idesc, 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int DP>
+__global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wb_raw = smem;                    // B[n = j][k = i] = W2[i][j]: 2 k-blocks x [64 rows][128 B]
+  uint8_t* Wb_lo = smem + 16384;
+  uint8_t* A_raw = smem + 32768;             // H1 [s][i]: 2 k-blocks x [128 rows][128 B]
+  uint8_t* A_lo = smem + 65536;
+  __shared__ __align__(16) float W1s[DP * H];
+  __shared__ __align__(16) float b1s[H], b2s[H], W3s[H * MAXO], b3s[MAXO];
+  __shared__ __align__(16) float part[TM * MAXO];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, ch = warp >> 2, s = q * 32 + lane, c0 = ch * 32;
+  const int g = blockIdx.y, o = p.o[g], D = p.D, ldw = p.G * H;
+
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  stage_weight(Wb_raw, Wb_lo, p.W2 + (size_t)g * H * H, true, tid);
+  for (int e = tid; e < DP * H; e += NT) {
+    const int k = e >> 6, c = e & 63;
+    W1s[e] = k < D ? __ldg(p.W1 + (size_t)k * ldw + g * H + c) : 0.f;
+  }
+  for (int e = tid; e < H * MAXO; e += NT) {
+    const int c = e >> 2, j = e & 3;
+    W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+  }
+  if (tid < H) { b1s[tid] = __ldg(p.b1 + g * H + tid); b2s[tid] = __ldg(p.b2 + g * H + tid); }
+  if (tid < MAXO) b3s[tid] = tid < o ? __ldg(p.b3[g] + tid) : 0.f;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
+    const int m0 = tile * TM;
+    const bool live = m0 + s < p.M;
+    float* h1t = p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
+    float* h2t = p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
+    // ---- layer 1 (K = D): registers, W1 by broadcast shared-memory reads ----
+    float v[32];
+    {
+      float x[DP];
+      load_x_row<DP>(p.X + (size_t)(m0 + s) * p.ldx, p.ldx, D, live, x);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&b1s[c0 + c]);
+        v[c] = b.x; v[c + 1] = b.y; v[c + 2] = b.z; v[c + 3] = b.w;
+      }
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        if (k < D) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(&W1s[k * H + c0 + c]);
+            v[c] = fmaf(x[k], w.x, v[c]); v[c + 1] = fmaf(x[k], w.y, v[c + 1]);
+            v[c + 2] = fmaf(x[k], w.z, v[c + 2]); v[c + 3] = fmaf(x[k], w.w, v[c + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = tanh_fast(v[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) __stcs(h1t + c * TM, v[c]);          // warp = 128 contiguous bytes per column
+    store_row_images(A_raw + ch * 16384, A_lo + ch * 16384, s, v);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2 on the tensor core: Z2[s][j] = sum_i H1[s][i] W2[i][j] ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_3xtf32(tmem, smem_u32(A_raw), smem_u32(A_lo), 16384, smem_u32(Wb_raw), smem_u32(Wb_lo), 8192, 8);
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t z[32];
+    tmem_ld32(taddr, z);
+    // ---- epilogue: bias + tanh, H2 out, head layer (o <= 4) ----
+    float po[MAXO] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float h = tanh_fast(__uint_as_float(z[c]) + b2s[c0 + c]);
+      __stcs(h2t + c * TM, h);
+      const float4 w = *reinterpret_cast<const float4*>(&W3s[(c0 + c) * MAXO]);
+      po[0] = fmaf(h, w.x, po[0]); po[1] = fmaf(h, w.y, po[1]); po[2] = fmaf(h, w.z, po[2]); po[3] = fmaf(h, w.w, po[3]);
+    }
+    if (ch == 1) *reinterpret_cast<float4*>(&part[s * MAXO]) = make_float4(po[0], po[1], po[2], po[3]);
+    tc_fence_before();                       // the tcgen05.ld above is ordered before the next tile's MMAs
+    __syncthreads();
+    if (ch == 0 && live) {
+      const float4 t = *reinterpret_cast<const float4*>(&part[s * MAXO]);
+      const float r[MAXO] = {po[0] + t.x + b3s[0], po[1] + t.y + b3s[1], po[2] + t.z + b3s[2], po[3] + t.w + b3s[3]};
+      float* dst = p.out[g] + (size_t)(m0 + s) * o;
+#pragma unroll
+      for (int j = 0; j < MAXO; ++j)
+        if (j < o) dst[j] = r[j];
+    }
+    // `part` is rewritten only after the next tile's first barrier; the images only after this barrier + the MMA wait
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<64>(tmem); }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+struct BwdP {
+  const float* X; int ldx; int M, D, G, nTiles;
+  const float* W2; const float* W3[MAXG]; int o[MAXG];
+  const float* H1t; const float* H2t;
+  const float* dOut[MAXG];
+  const float* vh_v[MAXG]; const float* vh_ov[MAXG]; const float* vh_R[MAXG]; const double* vh_branch[MAXG];
+  float vh_scale[MAXG]; float vh_clip; float vh_Bt;
+  float* ws2;        // [G][nCta][H*H]   dW2 partials
+  float* wsr;        // [G][nCta][RS]    dW1 | db1 | db2 | dW3 | db3 partials
+  int RS;
+};
+
+// byte offset of element (s, c) of the fp32 staging tile S [128][64] (16-byte chunks XOR-swizzled by the row)
+__device__ __forceinline__ uint32_t stage_off(int s, int c) { return (uint32_t)(s * 256 + ((((c >> 2) ^ (s & 7)) << 4) | ((c & 3) << 2))); }
+
+template <int DP>
+__global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* W_raw = smem;                     // B of GEMM 2: B[n = i][k = j] = W2[i][j]: 2 k-blocks x [64][128 B]
+  uint8_t* W_lo = smem + 16384;
+  uint8_t* V_raw = smem + 32768;             // A of GEMM 1: H1^T [i][s]: 4 k-blocks x [64][128 B]
+  uint8_t* V_lo = smem + 65536;
+  uint8_t* U_raw = smem + 98304;             // phase 1: dP2 [s][j] (A of GEMM 2, 2 k-blocks x [128][128 B]);
+  uint8_t* U_lo = smem + 131072;             // phase 2: dP2^T [j][s] (B of GEMM 1, 4 k-blocks x [64][128 B])
+  uint8_t* S = smem + 163840;                // fp32 staging [128][64]: H2, then dP1
+  float* Xs = reinterpret_cast<float*>(smem + 196608);   // [TM][DP]
+  __shared__ __align__(16) float W3s[MAXO * H];          // [j][c]
+  __shared__ __align__(16) float dOs[TM * MAXO];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, ch = warp >> 2, s = q * 32 + lane, c0 = ch * 32;
+  const int tc = tid & 63, sg = tid >> 6;     // thin-reduction mapping: column tc, samples sg*32 .. +31
+  const int g = blockIdx.y, o = p.o[g], D = p.D;
+  const uint32_t barG2 = smem_u32(&bars[0]), barG1 = smem_u32(&bars[1]);
+
+  if (tid == 0) { mbar_init(barG2, 1); mbar_init(barG1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  stage_weight(W_raw, W_lo, p.W2 + (size_t)g * H * H, false, tid);
+  for (int e = tid; e < MAXO * H; e += NT) {
+    const int j = e >> 6, c = e & 63;
+    W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+
+  // accumulators that live across all tiles of this CTA
+  float dW2acc[32];                          // warps with q < 2: dW2[i = q*32+lane][c0 .. c0+31]
+  float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3[MAXO] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 32; ++c) dW2acc[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < DP; ++k) a_dW1[k] = 0.f;
+
+  // prefetch registers for the next tile
+  float h1[32], h2[32];
+  float xpre[(TM * DP) / NT];
+  float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int tile) {
+    const int m0 = tile * TM;
+    const float* h1t = p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
+    const float* h2t = p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { h1[c] = ld_stream(h1t + c * TM); h2[c] = ld_stream(h2t + c * TM); }
+#pragma unroll
+    for (int r = 0; r < (TM * DP) / NT; ++r) {                 // Xs element e = tid + r*NT: row e / DP, column e % DP
+      const int e = tid + r * NT, row = e / DP, k = e % DP;
+      xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
+    }
+    if (tid < TM) {                                            // output gradient of row tid
+      const int b = m0 + tid;
+      float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
+      if (b < p.M) {
+        if (p.vh_v[g] != nullptr) {                            // o == 1 (checked on the host); same formula as mlp_fused.cu
+          const float w1 = (float)p.vh_branch[g][0], w2 = (float)p.vh_branch[g][1], clip = p.vh_clip;
+          const float v = ld_stream(p.vh_v[g] + b), ov = ld_stream(p.vh_ov[g] + b), R = ld_stream(p.vh_R[g] + b);
+          const float dd = v - ov;
+          const float vc = ov + fminf(fmaxf(dd, -clip), clip);
+          const float pass = (dd >= -clip && dd <= clip) ? 1.f : 0.f;
+          const float gv = w1 * (-2.f * (R - v)) + w2 * (-2.f * (R - vc)) * pass;
+          d[0] = p.vh_scale[g] * gv / p.vh_Bt;
+        } else {
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j)
+            if (j < o) d[j] = ld_stream(p.dOut[g] + (size_t)b * o + j);
+        }
+      }
+      dpre = make_float4(d[0], d[1], d[2], d[3]);
+    }
+  };
+
+  int it = 0;
+  if ((int)blockIdx.x < p.nTiles) prefetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
+    const uint32_t ph = (uint32_t)(it & 1);
+    // ---- T1: publish X, dOut and H2 (staging tile S) ----
+#pragma unroll
+    for (int r = 0; r < (TM * DP) / NT; ++r) Xs[tid + r * NT] = xpre[r];
+    if (tid < TM) *reinterpret_cast<float4*>(&dOs[tid * MAXO]) = dpre;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(S + stage_off(s, c0 + 4 * j)) = make_float4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+    if (it > 0) {                             // GEMM 1 of the previous tile has finished reading U and V
+      mbar_wait(barG1, ph ^ 1);
+      tc_fence_after();
+    }
+    __syncthreads();                          // [B1]
+    // ---- T2: dP2 = (dOut W3^T)(1 - H2^2) -> K-major images (phase 1 of U) -> GEMM 2 ----
+    float dp2[32];
+    {
+      const float4 d = *reinterpret_cast<const float4*>(&dOs[s * MAXO]);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float dj[MAXO] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j)
+          if (j < o) {                        // CTA-uniform
+            const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
+            a.x = fmaf(dj[j], w.x, a.x); a.y = fmaf(dj[j], w.y, a.y); a.z = fmaf(dj[j], w.z, a.z); a.w = fmaf(dj[j], w.w, a.w);
+          }
+        dp2[c] = a.x * (1.f - h2[c] * h2[c]); dp2[c + 1] = a.y * (1.f - h2[c + 1] * h2[c + 1]);
+        dp2[c + 2] = a.z * (1.f - h2[c + 2] * h2[c + 2]); dp2[c + 3] = a.w * (1.f - h2[c + 3] * h2[c + 3]);
+      }
+    }
+    store_row_images(U_raw + ch * 16384, U_lo + ch * 16384, s, dp2);
+    // drain the previous tile's dW2 accumulator (rows i = TMEM lanes 0..63) before GEMM 1 of this tile restarts it
+    if (it > 0 && q < 2) {
+      uint32_t z[32];
+      tmem_ld32(taddr + 64, z);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dW2acc[c] += __uint_as_float(z[c]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();                          // [B2]
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_3xtf32(tmem, smem_u32(U_raw), smem_u32(U_lo), 16384, smem_u32(W_raw), smem_u32(W_lo), 8192, 8);
+        umma_commit(barG2);
+      }
+      __syncwarp();
+    }
+    // ---- T3 (under GEMM 2): H1^T images; dW3 / db2 / db3 sums over this thread's 32 samples ----
+    store_col_images(V_raw, V_lo, c0, s, h1);
+    {
+      float t3[MAXO] = {0.f, 0.f, 0.f, 0.f}, t2 = 0.f, tb[MAXO] = {0.f, 0.f, 0.f, 0.f};
+      const uint8_t* Ublk = U_raw + (tc >> 5) * 16384;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int ss = sg * 32 + r;
+        const float hv = *reinterpret_cast<const float*>(S + stage_off(ss, tc));
+        const float4 d = *reinterpret_cast<const float4*>(&dOs[ss * MAXO]);
+        t3[0] = fmaf(hv, d.x, t3[0]); t3[1] = fmaf(hv, d.y, t3[1]); t3[2] = fmaf(hv, d.z, t3[2]); t3[3] = fmaf(hv, d.w, t3[3]);
+        t2 += *reinterpret_cast<const float*>(Ublk + sw128_off(ss, tc & 31));
+        tb[0] += d.x; tb[1] += d.y; tb[2] += d.z; tb[3] += d.w;
+      }
+#pragma unroll
+      for (int j = 0; j < MAXO; ++j) { a_dW3[j] += t3[j]; a_db3[j] += tb[j]; }
+      a_db2 += t2;
+    }
+    __syncthreads();                          // [B3] every read of S (H2) done before dP1 overwrites it
+    // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2); transposed dP2 images (phase 2 of U) -> GEMM 1 ----
+    mbar_wait(barG2, ph);
+    tc_fence_after();
+    {
+      uint32_t z[32];
+      tmem_ld32(taddr, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 v;
+        v.x = __uint_as_float(z[4 * j]) * (1.f - h1[4 * j] * h1[4 * j]);
+        v.y = __uint_as_float(z[4 * j + 1]) * (1.f - h1[4 * j + 1] * h1[4 * j + 1]);
+        v.z = __uint_as_float(z[4 * j + 2]) * (1.f - h1[4 * j + 2] * h1[4 * j + 2]);
+        v.w = __uint_as_float(z[4 * j + 3]) * (1.f - h1[4 * j + 3] * h1[4 * j + 3]);
+        *reinterpret_cast<float4*>(S + stage_off(s, c0 + 4 * j)) = v;
+      }
+    }
+    store_col_images(U_raw, U_lo, c0, s, dp2);          // GEMM 2 has finished reading the phase-1 images
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();                          // [B4]
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_3xtf32(tmem + 64, smem_u32(V_raw), smem_u32(V_lo), 8192, smem_u32(U_raw), smem_u32(U_lo), 8192, 16);
+        umma_commit(barG1);
+      }
+      __syncwarp();
+    }
+    // ---- T5 (under GEMM 1): next tile's loads in flight; dW1 / db1 sums ----
+    if (tile + (int)gridDim.x < p.nTiles) prefetch(tile + gridDim.x);
+    {
+      float t1[DP], tb = 0.f;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) t1[k] = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int ss = sg * 32 + r;
+        const float dv = *reinterpret_cast<const float*>(S + stage_off(ss, tc));
+        tb += dv;
+#pragma unroll
+        for (int k = 0; k < DP; k += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(&Xs[ss * DP + k]);
+          t1[k] = fmaf(dv, x.x, t1[k]); t1[k + 1] = fmaf(dv, x.y, t1[k + 1]);
+          t1[k + 2] = fmaf(dv, x.z, t1[k + 2]); t1[k + 3] = fmaf(dv, x.w, t1[k + 3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < DP; ++k) a_dW1[k] += t1[k];
+      a_db1 += tb;
+    }
+    __syncthreads();                          // [B5] S, Xs, dOs free for the next tile
+  }
+  // ---- the last tile's dW2 contribution ----
+  if (it > 0) {
+    mbar_wait(barG1, (uint32_t)((it - 1) & 1));
+    tc_fence_after();
+    if (q < 2) {
+      uint32_t z[32];
+      tmem_ld32(taddr + 64, z);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dW2acc[c] += __uint_as_float(z[c]);
+    }
+  }
+  // ---- one partial per CTA: dW2 straight from registers; the thin sums of the 4 sample groups combined in order ----
+  float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
+  if (q < 2) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
+  }
+  constexpr int NQ = DP + 2 + 2 * MAXO;       // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3[4]
+  float* red = reinterpret_cast<float*>(U_raw);          // [4 groups][NQ][64]   (<= 4*42*64*4 = 43 KB of the 64 KB U)
+  {
+    float* r = red + (size_t)sg * NQ * H + tc;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) r[k * H] = a_dW1[k];
+    r[DP * H] = a_db1; r[(DP + 1) * H] = a_db2;
+#pragma unroll
+    for (int j = 0; j < MAXO; ++j) { r[(DP + 2 + j) * H] = a_dW3[j]; r[(DP + 2 + MAXO + j) * H] = a_db3[j]; }
+  }
+  __syncthreads();
+  float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
+  const int offb1 = D * H, offb2 = offb1 + H, offW3 = offb2 + H, offb3 = offW3 + H * o;
+  for (int e = tid; e < NQ * H; e += NT) {
+    const int n = e >> 6, c = e & 63;
+    const float v = ((red[e] + red[NQ * H + e]) + red[2 * NQ * H + e]) + red[3 * NQ * H + e];
+    if (n < DP) { if (n < D) wr[n * H + c] = v; }
+    else if (n == DP) wr[offb1 + c] = v;
+    else if (n == DP + 1) wr[offb2 + c] = v;
+    else if (n < DP + 2 + MAXO) { const int j = n - DP - 2; if (j < o) wr[offW3 + c * o + j] = v; }
+    else { const int j = n - DP - 2 - MAXO; if (j < o && c == 0) wr[offb3 + j] = v; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem); }
+}
+
+inline bool shape_ok(int D, int Hh, int G, const int* outs) {
+  if (Hh != H || D < 1 || D > MAXD || G < 1 || G > MAXG) return false;
+  for (int g = 0; g < G; ++g)
+    if (outs[g] < 1 || outs[g] > MAXO) return false;
+  return true;
+}
+inline int dp_of(int D) { return D <= 8 ? 8 : (D <= 16 ? 16 : 32); }
+inline int n_tiles(int M) { return (M + TM - 1) / TM; }
+inline int rest_size(int D, int o) { return D * H + 2 * H + H * o + o; }
+inline int omax_of(int G, const int* outs) { int m = 0; for (int g = 0; g < G; ++g) m = std::max(m, outs[g]); return m; }
+constexpr size_t kFwdSmem = 98304 + 1024;
+inline size_t bwd_smem(int DP) { return 196608 + (size_t)TM * DP * 4 + 1024; }
+inline int fwd_grid(int M, int G) { return std::max(1, std::min(n_tiles(M), 2 * sm_count() / G)); }
+inline int bwd_grid(int M, int G) { return std::max(1, std::min(n_tiles(M), sm_count() / G)); }
+
+template <int DP>
+int launch_fwd(const FwdP& p, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    configured = true;
+  }
+  mlp3_tc_fwd_kernel<DP><<<grid, NT, kFwdSmem, st>>>(p);
+  return after_launch("mlp3_tc_fwd");
+}
+template <int DP>
+int launch_bwd(const BwdP& p, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(DP)));
+    configured = true;
+  }
+  mlp3_tc_bwd_kernel<DP><<<grid, NT, bwd_smem(DP), st>>>(p);
+  return after_launch("mlp3_tc_bwd");
+}
+
+}  // namespace mt
+}  // namespace ppx
+
+using namespace ppx;
+
+extern "C" int ppx_mlp3_tc_supported(int D, int H, int G, const int* outs) {
+  return (outs && mt::shape_ok(D, H, G, outs)) ? 1 : 0;
+}
+
+extern "C" int64_t ppx_mlp3_tc_act_elems(int M, int H, int G) {
+  if (H != mt::H || M < 0 || G < 1) return -1;
+  return (int64_t)G * mt::n_tiles(M) * mt::H * mt::TM;
+}
+
+extern "C" int ppx_mlp3_tc_fwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs, const float* W1,
+                               const float* b1, const float* W2, const float* b2, const float* const* W3,
+                               const float* const* b3, float* H1t, float* H2t, float* const* out, void* stream) {
+  PPX_REQUIRE(X && outs && W1 && b1 && W2 && b2 && W3 && b3 && H1t && H2t && out, "mlp3_tc_fwd: null pointer");
+  PPX_REQUIRE(mt::shape_ok(D, H, G, outs), "mlp3_tc_fwd: unsupported shape D=%d H=%d G=%d", D, H, G);
+  PPX_REQUIRE(M >= 0 && ldx >= D, "mlp3_tc_fwd: M=%d ldx=%d", M, ldx);
+  if (M == 0) return PPX_OK;
+  mt::FwdP p{};
+  p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.nTiles = mt::n_tiles(M);
+  p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2; p.H1t = H1t; p.H2t = H2t;
+  for (int g = 0; g < G; ++g) { p.W3[g] = W3[g]; p.b3[g] = b3[g]; p.o[g] = outs[g]; p.out[g] = out[g]; }
+  dim3 grid((unsigned)mt::fwd_grid(M, G), (unsigned)G);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mt::dp_of(D)) {
+    case 8: return mt::launch_fwd<8>(p, grid, st);
+    case 16: return mt::launch_fwd<16>(p, grid, st);
+    default: return mt::launch_fwd<32>(p, grid, st);
+  }
+}
+
+extern "C" int64_t ppx_mlp3_tc_bwd_workspace(int M, int D, int H, int G, const int* outs) {
+  if (!outs || !mt::shape_ok(D, H, G, outs)) return -1;
+  const int n = mt::bwd_grid(M, G), RS = mt::round4(mt::rest_size(D, mt::omax_of(G, outs)));
+  return (int64_t)G * n * ((int64_t)mt::H * mt::H + RS);
+}
+
+extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs, const float* W2,
+                               const float* const* W3, const float* H1t, const float* H2t, const float* const* dOut,
+                               const ppx_value_head* vh, float clip_range, int64_t B_total, float* dW1, float* db1,
+                               float* dW2, float* db2, float* const* dW3, float* const* db3, float* workspace,
+                               double* sumsq_partials, int64_t* step_dev, void* stream) {
+  PPX_REQUIRE(X && outs && W2 && W3 && H1t && H2t && dOut && dW1 && db1 && dW2 && db2 && dW3 && db3 && workspace, "mlp3_tc_bwd: null pointer");
+  PPX_REQUIRE(mt::shape_ok(D, H, G, outs), "mlp3_tc_bwd: unsupported shape D=%d H=%d G=%d", D, H, G);
+  PPX_REQUIRE(M >= 1 && ldx >= D, "mlp3_tc_bwd: M=%d ldx=%d", M, ldx);
+  const int n = mt::bwd_grid(M, G), RS = mt::round4(mt::rest_size(D, mt::omax_of(G, outs)));
+  mt::BwdP p{};
+  p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.nTiles = mt::n_tiles(M); p.W2 = W2; p.H1t = H1t; p.H2t = H2t;
+  p.ws2 = workspace; p.wsr = workspace + (size_t)G * n * mt::H * mt::H; p.RS = RS;
+  p.vh_clip = clip_range; p.vh_Bt = (float)(B_total > 0 ? B_total : M);
+  for (int g = 0; g < G; ++g) {
+    p.W3[g] = W3[g]; p.o[g] = outs[g]; p.dOut[g] = dOut[g];
+    if (vh && vh[g].values) {
+      PPX_REQUIRE(outs[g] == 1 && vh[g].old_values && vh[g].returns && vh[g].branch, "mlp3_tc_bwd: value head %d needs o=1 and all inputs", g);
+      p.vh_v[g] = vh[g].values; p.vh_ov[g] = vh[g].old_values; p.vh_R[g] = vh[g].returns; p.vh_branch[g] = vh[g].branch;
+      p.vh_scale[g] = vh[g].scale;
+    } else {
+      PPX_REQUIRE(dOut[g], "mlp3_tc_bwd: dOut[%d] is null", g);
+    }
+  }
+  dim3 grid((unsigned)n, (unsigned)G);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (mt::dp_of(D)) {
+    case 8: rc = mt::launch_bwd<8>(p, grid, st); break;
+    case 16: rc = mt::launch_bwd<16>(p, grid, st); break;
+    default: rc = mt::launch_bwd<32>(p, grid, st); break;
+  }
+  if (rc) return rc;
+  return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
+                                sumsq_partials ? step_dev : nullptr, st);
+}

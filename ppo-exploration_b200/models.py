@@ -38,6 +38,8 @@ TC_MIN_K = 256
 TC_FUSE_NORM = os.environ.get("PPX_TC_FUSE_NORM", "0") == "1"
 # fused forward / backward of the D-h-h-o policy MLPs (mlp_fused.cu); PPX_FUSED_MLP=0 forces the layer-by-layer path
 FUSED_ENABLED = os.environ.get("PPX_FUSED_MLP", "1") != "0"
+# h = 64 policy MLPs: fused kernels with the 64x64 GEMMs on tcgen05 (mlp_tc.cu); PPX_MLP_TC=0 keeps the SIMT pair
+MLP_TC_ENABLED = os.environ.get("PPX_MLP_TC", "1") != "0"
 
 
 class ParamBank:
@@ -297,16 +299,27 @@ class ParallelMLP:
             ia, pa = (C.c_int * G), (C.c_void_p * G)
             outs = ia(*self.outs)
             ok = FUSED_ENABLED and L.call("ppx_mlp3_supported", self.D, self.h, G, outs) == 1
-            self._fa = dict(ok=ok, outs=outs, W3=pa(*[b.p(f"W3.{g}") for g in self.names]),
+            tc = ok and MLP_TC_ENABLED and L.call("ppx_mlp3_tc_supported", self.D, self.h, G, outs) == 1
+            self._fa = dict(ok=ok, tc=tc, outs=outs, W3=pa(*[b.p(f"W3.{g}") for g in self.names]),
                             b3=pa(*[b.p(f"b3.{g}") for g in self.names]),
                             dW3=pa(*[b.g(f"W3.{g}") for g in self.names]), db3=pa(*[b.g(f"b3.{g}") for g in self.names]))
         return self._fa
 
     def forward(self, x):
         M, G, h, D, b = x.shape[0], self.G, self.h, self.D, self.bank
+        fa = self._fused_args()
+        if fa["tc"]:                                            # tensor-core pair: opaque tile-transposed activations
+            n_act = L.call("ppx_mlp3_tc_act_elems", M, h, G)
+            H1 = self.scratch.get("pmlp.H1t", n_act)[:n_act]
+            H2 = self.scratch.get("pmlp.H2t", n_act)[:n_act]
+            outs = [self.scratch.get(f"pmlp.out.{g}", M * o)[:M * o].view(M, o) for g, o in zip(self.names, self.outs)]
+            L.call("ppx_mlp3_tc_fwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W1"), b.p("b1"), b.p("W2"),
+                   b.p("b2"), fa["W3"], fa["b3"], H1.data_ptr(), H2.data_ptr(),
+                   (C.c_void_p * G)(*[o.data_ptr() for o in outs]), L.stream())
+            self._saved = (x, H1, H2)
+            return outs
         H1 = self.scratch.get("pmlp.H1", M * G * h)[:M * G * h].view(M, G * h)
         H2 = self.scratch.get("pmlp.H2", M * G * h)[:M * G * h].view(M, G * h)
-        fa = self._fused_args()
         if fa["ok"]:
             outs = [self.scratch.get(f"pmlp.out.{g}", M * o)[:M * o].view(M, o) for g, o in zip(self.names, self.outs)]
             L.call("ppx_mlp3_fwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W1"), b.p("b1"), b.p("W2"),
@@ -342,7 +355,8 @@ class ParallelMLP:
         M, G, h, D, b, sc = x.shape[0], self.G, self.h, self.D, self.bank, self.scratch
         fa = self._fused_args()
         if fa["ok"]:
-            ws = sc.get("pmlp.fused_ws", L.call("ppx_mlp3_bwd_workspace", M, D, h, G, fa["outs"]))
+            sfx = "_tc" if fa["tc"] else ""
+            ws = sc.get("pmlp.fused_ws" + sfx, L.call(f"ppx_mlp3{sfx}_bwd_workspace", M, D, h, G, fa["outs"]))
             vh = None
             if value_heads:
                 vh = (L.ValueHead * G)()
@@ -354,7 +368,7 @@ class ParallelMLP:
                 n_ss = L.call("ppx_mlp3_sumsq_partials", D, h, G, fa["outs"])
                 ss = sc.get("pmlp.sumsq", n_ss, torch.float64)
                 self.sumsq = (ss, n_ss)
-            L.call("ppx_mlp3_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
+            L.call(f"ppx_mlp3{sfx}_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
                    H2.data_ptr(), dptr, vh, float(clip_range), int(B_total), b.g("W1"), b.g("b1"), b.g("W2"),
                    b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), ss.data_ptr() if ss is not None else None,
                    b.step_dev.data_ptr() if ss is not None else None, L.stream())

@@ -39,6 +39,7 @@ def test_fused_mlp_matches_autograd(M, D, h, box, intrinsic):
     space = ppx.Box((2,)) if box else ppx.Discrete(18)
     pol = _policy(D, h, space, intrinsic)
     assert pol.mlp._fused_args()["ok"], "fused path must be the one under test"
+    pol.mlp._fused_args()["tc"] = False                      # the SIMT pair (mlp_fused.cu); tensor-core pair: test_gpu_mlp_tc.py
     nets = _torch_nets(pol)
     g = torch.Generator().manual_seed(M)
     x = torch.randn(M, D, generator=g)
@@ -64,6 +65,7 @@ def test_fused_matches_layerwise_bitwise_shapes():
     import ppo_exploration_b200 as ppx
     from ppo_exploration_b200 import models as PM
     pol = _policy(8, 64, ppx.Box((2,)), True)
+    pol.mlp._fused_args()["tc"] = False
     x = torch.randn(777, 8, device="cuda")
     outs_f = [o.clone() for o in pol.forward_raw(x)]
     H1f, H2f = pol.mlp._saved[1].clone(), pol.mlp._saved[2].clone()
