@@ -32,6 +32,7 @@ HIDDEN = 64
 N_MINIBATCH = 4
 # DRAM bytes per launch of the fused MLP kernels at the C2 minibatch, from the committed ncu captures
 NCU_TRAFFIC = {"ppx_mlp3_bwd": 144.0e6, "ppx_mlp3_fwd": 81.9e6}
+NCU_TRAFFIC_SRC = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_mlp3_r01b.md)"
 WORKLOAD = ("C2: PPO+SimHash, obs 8, Box(2), k=64, 2048 envs x 256 steps per GPU, swimmer_ppo hparams, "
             "4 minibatches/epoch x 10 epochs")
 
@@ -160,7 +161,8 @@ class ClockSampler:
 class OpTimer:
     """CUDA-event brackets around selected C-ABI calls on the launching stream (roofline measurement)."""
     SHAPE_ARGS = {"ppx_linear_fwd": (4, 5, 6, 10), "ppx_linear_bwd_data": (3, 4, 5, 11), "ppx_linear_bwd_weight": (4, 5, 6, 10),
-                  "ppx_mlp3_fwd": (2, 3, 4, 5), "ppx_mlp3_bwd": (2, 3, 4, 5)}
+                  "ppx_mlp3_fwd": (2, 3, 4, 5), "ppx_mlp3_bwd": (2, 3, 4, 5),
+                  "ppx_mlp3_tc_fwd": (2, 3, 4, 5), "ppx_mlp3_tc_bwd": (2, 3, 4, 5)}
 
     def __init__(self, L, torch):
         self.L, self.torch, self.rec, self.orig = L, torch, [], L.call
@@ -355,14 +357,40 @@ def run_ppx(args):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     top = max(agg.items(), key=lambda kv: kv[1][0])
     (op, (M_, K_, N_, b_)), (tot_ms, cnt) = top
-    if op == "ppx_mlp3_fwd":          # shape = (M, D, H, G): 2 flops per MAC of the three layers of every net
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if op in ("ppx_mlp3_fwd", "ppx_mlp3_tc_fwd"):   # shape = (M, D, H, G): 2 flops per MAC of the three layers of every net
         flops = 2.0 * M_ * (b_ * (K_ * N_ + N_ * N_) + N_ * (A + b_ - 1))
-    elif op == "ppx_mlp3_bwd":        # dgrad (layers 3,2) + wgrad (layers 3,2,1)
+    elif op in ("ppx_mlp3_bwd", "ppx_mlp3_tc_bwd"):  # dgrad (layers 3,2) + wgrad (layers 3,2,1)
         flops = 2.0 * M_ * (b_ * (K_ * N_ + 2 * N_ * N_) + 2 * N_ * (A + b_ - 1))
     else:
         flops = 2.0 * M_ * K_ * N_ * b_
+    # algorithmic bytes of one fused-MLP launch: X read + the two saved activations of every net
+    # written (forward) or read (backward) + the head outputs / their gradients
+    mlp_bytes = 4.0 * M_ * (K_ + 2 * b_ * N_ + (A + b_ - 1))
     achieved = flops / (tot_ms / cnt / 1e3) / 1e12
     ops = sorted(((f"{k[0]}{list(k[1])}", round(v[0], 3), v[1]) for k, v in agg.items()), key=lambda x: -x[1])[:8]
+    ms_launch = tot_ms / cnt
+    if op.startswith("ppx_mlp3_tc"):
+        # the tensor-core pair: the 64x64 GEMMs are off the FMA pipe, what remains is elementwise work + HBM streams
+        # of the saved activations -> HBM roofline (the tensor pipe needs ~3 x flops / 1.1 PFLOP/s tf32 = a few us)
+        gbs = mlp_bytes / (ms_launch / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": f"{op} M={M_} D={K_} H={N_} G={b_}", "achieved": gbs, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": NCU_TRAFFIC.get(op),
+                    "traffic_source": NCU_TRAFFIC_SRC if op in NCU_TRAFFIC else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                    "alg_bytes_per_launch": mlp_bytes, "fp32_equiv_tflops": achieved,
+                    "tf32_mma_tflops": 3.0 * achieved, "tf32_frac_of_bf16_peak": 3.0 * achieved / tf_peak,
+                    "note": "fused policy-MLP kernel with its two 64x64 GEMMs on tcgen05 (3xTF32, fp32-equivalent); "
+                            "algorithmic bytes = 4 M (D + 2 G H + sum o); tf32_mma_tflops counts the three tensor passes",
+                    "ms_per_launch": ms_launch, "launches_per_step": cnt, "top_ops_ms_per_step": ops}
+    else:
+        roofline = {"bound": "tensor", "kernel": f"{op} M={M_} K/D={K_} N/H={N_} batch/G={b_}",
+                    "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                    "traffic": NCU_TRAFFIC.get(op), "traffic_source": NCU_TRAFFIC_SRC if op in NCU_TRAFFIC else None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                    "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
+                    "fp32_frac": achieved / 74.4,
+                    "ms_per_launch": ms_launch, "launches_per_step": cnt, "top_ops_ms_per_step": ops}
     line = {"metric": "transitions/s through GAE+bonus+PPO update", "value": value, "unit": "transitions/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -374,13 +402,7 @@ def run_ppx(args):
                     "d2h_bytes_per_step": int(HP["n_epochs"] * N_MINIBATCH * 64), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": f"{op} M={M_} K/D={K_} N/H={N_} batch/G={b_}",
-                         "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "traffic": NCU_TRAFFIC.get(op), "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_mlp3_r01b.md)" if op in NCU_TRAFFIC else None,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                         "note": "exact-fp32 SIMT kernel (FFMA-bound; 1e-5 parity path), fraction quoted against the bf16 tensor peak; fp32_frac = achieved / 74.4 TFLOP/s (148 SMs x 128 FMA/clk x 1.965 GHz)",
-                         "fp32_frac": achieved / 74.4,
-                         "ms_per_launch": tot_ms / cnt, "launches_per_step": cnt, "top_ops_ms_per_step": ops}}
+            "roofline": roofline}
     if os.environ.get("PPX_BENCH_TRACE") == "1":        # diagnosis: per-rank host timeline of one more pass
         from ppo_exploration_b200 import buffer as BUF
         marks, orig_next = [], BUF.HostRngStream.next

@@ -207,16 +207,21 @@ def bench_mlp3(rows, iters):
         assert pol.mlp._fused_args()["ok"]
         G, so = len(pol.outs), sum(pol.outs)
         x = torch.randn(M, D, device=DEV)
-        outs = pol.forward_raw(x)
-        d = [torch.randn_like(o) / M for o in outs]
-        ms, mn = timed(lambda: pol.forward_raw(x), iters)
-        fl = 2.0 * M * (G * (D * h + h * h) + h * so)
-        report(rows, "mlp3_fwd", f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn,
-               note=f"fp32 SIMT: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
-        ms, mn = timed(lambda: pol.mlp.backward(d), iters)
-        fl = 2.0 * M * (G * (D * h + 2 * h * h) + 2 * h * so)
-        report(rows, "mlp3_bwd", f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn, launches=2,
-               note=f"bwd + partial reduce; fp32 SIMT: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
+        fa = pol.mlp._fused_args()
+        for tc in ((True, False) if fa["tc"] else (False,)):
+            fa["tc"] = tc
+            tag = "_tc" if tc else ""
+            kind = "tcgen05 3xTF32 (fp32-equivalent flops)" if tc else "fp32 SIMT"
+            outs = pol.forward_raw(x)
+            d = [torch.randn_like(o) / M for o in outs]
+            ms, mn = timed(lambda: pol.forward_raw(x), iters)
+            fl = 2.0 * M * (G * (D * h + h * h) + h * so)
+            report(rows, "mlp3_fwd" + tag, f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn,
+                   note=f"{kind}: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
+            ms, mn = timed(lambda: pol.mlp.backward(d), iters)
+            fl = 2.0 * M * (G * (D * h + 2 * h * h) + 2 * h * so)
+            report(rows, "mlp3_bwd" + tag, f"M={M} D={D} H={h} G={G}", 4 * M * (D + 2 * G * h + so), fl, ms, mn, launches=2,
+                   note=f"bwd + partial reduce; {kind}: {fl / ms / 1e9 / 74.4:.3f} of 74.4 TFLOP/s FFMA peak")
 
 
 def bench_bonus(rows, iters):
