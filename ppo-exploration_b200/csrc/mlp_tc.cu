@@ -45,6 +45,22 @@ __device__ __forceinline__ float tanh_fast(float x) {   // same 5-instruction fo
   return fmaf(-2.f, r, 1.f);
 }
 __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// shared-memory accesses by 32-bit shared-window address (the image bases come from a run-time 1024-byte alignment, which
+// would otherwise turn every access into a generic LD/ST with 64-bit address arithmetic)
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
 
 struct FwdP {
   const float* X; int ldx; int M, D, G, nTiles;
@@ -72,35 +88,37 @@ __device__ __forceinline__ void load_x_row(const float* __restrict__ X, int ldx,
 }
 
 // one thread: v[32] = 32 consecutive columns (c0..c0+31, block kb = c0/32) of row s -> raw and lo K-major images
-__device__ __forceinline__ void store_row_images(uint8_t* raw, uint8_t* lo, int s, const float (&v)[32]) {
+__device__ __forceinline__ void store_row_images(uint32_t raw, uint32_t lo, int s, const float (&v)[32]) {
+  const uint32_t row = (uint32_t)(s * 128), x = (uint32_t)(s & 7);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t off = (uint32_t)(s * 128 + ((j ^ (s & 7)) << 4));
-    *reinterpret_cast<float4*>(raw + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    *reinterpret_cast<float4*>(lo + off) = make_float4(lo_of(v[4 * j]), lo_of(v[4 * j + 1]), lo_of(v[4 * j + 2]), lo_of(v[4 * j + 3]));
+    const uint32_t off = row + ((j ^ x) << 4);
+    sts128(raw + off, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    sts128(lo + off, lo_of(v[4 * j]), lo_of(v[4 * j + 1]), lo_of(v[4 * j + 2]), lo_of(v[4 * j + 3]));
   }
 }
 // one thread: v[32] = elements (row r0+c, column s) of a transposed image with 64-row k-blocks (block = s/32)
-__device__ __forceinline__ void store_col_images(uint8_t* raw, uint8_t* lo, int r0, int s, const float (&v)[32]) {
-  const int kb = s >> 5, l = s & 31;
+// (r0 is a multiple of 32, so (r0 + c) & 7 == c & 7 is a compile-time constant per store)
+__device__ __forceinline__ void store_col_images(uint32_t raw, uint32_t lo, int r0, int s, const float (&v)[32]) {
+  const uint32_t l = (uint32_t)(s & 31);
+  const uint32_t base = (uint32_t)((s >> 5) * 8192 + r0 * 128) + ((l & 3) << 2), ch = l >> 2;
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    const int r = r0 + c;
-    const uint32_t off = (uint32_t)(kb * 8192 + r * 128 + ((((l >> 2) ^ (r & 7)) << 4) | ((l & 3) << 2)));
-    *reinterpret_cast<float*>(raw + off) = v[c];
-    *reinterpret_cast<float*>(lo + off) = lo_of(v[c]);
+    const uint32_t off = base + (uint32_t)(c * 128) + ((ch ^ (uint32_t)(c & 7)) << 4);
+    sts32(raw + off, v[c]);
+    sts32(lo + off, lo_of(v[c]));
   }
 }
 
 // W [64][64] row-major (global) -> K-major image of B[n][k] = W[n][k] (transpose = false) or W[k][n] (transpose = true)
-__device__ __forceinline__ void stage_weight(uint8_t* raw, uint8_t* lo, const float* __restrict__ W, bool transpose, int tid) {
+__device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const float* __restrict__ W, bool transpose, int tid) {
   for (int e = tid; e < H * H; e += NT) {
     const int a = e >> 6, b = e & 63;                 // W[a][b]
     const float w = __ldg(W + e);
     const int n = transpose ? b : a, k = transpose ? a : b;
     const uint32_t off = (uint32_t)((k >> 5) * 8192) + sw128_off(n, k & 31);
-    *reinterpret_cast<float*>(raw + off) = w;
-    *reinterpret_cast<float*>(lo + off) = lo_of(w);
+    sts32(raw + off, w);
+    sts32(lo + off, lo_of(w));
   }
 }
 
@@ -124,11 +142,11 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint
 template <int DP>
 __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wb_raw = smem;                    // B[n = j][k = i] = W2[i][j]: 2 k-blocks x [64 rows][128 B]
-  uint8_t* Wb_lo = smem + 16384;
-  uint8_t* A_raw = smem + 32768;             // H1 [s][i]: 2 k-blocks x [128 rows][128 B]
-  uint8_t* A_lo = smem + 65536;
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 32-bit shared-window addresses from here on
+  const uint32_t Wb_raw = smem;              // B[n = j][k = i] = W2[i][j]: 2 k-blocks x [64 rows][128 B]
+  const uint32_t Wb_lo = smem + 16384;
+  const uint32_t A_raw = smem + 32768;       // H1 [s][i]: 2 k-blocks x [128 rows][128 B]
+  const uint32_t A_lo = smem + 65536;
   __shared__ __align__(16) float W1s[DP * H];
   __shared__ __align__(16) float b1s[H], b2s[H], W3s[H * MAXO], b3s[MAXO];
   __shared__ __align__(16) float part[TM * MAXO];
@@ -199,7 +217,7 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem, smem_u32(A_raw), smem_u32(A_lo), 16384, smem_u32(Wb_raw), smem_u32(Wb_lo), 8192, 8);
+        issue_3xtf32(tmem, A_raw, A_lo, 16384, Wb_raw, Wb_lo, 8192, 8);
         umma_commit(smem_u32(&bar));
       }
       __syncwarp();
@@ -255,15 +273,15 @@ __device__ __forceinline__ uint32_t stage_off(int s, int c) { return (uint32_t)(
 template <int DP>
 __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* W_raw = smem;                     // B of GEMM 2: B[n = i][k = j] = W2[i][j]: 2 k-blocks x [64][128 B]
-  uint8_t* W_lo = smem + 16384;
-  uint8_t* V_raw = smem + 32768;             // A of GEMM 1: H1^T [i][s]: 4 k-blocks x [64][128 B]
-  uint8_t* V_lo = smem + 65536;
-  uint8_t* U_raw = smem + 98304;             // phase 1: dP2 [s][j] (A of GEMM 2, 2 k-blocks x [128][128 B]);
-  uint8_t* U_lo = smem + 131072;             // phase 2: dP2^T [j][s] (B of GEMM 1, 4 k-blocks x [64][128 B])
-  uint8_t* S = smem + 163840;                // fp32 staging [128][64]: H2, then dP1
-  float* Xs = reinterpret_cast<float*>(smem + 196608);   // [TM][DP]
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 32-bit shared-window addresses from here on
+  const uint32_t W_raw = smem;               // B of GEMM 2: B[n = i][k = j] = W2[i][j]: 2 k-blocks x [64][128 B]
+  const uint32_t W_lo = smem + 16384;
+  const uint32_t V_raw = smem + 32768;       // A of GEMM 1: H1^T [i][s]: 4 k-blocks x [64][128 B]
+  const uint32_t V_lo = smem + 65536;
+  const uint32_t U_raw = smem + 98304;       // phase 1: dP2 [s][j] (A of GEMM 2, 2 k-blocks x [128][128 B]);
+  const uint32_t U_lo = smem + 131072;       // phase 2: dP2^T [j][s] (B of GEMM 1, 4 k-blocks x [64][128 B])
+  const uint32_t S = smem + 163840;          // fp32 staging [128][64]: H2, then dP1
+  const uint32_t Xs = smem + 196608;         // [TM][DP] fp32
   __shared__ __align__(16) float W3s[MAXO * H];          // [j][c]
   __shared__ __align__(16) float dOs[TM * MAXO];
   __shared__ __align__(8) uint64_t bars[2];
@@ -340,11 +358,11 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     const uint32_t ph = (uint32_t)(it & 1);
     // ---- T1: publish X, dOut and H2 (staging tile S) ----
 #pragma unroll
-    for (int r = 0; r < (TM * DP) / NT; ++r) Xs[tid + r * NT] = xpre[r];
+    for (int r = 0; r < (TM * DP) / NT; ++r) sts32(Xs + (uint32_t)(tid + r * NT) * 4, xpre[r]);
     if (tid < TM) *reinterpret_cast<float4*>(&dOs[tid * MAXO]) = dpre;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(S + stage_off(s, c0 + 4 * j)) = make_float4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+      sts128(S + stage_off(s, c0 + 4 * j), h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
     if (it > 0) {                             // GEMM 1 of the previous tile has finished reading U and V
       mbar_wait(barG1, ph ^ 1);
       tc_fence_after();
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem, smem_u32(U_raw), smem_u32(U_lo), 16384, smem_u32(W_raw), smem_u32(W_lo), 8192, 8);
+        issue_3xtf32(tmem, U_raw, U_lo, 16384, W_raw, W_lo, 8192, 8);
         umma_commit(barG2);
       }
       __syncwarp();
@@ -391,14 +409,14 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     store_col_images(V_raw, V_lo, c0, s, h1);
     {
       float t3[MAXO] = {0.f, 0.f, 0.f, 0.f}, t2 = 0.f, tb[MAXO] = {0.f, 0.f, 0.f, 0.f};
-      const uint8_t* Ublk = U_raw + (tc >> 5) * 16384;
+      const uint32_t Ublk = U_raw + (uint32_t)((tc >> 5) * 16384);
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const int ss = sg * 32 + r;
-        const float hv = *reinterpret_cast<const float*>(S + stage_off(ss, tc));
+        const float hv = lds32(S + stage_off(ss, tc));
         const float4 d = *reinterpret_cast<const float4*>(&dOs[ss * MAXO]);
         t3[0] = fmaf(hv, d.x, t3[0]); t3[1] = fmaf(hv, d.y, t3[1]); t3[2] = fmaf(hv, d.z, t3[2]); t3[3] = fmaf(hv, d.w, t3[3]);
-        t2 += *reinterpret_cast<const float*>(Ublk + sw128_off(ss, tc & 31));
+        t2 += lds32(Ublk + sw128_off(ss, tc & 31));
         tb[0] += d.x; tb[1] += d.y; tb[2] += d.z; tb[3] += d.w;
       }
 #pragma unroll
@@ -419,7 +437,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
         v.y = __uint_as_float(z[4 * j + 1]) * (1.f - h1[4 * j + 1] * h1[4 * j + 1]);
         v.z = __uint_as_float(z[4 * j + 2]) * (1.f - h1[4 * j + 2] * h1[4 * j + 2]);
         v.w = __uint_as_float(z[4 * j + 3]) * (1.f - h1[4 * j + 3] * h1[4 * j + 3]);
-        *reinterpret_cast<float4*>(S + stage_off(s, c0 + 4 * j)) = v;
+        sts128(S + stage_off(s, c0 + 4 * j), v.x, v.y, v.z, v.w);
       }
     }
     store_col_images(U_raw, U_lo, c0, s, dp2);          // GEMM 2 has finished reading the phase-1 images
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem + 64, smem_u32(V_raw), smem_u32(V_lo), 8192, smem_u32(U_raw), smem_u32(U_lo), 8192, 16);
+        issue_3xtf32(tmem + 64, V_raw, V_lo, 8192, U_raw, U_lo, 8192, 16);
         umma_commit(barG1);
       }
       __syncwarp();
@@ -443,11 +461,11 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
 #pragma unroll 4
       for (int r = 0; r < 32; ++r) {
         const int ss = sg * 32 + r;
-        const float dv = *reinterpret_cast<const float*>(S + stage_off(ss, tc));
+        const float dv = lds32(S + stage_off(ss, tc));
         tb += dv;
 #pragma unroll
         for (int k = 0; k < DP; k += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(&Xs[ss * DP + k]);
+          const float4 x = lds128(Xs + (uint32_t)(ss * DP + k) * 4);
           t1[k] = fmaf(dv, x.x, t1[k]); t1[k + 1] = fmaf(dv, x.y, t1[k + 1]);
           t1[k + 2] = fmaf(dv, x.z, t1[k + 2]); t1[k + 3] = fmaf(dv, x.w, t1[k + 3]);
         }
@@ -477,21 +495,22 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
       *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
   }
   constexpr int NQ = DP + 2 + 2 * MAXO;       // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3[4]
-  float* red = reinterpret_cast<float*>(U_raw);          // [4 groups][NQ][64]   (<= 4*42*64*4 = 43 KB of the 64 KB U)
+  const uint32_t red = U_raw;                 // [4 groups][NQ][64] fp32  (<= 4*42*64*4 = 43 KB of the 64 KB U)
   {
-    float* r = red + (size_t)sg * NQ * H + tc;
+    const uint32_t r = red + (uint32_t)(sg * NQ * H + tc) * 4;
 #pragma unroll
-    for (int k = 0; k < DP; ++k) r[k * H] = a_dW1[k];
-    r[DP * H] = a_db1; r[(DP + 1) * H] = a_db2;
+    for (int k = 0; k < DP; ++k) sts32(r + k * H * 4, a_dW1[k]);
+    sts32(r + DP * H * 4, a_db1); sts32(r + (DP + 1) * H * 4, a_db2);
 #pragma unroll
-    for (int j = 0; j < MAXO; ++j) { r[(DP + 2 + j) * H] = a_dW3[j]; r[(DP + 2 + MAXO + j) * H] = a_db3[j]; }
+    for (int j = 0; j < MAXO; ++j) { sts32(r + (DP + 2 + j) * H * 4, a_dW3[j]); sts32(r + (DP + 2 + MAXO + j) * H * 4, a_db3[j]); }
   }
   __syncthreads();
   float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
   const int offb1 = D * H, offb2 = offb1 + H, offW3 = offb2 + H, offb3 = offW3 + H * o;
   for (int e = tid; e < NQ * H; e += NT) {
     const int n = e >> 6, c = e & 63;
-    const float v = ((red[e] + red[NQ * H + e]) + red[2 * NQ * H + e]) + red[3 * NQ * H + e];
+    const uint32_t a = red + (uint32_t)e * 4;
+    const float v = ((lds32(a) + lds32(a + NQ * H * 4)) + lds32(a + 2 * NQ * H * 4)) + lds32(a + 3 * NQ * H * 4);
     if (n < DP) { if (n < D) wr[n * H + c] = v; }
     else if (n == DP) wr[offb1 + c] = v;
     else if (n == DP + 1) wr[offb2 + c] = v;
