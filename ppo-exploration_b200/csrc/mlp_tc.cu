@@ -122,19 +122,23 @@ __device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const fl
   }
 }
 
-// 3xTF32 product of two K-major image pairs: D[128 x 64] (+)= A . B^T over `ksteps` k-steps of 8.
-// Blocks of 32 k are a_kb / b_kb bytes apart.  Small terms first, then the hi.hi pass.
-__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t a_kb, uint32_t b_raw,
-                                             uint32_t b_lo, uint32_t b_kb, int ksteps) {
+// 3xTF32 product of two K-major image pairs: D[128 x 64] (+)= A . B^T over KSTEPS k-steps of 8.
+// Blocks of 32 k are A_KB / B_KB bytes apart.  Small terms first, then the hi.hi pass.  The four base descriptors are
+// built once; every MMA only adds a compile-time constant to the 14-bit address field.
+template <int A_KB, int B_KB, int KSTEPS>
+__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo) {
   constexpr uint32_t idesc = make_idesc(64);
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t oa = (ks >> 2) * a_kb + (ks & 3) * 32, ob = (ks >> 2) * b_kb + (ks & 3) * 32;
-    umma_tf32(tacc, make_desc(a_lo + oa), make_desc(b_raw + ob), idesc, ks ? 1u : 0u);
-    umma_tf32(tacc, make_desc(a_raw + oa), make_desc(b_lo + ob), idesc, 1u);
+  const uint64_t dar = make_desc(a_raw), dal = make_desc(a_lo), dbr = make_desc(b_raw), dbl = make_desc(b_lo);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
+    umma_tf32(tacc, dal + oa, dbr + ob, idesc, ks ? 1u : 0u);
+    umma_tf32(tacc, dar + oa, dbl + ob, idesc, 1u);
   }
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t oa = (ks >> 2) * a_kb + (ks & 3) * 32, ob = (ks >> 2) * b_kb + (ks & 3) * 32;
-    umma_tf32(tacc, make_desc(a_raw + oa), make_desc(b_raw + ob), idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
+    umma_tf32(tacc, dar + oa, dbr + ob, idesc, 1u);
   }
 }
 
@@ -178,6 +182,9 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 
   uint32_t phase = 0;
+  float x[DP];                               // this tile's X row; the next tile's is loaded under the MMA
+  if ((int)blockIdx.x < p.nTiles)
+    load_x_row<DP>(p.X + (size_t)(blockIdx.x * TM + s) * p.ldx, p.ldx, D, blockIdx.x * TM + s < p.M, x);
   for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
     const int m0 = tile * TM;
     const bool live = m0 + s < p.M;
@@ -186,8 +193,6 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     // ---- layer 1 (K = D): registers, W1 by broadcast shared-memory reads ----
     float v[32];
     {
-      float x[DP];
-      load_x_row<DP>(p.X + (size_t)(m0 + s) * p.ldx, p.ldx, D, live, x);
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const float4 b = *reinterpret_cast<const float4*>(&b1s[c0 + c]);
@@ -217,10 +222,14 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem, A_raw, A_lo, 16384, Wb_raw, Wb_lo, 8192, 8);
+        issue_3xtf32<16384, 8192, 8>(tmem, A_raw, A_lo, Wb_raw, Wb_lo);
         umma_commit(smem_u32(&bar));
       }
       __syncwarp();
+    }
+    {
+      const int nt = tile + (int)gridDim.x;
+      if (nt < p.nTiles) load_x_row<DP>(p.X + (size_t)(nt * TM + s) * p.ldx, p.ldx, D, nt * TM + s < p.M, x);
     }
     mbar_wait(smem_u32(&bar), phase);
     phase ^= 1;
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem, U_raw, U_lo, 16384, W_raw, W_lo, 8192, 8);
+        issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo);
         umma_commit(barG2);
       }
       __syncwarp();
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32(tmem + 64, V_raw, V_lo, 8192, U_raw, U_lo, 8192, 16);
+        issue_3xtf32<8192, 8192, 16>(tmem + 64, V_raw, V_lo, U_raw, U_lo);
         umma_commit(barG1);
       }
       __syncwarp();
