@@ -22,6 +22,7 @@
 //
 // Replaces, for H = 64, the nn.Linear/Tanh stacks + autograd of Policy.evaluate inside train()
 // (models.py:52-73, 101-124; algorithms.py:213, 242, 425, 464, 665, 696).
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace ppx {
@@ -98,27 +99,31 @@ __device__ __forceinline__ void store_row_images(uint32_t raw, uint32_t lo, int 
   }
 }
 // one thread: v[32] = elements (row r0+c, column s) of a transposed image with 64-row k-blocks (block = s/32)
-// (r0 is a multiple of 32, so (r0 + c) & 7 == c & 7 is a compile-time constant per store)
-__device__ __forceinline__ void store_col_images(uint32_t raw, uint32_t lo, int r0, int s, const float (&v)[32]) {
+// (r0 is a multiple of 32 and every other term of the base has zero bits [4,7), so the row swizzle is an XOR of the base
+// with the compile-time constant (c & 7) << 4 and the row pitch is an immediate offset)
+__device__ __forceinline__ void store_col_images(uint32_t raw, uint32_t lo_delta, int r0, int s, const float (&v)[32]) {
   const uint32_t l = (uint32_t)(s & 31);
-  const uint32_t base = (uint32_t)((s >> 5) * 8192 + r0 * 128) + ((l & 3) << 2), ch = l >> 2;
+  const uint32_t base = raw + (uint32_t)((s >> 5) * 8192 + r0 * 128) + ((l & 3) << 2) + ((l >> 2) << 4);
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    const uint32_t off = base + (uint32_t)(c * 128) + ((ch ^ (uint32_t)(c & 7)) << 4);
-    sts32(raw + off, v[c]);
-    sts32(lo + off, lo_of(v[c]));
+    const uint32_t a = (base ^ (uint32_t)((c & 7) << 4)) + (uint32_t)(c * 128);
+    sts32(a, v[c]);
+    sts32(a + lo_delta, lo_of(v[c]));
   }
 }
 
 // W [64][64] row-major (global) -> K-major image of B[n][k] = W[n][k] (transpose = false) or W[k][n] (transpose = true)
 __device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const float* __restrict__ W, bool transpose, int tid) {
-  for (int e = tid; e < H * H; e += NT) {
-    const int a = e >> 6, b = e & 63;                 // W[a][b]
-    const float w = __ldg(W + e);
+  float w[H * H / NT];
+#pragma unroll
+  for (int r = 0; r < H * H / NT; ++r) w[r] = __ldg(W + tid + r * NT);          // all loads in flight before the first store
+#pragma unroll
+  for (int r = 0; r < H * H / NT; ++r) {
+    const int e = tid + r * NT, a = e >> 6, b = e & 63;                          // W[a][b]
     const int n = transpose ? b : a, k = transpose ? a : b;
     const uint32_t off = (uint32_t)((k >> 5) * 8192) + sw128_off(n, k & 31);
-    sts32(raw + off, w);
-    sts32(lo + off, lo_of(w));
+    sts32(raw + off, w[r]);
+    sts32(lo + off, lo_of(w[r]));
   }
 }
 
@@ -238,12 +243,27 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     tmem_ld32(taddr, z);
     // ---- epilogue: bias + tanh, H2 out, head layer (o <= 4) ----
     float po[MAXO] = {0.f, 0.f, 0.f, 0.f};
+    float h2v[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-      const float h = tanh_fast(__uint_as_float(z[c]) + b2s[c0 + c]);
-      __stcs(h2t + c * TM, h);
-      const float4 w = *reinterpret_cast<const float4*>(&W3s[(c0 + c) * MAXO]);
-      po[0] = fmaf(h, w.x, po[0]); po[1] = fmaf(h, w.y, po[1]); po[2] = fmaf(h, w.z, po[2]); po[3] = fmaf(h, w.w, po[3]);
+      h2v[c] = tanh_fast(__uint_as_float(z[c]) + b2s[c0 + c]);
+      __stcs(h2t + c * TM, h2v[c]);
+    }
+    auto head = [&](auto oc) {               // only the o live outputs (o is CTA-uniform)
+      constexpr int OC = decltype(oc)::value;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(&W3s[(c0 + c) * MAXO]);
+        const float wj[MAXO] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < OC; ++j) po[j] = fmaf(h2v[c], wj[j], po[j]);
+      }
+    };
+    switch (o) {
+      case 1: head(std::integral_constant<int, 1>{}); break;
+      case 2: head(std::integral_constant<int, 2>{}); break;
+      case 3: head(std::integral_constant<int, 3>{}); break;
+      default: head(std::integral_constant<int, 4>{}); break;
     }
     if (ch == 1) *reinterpret_cast<float4*>(&part[s * MAXO]) = make_float4(po[0], po[1], po[2], po[3]);
     tc_fence_before();                       // the tcgen05.ld above is ordered before the next tile's MMAs
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
 
   // accumulators that live across all tiles of this CTA
   float dW2acc[32];                          // warps with q < 2: dW2[i = q*32+lane][c0 .. c0+31]
-  float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3[MAXO] = {0.f, 0.f, 0.f, 0.f};
+  float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3 = 0.f;
 #pragma unroll
   for (int c = 0; c < 32; ++c) dW2acc[c] = 0.f;
 #pragma unroll
@@ -415,22 +435,28 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
       __syncwarp();
     }
     // ---- T3 (under GEMM 2): H1^T images; dW3 / db2 / db3 sums over this thread's 32 samples ----
-    store_col_images(V_raw, V_lo, c0, s, h1);
+    store_col_images(V_raw, 32768u, c0, s, h1);
     {
-      float t3[MAXO] = {0.f, 0.f, 0.f, 0.f}, t2 = 0.f, tb[MAXO] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t Ublk = U_raw + (uint32_t)((tc >> 5) * 16384);
-#pragma unroll 8
+      float t3[MAXO] = {0.f, 0.f, 0.f, 0.f}, t2 = 0.f;
+      // element (ss = sg*32 + r, tc): the row swizzle (ss & 7) == (r & 7) is an XOR of the base with a constant
+      const uint32_t sS = S + (uint32_t)(sg * 8192) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
+      const uint32_t sU = U_raw + (uint32_t)((tc >> 5) * 16384 + sg * 4096) + (uint32_t)((((tc & 31) >> 2) << 4) | ((tc & 3) << 2));
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const int ss = sg * 32 + r;
-        const float hv = lds32(S + stage_off(ss, tc));
-        const float4 d = *reinterpret_cast<const float4*>(&dOs[ss * MAXO]);
+        const float hv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
+        const float4 d = *reinterpret_cast<const float4*>(&dOs[(sg * 32 + r) * MAXO]);
         t3[0] = fmaf(hv, d.x, t3[0]); t3[1] = fmaf(hv, d.y, t3[1]); t3[2] = fmaf(hv, d.z, t3[2]); t3[3] = fmaf(hv, d.w, t3[3]);
-        t2 += lds32(Ublk + sw128_off(ss, tc & 31));
-        tb[0] += d.x; tb[1] += d.y; tb[2] += d.z; tb[3] += d.w;
+        t2 += lds32((sU ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 128));
       }
 #pragma unroll
-      for (int j = 0; j < MAXO; ++j) { a_dW3[j] += t3[j]; a_db3[j] += tb[j]; }
+      for (int j = 0; j < MAXO; ++j) a_dW3[j] += t3[j];
       a_db2 += t2;
+      if (tc < MAXO) {                        // db3[j = tc]: 16 threads, one column of dOut each
+        float tb = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tb += dOs[(sg * 32 + r) * MAXO + tc];
+        a_db3 += tb;
+      }
     }
     __syncthreads();                          // [B3] every read of S (H2) done before dP1 overwrites it
     // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2); transposed dP2 images (phase 2 of U) -> GEMM 1 ----
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
         sts128(S + stage_off(s, c0 + 4 * j), v.x, v.y, v.z, v.w);
       }
     }
-    store_col_images(U_raw, U_lo, c0, s, dp2);          // GEMM 2 has finished reading the phase-1 images
+    store_col_images(U_raw, 32768u, c0, s, dp2);          // GEMM 2 has finished reading the phase-1 images
     fence_async_smem();
     tc_fence_before();
     __syncthreads();                          // [B4]
@@ -467,14 +493,15 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
       float t1[DP], tb = 0.f;
 #pragma unroll
       for (int k = 0; k < DP; ++k) t1[k] = 0.f;
-#pragma unroll 4
+      const uint32_t sS = S + (uint32_t)(sg * 8192) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
+      const uint32_t sX = Xs + (uint32_t)(sg * 32 * DP * 4);
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const int ss = sg * 32 + r;
-        const float dv = lds32(S + stage_off(ss, tc));
+        const float dv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
         tb += dv;
 #pragma unroll
         for (int k = 0; k < DP; k += 4) {
-          const float4 x = lds128(Xs + (uint32_t)(ss * DP + k) * 4);
+          const float4 x = lds128(sX + (uint32_t)((r * DP + k) * 4));
           t1[k] = fmaf(dv, x.x, t1[k]); t1[k + 1] = fmaf(dv, x.y, t1[k + 1]);
           t1[k + 2] = fmaf(dv, x.z, t1[k + 2]); t1[k + 3] = fmaf(dv, x.w, t1[k + 3]);
         }
@@ -503,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     for (int c = 0; c < 32; c += 4)
       *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
   }
-  constexpr int NQ = DP + 2 + 2 * MAXO;       // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3[4]
+  constexpr int NQ = DP + 3 + MAXO;           // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3 (column j holds db3[j])
   const uint32_t red = U_raw;                 // [4 groups][NQ][64] fp32  (<= 4*42*64*4 = 43 KB of the 64 KB U)
   {
     const uint32_t r = red + (uint32_t)(sg * NQ * H + tc) * 4;
@@ -511,7 +538,8 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     for (int k = 0; k < DP; ++k) sts32(r + k * H * 4, a_dW1[k]);
     sts32(r + DP * H * 4, a_db1); sts32(r + (DP + 1) * H * 4, a_db2);
 #pragma unroll
-    for (int j = 0; j < MAXO; ++j) { sts32(r + (DP + 2 + j) * H * 4, a_dW3[j]); sts32(r + (DP + 2 + MAXO + j) * H * 4, a_db3[j]); }
+    for (int j = 0; j < MAXO; ++j) sts32(r + (DP + 2 + j) * H * 4, a_dW3[j]);
+    sts32(r + (DP + 2 + MAXO) * H * 4, a_db3);
   }
   __syncthreads();
   float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
@@ -524,7 +552,7 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
     else if (n == DP) wr[offb1 + c] = v;
     else if (n == DP + 1) wr[offb2 + c] = v;
     else if (n < DP + 2 + MAXO) { const int j = n - DP - 2; if (j < o) wr[offW3 + c * o + j] = v; }
-    else { const int j = n - DP - 2 - MAXO; if (j < o && c == 0) wr[offb3 + j] = v; }
+    else { if (c < o) wr[offb3 + c] = v; }
   }
   tc_fence_before();
   __syncthreads();
