@@ -11,8 +11,9 @@
 //   * MN-major tf32 operands need the 32-byte-atom swizzle and cannot share an image with a K-major use of the same
 //     data, so the weight-gradient GEMM (reduction over the samples) gets TRANSPOSED images, written with
 //     conflict-free scalar stores (lanes = consecutive samples = consecutive words of a 128-byte row).
-//   * the saved activations are private to this pair of kernels and are kept TRANSPOSED per tile in HBM
-//     (Ht [G][tile][64][128]): both kernels then read/write them with fully coalesced 128-byte warp accesses.
+//   * the saved activations are private to this pair of kernels and are kept per tile in HBM as
+//     Ht [G][tile][16 column quads][128 samples][4]: a thread moves its 32 columns of a sample as 8 float4 and a warp
+//     instruction covers 512 contiguous bytes in both kernels.
 //   * the tensor core's fp32 accumulator truncates on every MMA; small terms are accumulated first and dW2 is drained
 //     into fp32 registers after every tile (48 MMAs), so the drift stays ~1e-6 (tests/test_gpu_mlp_tc.py).
 // Forward: 2 CTAs/SM (96 KB of images each) so one CTA's MMA + epilogue overlaps the other's first layer.
@@ -22,6 +23,7 @@
 //
 // Replaces, for H = 64, the nn.Linear/Tanh stacks + autograd of Policy.evaluate inside train()
 // (models.py:52-73, 101-124; algorithms.py:213, 242, 425, 464, 665, 696).
+#include <cstdlib>
 #include <type_traits>
 #include "tc_common.cuh"
 
@@ -131,9 +133,17 @@ __device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const fl
 // Blocks of 32 k are A_KB / B_KB bytes apart.  Small terms first, then the hi.hi pass.  The four base descriptors are
 // built once; every MMA only adds a compile-time constant to the 14-bit address field.
 template <int A_KB, int B_KB, int KSTEPS>
-__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo) {
+__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, int dbg = 0) {
   constexpr uint32_t idesc = make_idesc(64);
   const uint64_t dar = make_desc(a_raw), dal = make_desc(a_lo), dbr = make_desc(b_raw), dbl = make_desc(b_lo);
+  if (dbg & 1) {                             // timing experiment only (PPX_MLP_TC_DBG): hi.hi pass alone, wrong to ~1e-3
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
+      umma_tf32(tacc, dar + oa, dbr + ob, idesc, ks ? 1u : 0u);
+    }
+    return;
+  }
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
     const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
@@ -193,8 +203,8 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
   for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
     const int m0 = tile * TM;
     const bool live = m0 + s < p.M;
-    float* h1t = p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
-    float* h2t = p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
+    float4* h1t = reinterpret_cast<float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;   // quad (c0/4 + j): + j*TM
+    float4* h2t = reinterpret_cast<float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
     // ---- layer 1 (K = D): registers, W1 by broadcast shared-memory reads ----
     float v[32];
     {
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
       for (int c = 0; c < 32; ++c) v[c] = tanh_fast(v[c]);
     }
 #pragma unroll
-    for (int c = 0; c < 32; ++c) __stcs(h1t + c * TM, v[c]);          // warp = 128 contiguous bytes per column
+    for (int j = 0; j < 8; ++j) __stcs(h1t + j * TM, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));   // warp = 512 contiguous bytes
     store_row_images(A_raw + ch * 16384, A_lo + ch * 16384, s, v);
     fence_async_smem();
     tc_fence_before();
@@ -247,8 +257,9 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       h2v[c] = tanh_fast(__uint_as_float(z[c]) + b2s[c0 + c]);
-      __stcs(h2t + c * TM, h2v[c]);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcs(h2t + j * TM, make_float4(h2v[4 * j], h2v[4 * j + 1], h2v[4 * j + 2], h2v[4 * j + 3]));
     auto head = [&](auto oc) {               // only the o live outputs (o is CTA-uniform)
       constexpr int OC = decltype(oc)::value;
 #pragma unroll
@@ -294,13 +305,48 @@ struct BwdP {
   float* ws2;        // [G][nCta][H*H]   dW2 partials
   float* wsr;        // [G][nCta][RS]    dW1 | db1 | db2 | dW3 | db3 partials
   int RS;
+  int dbg;           // timing experiments (PPX_MLP_TC_DBG): 1 = single-pass MMAs, 2 = skip dW3/db3 sums, 4 = skip dW1/db1/db2 sums
 };
 
 // byte offset of element (s, c) of the fp32 staging tile S [128][64] (16-byte chunks XOR-swizzled by the row)
 __device__ __forceinline__ uint32_t stage_off(int s, int c) { return (uint32_t)(s * 256 + ((((c >> 2) ^ (s & 7)) << 4) | ((c & 3) << 2))); }
 
-template <int DP>
-__global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&v)[CW]) {
+  if constexpr (CW == 32) tmem_ld32_nowait(taddr, v); else tmem_ld16_nowait(taddr, v);
+  tmem_ld_wait();
+}
+// v[CW] = CW consecutive columns (c0 .. c0+CW-1) of row s -> raw and lo K-major images (k-block c0/32)
+template <int CW>
+__device__ __forceinline__ void store_row_images_cw(uint32_t raw, uint32_t lo, int s, int c0, const float (&v)[CW]) {
+  const uint32_t row = (uint32_t)((c0 >> 5) * 16384 + s * 128), x = (uint32_t)(s & 7), cb = (uint32_t)((c0 & 31) >> 2);
+#pragma unroll
+  for (int j = 0; j < CW / 4; ++j) {
+    const uint32_t off = row + (((cb + j) ^ x) << 4);
+    sts128(raw + off, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    sts128(lo + off, lo_of(v[4 * j]), lo_of(v[4 * j + 1]), lo_of(v[4 * j + 2]), lo_of(v[4 * j + 3]));
+  }
+}
+// v[CW] = elements (row r0+c, column s) of a transposed image with 64-row k-blocks (block = s/32); r0 % 8 == 0
+template <int CW>
+__device__ __forceinline__ void store_col_images_cw(uint32_t raw, uint32_t lo_delta, int r0, int s, const float (&v)[CW]) {
+  const uint32_t l = (uint32_t)(s & 31);
+  const uint32_t base = raw + (uint32_t)((s >> 5) * 8192 + r0 * 128) + ((l & 3) << 2) + ((l >> 2) << 4);
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    const uint32_t a = (base ^ (uint32_t)((c & 7) << 4)) + (uint32_t)(c * 128);
+    sts32(a, v[c]);
+    sts32(a + lo_delta, lo_of(v[c]));
+  }
+}
+
+// Backward kernel: 128 x (64 / CW) compute threads -- thread = (sample s, CW hidden columns) -- plus one MMA warp that
+// only waits for "operands ready" mbarriers and issues the two GEMMs of every tile, so no compute warp ever carries the
+// issue latency.  CW = 16: 16 compute warps per SM (1 CTA/SM) hide the shared-memory latency of the thin reductions.
+template <int DP, int CW, bool MMAW>
+__global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_bwd_kernel(BwdP p) {
+  constexpr int NCQ = H / CW, NTC = TM * NCQ, NSG = NTC / H, SPG = TM / NSG;   // column groups, compute threads, sample groups
+  constexpr int XPT = (TM * DP) / NTC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 32-bit shared-window addresses from here on
   const uint32_t W_raw = smem;               // B of GEMM 2: B[n = i][k = j] = W2[i][j]: 2 k-blocks x [64][128 B]
@@ -313,173 +359,55 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
   const uint32_t Xs = smem + 196608;         // [TM][DP] fp32
   __shared__ __align__(16) float W3s[MAXO * H];          // [j][c]
   __shared__ __align__(16) float dOs[TM * MAXO];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = warp & 3, ch = warp >> 2, s = q * 32 + lane, c0 = ch * 32;
-  const int tc = tid & 63, sg = tid >> 6;     // thin-reduction mapping: column tc, samples sg*32 .. +31
   const int g = blockIdx.y, o = p.o[g], D = p.D;
-  const uint32_t barG2 = smem_u32(&bars[0]), barG1 = smem_u32(&bars[1]);
+  const uint32_t barG2 = smem_u32(&bars[0]), barG1 = smem_u32(&bars[1]);     // MMA completion (tcgen05.commit)
+  const uint32_t opsG2 = smem_u32(&bars[2]), opsG1 = smem_u32(&bars[3]);     // operands ready (one arrive per compute warp)
+  auto bar_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); };
 
-  if (tid == 0) { mbar_init(barG2, 1); mbar_init(barG1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) {
+    mbar_init(barG2, 1); mbar_init(barG1, 1); mbar_init(opsG2, NTC / 32); mbar_init(opsG1, NTC / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) tmem_alloc<128>(&tmem_slot);
-  stage_weight(W_raw, W_lo, p.W2 + (size_t)g * H * H, false, tid);
-  for (int e = tid; e < MAXO * H; e += NT) {
-    const int j = e >> 6, c = e & 63;
-    W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+  if (tid < NTC) {
+    float w[H * H / NTC];
+#pragma unroll
+    for (int r = 0; r < H * H / NTC; ++r) w[r] = __ldg(p.W2 + (size_t)g * H * H + tid + r * NTC);
+#pragma unroll
+    for (int r = 0; r < H * H / NTC; ++r) {
+      const int e = tid + r * NTC, i = e >> 6, j = e & 63;
+      const uint32_t off = (uint32_t)((j >> 5) * 8192) + sw128_off(i, j & 31);
+      sts32(W_raw + off, w[r]);
+      sts32(W_lo + off, lo_of(w[r]));
+    }
+    for (int e = tid; e < MAXO * H; e += NTC) {
+      const int j = e >> 6, c = e & 63;
+      W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 
-  // accumulators that live across all tiles of this CTA
-  float dW2acc[32];                          // warps with q < 2: dW2[i = q*32+lane][c0 .. c0+31]
-  float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) dW2acc[c] = 0.f;
-#pragma unroll
-  for (int k = 0; k < DP; ++k) a_dW1[k] = 0.f;
-
-  // prefetch registers for the next tile
-  float h1[32], h2[32];
-  float xpre[(TM * DP) / NT];
-  float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto prefetch = [&](int tile) {
-    const int m0 = tile * TM;
-    const float* h1t = p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
-    const float* h2t = p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM + s;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { h1[c] = ld_stream(h1t + c * TM); h2[c] = ld_stream(h2t + c * TM); }
-#pragma unroll
-    for (int r = 0; r < (TM * DP) / NT; ++r) {                 // Xs element e = tid + r*NT: row e / DP, column e % DP
-      const int e = tid + r * NT, row = e / DP, k = e % DP;
-      xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
-    }
-    if (tid < TM) {                                            // output gradient of row tid
-      const int b = m0 + tid;
-      float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
-      if (b < p.M) {
-        if (p.vh_v[g] != nullptr) {                            // o == 1 (checked on the host); same formula as mlp_fused.cu
-          const float w1 = (float)p.vh_branch[g][0], w2 = (float)p.vh_branch[g][1], clip = p.vh_clip;
-          const float v = ld_stream(p.vh_v[g] + b), ov = ld_stream(p.vh_ov[g] + b), R = ld_stream(p.vh_R[g] + b);
-          const float dd = v - ov;
-          const float vc = ov + fminf(fmaxf(dd, -clip), clip);
-          const float pass = (dd >= -clip && dd <= clip) ? 1.f : 0.f;
-          const float gv = w1 * (-2.f * (R - v)) + w2 * (-2.f * (R - vc)) * pass;
-          d[0] = p.vh_scale[g] * gv / p.vh_Bt;
-        } else {
-#pragma unroll
-          for (int j = 0; j < MAXO; ++j)
-            if (j < o) d[j] = ld_stream(p.dOut[g] + (size_t)b * o + j);
-        }
-      }
-      dpre = make_float4(d[0], d[1], d[2], d[3]);
-    }
-  };
-
-  int it = 0;
-  if ((int)blockIdx.x < p.nTiles) prefetch(blockIdx.x);
-  for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
-    const uint32_t ph = (uint32_t)(it & 1);
-    // ---- T1: publish X, dOut and H2 (staging tile S) ----
-#pragma unroll
-    for (int r = 0; r < (TM * DP) / NT; ++r) sts32(Xs + (uint32_t)(tid + r * NT) * 4, xpre[r]);
-    if (tid < TM) *reinterpret_cast<float4*>(&dOs[tid * MAXO]) = dpre;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(S + stage_off(s, c0 + 4 * j), h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
-    if (it > 0) {                             // GEMM 1 of the previous tile has finished reading U and V
-      mbar_wait(barG1, ph ^ 1);
-      tc_fence_after();
-    }
-    __syncthreads();                          // [B1]
-    // ---- T2: dP2 = (dOut W3^T)(1 - H2^2) -> K-major images (phase 1 of U) -> GEMM 2 ----
-    float dp2[32];
-    {
-      const float4 d = *reinterpret_cast<const float4*>(&dOs[s * MAXO]);
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float dj[MAXO] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int j = 0; j < MAXO; ++j)
-          if (j < o) {                        // CTA-uniform
-            const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
-            a.x = fmaf(dj[j], w.x, a.x); a.y = fmaf(dj[j], w.y, a.y); a.z = fmaf(dj[j], w.z, a.z); a.w = fmaf(dj[j], w.w, a.w);
-          }
-        dp2[c] = a.x * (1.f - h2[c] * h2[c]); dp2[c + 1] = a.y * (1.f - h2[c + 1] * h2[c + 1]);
-        dp2[c + 2] = a.z * (1.f - h2[c + 2] * h2[c + 2]); dp2[c + 3] = a.w * (1.f - h2[c + 3] * h2[c + 3]);
-      }
-    }
-    store_row_images(U_raw + ch * 16384, U_lo + ch * 16384, s, dp2);
-    // drain the previous tile's dW2 accumulator (rows i = TMEM lanes 0..63) before GEMM 1 of this tile restarts it
-    if (it > 0 && q < 2) {
-      uint32_t z[32];
-      tmem_ld32(taddr + 64, z);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) dW2acc[c] += __uint_as_float(z[c]);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();                          // [B2]
-    if (warp == 0) {
+  if (MMAW && warp == NTC / 32) {
+    // ------------------------------------------------ MMA warp ------------------------------------------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      mbar_wait(opsG2, ph);                   // dP2 images written (and the previous GEMM-2 accumulator read)
       tc_fence_after();
       if (elect_one()) {
         issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo);
         umma_commit(barG2);
       }
       __syncwarp();
-    }
-    // ---- T3 (under GEMM 2): H1^T images; dW3 / db2 / db3 sums over this thread's 32 samples ----
-    store_col_images(V_raw, 32768u, c0, s, h1);
-    {
-      float t3[MAXO] = {0.f, 0.f, 0.f, 0.f}, t2 = 0.f;
-      // element (ss = sg*32 + r, tc): the row swizzle (ss & 7) == (r & 7) is an XOR of the base with a constant
-      const uint32_t sS = S + (uint32_t)(sg * 8192) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
-      const uint32_t sU = U_raw + (uint32_t)((tc >> 5) * 16384 + sg * 4096) + (uint32_t)((((tc & 31) >> 2) << 4) | ((tc & 3) << 2));
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const float hv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
-        const float4 d = *reinterpret_cast<const float4*>(&dOs[(sg * 32 + r) * MAXO]);
-        t3[0] = fmaf(hv, d.x, t3[0]); t3[1] = fmaf(hv, d.y, t3[1]); t3[2] = fmaf(hv, d.z, t3[2]); t3[3] = fmaf(hv, d.w, t3[3]);
-        t2 += lds32((sU ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 128));
-      }
-#pragma unroll
-      for (int j = 0; j < MAXO; ++j) a_dW3[j] += t3[j];
-      a_db2 += t2;
-      if (tc < MAXO) {                        // db3[j = tc]: 16 threads, one column of dOut each
-        float tb = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) tb += dOs[(sg * 32 + r) * MAXO + tc];
-        a_db3 += tb;
-      }
-    }
-    __syncthreads();                          // [B3] every read of S (H2) done before dP1 overwrites it
-    // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2); transposed dP2 images (phase 2 of U) -> GEMM 1 ----
-    mbar_wait(barG2, ph);
-    tc_fence_after();
-    {
-      uint32_t z[32];
-      tmem_ld32(taddr, z);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v;
-        v.x = __uint_as_float(z[4 * j]) * (1.f - h1[4 * j] * h1[4 * j]);
-        v.y = __uint_as_float(z[4 * j + 1]) * (1.f - h1[4 * j + 1] * h1[4 * j + 1]);
-        v.z = __uint_as_float(z[4 * j + 2]) * (1.f - h1[4 * j + 2] * h1[4 * j + 2]);
-        v.w = __uint_as_float(z[4 * j + 3]) * (1.f - h1[4 * j + 3] * h1[4 * j + 3]);
-        sts128(S + stage_off(s, c0 + 4 * j), v.x, v.y, v.z, v.w);
-      }
-    }
-    store_col_images(U_raw, 32768u, c0, s, dp2);          // GEMM 2 has finished reading the phase-1 images
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();                          // [B4]
-    if (warp == 0) {
+      mbar_wait(opsG1, ph);                   // H1^T and dP2^T images written, previous dW2 accumulator drained
       tc_fence_after();
       if (elect_one()) {
         issue_3xtf32<8192, 8192, 16>(tmem + 64, V_raw, V_lo, U_raw, U_lo);
@@ -487,72 +415,240 @@ __global__ void __launch_bounds__(NT, 1) mlp3_tc_bwd_kernel(BwdP p) {
       }
       __syncwarp();
     }
-    // ---- T5 (under GEMM 1): next tile's loads in flight; dW1 / db1 sums ----
-    if (tile + (int)gridDim.x < p.nTiles) prefetch(tile + gridDim.x);
-    {
-      float t1[DP], tb = 0.f;
-#pragma unroll
-      for (int k = 0; k < DP; ++k) t1[k] = 0.f;
-      const uint32_t sS = S + (uint32_t)(sg * 8192) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
-      const uint32_t sX = Xs + (uint32_t)(sg * 32 * DP * 4);
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const float dv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
-        tb += dv;
-#pragma unroll
-        for (int k = 0; k < DP; k += 4) {
-          const float4 x = lds128(sX + (uint32_t)((r * DP + k) * 4));
-          t1[k] = fmaf(dv, x.x, t1[k]); t1[k + 1] = fmaf(dv, x.y, t1[k + 1]);
-          t1[k + 2] = fmaf(dv, x.z, t1[k + 2]); t1[k + 3] = fmaf(dv, x.w, t1[k + 3]);
+  } else {
+    // ------------------------------------------------ compute warps ------------------------------------------------
+    const int q = warp & 3, cq = warp >> 2, s = q * 32 + lane, c0 = cq * CW;
+    const int tc = tid & 63, sg = tid >> 6;   // thin-reduction mapping: column tc, samples sg*SPG .. +SPG-1
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+    // this thread's image writes -> visible to the tensor core; then either one arrive per warp for the MMA warp, or
+    // (no MMA warp) a barrier after which warp 0 issues the GEMM itself
+    auto ops_ready = [&](uint32_t bar, int which) {
+      fence_async_smem();
+      tc_fence_before();
+      if constexpr (MMAW) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+      } else {
+        bar_compute();
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            if (which == 2) { issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo, p.dbg); umma_commit(barG2); }
+            else { issue_3xtf32<8192, 8192, 16>(tmem + 64, V_raw, V_lo, U_raw, U_lo, p.dbg); umma_commit(barG1); }
+          }
+          __syncwarp();
         }
       }
+    };
+
+    float dW2acc[CW];                         // warps with q < 2: dW2[i = q*32+lane][c0 .. c0+CW-1]
+    float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3 = 0.f;
 #pragma unroll
-      for (int k = 0; k < DP; ++k) a_dW1[k] += t1[k];
-      a_db1 += tb;
+    for (int c = 0; c < CW; ++c) dW2acc[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) a_dW1[k] = 0.f;
+
+    float h1[CW], h2[CW], xpre[XPT];
+    float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](int tile) {
+      const int m0 = tile * TM;
+      const float4* h1t = reinterpret_cast<const float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
+      const float4* h2t = reinterpret_cast<const float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 a = ld_stream4(h1t + j * TM), b = ld_stream4(h2t + j * TM);
+        h1[4 * j] = a.x; h1[4 * j + 1] = a.y; h1[4 * j + 2] = a.z; h1[4 * j + 3] = a.w;
+        h2[4 * j] = b.x; h2[4 * j + 1] = b.y; h2[4 * j + 2] = b.z; h2[4 * j + 3] = b.w;
+      }
+#pragma unroll
+      for (int r = 0; r < XPT; ++r) {                        // Xs element e = tid + r*NTC: row e / DP, column e % DP
+        const int e = tid + r * NTC, row = e / DP, k = e % DP;
+        xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
+      }
+      if (tid < TM) {                                        // output gradient of row tid
+        const int b = m0 + tid;
+        float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
+        if (b < p.M) {
+          if (p.vh_v[g] != nullptr) {                        // o == 1 (checked on the host); same formula as mlp_fused.cu
+            const float w1 = (float)p.vh_branch[g][0], w2 = (float)p.vh_branch[g][1], clip = p.vh_clip;
+            const float v = ld_stream(p.vh_v[g] + b), ov = ld_stream(p.vh_ov[g] + b), R = ld_stream(p.vh_R[g] + b);
+            const float dd = v - ov;
+            const float vc = ov + fminf(fmaxf(dd, -clip), clip);
+            const float pass = (dd >= -clip && dd <= clip) ? 1.f : 0.f;
+            const float gv = w1 * (-2.f * (R - v)) + w2 * (-2.f * (R - vc)) * pass;
+            d[0] = p.vh_scale[g] * gv / p.vh_Bt;
+          } else {
+#pragma unroll
+            for (int j = 0; j < MAXO; ++j)
+              if (j < o) d[j] = ld_stream(p.dOut[g] + (size_t)b * o + j);
+          }
+        }
+        dpre = make_float4(d[0], d[1], d[2], d[3]);
+      }
+    };
+
+    int it = 0;
+    if ((int)blockIdx.x < p.nTiles) prefetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      // ---- T1: publish X, dOut and H2 (staging tile S) ----
+#pragma unroll
+      for (int r = 0; r < XPT; ++r) sts32(Xs + (uint32_t)(tid + r * NTC) * 4, xpre[r]);
+      if (tid < TM) *reinterpret_cast<float4*>(&dOs[tid * MAXO]) = dpre;
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j)
+        sts128(S + stage_off(s, c0 + 4 * j), h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+      bar_compute();                          // [B1]
+      // ---- T2: dP2 = (dOut W3^T)(1 - H2^2) -> K-major images (phase 1 of U) -> GEMM 2 ----
+      float dp2[CW];
+      {
+        const float4 d = *reinterpret_cast<const float4*>(&dOs[s * MAXO]);
+        const float dj[MAXO] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int c = 0; c < CW; c += 4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j)
+            if (j < o) {                      // CTA-uniform
+              const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
+              a.x = fmaf(dj[j], w.x, a.x); a.y = fmaf(dj[j], w.y, a.y); a.z = fmaf(dj[j], w.z, a.z); a.w = fmaf(dj[j], w.w, a.w);
+            }
+          dp2[c] = a.x * (1.f - h2[c] * h2[c]); dp2[c + 1] = a.y * (1.f - h2[c + 1] * h2[c + 1]);
+          dp2[c + 2] = a.z * (1.f - h2[c + 2] * h2[c + 2]); dp2[c + 3] = a.w * (1.f - h2[c + 3] * h2[c + 3]);
+        }
+      }
+      if (it > 0) {                           // GEMM 1 of the previous tile has finished reading U and V
+        mbar_wait(barG1, ph ^ 1);
+        tc_fence_after();
+        if (q < 2) {                          // ... and its dW2 accumulator (rows i = TMEM lanes 0..63) is drained
+          uint32_t z[CW];
+          tmem_ld_cw<CW>(taddr + 64, z);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) dW2acc[c] += __uint_as_float(z[c]);
+        }
+      }
+      store_row_images_cw<CW>(U_raw, U_lo, s, c0, dp2);
+      ops_ready(opsG2, 2);
+      // ---- T3 (under GEMM 2): H1^T images; dW3 / db3 sums over this thread's SPG samples ----
+      store_col_images_cw<CW>(V_raw, 32768u, c0, s, h1);
+      if (!(p.dbg & 2)) {
+        float t3[MAXO] = {0.f, 0.f, 0.f, 0.f};
+        // element (ss = sg*SPG + r, tc): the row swizzle (ss & 7) == (r & 7) is an XOR of the base with a constant
+        const uint32_t sS = S + (uint32_t)(sg * SPG * 256) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
+#pragma unroll
+        for (int r = 0; r < SPG; ++r) {
+          const float hv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
+          const float4 d = *reinterpret_cast<const float4*>(&dOs[(sg * SPG + r) * MAXO]);
+          t3[0] = fmaf(hv, d.x, t3[0]); t3[1] = fmaf(hv, d.y, t3[1]); t3[2] = fmaf(hv, d.z, t3[2]); t3[3] = fmaf(hv, d.w, t3[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) a_dW3[j] += t3[j];
+        if (tc < MAXO) {                      // db3[j = tc]: one column of dOut
+          float tb = 0.f;
+#pragma unroll
+          for (int r = 0; r < SPG; ++r) tb += dOs[(sg * SPG + r) * MAXO + tc];
+          a_db3 += tb;
+        }
+      }
+      bar_compute();                          // [B3] every read of S (H2) done before dP1 overwrites it
+      // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2); transposed dP2 images (phase 2 of U) -> GEMM 1 ----
+      mbar_wait(barG2, ph);
+      tc_fence_after();
+      {
+        uint32_t z[CW];
+        tmem_ld_cw<CW>(taddr, z);
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          float4 v;
+          v.x = __uint_as_float(z[4 * j]) * (1.f - h1[4 * j] * h1[4 * j]);
+          v.y = __uint_as_float(z[4 * j + 1]) * (1.f - h1[4 * j + 1] * h1[4 * j + 1]);
+          v.z = __uint_as_float(z[4 * j + 2]) * (1.f - h1[4 * j + 2] * h1[4 * j + 2]);
+          v.w = __uint_as_float(z[4 * j + 3]) * (1.f - h1[4 * j + 3] * h1[4 * j + 3]);
+          sts128(S + stage_off(s, c0 + 4 * j), v.x, v.y, v.z, v.w);
+        }
+      }
+      store_col_images_cw<CW>(U_raw, 32768u, c0, s, dp2);   // GEMM 2 has finished reading the phase-1 images
+      ops_ready(opsG1, 1);
+      if constexpr (MMAW) bar_compute();      // [B4] dP1 (S) and the dP2^T image published to the thin reductions
+      // ---- T5 (under GEMM 1): next tile's loads in flight; dW1 / db1 / db2 sums ----
+      if (tile + (int)gridDim.x < p.nTiles) prefetch(tile + gridDim.x);
+      if (!(p.dbg & 4)) {
+        float t1[DP], tb = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) t1[k] = 0.f;
+        const uint32_t sS = S + (uint32_t)(sg * SPG * 256) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
+        const uint32_t sX = Xs + (uint32_t)(sg * SPG * DP * 4);
+#pragma unroll
+        for (int r = 0; r < SPG; ++r) {
+          const float dv = lds32((sS ^ (uint32_t)((r & 7) << 4)) + (uint32_t)(r * 256));
+          tb += dv;
+#pragma unroll
+          for (int k = 0; k < DP; k += 4) {
+            const float4 x = lds128(sX + (uint32_t)((r * DP + k) * 4));
+            t1[k] = fmaf(dv, x.x, t1[k]); t1[k + 1] = fmaf(dv, x.y, t1[k + 1]);
+            t1[k + 2] = fmaf(dv, x.z, t1[k + 2]); t1[k + 3] = fmaf(dv, x.w, t1[k + 3]);
+          }
+        }
+        // db2[tc] += sum over this group's samples of dP2: row tc of the transposed raw image, SPG consecutive samples
+        const uint32_t uR = U_raw + (uint32_t)(((sg * SPG) >> 5) * 8192 + tc * 128);
+        const uint32_t m0 = (uint32_t)(((sg * SPG) & 31) >> 2), x7 = (uint32_t)(tc & 7);
+#pragma unroll
+        for (int m = 0; m < SPG / 4; ++m) {
+          const float4 v = lds128(uR + (((m0 + m) ^ x7) << 4));
+          t2 += (v.x + v.y) + (v.z + v.w);
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k) a_dW1[k] += t1[k];
+        a_db1 += tb;
+        a_db2 += t2;
+      }
+      bar_compute();                          // [B5] S, Xs, dOs free for the next tile
     }
-    __syncthreads();                          // [B5] S, Xs, dOs free for the next tile
-  }
-  // ---- the last tile's dW2 contribution ----
-  if (it > 0) {
-    mbar_wait(barG1, (uint32_t)((it - 1) & 1));
-    tc_fence_after();
+    // ---- the last tile's dW2 contribution ----
+    if (it > 0) {
+      mbar_wait(barG1, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      if (q < 2) {
+        uint32_t z[CW];
+        tmem_ld_cw<CW>(taddr + 64, z);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) dW2acc[c] += __uint_as_float(z[c]);
+      }
+    }
+    // ---- one partial per CTA: dW2 straight from registers; the thin sums of the sample groups combined in order ----
+    float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
     if (q < 2) {
-      uint32_t z[32];
-      tmem_ld32(taddr + 64, z);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) dW2acc[c] += __uint_as_float(z[c]);
+      for (int c = 0; c < CW; c += 4)
+        *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
     }
-  }
-  // ---- one partial per CTA: dW2 straight from registers; the thin sums of the 4 sample groups combined in order ----
-  float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
-  if (q < 2) {
+    constexpr int NQ = DP + 3 + MAXO;         // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3 (column j holds db3[j])
+    static_assert(NSG * NQ * H * 4 <= 98304, "reduction scratch must fit U + S");
+    const uint32_t red = U_raw;               // [NSG groups][NQ][64] fp32 over U (and S for DP = 32)
+    {
+      const uint32_t r = red + (uint32_t)(sg * NQ * H + tc) * 4;
 #pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
-  }
-  constexpr int NQ = DP + 3 + MAXO;           // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3 (column j holds db3[j])
-  const uint32_t red = U_raw;                 // [4 groups][NQ][64] fp32  (<= 4*42*64*4 = 43 KB of the 64 KB U)
-  {
-    const uint32_t r = red + (uint32_t)(sg * NQ * H + tc) * 4;
+      for (int k = 0; k < DP; ++k) sts32(r + k * H * 4, a_dW1[k]);
+      sts32(r + DP * H * 4, a_db1); sts32(r + (DP + 1) * H * 4, a_db2);
 #pragma unroll
-    for (int k = 0; k < DP; ++k) sts32(r + k * H * 4, a_dW1[k]);
-    sts32(r + DP * H * 4, a_db1); sts32(r + (DP + 1) * H * 4, a_db2);
+      for (int j = 0; j < MAXO; ++j) sts32(r + (DP + 2 + j) * H * 4, a_dW3[j]);
+      sts32(r + (DP + 2 + MAXO) * H * 4, a_db3);
+    }
+    bar_compute();
+    float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
+    const int offb1 = D * H, offb2 = offb1 + H, offW3 = offb2 + H, offb3 = offW3 + H * o;
+    for (int e = tid; e < NQ * H; e += NTC) {
+      const int n = e >> 6, c = e & 63;
+      const uint32_t a = red + (uint32_t)e * 4;
+      float v = lds32(a);
 #pragma unroll
-    for (int j = 0; j < MAXO; ++j) sts32(r + (DP + 2 + j) * H * 4, a_dW3[j]);
-    sts32(r + (DP + 2 + MAXO) * H * 4, a_db3);
-  }
-  __syncthreads();
-  float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
-  const int offb1 = D * H, offb2 = offb1 + H, offW3 = offb2 + H, offb3 = offW3 + H * o;
-  for (int e = tid; e < NQ * H; e += NT) {
-    const int n = e >> 6, c = e & 63;
-    const uint32_t a = red + (uint32_t)e * 4;
-    const float v = ((lds32(a) + lds32(a + NQ * H * 4)) + lds32(a + 2 * NQ * H * 4)) + lds32(a + 3 * NQ * H * 4);
-    if (n < DP) { if (n < D) wr[n * H + c] = v; }
-    else if (n == DP) wr[offb1 + c] = v;
-    else if (n == DP + 1) wr[offb2 + c] = v;
-    else if (n < DP + 2 + MAXO) { const int j = n - DP - 2; if (j < o) wr[offW3 + c * o + j] = v; }
-    else { if (c < o) wr[offb3 + c] = v; }
+      for (int k = 1; k < NSG; ++k) v += lds32(a + (uint32_t)(k * NQ * H * 4));
+      if (n < DP) { if (n < D) wr[n * H + c] = v; }
+      else if (n == DP) wr[offb1 + c] = v;
+      else if (n == DP + 1) wr[offb2 + c] = v;
+      else if (n < DP + 2 + MAXO) { const int j = n - DP - 2; if (j < o) wr[offW3 + c * o + j] = v; }
+      else { if (c < o) wr[offb3 + c] = v; }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -584,15 +680,25 @@ int launch_fwd(const FwdP& p, dim3 grid, cudaStream_t st) {
   mlp3_tc_fwd_kernel<DP><<<grid, NT, kFwdSmem, st>>>(p);
   return after_launch("mlp3_tc_fwd");
 }
-template <int DP>
+template <int DP, int CW, bool MMAW>
 int launch_bwd(const BwdP& p, dim3 grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(DP)));
+    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_bwd_kernel<DP, CW, MMAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(DP)));
     configured = true;
   }
-  mlp3_tc_bwd_kernel<DP><<<grid, NT, bwd_smem(DP), st>>>(p);
+  mlp3_tc_bwd_kernel<DP, CW, MMAW><<<grid, TM * (H / CW) + (MMAW ? 32 : 0), bwd_smem(DP), st>>>(p);
   return after_launch("mlp3_tc_bwd");
+}
+inline bool bwd_mmaw() {                     // PPX_MLP_TC_MMAW=1: dedicated MMA-issue warp (costs registers: 17 / 9 warps per CTA)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PPX_MLP_TC_MMAW"); v = (e && atoi(e) == 1) ? 1 : 0; }
+  return v == 1;
+}
+inline int bwd_cw() {                        // PPX_MLP_TC_CW=32: 8 compute warps per CTA instead of 16
+  static int cw = 0;
+  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW"); cw = (e && atoi(e) == 32) ? 32 : 16; }
+  return cw;
 }
 
 }  // namespace mt
@@ -648,6 +754,7 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
   p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.nTiles = mt::n_tiles(M); p.W2 = W2; p.H1t = H1t; p.H2t = H2t;
   p.ws2 = workspace; p.wsr = workspace + (size_t)G * n * mt::H * mt::H; p.RS = RS;
   p.vh_clip = clip_range; p.vh_Bt = (float)(B_total > 0 ? B_total : M);
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PPX_MLP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   for (int g = 0; g < G; ++g) {
     p.W3[g] = W3[g]; p.o[g] = outs[g]; p.dOut[g] = dOut[g];
     if (vh && vh[g].values) {
@@ -661,11 +768,16 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
   dim3 grid((unsigned)n, (unsigned)G);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  const bool w16 = mt::bwd_cw() == 16, mw = mt::bwd_mmaw();
+#define PPX_BWD(DPV)                                                                                          \
+  rc = w16 ? (mw ? mt::launch_bwd<DPV, 16, true>(p, grid, st) : mt::launch_bwd<DPV, 16, false>(p, grid, st))   \
+           : (mw ? mt::launch_bwd<DPV, 32, true>(p, grid, st) : mt::launch_bwd<DPV, 32, false>(p, grid, st))
   switch (mt::dp_of(D)) {
-    case 8: rc = mt::launch_bwd<8>(p, grid, st); break;
-    case 16: rc = mt::launch_bwd<16>(p, grid, st); break;
-    default: rc = mt::launch_bwd<32>(p, grid, st); break;
+    case 8: PPX_BWD(8); break;
+    case 16: PPX_BWD(16); break;
+    default: PPX_BWD(32); break;
   }
+#undef PPX_BWD
   if (rc) return rc;
   return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
                                 sumsq_partials ? step_dev : nullptr, st);
