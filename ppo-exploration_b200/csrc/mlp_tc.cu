@@ -132,9 +132,9 @@ __device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const fl
 // 3xTF32 product of two K-major image pairs: D[128 x 64] (+)= A . B^T over KSTEPS k-steps of 8.
 // Blocks of 32 k are A_KB / B_KB bytes apart.  Small terms first, then the hi.hi pass.  The four base descriptors are
 // built once; every MMA only adds a compile-time constant to the 14-bit address field.
-template <int A_KB, int B_KB, int KSTEPS>
+template <int A_KB, int B_KB, int KSTEPS, int MM = 128>
 __device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, int dbg = 0) {
-  constexpr uint32_t idesc = make_idesc(64);
+  constexpr uint32_t idesc = make_idesc(64, MM);
   const uint64_t dar = make_desc(a_raw), dal = make_desc(a_lo), dbr = make_desc(b_raw), dbl = make_desc(b_lo);
   if (dbg & 1) {                             // timing experiment only (PPX_MLP_TC_DBG): hi.hi pass alone, wrong to ~1e-3
 #pragma unroll
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       mbar_wait(opsG1, ph);                   // H1^T and dP2^T images written, previous dW2 accumulator drained
       tc_fence_after();
       if (elect_one()) {
-        issue_3xtf32<8192, 8192, 16>(tmem + 64, V_raw, V_lo, U_raw, U_lo);
+        issue_3xtf32<8192, 8192, 16, 64>(tmem + 64, V_raw, V_lo, U_raw, U_lo);
         umma_commit(barG1);
       }
       __syncwarp();
@@ -434,14 +434,14 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
           tc_fence_after();
           if (elect_one()) {
             if (which == 2) { issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo, p.dbg); umma_commit(barG2); }
-            else { issue_3xtf32<8192, 8192, 16>(tmem + 64, V_raw, V_lo, U_raw, U_lo, p.dbg); umma_commit(barG1); }
+            else { issue_3xtf32<8192, 8192, 16, 64>(tmem + 64, V_raw, V_lo, U_raw, U_lo, p.dbg); umma_commit(barG1); }
           }
           __syncwarp();
         }
       }
     };
 
-    float dW2acc[CW];                         // warps with q < 2: dW2[i = q*32+lane][c0 .. c0+CW-1]
+    float dW2acc[CW];                         // lanes < 16: dW2[i = q*16+lane][c0 .. c0+CW-1]
     float a_dW1[DP], a_db1 = 0.f, a_db2 = 0.f, a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}, a_db3 = 0.f;
 #pragma unroll
     for (int c = 0; c < CW; ++c) dW2acc[c] = 0.f;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       if (it > 0) {                           // GEMM 1 of the previous tile has finished reading U and V
         mbar_wait(barG1, ph ^ 1);
         tc_fence_after();
-        if (q < 2) {                          // ... and its dW2 accumulator (rows i = TMEM lanes 0..63) is drained
+        {                                     // ... and its dW2 accumulator is drained (UMMA M = 64: row i sits in lane i%16 of quarter i/16)
           uint32_t z[CW];
           tmem_ld_cw<CW>(taddr + 64, z);
 #pragma unroll
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
     if (it > 0) {
       mbar_wait(barG1, (uint32_t)((it - 1) & 1));
       tc_fence_after();
-      if (q < 2) {
+      {
         uint32_t z[CW];
         tmem_ld_cw<CW>(taddr + 64, z);
 #pragma unroll
@@ -617,10 +617,10 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
     }
     // ---- one partial per CTA: dW2 straight from registers; the thin sums of the sample groups combined in order ----
     float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
-    if (q < 2) {
+    if (lane < 16) {
 #pragma unroll
       for (int c = 0; c < CW; c += 4)
-        *reinterpret_cast<float4*>(&w2[(q * 32 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
+        *reinterpret_cast<float4*>(&w2[(q * 16 + lane) * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
     }
     constexpr int NQ = DP + 3 + MAXO;         // per (column, group): dW1[DP] | db1 | db2 | dW3[4] | db3 (column j holds db3[j])
     static_assert(NSG * NQ * H * 4 <= 98304, "reduction scratch must fit U + S");
@@ -695,9 +695,9 @@ inline bool bwd_mmaw() {                     // PPX_MLP_TC_MMAW=1: dedicated MMA
   if (v < 0) { const char* e = getenv("PPX_MLP_TC_MMAW"); v = (e && atoi(e) == 1) ? 1 : 0; }
   return v == 1;
 }
-inline int bwd_cw() {                        // PPX_MLP_TC_CW=32: 8 compute warps per CTA instead of 16
+inline int bwd_cw() {                        // PPX_MLP_TC_CW=16: 16 compute warps per CTA (16 columns per thread) instead of 8
   static int cw = 0;
-  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW"); cw = (e && atoi(e) == 32) ? 32 : 16; }
+  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW"); cw = (e && atoi(e) == 16) ? 16 : 32; }
   return cw;
 }
 

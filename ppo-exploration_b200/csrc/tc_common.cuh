@@ -61,8 +61,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
