@@ -31,8 +31,9 @@ HP = dict(lr=3e-4, gamma=0.999, gae_lam=0.95, vf_coef=1, max_grad_norm=5, n_epoc
 HIDDEN = 64
 N_MINIBATCH = 4
 # DRAM bytes per launch of the fused MLP kernels at the C2 minibatch, from the committed ncu captures
-NCU_TRAFFIC = {"ppx_mlp3_bwd": 144.0e6, "ppx_mlp3_fwd": 81.9e6}
-NCU_TRAFFIC_SRC = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_mlp3_r01b.md)"
+NCU_TRAFFIC = {"ppx_mlp3_bwd": 144.0e6, "ppx_mlp3_fwd": 81.9e6, "ppx_mlp3_tc_bwd": 143.3e6, "ppx_mlp3_tc_fwd": 80.1e6}
+NCU_TRAFFIC_SRC = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_mlp_tc_r01d.md; "
+                   "SIMT pair: profiles/ncu_mlp3_r01b.md)")
 WORKLOAD = ("C2: PPO+SimHash, obs 8, Box(2), k=64, 2048 envs x 256 steps per GPU, swimmer_ppo hparams, "
             "4 minibatches/epoch x 10 epochs")
 
@@ -330,7 +331,7 @@ def run_ppx(args):
         return
     clocks = ClockSampler(local_rank)                   # sampled over warm-up + timed region (same load; nvidia-smi
     clocks.start()                                      # needs a few hundred ms to produce its first line)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 5)):
         step_resident()
     torch.cuda.synchronize()
     l0 = L.launch_count()
@@ -392,7 +393,7 @@ def run_ppx(args):
                     "fp32_frac": achieved / 74.4,
                     "ms_per_launch": ms_launch, "launches_per_step": cnt, "top_ops_ms_per_step": ops}
     line = {"metric": "transitions/s through GAE+bonus+PPO update", "value": value, "unit": "transitions/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 5), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed every step (256 MiB memset inside the timed region)",
                        "shuffle": "np.random.permutation on the host each epoch (bit-exact reference stream), inside the timed region",
