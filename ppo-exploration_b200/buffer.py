@@ -56,7 +56,8 @@ def _stop_streams_at_exit():
         st.cancel()
     for st in list(_live_streams):
         st.t1.join(timeout=2.0)
-        st.t2.join(timeout=2.0)
+        for t in st.t2:
+            t.join(timeout=2.0)
 
 
 atexit.register(_stop_streams_at_exit)
@@ -68,6 +69,21 @@ def rng_states_equal(a, b):
             and np.array_equal(a[1], b[1]))
 
 
+def _apply_workers():
+    """Stage-2 threads of a HostRngStream: 2 (measured on the bench host: 50 -> 66M transitions/s at C2; 3-4 workers gain
+    nothing more, the draw stage and the GIL hand-offs then pace the stream), 1 when the ranks of this node have to share
+    the host cores.  PPX_SHUFFLE_WORKERS overrides."""
+    env = os.environ.get("PPX_SHUFFLE_WORKERS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 4
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(2, cores // ranks - 2))
+
+
 class HostRngStream:
     """Replays a fixed script of draws of the numpy legacy RNG in worker threads, in order, so the host shuffle
     (buffer.py:239) and RND's per-minibatch randn() (algorithms.py:468) overlap the GPU work while consuming exactly
@@ -76,14 +92,21 @@ class HostRngStream:
     The stream works on a PRIVATE RandomState seeded with `state` (default: a snapshot of the global np.random state)
     and never touches the global one; the caller commits `final_state()` with np.random.set_state once the script has
     been consumed.  That makes a stream safe to start speculatively (before the caller knows it will be needed) and to
-    cancel.  Two pipelined stages (both release the GIL inside libppx): stage 1 owns the RNG -- it draws the
-    Fisher-Yates partner sequence of each permutation and the scalar randn()s; stage 2 applies the swaps into a pinned
-    buffer, running behind stage 1's published progress inside the SAME permutation.  At most `ahead` finished items
-    wait in the output queue (the workers then sleep)."""
+    cancel.  Two pipelined stages (both release the GIL inside libppx): stage 1 (one thread) owns the RNG -- it draws
+    the Fisher-Yates partner sequence of each permutation and the scalar randn()s; stage 2 (`workers` threads, dealt the
+    permutations round-robin: only the DRAWS of successive permutations are sequential, their swaps are independent)
+    applies the swaps into a pinned buffer, running behind stage 1's published progress inside the permutation being
+    drawn.  Results come out in script order; at most `ahead` items are in flight or waiting."""
 
-    def __init__(self, script, state=None, ahead=3):
+    def __init__(self, script, state=None, ahead=None, workers=None):
         self.script = list(script)
-        self.q, self.mid = queue.Queue(maxsize=max(1, int(ahead))), queue.Queue(maxsize=2)
+        nw = int(workers) if workers is not None else _apply_workers()
+        self.nw = max(1, nw)
+        ahead = self.nw + 2 if ahead is None else ahead
+        # results are delivered in script order through `q`: stage 1 enqueues one slot [event, value] per item BEFORE
+        # it dispatches the work, the stage-2 worker that owns the item fills it
+        self.q = queue.Queue(maxsize=max(1, int(ahead)))
+        self.mids = [queue.Queue(maxsize=2) for _ in range(self.nw)]
         self.err = None
         self.cancelled = False
         self._final = None
@@ -96,13 +119,14 @@ class HostRngStream:
                 sc.append(('reuse',) if (op[0] == 'perm' and seen) else op)
                 seen = seen or op[0] == 'perm'
             script = sc
-        self._jbufs = {}                                        # rotating partner buffers (<= 4 in flight per size)
-        self._scratch32 = None
+        self._jbufs = {}                                        # rotating partner buffers (<= ahead + 1 in flight per size)
+        self._first_perm = None
         self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
-        self.t2 = threading.Thread(target=self._apply, daemon=True)
+        self.t2 = [threading.Thread(target=self._apply, args=(w,), daemon=True) for w in range(self.nw)]
         _live_streams.add(self)
         self.t1.start()
-        self.t2.start()
+        for t in self.t2:
+            t.start()
 
     def _put(self, qq, item):
         while not self.cancelled:
@@ -114,9 +138,15 @@ class HostRngStream:
         return False
 
     def _draw(self, script):
+        """Stage 1 (one thread, owns the RNG): draws in script order; permutations are handed round-robin to the
+        stage-2 workers -- the swaps of different permutations are independent, only the draws are sequential."""
+        k = 0
         try:
             for op in script:
                 if self.cancelled:
+                    break
+                slot = [threading.Event(), None]
+                if not self._put(self.q, slot):
                     break
                 if op[0] == 'perm':
                     n = int(op[1])
@@ -124,14 +154,19 @@ class HostRngStream:
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
                     small = n <= 0x7fffffff
+                    nbuf = self.q.maxsize + 2
                     pool = self._jbufs.setdefault(n, [[(np.empty(max(n, 1), np.int32 if small else np.int64),
-                                                        np.zeros(1, np.int64)) for _ in range(6)], 0])
-                    j, prog = pool[0][pool[1] % 6]
+                                                        np.zeros(1, np.int64)) for _ in range(nbuf)], 0])
+                    j, prog = pool[0][pool[1] % nbuf]
                     pool[1] += 1
+                    mid = self.mids[k % self.nw]
+                    k += 1
+                    if self._first_perm is None:
+                        self._first_perm = slot
                     if small:
                         # streaming: hand the buffer to stage 2 first, it runs behind the published progress counter
                         prog[0] = 0
-                        if not self._put(self.mid, ('perm', j, n, prog)):
+                        if not self._put(mid, ('perm', j, n, prog, slot)):
                             break
                         try:
                             L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, j.ctypes.data,
@@ -141,57 +176,63 @@ class HostRngStream:
                             raise
                     else:
                         L.call("ppx_np_shuffle_draws", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
-                        if not self._put(self.mid, ('perm', j, n, None)):
+                        if not self._put(mid, ('perm', j, n, None, slot)):
                             break
                     self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
                 elif op[0] == 'reuse':
-                    if not self._put(self.mid, ('reuse',)):
-                        break
+                    slot[1] = self._first_perm                  # resolved by next(): the first permutation's slot
+                    slot[0].set()
                 else:
-                    if not self._put(self.mid, ('val', float(self.rs.randn()))):
-                        break
+                    slot[1] = float(self.rs.randn())
+                    slot[0].set()
             else:
                 self._final = self.rs.get_state()
         except Exception as e:
             self.err = e
-        self._put(self.mid, None)
+        self._put(self.q, None)
+        for mid in self.mids:
+            self._put(mid, None)
 
-    def _apply(self):
+    def _apply(self, w):
+        """Stage 2 worker w: applies the swaps of the permutations dealt to it into a pinned buffer."""
+        scratch32 = None
+        mid = self.mids[w]
         try:
             while not self.cancelled:
                 try:
-                    item = self.mid.get(timeout=0.05)
+                    item = mid.get(timeout=0.05)
                 except queue.Empty:
                     continue
                 if item is None:
                     break
-                if item[0] == 'perm':
-                    _, j, n, prog = item
-                    out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
-                    if prog is not None:
-                        if self._scratch32 is None or self._scratch32.size < n:
-                            self._scratch32 = np.empty(max(n, 1), np.int32)
-                        L.call("ppx_np_shuffle_apply32_stream", j.ctypes.data, n, prog.ctypes.data,
-                               self._scratch32.ctypes.data, out.data_ptr())
-                    else:
-                        L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
-                    self._last = out
-                    if not self._put(self.q, out):
-                        break
-                elif item[0] == 'reuse':
-                    if not self._put(self.q, self._last):
-                        break
+                _, j, n, prog, slot = item
+                out = torch.empty(n, dtype=torch.int64, pin_memory=torch.cuda.is_available())
+                if prog is not None:
+                    if scratch32 is None or scratch32.size < n:
+                        scratch32 = np.empty(max(n, 1), np.int32)
+                    L.call("ppx_np_shuffle_apply32_stream", j.ctypes.data, n, prog.ctypes.data,
+                           scratch32.ctypes.data, out.data_ptr())
                 else:
-                    if not self._put(self.q, item[1]):
-                        break
+                    L.call("ppx_np_shuffle_apply", j.ctypes.data, n, out.data_ptr())
+                slot[1] = out
+                slot[0].set()
         except Exception as e:
             self.err = e
-        self._put(self.q, None)
+            self.cancelled = True                               # unblock everything; next() reports the error
 
     def next(self):
-        v = self.q.get()
-        if v is None:
+        slot = self.q.get()
+        if slot is None:
             raise self.err if self.err is not None else RuntimeError("HostRngStream: script exhausted")
+        while not slot[0].wait(timeout=0.05):
+            if self.err is not None:
+                raise self.err
+        v = slot[1]
+        if isinstance(v, list):                                 # 'reuse' (diagnosis): the first permutation again
+            while not v[0].wait(timeout=0.05):
+                if self.err is not None:
+                    raise self.err
+            v = v[1]
         return v
 
     def final_state(self):
@@ -207,7 +248,8 @@ class HostRngStream:
 
     def drain(self):
         self.t1.join()
-        self.t2.join()
+        for t in self.t2:
+            t.join()
 
 
 class BaseBuffer(object):
