@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     const int k = e >> 6, c = e & 63;
     W1s[e] = k < D ? __ldg(p.W1 + (size_t)k * ldw + g * H + c) : 0.f;
   }
-  for (int e = tid; e < H * MAXO; e += NT) {
-    const int c = e >> 2, j = e & 3;
+  for (int e = tid; e < H * MAXO; e += NT) {                // W3s [j][c]: one 16-byte read = 4 columns of output j
+    const int j = e >> 6, c = e & 63;
     W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
   }
   if (tid < H) { b1s[tid] = __ldg(p.b1 + g * H + tid); b2s[tid] = __ldg(p.b2 + g * H + tid); }
@@ -263,11 +263,12 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
     auto head = [&](auto oc) {               // only the o live outputs (o is CTA-uniform)
       constexpr int OC = decltype(oc)::value;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float4 w = *reinterpret_cast<const float4*>(&W3s[(c0 + c) * MAXO]);
-        const float wj[MAXO] = {w.x, w.y, w.z, w.w};
+      for (int c = 0; c < 32; c += 4) {
 #pragma unroll
-        for (int j = 0; j < OC; ++j) po[j] = fmaf(h2v[c], wj[j], po[j]);
+        for (int j = 0; j < OC; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
+          po[j] = fmaf(h2v[c + 3], w.w, fmaf(h2v[c + 2], w.z, fmaf(h2v[c + 1], w.y, fmaf(h2v[c], w.x, po[j]))));
+        }
       }
     };
     switch (o) {
@@ -465,8 +466,8 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
         const int e = tid + r * NTC, row = e / DP, k = e % DP;
         xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
       }
-      if (tid < TM) {                                        // output gradient of row tid
-        const int b = m0 + tid;
+      {                                                      // output gradient of this thread's row s (every column group loads it: dP2 then needs no barrier)
+        const int b = m0 + s;
         float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
         if (b < p.M) {
           if (p.vh_v[g] != nullptr) {                        // o == 1 (checked on the host); same formula as mlp_fused.cu
@@ -494,16 +495,15 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       // ---- T1: publish X, dOut and H2 (staging tile S) ----
 #pragma unroll
       for (int r = 0; r < XPT; ++r) sts32(Xs + (uint32_t)(tid + r * NTC) * 4, xpre[r]);
-      if (tid < TM) *reinterpret_cast<float4*>(&dOs[tid * MAXO]) = dpre;
+      if (c0 == 0) *reinterpret_cast<float4*>(&dOs[s * MAXO]) = dpre;
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j)
         sts128(S + stage_off(s, c0 + 4 * j), h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
-      bar_compute();                          // [B1]
+      // (no barrier: T2 works from registers; X / dOut / H2 are published to the thin reductions by [B2])
       // ---- T2: dP2 = (dOut W3^T)(1 - H2^2) -> K-major images (phase 1 of U) -> GEMM 2 ----
       float dp2[CW];
       {
-        const float4 d = *reinterpret_cast<const float4*>(&dOs[s * MAXO]);
-        const float dj[MAXO] = {d.x, d.y, d.z, d.w};
+        const float dj[MAXO] = {dpre.x, dpre.y, dpre.z, dpre.w};
 #pragma unroll
         for (int c = 0; c < CW; c += 4) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       }
       store_row_images_cw<CW>(U_raw, U_lo, s, c0, dp2);
       ops_ready(opsG2, 2);
+      if constexpr (MMAW) bar_compute();      // [B2] X / dOut / H2 published to the thin reductions
       // ---- T3 (under GEMM 2): H1^T images; dW3 / db3 sums over this thread's SPG samples ----
       store_col_images_cw<CW>(V_raw, 32768u, c0, s, h1);
       if (!(p.dbg & 2)) {
