@@ -148,6 +148,10 @@ def bench_es(rows, iters):
                          out.data_ptr(), 0, L.stream())
     ms, mn = timed(fnp, iters)
     report(rows, "es_perturb", f"P={P} D={D} f32 out", P * D * 8, 0, ms, mn)
+    obs = torch.randn(P, 8, dtype=torch.float64, device=DEV)
+    ms, mn = timed(lambda: es.predict_population(off, obs), iters)
+    report(rows, "es_forward", f"P={P} D={D} (8-64-64-2)", P * (D * 4 + 8 * 8 + 2 * 8), 2.0 * P * D, ms, mn,
+           note=f"{P / ms * 1e3:.0f} member-steps/s; weights theta + sigma*eps formed on the fly (alg bytes = one read of eps)")
     ms, mn = timed(lambda: es._update_weights(r, off, 0.5), iters)
     report(rows, "es_update", f"P={P} D={D}", P * D * 4, 0, ms, mn, launches=3, note="stats+coef, gemv, apply")
     es.fitness_shaping = "centered_rank"

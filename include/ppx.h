@@ -359,6 +359,14 @@ int ppx_noise_fill(float* table, int64_t n, uint64_t seed, void* stream);
  * rows; ppx_es_perturb and ppx_es_update read them as 16-byte vectors). */
 int ppx_es_perturb(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P, int D,
                    void* out, int out_is_f64, void* stream);
+/* FeedForwardNetwork.predict (evolution_strategies.py:48-61) for the whole population at once: member p
+ * acts on obs[p, :] with weights theta + sigma*eps_p formed on the fly from the noise table (offsets) or the dense eps
+ * rows (offsets == NULL) -- never materialised.  Bias-free MLP layer_sizes_host[0..n_layers] (D0, h1, ..., A), hidden
+ * activation arctan; fp32 arithmetic on f64 inputs / outputs (1e-5 relative against the f64 reference; the FP64 pipe
+ * made an f64 version 6x slower); squash_tanh = 1 applies continuous_action's tanh (:84-89), 0 leaves the logits
+ * (Discrete: the categorical draw stays with the host RNG).  out is [P, A] f64. */
+int ppx_es_forward(const double* theta, const float* noise, const int64_t* offsets, double sigma, int P,
+                   const int* layer_sizes_host, int n_layers, const double* obs, int squash_tanh, double* out, void* stream);
 /* _update_weights (evolution_strategies.py:217-239): z-score rewards (ddof 0); skip entirely if std==0;
  * theta += lr/(P*sigma) * sum_p w_p eps_p with w_p = ((1-nw)*z_p + nw*novelty)/2 (use_novelty=1) or z_p;
  * then *lr_inout *= decay.  rank_mode=1 replaces the z-score by centred ranks (BASELINE north_star;

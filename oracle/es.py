@@ -16,6 +16,25 @@ def get_population(shapes, P):
     return [[np.random.randn(*s) for s in shapes] for _ in range(P)]
 
 
+def predict_logits(weights, obs):
+    """Bias-free MLP forward: arctan hidden layers, linear last layer.  evolution_strategies.py:48-59."""
+    out = np.expand_dims(np.asarray(obs).flatten(), 0)
+    for i in range(len(weights) - 1):
+        out = np.dot(out, weights[i])
+        out = np.arctan(out)
+    return np.dot(out, weights[-1]).astype(float)
+
+
+def predict(weights, obs, discrete=False):
+    """FeedForwardNetwork.predict.  :48-61 with get_action :91-95: tanh(logits) for Box (:84-89), one
+    np.random.choice over softmax(logits) for Discrete (:75-82)."""
+    logits = predict_logits(weights, obs)
+    if discrete:
+        p = np.exp(logits) / np.sum(np.exp(logits))
+        return np.random.choice(np.arange(logits.shape[1]), p=p.squeeze()).astype(int)
+    return np.tanh(logits).astype(np.double)
+
+
 def weights_try(w, member, sigma):
     """theta_l + sigma * eps_l per layer.  :137-145."""
     return [w[l] + sigma * member[l] for l in range(len(w))]

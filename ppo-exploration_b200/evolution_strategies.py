@@ -2,9 +2,11 @@
 
 Mirrors EvolutionStrategy of evolution_strategies.py (:100-384) for the parts on the learner hot
 path: _get_population (:172-182), _get_weights_try (:137-145), _update_weights (:217-239), get_kNN
-(:264-281), the novelty lines (:318-325) and calc_noveltiy_distribution (:283-290).  Episode
-evaluation (evaluate / get_behavior_char / run's env loop) is the simulator side and stays with the
-caller: feed the fitness vector back through `_update_weights`.
+(:264-281), the novelty lines (:318-325) and calc_noveltiy_distribution (:283-290), plus the policy forward
+of episode evaluation (FeedForwardNetwork.predict :48-61) batched over the population
+(`predict_population`).  Stepping the environments (evaluate / get_behavior_char / run's env
+loop) is the simulator side and stays with the caller: feed the fitness vector back through
+`_update_weights`.
 
 Build-side design: the population is a vector of offsets into ONE resident f32 noise
 table instead of P fresh f64 randn tensors; theta is one flat f64 device vector over all layers.
@@ -111,6 +113,40 @@ class EvolutionStrategy(object):
         L.call("ppx_es_perturb", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
                float(self.SIGMA), P, self.D, out.data_ptr(), int(out_f64), L.stream())
         return out
+
+    def predict_population(self, population, obs, discrete=False, sigma=None):
+        """FeedForwardNetwork.predict (:48-61) for every member at once: member p sees obs[p] and acts with
+        theta + sigma*eps_p, formed on the fly from the noise table (the perturbed weights are never materialised).
+        obs [P, obs_dim] -> f64 CUDA [P, n_actions]: tanh(logits) for Box (continuous_action :84-89); the raw logits
+        with discrete=True (sample them with `discrete_action`, which keeps the reference's host RNG draw)."""
+        noise, off = self._as_eps(population)
+        P = off.numel() if off is not None else noise.shape[0]
+        obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).double().contiguous()
+        sizes = [self.shapes[0][0]] + [sh[1] for sh in self.shapes]
+        if tuple(obs.shape) != (P, sizes[0]):
+            raise ValueError(f"obs must be [{P}, {sizes[0]}], got {tuple(obs.shape)}")
+        out = torch.empty(P, sizes[-1], dtype=torch.float64, device=self.device)
+        import ctypes as C
+        L.call("ppx_es_forward", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
+               float(self.SIGMA if sigma is None else sigma), P, (C.c_int * len(sizes))(*sizes), len(sizes) - 1,
+               obs.data_ptr(), 0 if discrete else 1, out.data_ptr(), L.stream())
+        return out
+
+    def predict(self, obs, discrete=False):
+        """FeedForwardNetwork.predict (:48-61) of the CURRENT weights for one observation (or a batch [n, obs_dim])."""
+        obs = np.asarray(obs, dtype=np.float64)
+        obs = obs.reshape(1, -1) if obs.ndim == 1 or obs.size == self.shapes[0][0] else obs
+        zero = np.zeros((obs.shape[0], self.D), dtype=np.float32)
+        return self.predict_population(zero, obs, discrete=discrete, sigma=0.0)
+
+    @staticmethod
+    def discrete_action(logits):
+        """discrete_action (:81-82) on the host: softmax then one np.random.choice per member (the reference's RNG)."""
+        out = []
+        for row in np.asarray(logits.cpu() if isinstance(logits, torch.Tensor) else logits, dtype=np.float64):
+            p = np.exp(row) / np.sum(np.exp(row))
+            out.append(int(np.random.choice(np.arange(row.size), p=p.squeeze())))
+        return np.array(out)
 
     def _get_weights_try(self, w, p):
         """:137-145 for ONE member given as the reference's list of per-layer eps arrays; returns a list of

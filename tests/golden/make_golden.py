@@ -350,7 +350,27 @@ def g_es():
     save("es", **out)
 
 
+def g_es_predict():
+    """FeedForwardNetwork.predict (evolution_strategies.py:48-61) of the unmodified reference on a Box and a Discrete env."""
+    out = {}
+    for tag, space in (("box", ref_shim.Box((2,))), ("disc", ref_shim.Discrete(3))):
+        env = ref_shim.FakeVecEnv(1, 8, space, seed=11)
+        np.random.seed(21)
+        net = refes.FeedForwardNetwork(env, hidden_sizes=[16, 16])
+        for i, w in enumerate(net.weights):
+            out[f"{tag}/w/{i}"] = w.copy()
+        obs = np.random.randn(6, 8)
+        out[f"{tag}/obs"] = obs
+        np.random.seed(31)
+        out[f"{tag}/actions"] = np.array([net.predict(o) for o in obs]).reshape(6, -1)
+    save("es_predict", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "es_predict":           # added later: regenerate this fixture alone
+        g_es_predict()
+        sys.exit(0)
+    g_es_predict()
     g_gae(); g_gae_dual(); g_discount(); g_simhash(); g_get(); g_rnd_bonus(); g_es()
     # C1: the reference's own CPU-runnable case (8 envs x 128 steps, obs 4, Discrete(2), defaults)
     g_ppo("ppo_c1_discrete", 8, 4, ref_shim.Discrete(2), seed=1, nstep=128)

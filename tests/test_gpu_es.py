@@ -129,3 +129,45 @@ def test_centered_rank_update_mode():
     _, c = OE.centered_ranks(r)
     want = th0 + 0.01 / (64 * 0.1) * (eps.astype(np.float64).T @ c)
     np.testing.assert_allclose(es.theta.cpu().numpy(), want, rtol=1e-12, atol=1e-14)
+
+
+def test_predict_matches_reference_fixture():
+    """Population forward with sigma-free weights == FeedForwardNetwork.predict of the reference (Box: tanh(logits);
+    Discrete: logits on the device, the categorical draw on the host RNG -> the reference's actions under its seed)."""
+    import ppo_exploration_b200 as ppx
+    g = Golden("es_predict")
+    for tag, disc, nact in (("box", False, 2), ("disc", True, 3)):
+        np.random.seed(0)
+        es = ppx.EvolutionStrategy(hidden_sizes=[16, 16], obs_dim=8, n_actions=nact, population_size=6)
+        es.set_weights([g[f"{tag}/w/{i}"] for i in range(3)])
+        out = es.predict(g[f"{tag}/obs"], discrete=disc)
+        if disc:
+            np.random.seed(31)
+            assert np.array_equal(ppx.EvolutionStrategy.discrete_action(out).reshape(6, 1), g[f"{tag}/actions"])
+        else:
+            np.testing.assert_allclose(out.cpu().numpy(), g[f"{tag}/actions"], rtol=1e-5, atol=1e-6)      # fp32 arithmetic on the device
+
+
+@pytest.mark.parametrize("P,hidden,table", [(1, [16, 16], False), (37, [64, 64], False), (1000, [64, 64], True), (50, [40, 130, 7], True)])
+def test_predict_population_matches_oracle(P, hidden, table):
+    """Member p = MLP(theta + sigma*eps_p) on obs[p], weights formed on the fly (dense eps rows or noise-table offsets)."""
+    import ppo_exploration_b200 as ppx
+    np.random.seed(5)
+    es = ppx.EvolutionStrategy(hidden_sizes=hidden, obs_dim=8, n_actions=2, population_size=P, sigma=0.1,
+                               noise_table_size=1 << 20)
+    rs = np.random.RandomState(6)
+    obs = rs.randn(P, 8)
+    if table:
+        pop = es._get_population()
+        eps = es.noise_table()[(pop[:, None] + torch.arange(es.D, device=pop.device)[None, :])].cpu().numpy().astype(np.float64)
+    else:
+        pop = rs.randn(P, es.D).astype(np.float32)
+        eps = pop.astype(np.float64)
+    got = es.predict_population(pop, obs).cpu().numpy()
+    theta = es.theta.cpu().numpy()
+    sizes = np.cumsum([0] + es.layer_sizes)
+    for p in range(0, P, max(1, P // 40)):
+        w = [(theta[sizes[l]:sizes[l + 1]] + 0.1 * eps[p, sizes[l]:sizes[l + 1]]).reshape(es.shapes[l]) for l in range(len(es.shapes))]
+        # fp32 arithmetic on the device: 1e-5 of the output scale (tanh outputs are bounded by 1; the logits behind them
+        # are O(10) sums of 64 products, so their fp32 rounding already is ~1e-6 absolute)
+        np.testing.assert_allclose(got[p], OE.predict(w, obs[p])[0], rtol=1e-5, atol=1e-5)

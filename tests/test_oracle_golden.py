@@ -256,3 +256,17 @@ def test_centered_ranks_spec():
     ranks, c = OE.centered_ranks(r)
     assert ranks.tolist() == [2, 0, 3, 4, 1]
     assert c.min() == -0.5 and c.max() == 0.5
+
+
+def test_es_predict_matches_reference():
+    """FeedForwardNetwork.predict (evolution_strategies.py:48-61): Box -> tanh(logits); Discrete -> the same
+    np.random.choice draws as the reference under the same seed."""
+    g = Golden("es_predict")
+    for tag, disc in (("box", False), ("disc", True)):
+        w = [g[f"{tag}/w/{i}"] for i in range(3)]
+        np.random.seed(31)
+        got = np.array([OE.predict(w, o, discrete=disc) for o in g[f"{tag}/obs"]]).reshape(6, -1)
+        if disc:
+            assert np.array_equal(got, g[f"{tag}/actions"])
+        else:
+            np.testing.assert_allclose(got, g[f"{tag}/actions"], rtol=1e-14, atol=0)
