@@ -69,6 +69,28 @@ def rng_states_equal(a, b):
             and np.array_equal(a[1], b[1]))
 
 
+class DevicePartners:
+    """A permutation delivered as its Fisher-Yates partner list (pinned int32 [n], entry i = partner of position i):
+    the swaps are applied on the device (ppx_np_shuffle_apply_device)."""
+    __slots__ = ("j",)
+
+    def __init__(self, j):
+        self.j = j
+
+
+def device_shuffle_default():
+    """Apply the shuffle's swaps on the GPU?  PPX_SHUFFLE_DEVICE=1/0 forces it; by default only when the ranks of this node
+    leave fewer than 4 host cores each (8 ranks on 16 cores: the host swaps, 0.9 ms per 524 288, pace the pass there)."""
+    env = os.environ.get("PPX_SHUFFLE_DEVICE", "auto")
+    if env in ("0", "1"):
+        return env == "1"
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 4
+    return cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) < 4
+
+
 def _apply_workers():
     """Stage-2 threads of a HostRngStream: 2 (measured on the bench host: 50 -> 66M transitions/s at C2; 3-4 workers gain
     nothing more, the draw stage and the GIL hand-offs then pace the stream), 1 when the ranks of this node have to share
@@ -98,8 +120,9 @@ class HostRngStream:
     applies the swaps into a pinned buffer, running behind stage 1's published progress inside the permutation being
     drawn.  Results come out in script order; at most `ahead` items are in flight or waiting."""
 
-    def __init__(self, script, state=None, ahead=None, workers=None):
+    def __init__(self, script, state=None, ahead=None, workers=None, device_apply=False):
         self.script = list(script)
+        self.device_apply = bool(device_apply)                  # 'perm' items come out as DevicePartners (n <= 2^24)
         nw = int(workers) if workers is not None else _apply_workers()
         self.nw = max(1, nw)
         ahead = self.nw + 2 if ahead is None else ahead
@@ -153,6 +176,14 @@ class HostRngStream:
                     st = self.rs.get_state()
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
+                    if self.device_apply and 2 <= n <= (1 << 24):
+                        # draws only: the partner list goes to the device, which applies the swaps (shuffle_dev.cu)
+                        jt = torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+                        L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, jt.data_ptr())
+                        self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
+                        slot[1] = DevicePartners(jt)
+                        slot[0].set()
+                        continue
                     small = n <= 0x7fffffff
                     nbuf = self.q.maxsize + 2
                     pool = self._jbufs.setdefault(n, [[(np.empty(max(n, 1), np.int32 if small else np.int64),

@@ -72,3 +72,53 @@ def test_gather_vs_oracle_sizes(T, N, D, A, B):
     # a permutation gathers every row exactly once: checksum over the whole epoch
     tot = b0.returns.double().sum().item() + sum(b.returns.double().sum().item() for b in it)
     np.testing.assert_allclose(tot, arrs["returns"].astype(np.float64).sum(), rtol=1e-9)
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 1000, 4097, 524288, (1 << 21) + 5])
+def test_device_shuffle_apply_matches_numpy(n):
+    """Fisher-Yates swaps resolved in parallel on the device (shuffle_dev.cu) == np.random.permutation, bit for bit;
+    the draws (the RNG stream itself) stay on the host and leave numpy's state where numpy would."""
+    import ctypes as C
+    from ppo_exploration_b200 import _lib as L
+    np.random.seed(n % 1000)
+    st = np.random.get_state()
+    want = np.random.permutation(n)
+    after = np.random.get_state()
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int(int(st[2]))
+    j = np.zeros(n, np.int32)
+    L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
+    assert np.array_equal(key, after[1]) and pos.value == after[2]
+    jd = torch.as_tensor(j).cuda()
+    ws = torch.empty(L.call("ppx_np_shuffle_apply_device_workspace", n), dtype=torch.uint8, device="cuda")
+    out = torch.full((n,), -1, dtype=torch.int64, device="cuda")
+    for _ in range(2):                                       # twice: the workspace is reusable, the result does not depend on atomic order
+        L.call("ppx_np_shuffle_apply_device", jd.data_ptr(), n, ws.data_ptr(), out.data_ptr(), L.stream())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_train_identical_with_device_shuffle():
+    """PPO.train() with the swaps applied on the device consumes the same RNG stream and produces the same minibatches:
+    bit-identical weights and the same numpy state afterwards (speculative streams included)."""
+    import ppo_exploration_b200 as ppx
+    rs = np.random.RandomState(0)
+    T, N, D, A = 32, 16, 8, 2
+    arrs = dict(observations=rs.randn(T, N, D).astype(np.float32), actions=rs.randn(T, N, A), rewards=rs.randn(T, N).astype(np.float32),
+                values=rs.randn(T, N).astype(np.float32), masks=(rs.rand(T, N) < 0.05).astype(np.uint8),
+                action_log_probs=(-1.0 + 0.1 * rs.randn(T, N, A)).astype(np.float32))
+    res = []
+    for dev in (False, True):
+        np.random.seed(3); torch.manual_seed(3)
+        env = ppx.SyntheticVecEnv(N, D, ppx.Box((A,)), seed=0)
+        m = ppx.PPO(env=env, nstep=T, hidden_size=64, batch_size=128, n_epochs=3)
+        m.device_shuffle = dev
+        m.rollout.load_rollout(**arrs)
+        m.rollout.compute_returns_and_advantages(torch.zeros(N), arrs["masks"][-1])
+        for _ in range(3):                                   # the 2nd and 3rd calls run on the speculative stream
+            m.train()
+        torch.cuda.synchronize()
+        res.append(({k: v.clone() for k, v in m.policy.state_dict().items()}, np.random.get_state()))
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k], res[1][0][k]), k
+    assert np.array_equal(res[0][1][1], res[1][1][1]) and res[0][1][2] == res[1][1][2]
