@@ -122,12 +122,14 @@ int ppx_np_shuffle_draws32_stream(uint32_t* key624_host, int* pos_host, int64_t 
                                   int64_t* progress_host);
 int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int64_t* progress_host,
                                   int32_t* scratch_host, int64_t* out_host);
-/* The same swaps applied ON THE DEVICE, in parallel and bit-exactly (shuffle_dev.cu): j_dev[i] (i = 1 .. n-1) is the
- * partner list ppx_np_shuffle_draws32 produced, uploaded by the caller; out_dev [n] int64 is arange(n) after the swaps
- * = np.random.permutation(n).  For hosts whose cores are shared by many ranks (the draws stay on the host: they ARE the
+/* The same swaps applied ON THE DEVICE, in parallel and bit-exactly (shuffle_dev.cu): j_dev is the uploaded partner
+ * list, either indexed by position (acceptance_order = 0: j_dev[i], i = 1 .. n-1, from ppx_np_shuffle_draws32) or in
+ * acceptance order (1: entry r belongs to position n-1-r, from ppx_np_shuffle_draws32_stream, the AVX-512 draw loop);
+ * out_dev [n] int64 is arange(n) after the swaps = np.random.permutation(n).  For hosts whose cores are shared by many ranks (the draws stay on the host: they ARE the
  * RNG stream).  n <= 2^24; workspace of ppx_np_shuffle_apply_device_workspace(n) bytes; asynchronous on `stream`. */
 int64_t ppx_np_shuffle_apply_device_workspace(int64_t n);
-int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, void* workspace, int64_t* out_dev, void* stream);
+int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, int acceptance_order, void* workspace, int64_t* out_dev,
+                                void* stream);
 
 
 /* Sharded minibatches: rec3 = {n, mean, M2} from the local {mean, std}; after an all-gather of the

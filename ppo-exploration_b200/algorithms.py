@@ -289,7 +289,7 @@ class BaseAlgorithm(object):
                 self._copy_stream.wait_event(self._perm_free[slot])
             if on_device:                                       # 2 MB up instead of 4, swaps resolved in parallel on the copy stream
                 self._perm_j[slot].copy_(perm.j, non_blocking=True)
-                L.call("ppx_np_shuffle_apply_device", self._perm_j[slot].data_ptr(), total, self._perm_ws.data_ptr(),
+                L.call("ppx_np_shuffle_apply_device", self._perm_j[slot].data_ptr(), total, 1, self._perm_ws.data_ptr(),
                        self._perm_bufs[slot].data_ptr(), L.stream())
             else:
                 self._perm_bufs[slot].copy_(perm, non_blocking=True)

@@ -70,8 +70,8 @@ def rng_states_equal(a, b):
 
 
 class DevicePartners:
-    """A permutation delivered as its Fisher-Yates partner list (pinned int32 [n], entry i = partner of position i):
-    the swaps are applied on the device (ppx_np_shuffle_apply_device)."""
+    """A permutation delivered as its Fisher-Yates partner list (pinned int32 [n] in acceptance order: entry r = partner
+    of position n-1-r): the swaps are applied on the device (ppx_np_shuffle_apply_device, acceptance_order=1)."""
     __slots__ = ("j",)
 
     def __init__(self, j):
@@ -79,16 +79,11 @@ class DevicePartners:
 
 
 def device_shuffle_default():
-    """Apply the shuffle's swaps on the GPU?  PPX_SHUFFLE_DEVICE=1/0 forces it; by default only when the ranks of this node
-    leave fewer than 4 host cores each (8 ranks on 16 cores: the host swaps, 0.9 ms per 524 288, pace the pass there)."""
-    env = os.environ.get("PPX_SHUFFLE_DEVICE", "auto")
-    if env in ("0", "1"):
-        return env == "1"
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 4
-    return cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) < 4
+    """Apply the shuffle's swaps on the GPU (shuffle_dev.cu: 58 us per 524 288 on the copy stream, against 0.9 ms on a host
+    core)?  Yes unless PPX_SHUFFLE_DEVICE=0: the host then only draws (0.3 ms per permutation), so a pass no longer depends
+    on how many cores the ranks of a node have to share (8 ranks on 16 cores) or on a noisy host.  The host-side swaps
+    remain for the sharded "global" shuffle (which needs the permutation on the host) and for n > 2^24."""
+    return os.environ.get("PPX_SHUFFLE_DEVICE", "1") != "0"
 
 
 def _apply_workers():
@@ -179,7 +174,8 @@ class HostRngStream:
                     if self.device_apply and 2 <= n <= (1 << 24):
                         # draws only: the partner list goes to the device, which applies the swaps (shuffle_dev.cu)
                         jt = torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available())
-                        L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, jt.data_ptr())
+                        prog = np.zeros(1, np.int64)
+                        L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, jt.data_ptr(), prog.ctypes.data)
                         self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
                         slot[1] = DevicePartners(jt)
                         slot[0].set()

@@ -22,9 +22,9 @@ namespace {
 
 constexpr int kScanBlock = 1024;       // elements per scan block (256 threads x 4)
 
-__global__ void __launch_bounds__(256) fy_count_kernel(const int32_t* __restrict__ j, int n, int32_t* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) fy_count_kernel(const int32_t* __restrict__ j, int n, int rev, int32_t* __restrict__ cnt) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x) {
-    const int t = j[i];
+    const int t = j[rev ? n - 1 - i : i];
     if (t != i) atomicAdd(&cnt[t], 1);
   }
 }
@@ -70,11 +70,11 @@ __global__ void __launch_bounds__(1024) fy_scan2_kernel(int32_t* __restrict__ bs
     if (b0 + k < nb) { const int t = bsum[b0 + k]; bsum[b0 + k] = run; run += t; }
 }
 // pass 3 fused into the scatter: start[t] = local[t] + bsum[t / 1024]
-__global__ void __launch_bounds__(256) fy_scatter_kernel(const int32_t* __restrict__ j, int n, const int32_t* __restrict__ local,
+__global__ void __launch_bounds__(256) fy_scatter_kernel(const int32_t* __restrict__ j, int n, int rev, const int32_t* __restrict__ local,
                                                          const int32_t* __restrict__ bsum, int32_t* __restrict__ cursor,
                                                          int32_t* __restrict__ grp) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x) {
-    const int t = j[i];
+    const int t = j[rev ? n - 1 - i : i];
     if (t != i) grp[local[t] + bsum[t / kScanBlock] + atomicAdd(&cursor[t], 1)] = i;
   }
 }
@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(256) fy_links_kernel(int n, const int32_t* __r
   }
 }
 // out[i]: follow the (strictly increasing) first[] chain from the step that last wrote the source position
-__global__ void __launch_bounds__(256) fy_resolve_kernel(const int32_t* __restrict__ j, int n, const int32_t* __restrict__ first,
+__global__ void __launch_bounds__(256) fy_resolve_kernel(const int32_t* __restrict__ j, int n, int rev, const int32_t* __restrict__ first,
                                                          const int32_t* __restrict__ nxt, int64_t* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int t = i ? j[i] : 0;
+    const int t = i ? j[rev ? n - 1 - i : i] : 0;
     int q;
     if (t == i) q = i;                                       // self-swap (and position 0): the content position i ends up with
     else { q = nxt[i]; if (q < 0) { out[i] = t; continue; } }
@@ -122,12 +122,13 @@ extern "C" int64_t ppx_np_shuffle_apply_device_workspace(int64_t n) {
   return (int64_t)sizeof(int32_t) * (6 * std::max<int64_t>(n, 1) + nb + 64);
 }
 
-extern "C" int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, void* workspace, int64_t* out_dev, void* stream) {
+extern "C" int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, int acceptance_order, void* workspace, int64_t* out_dev,
+                                           void* stream) {
   PPX_REQUIRE(n >= 0 && n <= (1ll << 24), "np_shuffle_apply_device: n=%lld (supported up to 2^24)", (long long)n);
   if (n == 0) return PPX_OK;
   PPX_REQUIRE(j_dev && workspace && out_dev, "np_shuffle_apply_device: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int N = (int)n, nb = (int)ceil_div(n, kScanBlock);
+  const int N = (int)n, nb = (int)ceil_div(n, kScanBlock), rev = acceptance_order ? 1 : 0;
   int32_t* cnt = (int32_t*)workspace;                        // [n] steps targeting p (self-swaps excluded)
   int32_t* cursor = cnt + n;                                 // [n]
   int32_t* local = cursor + n;                               // [n] exclusive scan inside the 1024-block
@@ -137,11 +138,11 @@ extern "C" int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, void
   int32_t* bsum = nxt + n;                                   // [nb]
   PPX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * 2 * n, st));          // cnt + cursor
   const unsigned g = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
-  fy_count_kernel<<<g, 256, 0, st>>>(j_dev, N, cnt);
+  fy_count_kernel<<<g, 256, 0, st>>>(j_dev, N, rev, cnt);
   fy_scan1_kernel<<<(unsigned)nb, 256, 0, st>>>(cnt, N, local, bsum);
   fy_scan2_kernel<<<1, 1024, 0, st>>>(bsum, nb);
-  fy_scatter_kernel<<<g, 256, 0, st>>>(j_dev, N, local, bsum, cursor, grp);
+  fy_scatter_kernel<<<g, 256, 0, st>>>(j_dev, N, rev, local, bsum, cursor, grp);
   fy_links_kernel<<<g, 256, 0, st>>>(N, cnt, local, bsum, grp, first, nxt);
-  fy_resolve_kernel<<<g, 256, 0, st>>>(j_dev, N, first, nxt, out_dev);
+  fy_resolve_kernel<<<g, 256, 0, st>>>(j_dev, N, rev, first, nxt, out_dev);
   return after_launch("np_shuffle_apply_device", 6);
 }

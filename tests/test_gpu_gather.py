@@ -89,11 +89,17 @@ def test_device_shuffle_apply_matches_numpy(n):
     j = np.zeros(n, np.int32)
     L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
     assert np.array_equal(key, after[1]) and pos.value == after[2]
-    jd = torch.as_tensor(j).cuda()
+    # the streaming (AVX-512) draw loop leaves the same list in acceptance order: entry r belongs to position n-1-r
+    key2 = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos2, acc, prog = C.c_int(int(st[2])), np.zeros(n, np.int32), np.zeros(1, np.int64)
+    L.call("ppx_np_shuffle_draws32_stream", key2.ctypes.data, C.byref(pos2), n, acc.ctypes.data, prog.ctypes.data)
+    assert np.array_equal(key2, after[1]) and pos2.value == after[2]
     ws = torch.empty(L.call("ppx_np_shuffle_apply_device_workspace", n), dtype=torch.uint8, device="cuda")
     out = torch.full((n,), -1, dtype=torch.int64, device="cuda")
-    for _ in range(2):                                       # twice: the workspace is reusable, the result does not depend on atomic order
-        L.call("ppx_np_shuffle_apply_device", jd.data_ptr(), n, ws.data_ptr(), out.data_ptr(), L.stream())
+    for lst, order in ((j, 0), (acc, 1), (j, 0)):            # repeated: the workspace is reusable, the result does not depend on atomic order
+        jd = torch.as_tensor(lst).cuda()
+        out.fill_(-1)
+        L.call("ppx_np_shuffle_apply_device", jd.data_ptr(), n, order, ws.data_ptr(), out.data_ptr(), L.stream())
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), want)
 
