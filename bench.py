@@ -271,7 +271,8 @@ def run_ppx(args):
     pinned = {k: torch.as_tensor(v).pin_memory() for k, v in host.items()}
     dones = pinned["masks"][-1].clone().pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + dones.numel()
-    perm_bytes = HP["n_epochs"] * T * N * world * 8
+    # per epoch: the int32 Fisher-Yates partner list when the swaps run on the device (default), else the int64 permutation
+    perm_bytes = HP["n_epochs"] * T * N * world * (4 if m._device_apply() else 8)
 
     def load():
         ro.load_rollout(**{k: v for k, v in pinned.items() if k != "last_value"})
@@ -396,7 +397,8 @@ def run_ppx(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 5), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed every step (256 MiB memset inside the timed region)",
-                       "shuffle": "np.random.permutation on the host each epoch (bit-exact reference stream), inside the timed region",
+                       "shuffle": ("np.random.permutation each epoch inside the timed region (bit-exact reference stream): draws on the host, "
+                                   + ("swaps on the GPU (copy stream)" if m._device_apply() else "swaps on host worker threads")),
                        "global_minibatch": B * world, "cuda_graph": "per-minibatch launch sequence (incl. the NCCL collectives when N>1) replayed as a CUDA graph",
                        "shard_shuffle": "local (per-rank shuffle stream)" if world > 1 else "n/a (1 GPU)"},
             "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d + perm_bytes // world),
