@@ -134,3 +134,34 @@ def test_speculative_rng_stream_is_exact_and_cancellable():
     assert not rng_states_equal(np.random.get_state(), snap2)
     spec2.cancel()
     spec2.drain()
+
+
+def test_rng_stream_device_apply_mode_delivers_exact_partner_lists():
+    """device_apply=True: permutations come out as Fisher-Yates partner lists in acceptance order (entry r belongs to
+    position n-1-r) and the scalar draws in between stay in sequence; replaying the swaps (here on the CPU -- the GPU
+    kernels of shuffle_dev.cu are checked in tests/test_gpu_gather.py) gives numpy's permutations, and the final state is
+    numpy's."""
+    import torch
+    from ppo_exploration_b200.buffer import HostRngStream, DevicePartners, rng_states_equal
+    for n in (2, 17, 1000, 70001):
+        np.random.seed(n)
+        want = []
+        for _ in range(3):
+            want.append(np.random.permutation(n))
+            want.append(np.random.randn())
+        after = np.random.get_state()
+        np.random.seed(n)
+        s = HostRngStream(sum([[('perm', n), ('randn',)] for _ in range(3)], []), device_apply=True)
+        for w in want:
+            g = s.next()
+            if isinstance(w, np.ndarray):
+                assert isinstance(g, DevicePartners) and g.j.dtype == torch.int32 and g.j.numel() == n
+                acc, a = g.j.numpy(), np.arange(n)
+                for r in range(n - 1):
+                    i = n - 1 - r
+                    a[i], a[acc[r]] = a[acc[r]], a[i]
+                assert np.array_equal(a, w), n
+            else:
+                assert g == w
+        s.drain()
+        assert rng_states_equal(s.final_state(), after)
