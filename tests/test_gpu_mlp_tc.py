@@ -123,3 +123,36 @@ def test_tc_mlp_deterministic_and_value_head():
     n = n[0] if isinstance(n, tuple) else n
     assert torch.equal(g_inkernel[:n], pol.bank.grad[:n])
     torch.testing.assert_close(g_inkernel[:n], g_explicit[:n], rtol=1e-5, atol=1e-6 * float(g_explicit[:n].abs().max()))
+
+
+@pytest.mark.parametrize("M,D", [(1, 4), (129, 8), (1000, 17), (4099, 32)])
+def test_tc_mlp_stays_inside_its_buffers(M, D):
+    """Every scratch buffer of the pair (tile-transposed activations, outputs, backward partials, sum-of-squares
+    partials) is followed by a guard band; no kernel of the forward / backward / reduce sequence may touch it
+    (ragged last tiles, D not a multiple of 4)."""
+    import ppo_exploration_b200 as ppx
+    pol = _policy(D, 64, ppx.Box((2,)), True)
+    assert pol.mlp._fused_args()["tc"]
+    sc, guard, SENT = pol.mlp.scratch, 4096, -12345.0
+    taken = {}
+    orig = sc.get
+
+    def get(name, numel, dtype=torch.float32):
+        b = sc.bufs.get(name)
+        if name not in taken or taken[name][1] < numel or b.dtype != dtype:
+            b = torch.full((int(numel) + guard,), SENT, dtype=dtype, device=sc.device)
+            sc.bufs[name] = b
+            taken[name] = (b, int(numel))
+        return b
+
+    sc.get = get
+    try:
+        x = torch.randn(M, D, device="cuda")
+        outs = pol.forward_raw(x)
+        pol.mlp.backward([torch.randn_like(o) for o in outs], with_sumsq=True)
+        torch.cuda.synchronize()
+    finally:
+        sc.get = orig
+    assert {"pmlp.H1t", "pmlp.H2t", "pmlp.fused_ws_tc"} <= set(taken)
+    for name, (b, n) in taken.items():
+        assert bool((b[n:] == SENT).all()), f"{name}: wrote past its {n} elements"
