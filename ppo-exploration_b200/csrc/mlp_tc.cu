@@ -341,9 +341,13 @@ __device__ __forceinline__ void store_col_images_cw(uint32_t raw, uint32_t lo_de
   }
 }
 
-// Backward kernel: 128 x (64 / CW) compute threads -- thread = (sample s, CW hidden columns) -- plus one MMA warp that
-// only waits for "operands ready" mbarriers and issues the two GEMMs of every tile, so no compute warp ever carries the
-// issue latency.  CW = 16: 16 compute warps per SM (1 CTA/SM) hide the shared-memory latency of the thin reductions.
+// Backward kernel: 128 x (64 / CW) compute threads -- thread = (sample s, CW hidden columns).  The shipped configuration is
+// CW = 32, MMAW = false (8 warps, 255 registers, warp 0 issues the MMAs after the publishing barrier): 97 us at C2.
+// The other instantiations are measured alternatives kept behind PPX_MLP_TC_CW=16 / PPX_MLP_TC_MMAW=1
+// (profiles/mlp_tc_r01d.md): 16 compute warps with 16 columns each (105 us: the kernel is not bound by warps in flight),
+// and a dedicated MMA-issue warp that waits on "operands ready" mbarriers (a tcgen05.mma stalls its issuing thread for
+// about its own duration -- 48 cycles at M=128,N=64 -- but 9 or 17 warps per CTA put 3 or 5 warps on one of the four
+// register files: 168 / 96 registers, spills, 130-155 us).
 template <int DP, int CW, bool MMAW>
 __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_bwd_kernel(BwdP p) {
   constexpr int NCQ = H / CW, NTC = TM * NCQ, NSG = NTC / H, SPG = TM / NSG;   // column groups, compute threads, sample groups
