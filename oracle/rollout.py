@@ -221,3 +221,49 @@ class RunningMeanStd:
 def normalize_obs(obs, mean, var):
     """clip((obs-mean)/sqrt(var+1e-10), -5, 5) in f64.  algorithms.py:117."""
     return np.clip((obs - mean) / np.sqrt(var + 1e-10), -5, 5).astype(float)
+
+
+def fy_apply_sequential(j):
+    """The swaps of numpy's legacy shuffle given its partner list: for i = n-1 .. 1: swap(a[i], a[j[i]]) on arange(n)
+    (what buffer.py:239's np.random.permutation does after drawing j_i = random_interval(i)).  j[0] is unused."""
+    n = len(j)
+    a = np.arange(n)
+    for i in range(n - 1, 0, -1):
+        a[i], a[j[i]] = a[j[i]], a[i]
+    return a
+
+
+def fy_apply_parallel(j):
+    """The same result without the sequential dependence -- the algorithm of csrc/shuffle_dev.cu restated in numpy
+    (test infrastructure: pins the algorithm on the CPU, the kernels are checked against numpy on the GPU).
+
+    Position i is final after its own step and receives what position j[i] held just before it; a position p holds,
+    before step i, what the most recent earlier step that targeted p (smallest s > i with j[s] == p) moved in -- the
+    content position s had before ITS step -- or p itself.  first[p] = smallest step targeting p, nxt[s] = next larger
+    step with the same target; V(s) = V(first[s]) follows a strictly increasing chain."""
+    n = len(j)
+    steps = [i for i in range(1, n) if j[i] != i]                      # self-swaps move nothing
+    groups = {}
+    for i in sorted(steps):
+        groups.setdefault(int(j[i]), []).append(i)
+    first = {p: g[0] for p, g in groups.items()}
+    nxt = {}
+    for g in groups.values():
+        for a, b in zip(g, g[1:]):
+            nxt[a] = b
+
+    def chase(q):
+        while q in first:
+            q = first[q]
+        return q
+
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        t = int(j[i]) if i else 0
+        if t == i:
+            out[i] = chase(i)
+        elif i in nxt:
+            out[i] = chase(nxt[i])
+        else:
+            out[i] = t
+    return out

@@ -270,3 +270,29 @@ def test_es_predict_matches_reference():
             assert np.array_equal(got, g[f"{tag}/actions"])
         else:
             np.testing.assert_allclose(got, g[f"{tag}/actions"], rtol=1e-14, atol=0)
+
+
+def test_parallel_fisher_yates_equals_sequential():
+    """The dependence-free resolution of the shuffle's swaps (the algorithm of csrc/shuffle_dev.cu, restated in
+    oracle/rollout.py) equals the sequential swaps on random and adversarial partner lists, and numpy's own
+    permutation when fed numpy's draws."""
+    rs = np.random.RandomState(0)
+    cases = []
+    for n in (1, 2, 3, 5, 8, 33, 257, 2000):
+        for _ in range(6):
+            cases.append(np.array([0] + [rs.randint(0, i + 1) for i in range(1, n)]))
+        cases.append(np.zeros(n, dtype=np.int64))                      # everything swaps with position 0 (longest group)
+        cases.append(np.arange(n))                                     # only self-swaps
+        cases.append(np.maximum(np.arange(n) - 1, 0))                  # a chain: step i targets i-1
+    for j in cases:
+        assert np.array_equal(OR.fy_apply_parallel(j), OR.fy_apply_sequential(j)), j
+    # numpy's own draws (restated bit-exactly in host_rng.cpp, a host function of libppx) -> numpy's permutation
+    import ctypes as C
+    from ppo_exploration_b200 import _lib as L
+    for n in (2, 10, 1000, 4097):
+        np.random.seed(n)
+        st = np.random.get_state()
+        want = np.random.permutation(n)
+        key, pos, j = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int(int(st[2])), np.zeros(n, np.int32)
+        L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
+        assert np.array_equal(OR.fy_apply_parallel(j), want), n
