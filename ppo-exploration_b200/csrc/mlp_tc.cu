@@ -660,6 +660,424 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
   if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem); }
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward, v2
+// Round-2 restructure.  v1 above spends ~1900 instructions per thread and tile, most of them on
+// (a) the transposed scalar-store images of H1 and dP2 that the weight-gradient GEMM needs, (b) the thin reductions
+// dW1 / db1 / db2 / dW3 on the FMA pipe behind CTA barriers, and its MMA-issuing warp is a ~2700-cycle straggler at every
+// barrier (a tcgen05.mma blocks its issuing thread for about its own duration).  v2 (operand forms and MMA costs probed
+// by tools/umma_probe3.cu / umma_probe4.cu):
+//   * GEMM 2 (dP1 = dP2 W2^T) takes its A operand from TENSOR MEMORY: the owning threads write their 32 dP2 columns
+//     (raw | lo) with two tcgen05.st -- no shared-memory image, no swizzle arithmetic, and the MMA is faster (32 vs 48
+//     cycles at M 128, N 64);
+//   * GEMM 1 (dW2 += H1^T dP2, reduction over the samples) reads MN-major SWIZZLE_128B_BASE32B images: a thread's 32
+//     columns of a sample ARE 128 contiguous bytes of that layout, so the images are 16-byte vector stores;
+//   * dW1, db1 and db2 come off the tensor pipe as well: GEMM 3 = [dP1 | dP2]^T [X | 1] (M = 128: the dP1 image takes
+//     the place of the H1 image once GEMM 1 has read it and sits next to the dP2 image; B = a small K-major image of
+//     X^T with a ones row, N = DP + 8);
+//   * dW3 / db3 (64 x o numbers) are reduced inside each warp with a transposing shuffle network and kept in one
+//     register per output across the tiles -- with that the tile loop has NO CTA barrier: a compute warp only meets the
+//     MMA warp, through mbarriers;
+//   * a dedicated MMA warp (warp 8; its warpgroup gives its registers to the 8 compute warps) issues the three GEMMs
+//     of a tile behind "operands ready" mbarriers, so no compute warp ever stalls on an MMA.
+namespace v2 {
+// shared-memory bytes from the 1024-aligned base; the raw images of V and Q (and their lo images) are adjacent so that
+// GEMM 3 reads [V ; Q] as one M = 128 MN-major operand (4 blocks of 32 rows, 16 KB apart)
+constexpr uint32_t ACC2 = 0, ACC1 = 64, ACC3 = 128, A_RAW = 192, A_LO = 256;     // tensor-memory columns
+constexpr uint32_t W_RAW = 0, W_LO = 16384, V_RAW = 32768, Q_RAW = 65536, LO_DELTA = 65536, XE_OFF = 163840;
+constexpr int REGS_MMA = 56;
+template <int CW> struct Cfg {
+  static constexpr int NCQ = H / CW;                // column groups
+  static constexpr int NTC = TM * NCQ;              // compute threads: thread = (sample s, CW hidden columns)
+  static constexpr int NTH = NTC + 128;             // + the MMA warpgroup (its first warp issues; the others only lend registers)
+  // 64 K registers: NTC x REGS + 128 x REGS_MMA <= 65536
+  static constexpr int REGS = CW == 32 ? 224 : 112;
+};
+}  // namespace v2
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[N]) {
+  if constexpr (N == 32) tmem_ld32_nowait(taddr, v); else tmem_ld16_nowait(taddr, v);
+  tmem_ld_wait();
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&v)[N]) {
+  if constexpr (N == 32) tmem_st32(taddr, v); else tmem_st16(taddr, v);
+}
+// v[CW] = columns c0 .. c0+CW-1 of row s -> MN-major BASE32B images (raw at `img`, lo at `img + lo_delta`); img = image base
+template <int CW>
+__device__ __forceinline__ void store_mn_images(uint32_t img, uint32_t lo_delta, int s, int c0, const float (&v)[CW]) {
+  // bits [5,7) of the block base are zero: the 32-byte-chunk swizzle is an XOR with (s & 3) << 5
+  const uint32_t row = (img + (uint32_t)((c0 >> 5) * 16384 + s * 128)) | (uint32_t)((s & 3) << 5);
+  const int j0 = (c0 & 31) >> 2;                    // first 16-byte chunk of this thread inside the 128-byte row
+#pragma unroll
+  for (int jj = 0; jj < CW / 4; ++jj) {
+    const int j = j0 + jj;
+    const uint32_t a = (row ^ (uint32_t)((j >> 1) << 5)) + (uint32_t)((j & 1) << 4);
+    sts128(a, v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+    sts128(a + lo_delta, lo_of(v[4 * jj]), lo_of(v[4 * jj + 1]), lo_of(v[4 * jj + 2]), lo_of(v[4 * jj + 3]));
+  }
+}
+// every lane holds v[0..CW-1]; afterwards column k's sum over the 32 lanes sits in lane k (CW = 32) or in lanes 2k and
+// 2k+1 (CW = 16).  Fixed shuffle network -> deterministic.
+template <int CW>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[CW], int lane) {
+  constexpr int L0 = 16;
+#pragma unroll
+  for (int off = L0, n = CW / 2; n >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const float keep = up ? v[k + n] : v[k], send = up ? v[k] : v[k + n];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if constexpr (CW == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+template <int DP, int CW>
+__global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP p) {
+  using namespace v2;
+  using C = Cfg<CW>;
+  constexpr int NTC = C::NTC, NTH = C::NTH, NCW = NTC / 32;
+  constexpr int NX = DP + 8;                        // rows of the thin B operand: X^T (DP rows) | ones | 7 zero rows
+  constexpr uint32_t XE_KB = NX * 128;              // bytes of one 32-sample k-block of that image
+  constexpr uint32_t XE_BYTES = 4 * XE_KB;          // one image (raw or lo)
+  constexpr int XPT = (TM * DP) / NTC;
+  static_assert((TM * DP) % NTC == 0, "X tile must divide over the compute threads");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t W_raw = smem + W_RAW, W_lo = smem + W_LO;          // B of GEMM 2: B[n = i][k = j] = W2[i][j], K-major
+  const uint32_t V_raw = smem + V_RAW;                               // MN-major [2 blocks][128 s][128 B]: H1, then dP1
+  const uint32_t Q_raw = smem + Q_RAW;                               // MN-major: dP2
+  const uint32_t Xe_raw = smem + XE_OFF, Xe_lo = Xe_raw + XE_BYTES;  // K-major [4 k-blocks][NX rows][128 B]
+  __shared__ __align__(16) float W3s[MAXO * H];                      // [j][c]
+  __shared__ __align__(16) float red3[4][MAXO + 1][H];               // end of kernel: per-sample-quarter dW3 / db3 partials
+  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.y, o = p.o[g], D = p.D;
+  const uint32_t barG2 = smem_u32(&bars[0]), barG1 = smem_u32(&bars[1]), barG3 = smem_u32(&bars[2]);   // tcgen05.commit
+  const uint32_t opsG2 = smem_u32(&bars[3]), opsG1 = smem_u32(&bars[4]), opsG3 = smem_u32(&bars[5]);   // one arrive per compute warp
+  auto bar_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); };
+
+  if (tid == 0) {
+    mbar_init(barG2, 1); mbar_init(barG1, 1); mbar_init(barG3, 1);
+    mbar_init(opsG2, NCW); mbar_init(opsG1, NCW); mbar_init(opsG3, NCW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  {                                                 // W2 -> K-major images; loads batched ahead of the stores
+    constexpr int WPT = (H * H + NTH - 1) / NTH;
+    float w[WPT];
+#pragma unroll
+    for (int r = 0; r < WPT; ++r) { const int e = tid + r * NTH; w[r] = e < H * H ? __ldg(p.W2 + (size_t)g * H * H + e) : 0.f; }
+#pragma unroll
+    for (int r = 0; r < WPT; ++r) {
+      const int e = tid + r * NTH, i = e >> 6, j = e & 63;
+      if (e < H * H) {
+        const uint32_t off = (uint32_t)((j >> 5) * 8192) + sw128_off(i, j & 31);
+        sts32(W_raw + off, w[r]);
+        sts32(W_lo + off, lo_of(w[r]));
+      }
+    }
+  }
+  for (int e = tid; e < MAXO * H; e += NTH) {
+    const int j = e >> 6, c = e & 63;
+    W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+  }
+  for (uint32_t e = tid; e < 2 * XE_BYTES / 4; e += NTH) sts32(Xe_raw + e * 4, 0.f);
+  __syncthreads();
+  if (tid < TM) sts32(Xe_raw + (uint32_t)(tid >> 5) * XE_KB + sw128_off(DP, tid & 31), 1.f);      // the ones row (its lo part is zero)
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp >= NCW) {
+    // ------------------------------------------------ MMA warpgroup ------------------------------------------------
+    setmaxnreg_dec<REGS_MMA>();
+    if (warp == NCW) {
+      // (loops deliberately not unrolled: an MMA occupies its issuer for 23-32 cycles anyway, and the unrolled form keeps
+      // ~100 precomputed descriptors alive -- spills at the 56 registers this warpgroup keeps)
+      const uint64_t dwr = make_desc(W_raw), dwl = make_desc(W_lo);
+      const uint64_t dvr = make_desc_mn32(V_raw, 16384, 512), dvl = make_desc_mn32(V_raw + LO_DELTA, 16384, 512);
+      const uint64_t dqr = make_desc_mn32(Q_raw, 16384, 512), dql = make_desc_mn32(Q_raw + LO_DELTA, 16384, 512);
+      const uint64_t dxr = make_desc(Xe_raw), dxl = make_desc(Xe_lo);
+      constexpr uint32_t id2 = make_idesc_full(128, 64, 0, 0), id1 = make_idesc_full(64, 64, 1, 1), id3 = make_idesc_full(128, NX, 1, 0);
+      const bool leader = elect_one();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        // GEMM 2: dP1pre [128 x 64] = dP2 (tensor memory) . W2^T; small terms first
+        mbar_wait(opsG2, ph);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ob = (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+            umma_tf32_ts(tmem + ACC2, tmem + A_LO + ks * 8, dwr + ob, id2, ks ? 1u : 0u);
+            umma_tf32_ts(tmem + ACC2, tmem + A_RAW + ks * 8, dwl + ob, id2, 1u);
+          }
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ob = (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+            umma_tf32_ts(tmem + ACC2, tmem + A_RAW + ks * 8, dwr + ob, id2, 1u);
+          }
+          umma_commit(barG2);
+        }
+        __syncwarp();
+        // GEMM 1: dW2 [64 x 64] = H1^T dP2 over the 128 samples (both operands MN-major)
+        mbar_wait(opsG1, ph);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll 1
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t oo = (uint64_t)(ks * 64);
+            umma_tf32(tmem + ACC1, dvl + oo, dqr + oo, id1, ks ? 1u : 0u);
+            umma_tf32(tmem + ACC1, dvr + oo, dql + oo, id1, 1u);
+          }
+#pragma unroll 1
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t oo = (uint64_t)(ks * 64);
+            umma_tf32(tmem + ACC1, dvr + oo, dqr + oo, id1, 1u);
+          }
+          umma_commit(barG1);
+        }
+        __syncwarp();
+        // GEMM 3: [dP1 | dP2]^T [X | 1] over the 128 samples: rows 0..63 = dW1^T | db1, rows 64..127 = (unused) | db2
+        mbar_wait(opsG3, ph);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll 1
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t oa = (uint64_t)(ks * 64), ob = (uint64_t)(((ks >> 2) * XE_KB + (ks & 3) * 32) >> 4);
+            umma_tf32(tmem + ACC3, dvl + oa, dxr + ob, id3, ks ? 1u : 0u);
+            umma_tf32(tmem + ACC3, dvr + oa, dxl + ob, id3, 1u);
+          }
+#pragma unroll 1
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t oa = (uint64_t)(ks * 64), ob = (uint64_t)(((ks >> 2) * XE_KB + (ks & 3) * 32) >> 4);
+            umma_tf32(tmem + ACC3, dvr + oa, dxr + ob, id3, 1u);
+          }
+          umma_commit(barG3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ compute warps ------------------------------------------------
+    setmaxnreg_inc<C::REGS>();
+    const int q = warp & 3, cq = warp >> 2, s = q * 32 + lane, c0 = cq * CW;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    auto arrive = [&](uint32_t bar) {         // this warp's operand writes -> visible to the tensor core; one arrive per warp
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+
+    float dW2acc[CW];                         // lanes < 16: dW2[i = q*16+lane][c0 .. c0+CW-1]
+    float acc3[NX];                           // cq == 0: row r = q*32+lane of GEMM 3: r < 64: dW1[n][r] (n < DP), db1[r] (n == DP);
+                                              //          r >= 64: db2[r - 64] (n == DP)
+    float a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}; // dW3[column of this lane][j] over this warp's samples (see warp_transpose_sum)
+    float a_db3 = 0.f;                        // lane j < o: db3[j] over this warp's samples
+#pragma unroll
+    for (int c = 0; c < CW; ++c) dW2acc[c] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) acc3[n] = 0.f;
+
+    float h1[CW], h2[CW], xpre[XPT];
+    float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    // prefetches are unconditional (the tile index is clamped): a conditional load makes the compiler merge old and new
+    // values with register moves at the loop edge, and those moves wait for the loads
+    auto prefetch_a = [&](int tile_) {        // H2, X and the output gradient of the tile
+      const int tile = min(tile_, p.nTiles - 1);
+      const int m0 = tile * TM;
+      const float4* h2t = reinterpret_cast<const float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 b = ld_stream4(h2t + j * TM);
+        h2[4 * j] = b.x; h2[4 * j + 1] = b.y; h2[4 * j + 2] = b.z; h2[4 * j + 3] = b.w;
+      }
+#pragma unroll
+      for (int r = 0; r < XPT; ++r) {
+        const int e = tid + r * NTC, row = e / DP, k = e % DP;
+        xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
+      }
+      const int b = m0 + s;
+      float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
+      if (b < p.M) {
+        if (p.vh_v[g] != nullptr) {           // o == 1 (checked on the host); same formula as mlp_fused.cu
+          const float w1 = (float)p.vh_branch[g][0], w2 = (float)p.vh_branch[g][1], clip = p.vh_clip;
+          const float v = ld_stream(p.vh_v[g] + b), ov = ld_stream(p.vh_ov[g] + b), R = ld_stream(p.vh_R[g] + b);
+          const float dd = v - ov;
+          const float vc = ov + fminf(fmaxf(dd, -clip), clip);
+          const float pass = (dd >= -clip && dd <= clip) ? 1.f : 0.f;
+          const float gv = w1 * (-2.f * (R - v)) + w2 * (-2.f * (R - vc)) * pass;
+          d[0] = p.vh_scale[g] * gv / p.vh_Bt;
+        } else {
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j)
+            if (j < o) d[j] = ld_stream(p.dOut[g] + (size_t)b * o + j);
+        }
+      }
+      dpre = make_float4(d[0], d[1], d[2], d[3]);
+    };
+    auto prefetch_b = [&](int tile_) {        // H1 of the tile
+      const int tile = min(tile_, p.nTiles - 1);
+      const float4* h1t = reinterpret_cast<const float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 a = ld_stream4(h1t + j * TM);
+        h1[4 * j] = a.x; h1[4 * j + 1] = a.y; h1[4 * j + 2] = a.z; h1[4 * j + 3] = a.w;
+      }
+    };
+    auto drain = [&] {                        // finished GEMM 1 / GEMM 3 accumulators -> fp32 registers (round to nearest)
+      uint32_t z[CW];
+      tmem_ld_n<CW>(tlane + ACC1 + c0, z);
+#pragma unroll
+      for (int c = 0; c < CW; ++c) dW2acc[c] += __uint_as_float(z[c]);
+      if (cq == 0) {
+#pragma unroll
+        for (int n0 = 0; n0 < NX; n0 += 8) {
+          uint32_t y[8];
+          tmem_ld8_nowait(tlane + ACC3 + n0, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int n = 0; n < 8; ++n) acc3[n0 + n] += __uint_as_float(y[n]);
+        }
+      }
+    };
+
+    int it = 0;
+    prefetch_a(blockIdx.x);
+    prefetch_b(blockIdx.x);
+    for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int nxt = tile + (int)gridDim.x;
+      const float dj[MAXO] = {dpre.x, dpre.y, dpre.z, dpre.w};
+      // ---- T1: dP2 = (dOut W3^T)(1 - H2^2) -> tensor memory (A of GEMM 2) ----
+      float dp2[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j)
+          if (j < o) {                        // CTA-uniform
+            const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
+            a.x = fmaf(dj[j], w.x, a.x); a.y = fmaf(dj[j], w.y, a.y); a.z = fmaf(dj[j], w.z, a.z); a.w = fmaf(dj[j], w.w, a.w);
+          }
+        dp2[c] = a.x * (1.f - h2[c] * h2[c]); dp2[c + 1] = a.y * (1.f - h2[c + 1] * h2[c + 1]);
+        dp2[c + 2] = a.z * (1.f - h2[c + 2] * h2[c + 2]); dp2[c + 3] = a.w * (1.f - h2[c + 3] * h2[c + 3]);
+      }
+      {                                       // (GEMM 2 of the previous tile was waited for in its T4: the columns are free)
+        uint32_t u[CW];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) u[c] = __float_as_uint(dp2[c]);
+        tmem_st_n<CW>(tlane + A_RAW + c0, u);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) u[c] = __float_as_uint(lo_of(dp2[c]));
+        tmem_st_n<CW>(tlane + A_LO + c0, u);
+        tmem_st_wait();
+      }
+      arrive(opsG2);
+      // ---- T3: previous tile's accumulators out; MN-major images of dP2 and H1, the X^T image -> GEMM 1 ----
+      if (it > 0) {
+        mbar_wait(barG1, ph ^ 1);
+        mbar_wait(barG3, ph ^ 1);             // GEMM 3 has read V (dP1), Q (dP2) and the X^T image
+        tc_fence_after();
+        drain();
+      }
+      store_mn_images<CW>(Q_raw, LO_DELTA, s, c0, dp2);
+      store_mn_images<CW>(V_raw, LO_DELTA, s, c0, h1);
+#pragma unroll
+      for (int r = 0; r < XPT; ++r) {
+        const int e = tid + r * NTC, row = e / DP, k = e % DP;
+        const uint32_t off = (uint32_t)(row >> 5) * XE_KB + sw128_off(k, row & 31);
+        sts32(Xe_raw + off, xpre[r]);
+        sts32(Xe_lo + off, lo_of(xpre[r]));
+      }
+      arrive(opsG1);
+      // ---- T3b (under GEMM 2 / GEMM 1): dW3 / db3 over this warp's 32 samples, inside the warp ----
+#pragma unroll
+      for (int j = 0; j < MAXO; ++j)
+        if (j < o) {                          // CTA-uniform
+          float v[CW];
+#pragma unroll
+          for (int c = 0; c < CW; ++c) v[c] = h2[c] * dj[j];
+          a_dW3[j] += warp_transpose_sum<CW>(v, lane);
+          const float t = warp_sum(dj[j]);
+          if (lane == j) a_db3 += t;
+        }
+      prefetch_a(nxt);                        // H2 / X / dOut registers are free: next tile's loads fly under the rest of this one
+      // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2) -> its MN-major image where H1 was -> GEMM 3 ----
+      mbar_wait(barG2, ph);
+      tc_fence_after();
+      float dp1[CW];
+      {
+        uint32_t z[CW];
+        tmem_ld_n<CW>(tlane + ACC2 + c0, z);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) dp1[c] = __uint_as_float(z[c]) * (1.f - h1[c] * h1[c]);
+      }
+      prefetch_b(nxt);                        // H1 registers are free
+      mbar_wait(barG1, ph);                   // GEMM 1 has read the H1 images
+      store_mn_images<CW>(V_raw, LO_DELTA, s, c0, dp1);
+      arrive(opsG3);
+    }
+    if (it > 0) {                             // the last tile's accumulators
+      mbar_wait(barG1, (uint32_t)((it - 1) & 1));
+      mbar_wait(barG3, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      drain();
+    }
+    // ---- one partial per CTA ----
+    float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
+    float* wr = p.wsr + ((size_t)g * gridDim.x + blockIdx.x) * p.RS;
+    const int offb1 = D * H, offb2 = offb1 + H, offW3 = offb2 + H, offb3 = offW3 + H * o;
+    if (lane < 16) {
+      const int i = q * 16 + lane;
+#pragma unroll
+      for (int c = 0; c < CW; c += 4)
+        *reinterpret_cast<float4*>(&w2[i * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
+    }
+    if (cq == 0) {
+      const int r = q * 32 + lane;
+      if (r < H) {
+#pragma unroll
+        for (int n = 0; n < DP; ++n)
+          if (n < D) wr[n * H + r] = acc3[n];
+        wr[offb1 + r] = acc3[DP];
+      } else {
+        wr[offb2 + (r - H)] = acc3[DP];
+      }
+    }
+    {                                         // this warp's dW3 / db3 partials: column of lane l is c0 + l (CW = 32) or c0 + l/2
+      const bool own = CW == 32 || (lane & 1) == 0;
+      const int c = c0 + (CW == 32 ? lane : (lane >> 1));
+      if (own) {
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) red3[q][j][c] = a_dW3[j];
+      }
+      if (cq == 0 && lane < MAXO) red3[q][MAXO][lane] = a_db3;
+    }
+    bar_compute();
+    for (int e = tid; e < (MAXO + 1) * H; e += NTC) {     // combine the four sample quarters in a fixed order
+      const int n = e >> 6, c = e & 63;
+      const float v = (red3[0][n][c] + red3[1][n][c]) + (red3[2][n][c] + red3[3][n][c]);
+      if (n < MAXO) { if (n < o) wr[offW3 + c * o + n] = v; }
+      else if (c < o) wr[offb3 + c] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
 inline bool shape_ok(int D, int Hh, int G, const int* outs) {
   if (Hh != H || D < 1 || D > MAXD || G < 1 || G > MAXG) return false;
   for (int g = 0; g < G; ++g)
@@ -694,6 +1112,28 @@ int launch_bwd(const BwdP& p, dim3 grid, cudaStream_t st) {
   }
   mlp3_tc_bwd_kernel<DP, CW, MMAW><<<grid, TM * (H / CW) + (MMAW ? 32 : 0), bwd_smem(DP), st>>>(p);
   return after_launch("mlp3_tc_bwd");
+}
+
+template <int DP, int CW>
+int launch_bwd2(const BwdP& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = v2::XE_OFF + 2 * 4 * (size_t)(DP + 8) * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_bwd2_kernel<DP, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  mlp3_tc_bwd2_kernel<DP, CW><<<grid, v2::Cfg<CW>::NTH, smem, st>>>(p);
+  return after_launch("mlp3_tc_bwd2");
+}
+inline int bwd2_cw() {                       // PPX_MLP_TC_CW2=32: 8 compute warps with 32 columns per thread instead of 16 x 16
+  static int cw = 0;
+  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW2"); cw = (e && atoi(e) == 32) ? 32 : 16; }
+  return cw;
+}
+inline bool bwd_v1() {                       // PPX_MLP_TC_V1=1: the round-1 backward (comparison runs)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PPX_MLP_TC_V1"); v = (e && atoi(e) == 1) ? 1 : 0; }
+  return v == 1;
 }
 inline bool bwd_mmaw() {                     // PPX_MLP_TC_MMAW=1: dedicated MMA-issue warp (costs registers: 17 / 9 warps per CTA)
   static int v = -1;
@@ -777,10 +1217,16 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
 #define PPX_BWD(DPV)                                                                                          \
   rc = w16 ? (mw ? mt::launch_bwd<DPV, 16, true>(p, grid, st) : mt::launch_bwd<DPV, 16, false>(p, grid, st))   \
            : (mw ? mt::launch_bwd<DPV, 32, true>(p, grid, st) : mt::launch_bwd<DPV, 32, false>(p, grid, st))
-  switch (mt::dp_of(D)) {
-    case 8: PPX_BWD(8); break;
-    case 16: PPX_BWD(16); break;
-    default: PPX_BWD(32); break;
+  if (!mt::bwd_v1() && D <= 16) {            // v2: A of GEMM 2 from tensor memory, MN-major images, dW1 / db1 on the tensor pipe
+    const bool w32 = mt::bwd2_cw() == 32;
+    if (mt::dp_of(D) == 8) rc = w32 ? mt::launch_bwd2<8, 32>(p, grid, st) : mt::launch_bwd2<8, 16>(p, grid, st);
+    else rc = w32 ? mt::launch_bwd2<16, 32>(p, grid, st) : mt::launch_bwd2<16, 16>(p, grid, st);
+  } else {
+    switch (mt::dp_of(D)) {
+      case 8: PPX_BWD(8); break;
+      case 16: PPX_BWD(16); break;
+      default: PPX_BWD(32); break;
+    }
   }
 #undef PPX_BWD
   if (rc) return rc;
