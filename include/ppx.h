@@ -96,9 +96,22 @@ int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, c
 /* Same gather, and on the way {mean, unbiased std} (f64, device) of up to two gathered f32 [B] fields -- the
  * advantage normalisation statistics of algorithms.py:219 / :431-434 -- finished by the field's last CTA in a fixed
  * order: stat_outs_host[k] receives 2 doubles for array index stat_fields_host[k]. */
+typedef struct {
+  /* > 0: the arrays are all-gathered env shards [N / n_shard ranks][T][n_shard][...] and idx is a flat index over the
+   * GLOBAL [T, N] rollout: row = ((n / n_shard) * T + t) * n_shard + n % n_shard with t = idx % T, n = idx / T */
+  int n_shard;
+  /* statistics range: the moments are taken over idx[stat_lo .. stat_lo + stat_n) (may start before this rank's slice:
+   * a rank that holds the replicated rollout evaluates the moments of the WHOLE global minibatch itself, identically on
+   * every rank); rows outside [0, B) are read, not stored.  stat_n == 0: the B rows of the call. */
+  int64_t stat_lo, stat_n;
+  /* optional device step cursor: idx += (row / n_mb) * epoch_stride + (row % n_mb) * mb_stride, row = *row_dev */
+  const int64_t* row_dev;
+  int64_t n_mb, epoch_stride, mb_stride;
+} ppx_gather_opts;
 int ppx_gather_minibatch_stats(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                                int n_arrays, const int64_t* idx, int64_t B, int T, int N, const int* stat_fields_host,
-                               double* const* stat_outs_host, int n_stats, void* stream);
+                               double* const* stat_outs_host, int n_stats, const ppx_gather_opts* opts_host /* optional */,
+                               void* stream);
 /* mean and unbiased std of a contiguous f32 vector, accumulated in f64 (advantages.mean()/.std(),
  * algorithms.py:219).  out[0]=mean, out[1]=std(ddof=1). */
 int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream);
@@ -197,13 +210,26 @@ typedef struct {
   const double* branch;                                                 /* device, 2 doubles */
   float scale;                                                          /* policy_weight*vf_coef or int_vf_coef */
 } ppx_value_head;
+/* Optional optimiser tail of the backward (algorithms.py:243-244 in the SAME launch sequence, no Adam kernel): the last
+ * block of the partial-sum reduce kernel combines the per-block sums of squares in a fixed order, adds the gradients
+ * outside the MLP (`extra_grads`, e.g. action_log_std), bumps *step_dev and applies clip_grad_norm_(max_norm) + Adam
+ * to the whole bank [0, n) (params / grads / exp_avg / exp_avg_sq are the bank's flat vectors; the MLP gradients are the
+ * ones this call writes).  max_norm <= 0: no clipping.  `ticket` = one zeroed device word owned by the bank. */
+typedef struct {
+  float* params; const float* grads; float* exp_avg; float* exp_avg_sq; int64_t n;
+  double max_norm, lr, beta1, beta2, eps;
+  int64_t* step_dev; double* norm_out /* optional */;
+  const float* extra_grads; int n_extra;
+  unsigned int* ticket;
+} ppx_fused_adam;
 int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W2,
                  const float* const* W3_host, const float* H1, const float* H2, const float* const* dOut_host,
                  const ppx_value_head* value_heads_host /* G entries or NULL */, float clip_range, int64_t B_total,
                  float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
                  float* workspace, double* sumsq_partials /* optional, ppx_mlp3_sumsq_partials() doubles: per-block sums of
                  squares of the final MLP gradients for ppx_clip_adam_pre; step_dev is then bumped here */,
-                 int64_t* step_dev, void* stream);
+                 int64_t* step_dev, const ppx_fused_adam* adam_host /* optional; needs sumsq_partials; step_dev ignored */,
+                 void* stream);
 int ppx_mlp3_sumsq_partials(int D, int H, int G, const int* outs_host);
 
 /* Tensor-core variant of the same pair for H = 64, D <= 32, o_g <= 4, G <= 4 (ppx_mlp3_tc_supported): the two
@@ -223,7 +249,7 @@ int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int G, const i
                     const float* const* W3_host, const float* H1t, const float* H2t, const float* const* dOut_host,
                     const ppx_value_head* value_heads_host, float clip_range, int64_t B_total,
                     float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
-                    float* workspace, double* sumsq_partials, int64_t* step_dev, void* stream);
+                    float* workspace, double* sumsq_partials, int64_t* step_dev, const ppx_fused_adam* adam_host, void* stream);
 
 /* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
 /* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma
@@ -271,7 +297,15 @@ typedef struct {
   int discrete;
   int dual;
   float clip_range, ent_coef, vf_coef, int_vf_coef, policy_weight;
+  /* optional device step cursor (one CUDA graph serves every minibatch of a train() call): the loss row written is
+   * losses_out + 8 * (*row_dev); the finalising thread then increments *row_dev unless row_hold (a later
+   * ppx_loss_row_commit does it).  ppx_gather_minibatch_stats reads the same counter to find its index slice. */
+  int64_t* row_dev;
+  int row_hold;
 } ppx_ppo_cfg;
+/* losses[8 * row + col] = *value; losses[8 * row] += *value if add_to_total; then ++*row_dev (row = *row_dev before).
+ * The ICM learner's second loss (algorithms.py:688-692) lands in the row its policy step left open (row_hold). */
+int ppx_loss_row_commit(double* losses, int64_t* row_dev, const double* value, int col, int add_to_total, void* stream);
 int64_t ppx_ppo_loss_workspace(int64_t B, int A);
 int ppx_ppo_loss_fwd_bwd(const ppx_ppo_cfg* cfg_host, const float* actor_out, const float* log_std,
                          const double* actions, const float* old_log_probs, const float* advantages,

@@ -5,7 +5,7 @@ This package restates, in plain numpy / torch-CPU, the algorithms of the referen
 sil_module.py) that the CUDA library in ``ppo-exploration_b200/csrc`` replaces.  Every function
 cites the reference file:line it follows.
 
-Rules (enforced by tests/test_no_oracle_in_product.py):
+Rules (enforced by tests/test_cabi_and_host.py::test_product_never_touches_the_oracle_or_cpu_fallbacks):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
     ``--impl reference`` legs may import this package;
   * the product package never imports it and has no CPU fallback.

@@ -22,7 +22,20 @@ c_d = C.c_double
 class PpoCfg(C.Structure):
     _fields_ = [("B", c_l), ("B_total", c_l), ("A", c_i), ("discrete", c_i), ("dual", c_i), ("clip_range", C.c_float),
                 ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("int_vf_coef", C.c_float),
-                ("policy_weight", C.c_float)]
+                ("policy_weight", C.c_float), ("row_dev", c_p), ("row_hold", c_i)]
+
+
+class GatherOpts(C.Structure):
+    """ppx_gather_opts: sharded source decode, statistics range, device step cursor."""
+    _fields_ = [("n_shard", c_i), ("stat_lo", c_l), ("stat_n", c_l), ("row_dev", c_p), ("n_mb", c_l), ("epoch_stride", c_l),
+                ("mb_stride", c_l)]
+
+
+class FusedAdam(C.Structure):
+    """ppx_fused_adam: the optimiser tail of the fused MLP backward (clip_grad_norm_ + Adam in the reduce kernel's last block)."""
+    _fields_ = [("params", c_p), ("grads", c_p), ("exp_avg", c_p), ("exp_avg_sq", c_p), ("n", c_l), ("max_norm", c_d), ("lr", c_d),
+                ("beta1", c_d), ("beta2", c_d), ("eps", c_d), ("step_dev", c_p), ("norm_out", c_p), ("extra_grads", c_p),
+                ("n_extra", c_i), ("ticket", c_p)]
 
 
 class ValueHead(C.Structure):
@@ -49,7 +62,8 @@ SIGNATURES = {
     "ppx_count_table_dump": (c_i, [c_p, c_p, c_p, c_u, C.POINTER(c_u)]),
     "ppx_gather_minibatch": (c_i, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_p, c_l, c_i, c_i, c_p]),
     "ppx_gather_minibatch_stats": (c_i, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_p, c_l, c_i, c_i, C.POINTER(c_i),
-                                         C.POINTER(c_p), c_i, c_p]),
+                                         C.POINTER(c_p), c_i, c_p, c_p]),
+    "ppx_loss_row_commit": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
     "ppx_mean_std": (c_i, [c_p, c_l, c_p, c_p]),
     "ppx_np_permutation": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),
     "ppx_np_shuffle_draws": (c_i, [c_p, C.POINTER(c_i), c_l, c_p]),
@@ -72,14 +86,14 @@ SIGNATURES = {
     "ppx_mlp3_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i, c_p]),
     "ppx_mlp3_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_float, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                           c_p, c_p, c_p]),
+                           c_p, c_p, c_p, c_p]),
     "ppx_mlp3_sumsq_partials": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_tc_supported": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_tc_act_elems": (c_l, [c_i, c_i, c_i]),
     "ppx_mlp3_tc_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_tc_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i, c_p]),
     "ppx_mlp3_tc_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_float, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                              c_p, c_p, c_p]),
+                              c_p, c_p, c_p, c_p]),
     "ppx_clip_adam_pre": (c_i, [c_p, c_p, c_p, c_p, c_l, c_d, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_i, c_p, c_i, c_p]),
     "ppx_tc_supported": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "ppx_tc_split": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

@@ -52,7 +52,7 @@ class BaseAlgorithm(object):
         self._n_updates = 0
         self.num_timesteps = 0
         self.num_episodes = 0
-        self.obs_rms = RunningMeanStd(shape=(self.state_dim,), device=self.device)
+        self.obs_rms = RunningMeanStd(shape=(self.state_dim,), device=self.device, sharded=True)
         self.logger = logger
         self.train_stats = {}
         self.last_losses = None
@@ -61,20 +61,24 @@ class BaseAlgorithm(object):
         self._sums = torch.zeros(32, dtype=torch.float64, device=self.device)
         self._branch = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.scale_batch_with_world = True     # sharded runs: batch_size is per rank (weak scaling)
-        # sharded minibatch composition: "global" = every rank draws the SAME permutation over the global
-        # [T, W*N] index space and keeps the rows it owns (bit-identical to one GPU holding all envs; host cost
-        # grows with W); "local" = every rank shuffles its own rollout with its own numpy stream (the reference's
-        # buffer semantics per rank; static shapes -> CUDA graphs, scales)
+        # sharded minibatch composition: "global" (default; exact) = every rank draws the SAME permutation over the
+        # global [T, W*N] index space -- the reference's np.random.permutation(T*N_total), bit for bit -- the rollout
+        # is replicated once per pass (all-gather of the env shards) and rank r takes rows [r*B, (r+1)*B) of every
+        # global minibatch: a W-GPU run equals the 1-GPU run over all envs, shapes are static (CUDA graphs);
+        # "local" = every rank shuffles its own rollout with its own numpy stream (the usual data-parallel sampler;
+        # NOT the reference's global permutation -- a labelled secondary number in bench.py)
         self.shard_shuffle = "global"
         self._mrec = None
         self._spec = None                      # (HostRngStream, rng snapshot) pre-drawn for the next train() call
         self.speculative_shuffle = True
         self._px = False                       # PeerExchange (NVLink peer-memory kernels) | None; False = not probed yet
         self.use_cuda_graph = True             # replay the per-minibatch launch sequence as one CUDA graph
-        self._graphs = {}
-        self._loss_row = torch.zeros(8, dtype=torch.float64, device=self.device)
-        self._perm_bufs, self._perm_ready, self._perm_free, self._copy_stream = None, [None, None], [None, None], None
+        self._graphs, self._graph_state = {}, None
+        self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)    # optimiser step of the running train() call
+        self._losses_buf = None                # [steps, 8] f64, persistent (graphs keep its address)
+        self._perm_all, self._perm_events, self._perm_keep, self._copy_stream = None, [], [], None
         self._perm_j, self._perm_ws = None, None
+        self._glob = None                      # sharded "global": the all-gathered rollout [W, T, N, ...] per field
         self.device_shuffle = device_shuffle_default()         # swaps of the epoch shuffle applied on the GPU (shuffle_dev.cu)
 
     def __del__(self):
@@ -97,16 +101,21 @@ class BaseAlgorithm(object):
     def _loss_workspace(self):
         return self._scratch.get("ppo_loss_ws", L.call("ppx_ppo_loss_workspace", 0, 0) // 8 + 1, torch.float64)
 
-    def _gather_with_stats(self, ro, sl, bufs, dual=False):
+    def _gather_with_stats(self, ro, sl, bufs, dual=False, opts=None, B=None, sources=None):
         """Minibatch gather; the advantage moments (algorithms.py:219, :431-434) come out of the same launch."""
+        B = sl.numel() if B is None else int(B)
+        n_stat = opts.stat_n if (opts is not None and opts.stat_n > 0) else B
         stats = [('advantages', self._stats.data_ptr())] + ([('int_advantages', self._stats.data_ptr() + 16)] if dual else [])
-        ro.gather_into(sl, bufs, stats=stats if sl.numel() >= 2 else None)
-        return sl.numel() >= 2
+        ro.gather_into(sl, bufs, stats=stats if n_stat >= 2 else None, opts=opts, sources=sources, B=B)
+        return n_stat >= 2
 
-    def _policy_step(self, bufs, B, losses_row, dual=False, policy_weight=1.0, int_vf_coef=0.0, B_total=0, stats_ready=False):
+    def _policy_step(self, bufs, B, losses_row, dual=False, policy_weight=1.0, int_vf_coef=0.0, B_total=0, stats_ready=False,
+                     stats_global=False, row_dev=None, row_hold=False, fuse_adam=False):
         """One minibatch: forward, fused loss fwd+bwd, backward.  Gradients land in policy.bank.grad.
-        Sharded runs (B_total = rows of the global minibatch) exchange only the advantage moments and the
-        32 loss partial sums; the caller all-reduces the flat gradient."""
+        Sharded runs (B_total = rows of the global minibatch) exchange only the 32 loss partial sums (and, with
+        per-rank shuffles, the advantage moments); the caller all-reduces the flat gradient.  `losses_row` is the
+        base of the loss log: with `row_dev` (device step counter) row *row_dev is written and the counter advanced
+        (unless row_hold).  fuse_adam: clip + Adam run inside the backward's reduce kernel (single GPU, fused MLP)."""
         pol, sc = self.policy, self._scratch
         A = pol.action_dim
         obs = bufs['observations'][:B]
@@ -118,17 +127,18 @@ class BaseAlgorithm(object):
             if dual:
                 iadv = bufs['int_advantages'][:B]
                 L.call("ppx_mean_std", iadv.data_ptr(), B, self._stats.data_ptr() + 16, L.stream())
-        if sharded:
+        if sharded and not stats_global:
             self._merge_stats(B, dual)
         d_actor = sc.get("d_actor", B * A)[:B * A].view(B, A)
         cfg = L.PpoCfg(B, int(B_total), A, int(self.discrete), int(dual), float(self.clip_range), float(self.ent_coef),
-                       float(self.vf_coef), float(int_vf_coef), float(policy_weight))
+                       float(self.vf_coef), float(int_vf_coef), float(policy_weight), row_dev, int(bool(row_hold)))
         g = lambda k: bufs[k][:B].data_ptr() if k in bufs else None
         ws = self._loss_workspace().data_ptr()
         head_args = (C.byref(cfg), outs[0].data_ptr(), pol.bank.p("action_log_std"), g('actions'),
                      g('old_log_probs'), adv.data_ptr(), self._stats.data_ptr(), outs[1].data_ptr(), g('old_values'),
                      g('returns'), g('int_advantages'), self._stats.data_ptr() + 16,
                      outs[2].data_ptr() if dual else None, g('int_values'), g('int_returns'), d_actor.data_ptr())
+        self._adam_fused = False
         if pol.mlp.fused():
             # head + partial sums (+ loss scalars / branch when single-GPU) in ONE launch; the value-head gradients are
             # evaluated inside the fused MLP backward from the branch weights.  Sharded: the 32 partial sums are
@@ -154,10 +164,15 @@ class BaseAlgorithm(object):
             if dual:
                 vh[2] = (outs[2], bufs['int_values'][:B], bufs['int_returns'][:B], self._branch.data_ptr() + 16,
                          float(int_vf_coef))
-            # single GPU with clipping: the reduce kernel also leaves the clip_grad_norm_ partials (no sumsq launch)
-            self._pre_sumsq = (not sharded) and self.max_grad_norm > 0
+            # single GPU: the reduce kernel also leaves the clip_grad_norm_ partials, and (fuse_adam) its last block
+            # applies clip + Adam to the whole bank -- no sumsq launch, no Adam launch
+            self._pre_sumsq = (not sharded) and (self.max_grad_norm > 0 or fuse_adam)
+            adam = None
+            if fuse_adam and not sharded:
+                adam = pol.bank.fused_adam(self.lr, self.max_grad_norm, extra_name="action_log_std")
+                self._adam_fused = True
             pol.mlp.backward([d_actor, None] + ([None] if dual else []), value_heads=vh, clip_range=self.clip_range,
-                             B_total=Bt, with_sumsq=self._pre_sumsq)
+                             B_total=Bt, with_sumsq=self._pre_sumsq, adam=adam)
             return
         self._pre_sumsq = False
         d_val = sc.get("d_val", B)[:B].view(B, 1)
@@ -173,7 +188,7 @@ class BaseAlgorithm(object):
 
     def _peer_exchange(self):
         """Lazily move the policy bank's gradient vector, the loss partial sums and the moment records into symmetric
-        peer memory so the three per-minibatch exchanges run as ppx kernels over NVLink (p2p.cu) instead of NCCL."""
+        peer memory so the per-minibatch exchanges run as ppx kernels over NVLink (p2p.cu) instead of NCCL."""
         if self._px is False:
             self._px = None
             if D.world_size() > 1 and self.policy.mlp.fused():
@@ -186,10 +201,11 @@ class BaseAlgorithm(object):
                     self._sums = px.sums[:32]
                     self._sums_global = torch.zeros(32, dtype=torch.float64, device=self.device)
                     self._px = px
+                    self._graphs.clear()
         return self._px
 
     def _merge_stats(self, B, dual):
-        """Sharded minibatch: local {mean, std} -> global, through one exchange of {n, mean, M2} records."""
+        """Per-rank shuffles ("local"): local {mean, std} -> global, through one exchange of {n, mean, M2} records."""
         W = D.world_size()
         px = self._peer_exchange()
         if px is not None:
@@ -213,16 +229,31 @@ class BaseAlgorithm(object):
             b = self._mrec_all[:, 3:6].contiguous()
             L.call("ppx_moments_merge", b.data_ptr(), W, self._stats.data_ptr() + 16, L.stream())
 
+    def _hp_state(self):
+        """Everything a captured graph bakes into kernel arguments or addresses: the scalar hyper-parameters (a schedule
+        that changes lr / clip_range between train() calls must not replay stale values) and the scratch generation (a
+        buffer that was re-allocated since the capture leaves the graph with a dangling pointer)."""
+        return (self.lr, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm, self.batch_size, self.n_epochs,
+                getattr(self, "int_lr", None), getattr(self, "int_vf_coef", None), getattr(self, "policy_weight", None),
+                getattr(self, "beta", None), self.shard_shuffle, D.world_size(), _Scratch.generation)
+
     def _graph_call(self, key, fn):
-        """Run fn() -- a fixed sequence of libppx launches (and, when sharded with local shuffles, NCCL collectives)
-        on static buffers -- through a CUDA graph: eager the first time a key is seen (allocations settle),
-        captured the second time, replayed afterwards."""
-        if not self.use_cuda_graph or (D.world_size() > 1 and self.shard_shuffle != "local"):
+        """Run fn() -- a fixed sequence of libppx launches (and NCCL collectives when sharded without peer memory) on
+        static buffers -- through a CUDA graph: eager the first time a key is seen (allocations settle), captured the
+        second time, replayed afterwards.  Captured graphs are dropped whenever `_hp_state()` changes."""
+        if not self.use_cuda_graph:
             return fn()
+        st = self._hp_state()
+        if st != self._graph_state:
+            self._graphs.clear()
+            self._graph_state = st
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "warm"
-            return fn()
+            fn()
+            if self._hp_state() != st:                          # the warm pass itself grew a buffer: warm once more
+                self._graph_state = self._hp_state()
+            return
         if ent == "warm":
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
@@ -235,10 +266,7 @@ class BaseAlgorithm(object):
         L.extra_launches += ent[1]
 
     def _rng_script(self, ro, randn_per_minibatch=False):
-        W = D.world_size() if self.shard_shuffle != "local" else 1
-        total = ro.buffer_size * ro.n_envs * W
-        Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
-        n_mb = -(-total // Bg)
+        total, Bg, n_mb = self._train_geometry(ro)
         script = []
         for _ in range(self.n_epochs):
             script.append(('perm', total))
@@ -261,8 +289,9 @@ class BaseAlgorithm(object):
         return HostRngStream(script, state=cur, device_apply=self._device_apply())
 
     def _device_apply(self):
-        """Device-side swaps need the permutation only on the device: single GPU or per-rank ("local") shuffles."""
-        return bool(self.device_shuffle) and (D.world_size() == 1 or self.shard_shuffle == "local")
+        """The swaps of the shuffle run on the GPU (only the draws ARE the RNG stream); the permutation is only ever
+        needed on the device."""
+        return bool(self.device_shuffle)
 
     def _rng_close(self, rng, speculate=True):
         """Commit the consumed draws to the global numpy RNG and pre-draw the next call's stream from there."""
@@ -271,75 +300,107 @@ class BaseAlgorithm(object):
         if speculate and self.speculative_shuffle:
             self._spec = (HostRngStream(rng.script, state=final, device_apply=self._device_apply()), final)
 
-    def _perm_prefetch(self, rng, total, slot):
-        """Upload the next epoch's permutation on a side stream into one of two static device buffers, so the
-        4 MB H2D copy overlaps the previous epoch's kernels instead of sitting in the compute stream."""
-        perm = rng.next()                                       # pinned int64 [total], or the partner list (DevicePartners)
-        if self._perm_bufs is None or self._perm_bufs[0].numel() != total:
-            self._perm_bufs = [torch.empty(total, dtype=torch.int64, device=self.device) for _ in range(2)]
-            self._perm_free = [None, None]
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+    def _train_geometry(self, ro):
+        """(indices per permutation, rows of a global minibatch, minibatches per epoch)."""
+        W = D.world_size() if self.shard_shuffle == "global" else 1
+        total = ro.buffer_size * ro.n_envs * W
+        Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
+        return total, Bg, -(-total // Bg)
+
+    def _begin_train(self, ro, randn_per_minibatch=False):
+        """Open the RNG stream, size the persistent per-call buffers (loss log, all-epoch permutation staging), zero the
+        device step cursor and -- sharded "global" -- replicate the rollout.  Returns the RNG stream."""
+        total, Bg, n_mb = self._train_geometry(ro)
+        steps = self.n_epochs * n_mb
+        if self._losses_buf is None or self._losses_buf.shape[0] != steps:
+            self._losses_buf = torch.zeros(steps, 8, dtype=torch.float64, device=self.device)
+            _Scratch.generation += 1
+        self._losses_buf.zero_()
+        self._cursor.zero_()
+        if self._perm_all is None or self._perm_all.numel() != self.n_epochs * total:
+            self._perm_all = torch.empty(self.n_epochs * total, dtype=torch.int64, device=self.device)
+            self._copy_stream = self._copy_stream or torch.cuda.Stream(device=self.device)
             self._perm_j = None
+            _Scratch.generation += 1
+        self._perm_events, self._perm_keep = [None] * self.n_epochs, []
+        self._copy_stream.wait_stream(torch.cuda.current_stream())      # the previous call's readers of the staging buffer
+        rng = self._rng_open(self._rng_script(ro, randn_per_minibatch))
+        if D.world_size() > 1 and self.shard_shuffle == "global":
+            self._replicate_rollout(ro)
+        return rng
+
+    def _replicate_rollout(self, ro):
+        """Sharded "global": all-gather the env shards of every RolloutSample source array -> [W, T, N, ...] (one
+        collective per field and pass; the gather kernel decodes the global flat index into this layout)."""
+        W = D.world_size()
+        srcs = sorted({src for _, src in ro._fields})
+        if self._glob is None or any(self._glob[k].shape[1:] != getattr(ro, k).shape for k in srcs):
+            self._glob = {k: torch.empty((W,) + tuple(getattr(ro, k).shape), dtype=getattr(ro, k).dtype, device=self.device) for k in srcs}
+            _Scratch.generation += 1
+        for k in srcs:
+            D.all_gather_into(self._glob[k], getattr(ro, k))
+
+    def _perm_upload(self, rng, epoch, total):
+        """Stage epoch `epoch`'s permutation in its slice of the all-epoch device buffer, on the copy stream (the H2D
+        copy and the device-side swaps overlap the previous epoch's kernels)."""
+        perm = rng.next()                                       # pinned int64 [total], or the partner list (DevicePartners)
         on_device = isinstance(perm, DevicePartners)
+        dst = self._perm_all[epoch * total:(epoch + 1) * total]
         if on_device and self._perm_j is None:
             self._perm_j = [torch.empty(total, dtype=torch.int32, device=self.device) for _ in range(2)]
             self._perm_ws = torch.empty(L.call("ppx_np_shuffle_apply_device_workspace", total), dtype=torch.uint8, device=self.device)
         with torch.cuda.stream(self._copy_stream):
-            if self._perm_free[slot] is not None:               # the epoch that last read this buffer must be done
-                self._copy_stream.wait_event(self._perm_free[slot])
-            if on_device:                                       # 2 MB up instead of 4, swaps resolved in parallel on the copy stream
-                self._perm_j[slot].copy_(perm.j, non_blocking=True)
-                L.call("ppx_np_shuffle_apply_device", self._perm_j[slot].data_ptr(), total, 1, self._perm_ws.data_ptr(),
-                       self._perm_bufs[slot].data_ptr(), L.stream())
+            if on_device:                                       # 4 bytes per index up instead of 8, swaps resolved in parallel on the copy stream
+                j = self._perm_j[epoch & 1]
+                j.copy_(perm.j, non_blocking=True)
+                L.call("ppx_np_shuffle_apply_device", j.data_ptr(), total, 1, self._perm_ws.data_ptr(), dst.data_ptr(), L.stream())
             else:
-                self._perm_bufs[slot].copy_(perm, non_blocking=True)
+                dst.copy_(perm, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._perm_ready[slot] = (ev, perm)                     # keep the pinned source alive until the copy ran
+        self._perm_events[epoch] = ev
+        self._perm_keep.append(perm)                            # keep the pinned source alive until train() has synchronised
 
     def _epoch_minibatches(self, ro, rng, epoch=0, n_epochs=1):
-        """Yields (idx_dev, B_local, B_total, key) for one epoch.  Single GPU: slices of the reference's
-        permutation (buffer.py:239,251-254), staged in a static device buffer (double-buffered, prefetched on a
-        copy stream).  Sharded: every rank draws the SAME permutation over the global [T, W*N] index space and
-        keeps the rows of each global minibatch whose env it owns (owner-computes)."""
+        """Yields (gather options, B_local, B_total, graph key, sources) for one epoch.  The indices are the reference's
+        own permutation (buffer.py:239, :251-254) over the (global) rollout, staged on the device; the gather kernel
+        finds the minibatch's slice through the device step cursor, so one CUDA graph serves every full minibatch.
+        Sharded "global": rank r takes rows [lo, lo + b) of each global minibatch from the replicated rollout and the
+        advantage moments over ALL its rows (identical on every rank, no exchange)."""
         W, r = D.world_size(), D.rank()
         T, N = ro.buffer_size, ro.n_envs
-        local = W > 1 and self.shard_shuffle == "local"
-        if local:
-            W_eff, W = W, 1                                     # per-rank shuffle: the single-GPU path + B_total
-        total = T * N * W
-        Bg = min(self.batch_size * (W if self.scale_batch_with_world else 1), total)
-        if W == 1:
-            slot = epoch & 1
-            if epoch == 0 or self._perm_ready[slot] is None:
-                self._perm_prefetch(rng, total, slot)
-            ev, _keep = self._perm_ready[slot]
-            torch.cuda.current_stream().wait_event(ev)
-            buf = self._perm_bufs[slot]
-            for s in range(0, total, Bg):
-                sl = buf[s:s + Bg]
-                yield sl, sl.numel(), (sl.numel() * W_eff if local else 0), (slot, s)
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream())
-            self._perm_free[slot] = done
-            self._perm_ready[slot] = None
-            if epoch + 1 < n_epochs:                            # after this epoch's randn()s were consumed (RND)
-                self._perm_prefetch(rng, total, slot ^ 1)
-            return
-        perm = rng.next().numpy()
-        for s in range(0, total, Bg):
-            g = perm[s:s + Bg]
-            loc = D.owned_slice(g, T, N, r)
-            yield torch.as_tensor(loc).to(self.device, non_blocking=True), len(loc), len(g), s
+        glob = W > 1 and self.shard_shuffle == "global"
+        total, Bg, n_mb = self._train_geometry(ro)
+        if self._perm_events[epoch] is None:
+            self._perm_upload(rng, epoch, total)
+        torch.cuda.current_stream().wait_event(self._perm_events[epoch])
+        for k in range(n_mb):
+            bg = min(Bg, total - k * Bg)
+            if glob:
+                base, rem = divmod(bg, W)
+                b, lo = base + (1 if r < rem else 0), r * base + min(r, rem)
+                if base < 2:
+                    raise RuntimeError(f"a global minibatch of {bg} rows cannot be split over {W} ranks")
+                opts = L.GatherOpts(N, -lo, bg, self._cursor.data_ptr(), n_mb, total, Bg)
+                yield opts, lo, b, bg, ("g", b, bg, lo), self._glob
+            else:
+                opts = L.GatherOpts(0, 0, 0, self._cursor.data_ptr(), n_mb, total, Bg)
+                yield opts, 0, bg, (bg * W if W > 1 else 0), ("l", bg), None
+        if epoch + 1 < n_epochs:                                # after this epoch's randn()s were consumed (RND)
+            self._perm_upload(rng, epoch + 1, total)
 
     def _sync_grads(self, bank):
         if D.world_size() > 1:
             D.all_reduce_sum_(bank.grad)
 
     def _policy_optim_step(self):
-        """Gradient exchange + clip + Adam for the policy bank.  Sharded with peer memory: ONE kernel reads every rank's
-        gradient over NVLink, sums in rank order, clips and applies Adam (weights stay bit-identical replicas)."""
+        """Gradient exchange + clip + Adam for the policy bank.  Single GPU with the fused MLP: already done by the last
+        block of the backward's reduce kernel (`_policy_step(fuse_adam=True)`).  Sharded with peer memory: ONE kernel reads
+        every rank's gradient over NVLink, sums in rank order, clips and applies Adam (weights stay bit-identical replicas)."""
         bank = self.policy.bank
+        if getattr(self, "_adam_fused", False):
+            bank.refresh_tc()
+            return
         px = self._peer_exchange() if D.world_size() > 1 else None
         if px is not None:
             n_clip = bank.size if self.max_grad_norm > 0 else 0
@@ -349,15 +410,19 @@ class BaseAlgorithm(object):
                    L.stream())
             bank.refresh_tc()
             return
-        if getattr(self, "_pre_sumsq", False):
+        if getattr(self, "_pre_sumsq", False) and self.max_grad_norm > 0:
             ss, n_ss = self.policy.mlp.sumsq
             bank.adam_step_pre(self.lr, self.max_grad_norm, ss, n_ss, extra_name="action_log_std")
             return
         self._sync_grads(bank)
         bank.adam_step(self.lr, self.max_grad_norm)
 
-    def _finish_train(self, losses_dev, keys):
-        losses = losses_dev.cpu().numpy()                         # the only D2H sync of train()
+    def _fuse_adam_ok(self):
+        return D.world_size() == 1 and self.policy.mlp.fused() and not self.policy.bank.tc_weights
+
+    def _finish_train(self, steps, keys):
+        losses = self._losses_buf[:steps].cpu().numpy()            # the only D2H sync of train()
+        self._perm_keep = []
         if self._px and int(self._px.status.item()) != 0:
             raise RuntimeError("ppx: a peer-memory barrier timed out (a rank fell out of the sharded update)")
         self.last_losses = losses
@@ -425,27 +490,24 @@ class PPO(BaseAlgorithm):
     def train(self):
         """algorithms.py:200-259."""
         ro = self.rollout
-        total = ro.buffer_size * ro.n_envs
-        B = min(self.batch_size, total)
-        n_mb = -(-total // B)
-        losses = torch.zeros(self.n_epochs * n_mb, 8, dtype=torch.float64, device=self.device)
-        bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
+        rng = self._begin_train(ro)
+        total, Bg, n_mb = self._train_geometry(ro)
+        bufs = ro._minibatch_buffers(-(-Bg // D.world_size()) if self.shard_shuffle == "global" else Bg)
+        fuse = self._fuse_adam_ok()
         step = 0
-        rng = self._rng_open(self._rng_script(ro))
-        self._perm_ready = [None, None]
         for ep in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
-                def fn(sl=sl, b=b, bt=bt):
-                    ok = self._gather_with_stats(ro, sl, bufs)
-                    self._policy_step(bufs, b, self._loss_row.data_ptr(), B_total=bt, stats_ready=ok)
+            for opts, lo, b, bt, key, src in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
+                def fn(opts=opts, lo=lo, b=b, bt=bt, src=src):
+                    ok = self._gather_with_stats(ro, self._perm_all[lo:], bufs, opts=opts, B=b, sources=src)
+                    self._policy_step(bufs, b, self._losses_buf.data_ptr(), B_total=bt, stats_ready=ok, stats_global=src is not None,
+                                      row_dev=self._cursor.data_ptr(), fuse_adam=fuse)
                     self._policy_optim_step()
-                self._graph_call(("ppo", off, b, bt), fn)
-                losses[step].copy_(self._loss_row)
+                self._graph_call(("ppo",) + key, fn)
                 step += 1
         ro.generator_ready = True
         self._rng_close(rng)
-        self._finish_train(losses[:step], ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
-                                           "train/entropy_loss"))
+        self._finish_train(step, ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
+                                  "train/entropy_loss"))
 
     def learn(self, total_timesteps, log_interval, reward_target=None, log_to_file=False):
         return self._learn_loop(total_timesteps, log_interval, reward_target)
@@ -468,7 +530,7 @@ class PPO_RND(BaseAlgorithm):
         self.rnd_start = rnd_start
         self.int_vf_coef = int_vf_coef
         self.last_obs = self.env.reset()
-        self.int_rew_rms = RunningMeanStd(device=self.device)
+        self.int_rew_rms = RunningMeanStd(device=self.device, sharded=True)
         self.normalize = True
         self.last_dones = np.array([0 for _ in range(self.num_envs)])
         self._rnd_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -478,9 +540,22 @@ class PPO_RND(BaseAlgorithm):
         normalise -> (pred-target)^2 -> int_rew_rms.update -> divide.  obs [N,D]; returns [N] f32 CUDA."""
         o = _dev(obs, torch.float32, self.device)
         r = self.rnd.int_reward(o, rms=self.obs_rms)
-        L.call("ppx_rnd_normalize_rollout", r.data_ptr(), 1, r.numel(), self.int_rew_rms.mean_dev.data_ptr(),
+        return self._normalize_int_rewards(r.view(1, -1)).view(-1)
+
+    def _normalize_int_rewards(self, r):
+        """int_rew_rms.update(step batch) + divide (algorithms.py:396-398), step by step in t order, for r [T, N].  Sharded:
+        a step's batch is the rewards of ALL W*N envs, so the raw rewards are all-gathered into global env order first
+        (T*N*W floats) and every rank runs the identical merge -- moments and divisors equal the 1-GPU ones bit for bit."""
+        W, rk = D.world_size(), D.rank()
+        T, N = r.shape
+        if W == 1:
+            L.call("ppx_rnd_normalize_rollout", r.data_ptr(), T, N, self.int_rew_rms.mean_dev.data_ptr(),
+                   self.int_rew_rms.var_dev.data_ptr(), self.int_rew_rms.count_dev.data_ptr(), L.stream())
+            return r
+        full = D.interleave_env_shards(D.all_gather_cat(r.contiguous())).contiguous()          # [T, W*N]
+        L.call("ppx_rnd_normalize_rollout", full.data_ptr(), T, W * N, self.int_rew_rms.mean_dev.data_ptr(),
                self.int_rew_rms.var_dev.data_ptr(), self.int_rew_rms.count_dev.data_ptr(), L.stream())
-        return r
+        return full[:, rk * N:(rk + 1) * N].contiguous()
 
     def rnd_bonus_rollout(self, next_obs):
         """Same arithmetic for a whole rollout at once: next_obs [T,N,D] -> [T,N].  Exact because obs_rms is
@@ -488,9 +563,7 @@ class PPO_RND(BaseAlgorithm):
         o = _dev(next_obs, torch.float32, self.device)
         T, N = o.shape[0], o.shape[1]
         r = self.rnd.int_reward(o.reshape(T * N, -1), rms=self.obs_rms)
-        L.call("ppx_rnd_normalize_rollout", r.data_ptr(), T, N, self.int_rew_rms.mean_dev.data_ptr(),
-               self.int_rew_rms.var_dev.data_ptr(), self.int_rew_rms.count_dev.data_ptr(), L.stream())
-        return r.view(T, N)
+        return self._normalize_int_rewards(r.view(T, N))
 
     def collect_samples(self):
         """algorithms.py:367-407."""
@@ -527,32 +600,29 @@ class PPO_RND(BaseAlgorithm):
     def train(self):
         """algorithms.py:409-485."""
         ro = self.rollout
-        total = ro.buffer_size * ro.n_envs
-        B = min(self.batch_size, total)
-        n_mb = -(-total // B)
-        losses = torch.zeros(self.n_epochs * n_mb, 8, dtype=torch.float64, device=self.device)
-        bufs = ro._minibatch_buffers(2 * B if D.world_size() > 1 else B)
+        rng = self._begin_train(ro, randn_per_minibatch=True)
+        total, Bg, n_mb = self._train_geometry(ro)
+        bufs = ro._minibatch_buffers(-(-Bg // D.world_size()) if self.shard_shuffle == "global" else Bg)
+        fuse = self._fuse_adam_ok()
         step = 0
         self.rnd_trained_steps = 0
-        rng = self._rng_open(self._rng_script(ro, randn_per_minibatch=True))
-        self._perm_ready = [None, None]
         for ep in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
-                def fn(sl=sl, b=b, bt=bt):
-                    ok = self._gather_with_stats(ro, sl, bufs, dual=True)
-                    self._policy_step(bufs, b, self._loss_row.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
-                                      B_total=bt, stats_ready=ok)
+            for opts, lo, b, bt, key, src in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
+                def fn(opts=opts, lo=lo, b=b, bt=bt, src=src):
+                    ok = self._gather_with_stats(ro, self._perm_all[lo:], bufs, dual=True, opts=opts, B=b, sources=src)
+                    self._policy_step(bufs, b, self._losses_buf.data_ptr(), dual=True, int_vf_coef=self.int_vf_coef,
+                                      B_total=bt, stats_ready=ok, stats_global=src is not None, row_dev=self._cursor.data_ptr(),
+                                      fuse_adam=fuse)
                     self._policy_optim_step()
-                self._graph_call(("rnd_policy", off, b, bt), fn)
-                losses[step].copy_(self._loss_row)
+                self._graph_call(("rnd_policy",) + key, fn)
                 if rng.next() < 0.25:                               # algorithms.py:468, same host RNG stream
-                    self._graph_call(("rnd_pred", b, bt), lambda b=b, bt=bt: self.train_rnd(bufs['observations'][:b], bt))
+                    self._graph_call(("rnd_pred",) + key, lambda b=b, bt=bt: self.train_rnd(bufs['observations'][:b], bt))
                     self.rnd_trained_steps += 1
                 step += 1
         ro.generator_ready = True
         self._rng_close(rng)
-        self._finish_train(losses[:step], ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
-                                           "train/entropy_loss", "train/intrinsic_loss"))
+        self._finish_train(step, ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
+                                  "train/entropy_loss", "train/intrinsic_loss"))
 
     def learn(self, total_timesteps, log_interval, reward_target=None, log_to_file=False):
         return self._learn_loop(total_timesteps, log_interval, reward_target)
@@ -610,42 +680,47 @@ class PPO_ICM(BaseAlgorithm):
         return True
 
     def train(self):
-        """algorithms.py:651-713.  (Single-GPU only for now: the shuffled-consecutive row pairing of :684 spans
-        the whole minibatch, so sharding it needs a halo row -- see DESIGN.md.)"""
-        if D.world_size() > 1:
-            raise NotImplementedError("PPO_ICM.train is not sharded yet")
+        """algorithms.py:651-713.  Sharded ("global"): the shuffled-consecutive pairing of :684 (rows i, i+1 of the
+        GLOBAL minibatch) is kept exactly -- rank r evaluates the pairs that start in its slice [lo, lo+b) and gathers
+        ONE halo row (the first row of the next rank's slice) for the last of them; the ICM losses are means over the
+        bg-1 global pairs, its gradients are summed over the ranks before its Adam step."""
         ro = self.rollout
-        total = ro.buffer_size * ro.n_envs
-        B = min(self.batch_size, total)
-        n_mb = -(-total // B)
-        losses = torch.zeros(self.n_epochs * n_mb, 8, dtype=torch.float64, device=self.device)
-        icm_losses = torch.zeros(self.n_epochs * n_mb, dtype=torch.float64, device=self.device)
-        bufs = ro._minibatch_buffers(B)
+        W = D.world_size()
+        if W > 1 and self.shard_shuffle != "global":
+            raise NotImplementedError("sharded PPO_ICM.train needs shard_shuffle='global' (the pairing spans the global minibatch)")
+        rng = self._begin_train(ro)
+        total, Bg, n_mb = self._train_geometry(ro)
+        bufs = ro._minibatch_buffers((-(-Bg // W) if W > 1 else Bg) + 1)
+        fuse = self._fuse_adam_ok()
+        icm_row = self._icm_loss
         step = 0
-        rng = self._rng_open(self._rng_script(ro))
-        icm_row = torch.zeros(1, dtype=torch.float64, device=self.device) if not hasattr(self, "_icm_row") else self._icm_row
-        self._icm_row = icm_row
-        self._perm_ready = [None, None]
         for ep in range(self.n_epochs):
-            for sl, b, bt, off in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
-                def fn(sl=sl, b=b):
-                    ok = self._gather_with_stats(ro, sl, bufs)
-                    self._policy_step(bufs, b, self._loss_row.data_ptr(), policy_weight=float(self.policy_weight),
-                                      stats_ready=ok)
+            for opts, lo, b, bt, key, src in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
+                halo = 1 if (W > 1 and lo + b < bt) else 0          # pairs starting in [lo, lo+b): the last one needs row lo+b
+                pairs_total = (bt if W > 1 else b) - 1
+
+                def fn(opts=opts, lo=lo, b=b, bt=bt, src=src, halo=halo, pairs_total=pairs_total):
+                    ok = self._gather_with_stats(ro, self._perm_all[lo:], bufs, opts=opts, B=b + halo, sources=src)
+                    self._policy_step(bufs, b, self._losses_buf.data_ptr(), policy_weight=float(self.policy_weight),
+                                      B_total=bt, stats_ready=ok, stats_global=src is not None, row_dev=self._cursor.data_ptr(),
+                                      row_hold=True, fuse_adam=fuse)
                     icm_row.zero_()
-                    self.intrinsic_module.train_step(bufs['observations'][:b], bufs['actions'][:b], self.beta, icm_row)
+                    self.intrinsic_module.train_step(bufs['observations'][:b + halo], bufs['actions'][:b + halo], self.beta,
+                                                     icm_row, pairs_total=pairs_total)
                     self._policy_optim_step()                                   # only policy grads are clipped (:697)
+                    if W > 1:
+                        D.all_reduce_sum_(self.intrinsic_module.bank.grad)
+                        D.all_reduce_sum_(icm_row)
                     self.intrinsic_module.bank.adam_step(self.int_lr, 0.0)
-                self._graph_call(("icm", off, b), fn)
-                losses[step].copy_(self._loss_row)
-                icm_losses[step:step + 1].copy_(icm_row)
+                    # total = pw*(...) + icm_loss (:692): the ICM loss lands in column 5 of the row the policy step left open
+                    L.call("ppx_loss_row_commit", self._losses_buf.data_ptr(), self._cursor.data_ptr(), icm_row.data_ptr(), 5, 1,
+                           L.stream())
+                self._graph_call(("icm",) + key, fn)
                 step += 1
         ro.generator_ready = True
         self._rng_close(rng)
-        losses[:, 5] = icm_losses
-        losses[:, 0] += icm_losses                                  # total = pw*(...) + icm_loss (:692)
         keys = ("train/total_loss", "train/policy_gradient_loss", "train/value_loss", "train/entropy_loss")
-        self._finish_train(losses[:step], keys)
+        self._finish_train(step, keys)
         self._record("train/icm_loss", float(np.mean(self.last_losses[:, 5])))
 
     def learn(self, total_timesteps, log_interval=5, reward_target=None, log_to_file=False):

@@ -460,6 +460,28 @@ class RolloutStorage(BaseBuffer):
             return rewards
         return rewards
 
+    def sim_hash_sharded(self, obs=None, rewards=None):
+        """buffer.py:188-200 for a rollout whose env columns are sharded over the ranks: this
+        rank holds columns [rank*N, (rank+1)*N) of the global [T, W*N] rollout.  Codes are computed locally; the
+        count table is global and its update order-dependent (t-major, env-minor over ALL envs), so the packed codes
+        are all-gathered and every rank replays the identical, globally ordered table update (tables stay replicas)
+        and applies the counts of its own columns -- bit-identical to one GPU holding all envs.  Mutates and returns
+        `rewards` ([T,N] CUDA f32; default: the stored rollout)."""
+        from . import dist as D
+        obs = self.observations if obs is None else obs
+        rewards = self.rewards if rewards is None else rewards
+        W, r = D.world_size(), D.rank()
+        if W == 1:
+            return self.sim_hash(obs, rewards)
+        T, N = obs.shape[0], obs.shape[1]
+        if not (isinstance(rewards, torch.Tensor) and rewards.is_cuda and rewards.dtype == torch.float32 and rewards.is_contiguous()):
+            raise RuntimeError("sim_hash_sharded: rewards must be a contiguous f32 CUDA tensor [T, N]")
+        codes = self.sim_hash_codes(obs).view(T, N)
+        allc = D.interleave_env_shards(D.all_gather_cat(codes)).reshape(-1)          # [T, W*N] in global env order
+        counts = self.count_table.update_codes(allc).view(T, W, N)[:, r].contiguous()
+        L.call("ppx_simhash_bonus", counts.data_ptr(), T * N, float(self.beta), rewards.data_ptr(), 0, L.stream())
+        return rewards
+
     def sim_hash_codes(self, obs):
         """packed uint64 codes (bit b = sign bit b of buffer.py:194) as an int64 CUDA tensor."""
         A = self._A()
@@ -495,28 +517,34 @@ class RolloutStorage(BaseBuffer):
             self._mb[key] = bufs
         return self._mb[key]
 
-    def gather_into(self, idx_dev, bufs, stats=None):
+    def gather_into(self, idx_dev, bufs, stats=None, opts=None, sources=None, B=None):
         """One fused launch: every RolloutSample field for the flat indices `idx_dev` (int64, CUDA).  stats: optional list
         of (field, device pointer to 2 doubles) -- {mean, unbiased std} of that gathered f32 [B] field (the advantage
         normalisation statistics) computed by the same launch."""
-        B = idx_dev.numel()
+        B = idx_dev.numel() if B is None else int(B)
         n = len(self._fields)
         srcs = (C.c_void_p * n)()
         dsts = (C.c_void_p * n)()
         rb = (C.c_int * n)()
+        n_envs = self.n_envs
         for i, (field, src) in enumerate(self._fields):
             s = getattr(self, src)
-            srcs[i] = s.data_ptr()
+            if B > bufs[field].shape[0]:
+                raise RuntimeError(f"gather_into: {B} rows do not fit the {bufs[field].shape[0]}-row minibatch buffer '{field}'")
+            srcs[i] = s.data_ptr() if sources is None else sources[src].data_ptr()
             dsts[i] = bufs[field].data_ptr()
             rb[i] = int(s[0, 0].numel() * s.element_size()) if s.dim() > 2 else s.element_size()
-        if stats:
+        if opts is not None and opts.n_shard > 0:
+            n_envs = sources[self._fields[0][1]].shape[0] * opts.n_shard     # sources: [W, T, n_shard, ...]
+        if stats or opts is not None:
             names = [f for f, _ in self._fields]
-            sf = (C.c_int * len(stats))(*[names.index(f) for f, _ in stats])
-            so = (C.c_void_p * len(stats))(*[p for _, p in stats])
-            L.call("ppx_gather_minibatch_stats", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, self.n_envs,
-                   sf, so, len(stats), L.stream())
+            stats = stats or []
+            sf = (C.c_int * max(1, len(stats)))(*[names.index(f) for f, _ in stats])
+            so = (C.c_void_p * max(1, len(stats)))(*[p for _, p in stats])
+            L.call("ppx_gather_minibatch_stats", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, n_envs,
+                   sf, so, len(stats), C.byref(opts) if opts is not None else None, L.stream())
             return
-        L.call("ppx_gather_minibatch", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, self.n_envs,
+        L.call("ppx_gather_minibatch", srcs, dsts, rb, n, idx_dev.data_ptr(), B, self.buffer_size, n_envs,
                L.stream())
 
     def _sample_from(self, bufs, B):

@@ -21,19 +21,35 @@ struct GatherArgs {
   double* stat_out[2];
   double* stat_part;             // [2][kStatMax][2]
   unsigned int* stat_ticket;     // [2]
+  int n_shard;                   // > 0: sources are all-gathered env shards [N / n_shard][T][n_shard][...]
+  int64_t stat_lo, stat_n;       // statistics over idx[stat_lo .. stat_lo + stat_n)
+  const int64_t* row_dev;        // optional step cursor
+  int64_t n_mb, epoch_stride, mb_stride;
 };
 constexpr int kStatMax = 4096;
 
+// flat index of the (global) env-major flatten (buffer.py:49-52) -> storage row
+__device__ __forceinline__ int64_t row_of(int64_t i, int T, int N, int n_shard) {
+  const int64_t t = i % T, n = i / T;
+  if (n_shard <= 0) return t * N + n;
+  return ((n / n_shard) * T + t) * n_shard + n % n_shard;
+}
+// this launch's index slice (step cursor: one CUDA graph serves every minibatch of a train() call)
+__device__ __forceinline__ const int64_t* idx_of(const GatherArgs& a, const int64_t* idx) {
+  if (!a.row_dev) return idx;
+  const int64_t row = *a.row_dev;
+  return idx + (row / a.n_mb) * a.epoch_stride + (row % a.n_mb) * a.mb_stride;
+}
+
 template <typename V>
 __device__ __forceinline__ void gather_rows(const char* __restrict__ src, char* __restrict__ dst, int row_bytes,
-                                            const int64_t* __restrict__ idx, int64_t B, int T, int N) {
+                                            const int64_t* __restrict__ idx, int64_t B, int T, int N, int n_shard) {
   const int words = row_bytes / (int)sizeof(V);
   const int64_t total = B * words;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = g / words;
     const int w = (int)(g - b * words);
-    const int64_t i = __ldg(idx + b);
-    const int64_t row = (i % T) * N + i / T;
+    const int64_t row = row_of(__ldg(idx + b), T, N, n_shard);
     reinterpret_cast<V*>(dst)[g] = __ldg(reinterpret_cast<const V*>(src + row * row_bytes) + w);
   }
 }
@@ -46,12 +62,17 @@ __device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot
   const float* src = reinterpret_cast<const float*>(args.src[a]);
   float* dst = reinterpret_cast<float*>(args.dst[a]);
   double s = 0.0, q = 0.0;
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = __ldg(idx + b);
-    const float v = __ldg(src + (i % T) * N + i / T);
-    dst[b] = v;
+  const int64_t lo = args.stat_n > 0 ? args.stat_lo : 0, n_stat = args.stat_n > 0 ? args.stat_n : B;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_stat; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = lo + k;
+    const float v = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
+    if (b >= 0 && b < B) dst[b] = v;
     s += (double)v;
     q += (double)v * (double)v;
+  }
+  if (args.stat_n > 0) {                                      // rows of the slice the statistics range does not cover
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
+      if (b < lo || b >= lo + n_stat) dst[b] = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
   }
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
@@ -72,19 +93,20 @@ __device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
   if (threadIdx.x == 0) {
-    const double mean = s / (double)B;
+    const double mean = s / (double)n_stat;
     args.stat_out[slot][0] = mean;
-    args.stat_out[slot][1] = sqrt(fmax(q - s * mean, 0.0) / (double)(B - 1));     // unbiased, like torch.Tensor.std()
+    args.stat_out[slot][1] = sqrt(fmax(q - s * mean, 0.0) / (double)(n_stat - 1));     // unbiased, like torch.Tensor.std()
   }
 }
 
 __global__ void __launch_bounds__(256)
-gather_kernel(GatherArgs args, const int64_t* __restrict__ idx, int64_t B, int T, int N) {
+gather_kernel(GatherArgs args, const int64_t* __restrict__ idx_base, int64_t B, int T, int N) {
   const int a = blockIdx.y;
+  const int64_t* idx = idx_of(args, idx_base);
   if (a == args.stat_field[0]) { gather_scalar_with_stats(args, a, 0, idx, B, T, N); return; }
   if (a == args.stat_field[1]) { gather_scalar_with_stats(args, a, 1, idx, B, T, N); return; }
-  if (args.vec16[a]) gather_rows<int4>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N);
-  else gather_rows<int>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N);
+  if (args.vec16[a]) gather_rows<int4>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N, args.n_shard);
+  else gather_rows<int>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N, args.n_shard);
 }
 
 // mean / unbiased std in two small launches: per-CTA f64 (sum, sum of squares) partials, then one CTA
@@ -151,7 +173,8 @@ extern "C" int ppx_moments_merge(const double* recs, int W, double* out2, void* 
 
 namespace {
 int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host, int n_arrays, const int64_t* idx,
-                int64_t B, int T, int N, const int* stat_fields, double* const* stat_outs, int n_stats, void* stream) {
+                int64_t B, int T, int N, const int* stat_fields, double* const* stat_outs, int n_stats, const ppx_gather_opts* opts,
+                void* stream) {
   PPX_REQUIRE(srcs_host && dsts_host && row_bytes_host && idx, "gather_minibatch: null pointer");
   PPX_REQUIRE(n_arrays >= 1 && n_arrays <= PPX_MAX_GATHER, "gather_minibatch: n_arrays=%d (1..%d)", n_arrays, PPX_MAX_GATHER);
   PPX_REQUIRE(B >= 0 && T > 0 && N > 0, "gather_minibatch: B=%lld T=%d N=%d", (long long)B, T, N);
@@ -172,6 +195,15 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
   args.stat_field[0] = args.stat_field[1] = -1;
   args.stat_out[0] = args.stat_out[1] = nullptr;
   args.stat_part = nullptr; args.stat_ticket = nullptr;
+  args.n_shard = 0; args.stat_lo = 0; args.stat_n = 0; args.row_dev = nullptr; args.n_mb = 1; args.epoch_stride = 0; args.mb_stride = 0;
+  if (opts) {
+    PPX_REQUIRE(opts->n_shard >= 0 && (opts->n_shard == 0 || N % opts->n_shard == 0), "gather_minibatch: n_shard=%d does not divide N=%d", opts->n_shard, N);
+    PPX_REQUIRE(opts->stat_n >= 0 && (opts->stat_n == 0 || opts->stat_n >= 2), "gather_minibatch: stat_n=%lld", (long long)opts->stat_n);
+    PPX_REQUIRE(!opts->row_dev || opts->n_mb >= 1, "gather_minibatch: cursor needs n_mb >= 1");
+    args.n_shard = opts->n_shard; args.stat_lo = opts->stat_lo; args.stat_n = opts->stat_n;
+    args.row_dev = opts->row_dev; args.n_mb = opts->n_mb; args.epoch_stride = opts->epoch_stride; args.mb_stride = opts->mb_stride;
+    if (opts->stat_n > max_words) max_words = opts->stat_n;
+  }
   int64_t gx = ppx::ceil_div(max_words, 256);
   const int64_t cap = (int64_t)ppx::sm_count() * 16;
   if (gx > cap) gx = cap;
@@ -183,7 +215,7 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
       PPX_CUDA(cudaMalloc((void**)&ticket, 2 * sizeof(unsigned int)));
       PPX_CUDA(cudaMemset(ticket, 0, 2 * sizeof(unsigned int)));
     }
-    PPX_REQUIRE(B >= 2, "gather_minibatch: statistics need B >= 2");
+    PPX_REQUIRE(B >= 2 || (opts && opts->stat_n >= 2), "gather_minibatch: statistics need B >= 2");
     for (int k = 0; k < n_stats; ++k) {
       PPX_REQUIRE(stat_fields && stat_outs && stat_fields[k] >= 0 && stat_fields[k] < n_arrays && stat_outs[k] &&
                   row_bytes_host[stat_fields[k]] == 4, "gather_minibatch: statistics field %d must be an f32 [B] field", k);
@@ -201,13 +233,13 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
 
 extern "C" int ppx_gather_minibatch(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                                     int n_arrays, const int64_t* idx, int64_t B, int T, int N, void* stream) {
-  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, nullptr, nullptr, 0, stream);
+  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int ppx_gather_minibatch_stats(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                                           int n_arrays, const int64_t* idx, int64_t B, int T, int N, const int* stat_fields_host,
-                                          double* const* stat_outs_host, int n_stats, void* stream) {
-  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, stat_fields_host, stat_outs_host, n_stats, stream);
+                                          double* const* stat_outs_host, int n_stats, const ppx_gather_opts* opts_host, void* stream) {
+  return gather_impl(srcs_host, dsts_host, row_bytes_host, n_arrays, idx, B, T, N, stat_fields_host, stat_outs_host, n_stats, opts_host, stream);
 }
 
 extern "C" int ppx_mean_std(const float* x, int64_t n, double* out2, void* stream) {

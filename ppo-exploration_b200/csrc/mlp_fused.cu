@@ -53,6 +53,7 @@ struct RedP {
   float* dW1; float* db1; float* dW2; float* db2; float* dW3[MAXG]; float* db3[MAXG]; int o[MAXG];
   double* sumsq;             // optional [G * gridDim.x]: per-block sum of squares of the final gradients (clip_grad_norm_)
   int64_t* step_dev;         // optional: optimiser step counter, bumped here when the sumsq launch is skipped
+  ppx_fused_adam adam;       // adam.params != nullptr: the last block applies clip + Adam to the whole bank
 };
 
 __host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
@@ -510,6 +511,76 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
   }
 }
 
+template <int H>
+__device__ __forceinline__ void mlp3_reduce_finish(const RedP& p, float (&sl)[8][33], float s, int e, int R, int g, int o, int D, int el) {
+  const bool live = e < H * H + R;
+  if (live) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += sl[q][el];
+  } else {
+    s = 0.f;
+  }
+  if (p.sumsq) {                                              // first warp: fixed-order sum of squares of this block's 32 gradients
+    const double ss = warp_sum((double)s * (double)s);
+    if (el == 0) p.sumsq[(size_t)g * gridDim.x + blockIdx.x] = ss;
+    if (p.step_dev && el == 0 && blockIdx.x == 0 && g == 0) *p.step_dev += 1;
+  }
+  if (live) {
+    if (e < H * H) p.dW2[(size_t)g * H * H + e] = s;
+    else {
+      const int r = e - H * H;
+      if (r < D * H) p.dW1[(size_t)(r / H) * (p.G * H) + g * H + r % H] = s;
+      else if (r < D * H + H) p.db1[g * H + (r - D * H)] = s;
+      else if (r < D * H + 2 * H) p.db2[g * H + (r - D * H - H)] = s;
+      else if (r < D * H + 2 * H + H * o) p.dW3[g][r - D * H - 2 * H] = s;
+      else p.db3[g][r - D * H - 2 * H - H * o] = s;
+    }
+  }
+}
+
+// Optimiser tail (ppx_fused_adam): every thread of every block of the reduce kernel calls this after its gradients are
+// written.  The LAST block to arrive re-reads the per-block sums of squares in a fixed order (so the clip coefficient does
+// not depend on which block that is), bumps the step counter and applies clip_grad_norm_ + torch's Adam update to the
+// whole bank.  The beta powers come from one f64 pow pair evaluated by a single thread.
+__device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, int n_partials) {
+  if (!last_block_done(a.ticket)) return;
+  __shared__ double s_red[32];
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  double ss = 0.0;
+  if (a.max_norm > 0.0) {
+    for (int k = threadIdx.x; k < n_partials; k += blockDim.x) ss += __ldcg(sumsq + k);
+    for (int k = threadIdx.x; k < a.n_extra; k += blockDim.x) { const double v = (double)__ldcg(a.extra_grads + k); ss += v * v; }
+    ss = block_sum(ss, s_red);
+  }
+  if (threadIdx.x == 0) {
+    const int64_t t_ = *a.step_dev + 1;
+    *a.step_dev = t_;
+    const double t = (double)t_;
+    s_step_size = (float)(a.lr / (1.0 - pow(a.beta1, t)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2, t));
+    float coef = 1.f;
+    if (a.max_norm > 0.0) {
+      const float norm = (float)sqrt(ss);
+      coef = fminf((float)a.max_norm / (norm + 1e-6f), 1.f);   // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
+      if (a.norm_out) *a.norm_out = sqrt(ss);
+    }
+    s_coef = coef;
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = (float)(1.0 - a.beta1), beta2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2), eps = (float)a.eps;
+  for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const float gi = __ldcg(a.grads + i) * coef;
+    float mi = a.exp_avg[i], vi = a.exp_avg_sq[i];
+    mi = mi + w1 * (gi - mi);                                 // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * beta2 + w2 * gi * gi;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    a.params[i] = a.params[i] - step_size * (mi / denom);     // param.addcdiv_(exp_avg, denom, -step_size)
+    a.exp_avg[i] = mi;
+    a.exp_avg_sq[i] = vi;
+  }
+}
+
 // grads[e] = sum over CTA partials in a fixed order.  Block = 32 consecutive parameters x 8 slices of the
 // partial list (slice s takes partials s, s+8, ...: many independent loads in flight), slices combined 0..7.
 template <int H>
@@ -533,27 +604,8 @@ __global__ void __launch_bounds__(256) mlp3_reduce_kernel(RedP p) {
   }
   sl[slice][el] = s;
   __syncthreads();
-  if (slice != 0) return;
-  const bool live = e < H * H + R;
-  if (live) {
-#pragma unroll
-    for (int q = 1; q < 8; ++q) s += sl[q][el];
-  } else {
-    s = 0.f;
-  }
-  if (p.sumsq) {                                              // first warp: fixed-order sum of squares of this block's 32 gradients
-    const double ss = warp_sum((double)s * (double)s);
-    if (el == 0) p.sumsq[(size_t)g * gridDim.x + blockIdx.x] = ss;
-    if (p.step_dev && el == 0 && blockIdx.x == 0 && g == 0) *p.step_dev += 1;
-  }
-  if (!live) return;
-  if (e < H * H) { p.dW2[(size_t)g * H * H + e] = s; return; }
-  const int r = e - H * H;
-  if (r < D * H) p.dW1[(size_t)(r / H) * (p.G * H) + g * H + r % H] = s;
-  else if (r < D * H + H) p.db1[g * H + (r - D * H)] = s;
-  else if (r < D * H + 2 * H) p.db2[g * H + (r - D * H - H)] = s;
-  else if (r < D * H + 2 * H + H * o) p.dW3[g][r - D * H - 2 * H] = s;
-  else p.db3[g][r - D * H - 2 * H - H * o] = s;
+  if (slice == 0) mlp3_reduce_finish<H>(p, sl, s, e, R, g, o, D, el);
+  if (p.adam.params) fused_adam_tail(p.adam, p.sumsq, (int)(gridDim.x * gridDim.y));
 }
 
 inline size_t fwd_smem(int H, int D, int o) {
@@ -598,12 +650,17 @@ inline int grid_x(int M, int G, int per_sm) {
 // fixed-order sum of the per-CTA partials of a backward kernel (this file's or mlp_tc.cu's) into the gradient tensors
 int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, const float* wsr, int n, int RS, float* dW1,
                        float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3, double* sumsq,
-                       int64_t* step_dev, cudaStream_t st) {
+                       int64_t* step_dev, const ppx_fused_adam* adam, cudaStream_t st) {
   int omax = 0;
   for (int g = 0; g < G; ++g) omax = std::max(omax, outs[g]);
   RedP r{};
   r.ws2 = ws2; r.wsr = wsr; r.n2 = n; r.nr = n; r.RS = RS; r.D = D; r.G = G;
   r.dW1 = dW1; r.db1 = db1; r.dW2 = dW2; r.db2 = db2; r.sumsq = sumsq; r.step_dev = step_dev;
+  if (adam) {
+    PPX_REQUIRE(adam->params && adam->grads && adam->exp_avg && adam->exp_avg_sq && adam->step_dev && adam->ticket && adam->n >= 1 &&
+                adam->n_extra >= 0 && (adam->n_extra == 0 || adam->extra_grads), "mlp3 fused adam: bad arguments");
+    r.adam = *adam;
+  }
   for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
   dim3 rgrid((unsigned)ceil_div(H * H + rest_size(H, D, omax), 32), (unsigned)G);
   if (H == 64) mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
@@ -672,9 +729,11 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
                             const float* const* W3, const float* H1, const float* H2, const float* const* dOut,
                             const ppx_value_head* vh, float clip_range, int64_t B_total,
                             float* dW1, float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3,
-                            float* workspace, double* sumsq_partials, int64_t* step_dev, void* stream) {
+                            float* workspace, double* sumsq_partials, int64_t* step_dev, const ppx_fused_adam* adam,
+                            void* stream) {
   mf::Shape s;
   PPX_REQUIRE(X && outs && W2 && W3 && H1 && H2 && dOut && dW1 && db1 && dW2 && db2 && dW3 && db3 && workspace, "mlp3_bwd: null pointer");
+  PPX_REQUIRE(!adam || sumsq_partials, "mlp3_bwd: the fused optimiser tail needs sumsq_partials");
   PPX_REQUIRE(mf::shape_ok(D, H, G, outs, &s), "mlp3_bwd: unsupported shape D=%d H=%d G=%d", D, H, G);
   PPX_REQUIRE(M >= 1 && ldx >= D, "mlp3_bwd: M=%d ldx=%d", M, ldx);
   const int n = bwd_grid(M, H, G);
@@ -710,5 +769,5 @@ extern "C" int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G,
   int rc = after_launch("mlp3_bwd");
   if (rc) return rc;
   return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, s.RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
-                                sumsq_partials ? step_dev : nullptr, st);
+                                (sumsq_partials && !adam) ? step_dev : nullptr, adam, st);
 }

@@ -32,7 +32,7 @@ namespace mf {
 // defined in mlp_fused.cu: fixed-order sum of the per-CTA partials (+ optional clip_grad_norm_ partial sums)
 int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, const float* wsr, int n, int RS, float* dW1,
                        float* db1, float* dW2, float* db2, float* const* dW3, float* const* db3, double* sumsq,
-                       int64_t* step_dev, cudaStream_t st);
+                       int64_t* step_dev, const ppx_fused_adam* adam, cudaStream_t st);
 }  // namespace mf
 
 namespace mt {
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
 
     float h1[CW], h2[CW], xpre[XPT];
     float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto prefetch = [&](int tile) {
+      auto prefetch = [&](int tile) {
       const int m0 = tile * TM;
       const float4* h1t = reinterpret_cast<const float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
       const float4* h2t = reinterpret_cast<const float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
 
     float h1[CW], h2[CW], xpre[XPT];
     float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
-    // prefetches are unconditional (the tile index is clamped): a conditional load makes the compiler merge old and new
+      // prefetches are unconditional (the tile index is clamped): a conditional load makes the compiler merge old and new
     // values with register moves at the loop edge, and those moves wait for the loads
     auto prefetch_a = [&](int tile_) {        // H2, X and the output gradient of the tile
       const int tile = min(tile_, p.nTiles - 1);
@@ -1190,10 +1190,12 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
                                const float* const* W3, const float* H1t, const float* H2t, const float* const* dOut,
                                const ppx_value_head* vh, float clip_range, int64_t B_total, float* dW1, float* db1,
                                float* dW2, float* db2, float* const* dW3, float* const* db3, float* workspace,
-                               double* sumsq_partials, int64_t* step_dev, void* stream) {
+                               double* sumsq_partials, int64_t* step_dev, const ppx_fused_adam* adam,
+                               void* stream) {
   PPX_REQUIRE(X && outs && W2 && W3 && H1t && H2t && dOut && dW1 && db1 && dW2 && db2 && dW3 && db3 && workspace, "mlp3_tc_bwd: null pointer");
   PPX_REQUIRE(mt::shape_ok(D, H, G, outs), "mlp3_tc_bwd: unsupported shape D=%d H=%d G=%d", D, H, G);
   PPX_REQUIRE(M >= 1 && ldx >= D, "mlp3_tc_bwd: M=%d ldx=%d", M, ldx);
+  PPX_REQUIRE(!adam || sumsq_partials, "mlp3_tc_bwd: the fused optimiser tail needs sumsq_partials");
   const int n = mt::bwd_grid(M, G), RS = mt::round4(mt::rest_size(D, mt::omax_of(G, outs)));
   mt::BwdP p{};
   p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.nTiles = mt::n_tiles(M); p.W2 = W2; p.H1t = H1t; p.H2t = H2t;
@@ -1231,5 +1233,5 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
 #undef PPX_BWD
   if (rc) return rc;
   return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
-                                sumsq_partials ? step_dev : nullptr, st);
+                                (sumsq_partials && !adam) ? step_dev : nullptr, adam, st);
 }

@@ -31,10 +31,14 @@ struct FinalArgs {
   double* losses; double* branch;       // branch[0..3] = w1, w2, iw1, iw2
   int64_t B; int A; int discrete; int dual;
   float ent_coef, vf_coef, int_vf_coef, pw;
+  int64_t* row_dev; int row_hold;       // optional step cursor (ppx_ppo_cfg)
 };
 
 // one thread: the five loss scalars, the max-of-means branch weights, d_log_std, from the 32 global sums s[]
 __device__ void finalize_body(const FinalArgs& p, const double* s) {
+  const int64_t row = p.row_dev ? *p.row_dev : 0;
+  double* const L = p.losses + 8 * row;
+  if (p.row_dev && !p.row_hold) *p.row_dev = row + 1;
   const double Bd = (double)p.B;
   const double n_terms = p.discrete ? Bd : Bd * p.A;
   const double pl = -s[0] / n_terms;
@@ -65,8 +69,8 @@ __device__ void finalize_body(const FinalArgs& p, const double* s) {
   }
   const double total = (double)p.pw * (pl + (double)p.ent_coef * el + (double)p.vf_coef * vl) +
                        (p.dual ? (double)p.int_vf_coef * ivl : 0.0);
-  p.losses[0] = total; p.losses[1] = pl; p.losses[2] = vl; p.losses[3] = el; p.losses[4] = ivl;
-  p.losses[5] = 0.0; p.losses[6] = 0.0; p.losses[7] = 0.0;
+  L[0] = total; L[1] = pl; L[2] = vl; L[3] = el; L[4] = ivl;
+  L[5] = 0.0; L[6] = 0.0; L[7] = 0.0;
   p.branch[0] = w1; p.branch[1] = 1.0 - w1; p.branch[2] = iw1; p.branch[3] = 1.0 - iw1;
 }
 
@@ -316,6 +320,15 @@ __global__ void accum_loss_kernel(const double* __restrict__ partials, int n, do
   }
 }
 
+__global__ void row_commit_kernel(double* losses, int64_t* row_dev, const double* value, int col, int add_to_total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int64_t row = *row_dev;
+  const double v = *value;
+  losses[8 * row + col] = v;
+  if (add_to_total) losses[8 * row] += v;
+  *row_dev = row + 1;
+}
+
 int grid_for(int64_t n) {
   int64_t g = ceil_div(n, 256);
   const int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 2);   // few partials: the last-CTA tail reads them all
@@ -372,7 +385,7 @@ int launch_head(const ppx_ppo_cfg* c, const float* actor_out, const float* log_s
     PPX_REQUIRE(branch_out && (c->discrete || d_log_std), "ppo_loss: fused finalize needs branch_out / d_log_std");
     h.do_final = 1;
     h.fin = FinalArgs{nullptr, log_std, d_log_std, losses_out, branch_out, total_rows(c), c->A, c->discrete, c->dual,
-                      c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight};
+                      c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight, c->row_dev, c->row_hold};
   }
   if (c->discrete) head_kernel<true><<<g, 256, 0, st>>>(h);
   else head_kernel<false><<<g, 256, 0, st>>>(h);
@@ -412,7 +425,7 @@ extern "C" int ppx_ppo_loss_finalize(const ppx_ppo_cfg* c, const double* sums, c
   PPX_REQUIRE(sums && losses_out && branch_out, "ppo_loss_finalize: null pointer");
   if (!c->discrete) PPX_REQUIRE(log_std && d_log_std, "ppo_loss_finalize: Box head needs log_std / d_log_std");
   FinalArgs f{sums, log_std, d_log_std, losses_out, branch_out, total_rows(c), c->A, c->discrete, c->dual,
-              c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight};
+              c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight, c->row_dev, c->row_hold};
   finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f);
   return after_launch("ppo_loss finalize");
 }
@@ -431,7 +444,7 @@ extern "C" int ppx_ppo_loss_finish(const ppx_ppo_cfg* c, const double* sums, con
   double* branch = (double*)workspace + (int64_t)kMaxBlocks * kPart + kPart;
   const int64_t Bt = total_rows(c);
   FinalArgs f{sums, log_std, d_log_std, losses_out, branch, Bt, c->A, c->discrete, c->dual,
-              c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight};
+              c->ent_coef, c->vf_coef, c->int_vf_coef, c->policy_weight, c->row_dev, c->row_hold};
   finalize_kernel<<<1, 32, 0, st>>>(f);
   rc = after_launch("ppo_loss finalize");
   if (rc) return rc;
@@ -484,4 +497,10 @@ extern "C" int ppx_xent_fwd_bwd(const float* logits, const double* targets, int 
   if (rc) return rc;
   accum_loss_kernel<<<1, 32, 0, st>>>(part, g, scale / (double)B, loss_accum);
   return after_launch("xent accum");
+}
+
+extern "C" int ppx_loss_row_commit(double* losses, int64_t* row_dev, const double* value, int col, int add_to_total, void* stream) {
+  PPX_REQUIRE(losses && row_dev && value && col >= 1 && col < 8, "loss_row_commit: bad arguments");
+  row_commit_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, row_dev, value, col, add_to_total);
+  return after_launch("loss_row_commit");
 }

@@ -241,3 +241,12 @@ class EvolutionStrategy(object):
     def calc_noveltiy_distribution(self, novelties):
         """:283-290 (host; MPS = 2 scalars)."""
         return [round((n / (sum(novelties))), 4) for n in novelties]
+
+    def pick_brain(self, novelties):
+        """:327-333: the meta-population member to train next -- probabilities from calc_noveltiy_distribution,
+        renormalised (the rounding to 4 digits breaks the unit sum), one np.random.choice draw from the reference's host
+        RNG.  Returns (brain_idx, novelty of that member)."""
+        probs = np.array(self.calc_noveltiy_distribution(novelties))
+        probs /= probs.sum()
+        idx = int(np.random.choice(list(range(len(probs))), p=probs))
+        return idx, novelties[idx]

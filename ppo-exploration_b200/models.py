@@ -59,6 +59,8 @@ class ParamBank:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.norm_dev = torch.zeros(1, dtype=torch.float64, device=device)
         self._ws = torch.zeros(4096, dtype=torch.float64, device=device)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=device)      # last-block detection of the fused optimiser tail
+        self._fused = None
         self.tc_weights = []                       # TcWeight shadows to refresh after every step
 
     def refresh_tc(self):
@@ -74,6 +76,19 @@ class ParamBank:
 
     def g(self, name, extra=0):
         return self.grad.data_ptr() + (self.offsets[name] + extra) * F4
+
+    def fused_adam(self, lr, max_norm, extra_name=None, betas=(0.9, 0.999), eps=1e-8):
+        """ppx_fused_adam record for this bank: clip_grad_norm_(max_norm) + Adam applied by the last block of the fused
+        MLP backward's reduce kernel (no separate optimiser launch).  `extra_name`: a parameter outside the MLP whose
+        gradient enters the norm (action_log_std)."""
+        key = (float(lr), float(max_norm), extra_name, betas, eps, self.grad.data_ptr())
+        if self._fused is None or self._fused[0] != key:
+            ex_ptr, ex_n = (self.g(extra_name), int(np.prod(self.shapes[extra_name]))) if extra_name else (None, 0)
+            rec = L.FusedAdam(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                              self.size, float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                              self.step_dev.data_ptr(), self.norm_dev.data_ptr(), ex_ptr, ex_n, self._ticket.data_ptr())
+            self._fused = (key, rec)
+        return self._fused[1]
 
     def adam_step_pre(self, lr, max_norm, sumsq, n_partials, extra_name=None, betas=(0.9, 0.999), eps=1e-8):
         """clip + Adam when the producer of the gradients already left sum-of-squares partials (and bumped the step)."""
@@ -134,7 +149,12 @@ def dense_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx, 
 
 
 class _Scratch:
-    """Named persistent device buffers that grow on demand (stable addresses between calls of equal size)."""
+    """Named persistent device buffers that grow on demand (stable addresses between calls of equal size).
+
+    `generation` (process-wide) counts every RE-allocation of an existing buffer: a captured CUDA graph that still
+    points at the old block must not be replayed, so the learners compare the counter before every replay and drop
+    their graphs when it moved (algorithms.BaseAlgorithm._graph_call)."""
+    generation = 0
 
     def __init__(self, device):
         self.device, self.bufs = device, {}
@@ -142,6 +162,8 @@ class _Scratch:
     def get(self, name, numel, dtype=torch.float32):
         b = self.bufs.get(name)
         if b is None or b.numel() < numel or b.dtype != dtype:
+            if b is not None:
+                _Scratch.generation += 1
             b = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
             self.bufs[name] = b
         return b
@@ -187,6 +209,8 @@ class DenseStack:
             return
         b, dev = self.bank, self.bank.device
         b.tc_weights = [t for t in b.tc_weights if t not in self.tc.values()]
+        if self.tc:
+            _Scratch.generation += 1               # captured refresh launches point at the shadows being dropped
         self.tc = {}
         for i, (K, N, _) in enumerate(self.layers):
             if K >= TC_MIN_K and K % 4 == 0 and N >= 16:
@@ -276,6 +300,8 @@ class ParallelMLP:
             return
         b, G, h, D, dev = self.bank, self.G, self.h, self.D, self.bank.device
         b.tc_weights = [t for t in b.tc_weights if t not in ([self.tc1] if self.tc1 else []) + (self.tc2 or [])]
+        if self.tc1 is not None or self.tc2:
+            _Scratch.generation += 1
         self.tc1 = self.tc2 = None
         if TC_POLICY or (D >= TC_MIN_K and D % 4 == 0):
             self.tc1 = TcWeight(b.p("W1"), D, G * h, dev, transposed_only=not TC_POLICY)
@@ -347,7 +373,7 @@ class ParallelMLP:
     def fused(self):
         return self._fused_args()["ok"]
 
-    def backward(self, d_outs, value_heads=None, clip_range=0.0, B_total=0, with_sumsq=False):
+    def backward(self, d_outs, value_heads=None, clip_range=0.0, B_total=0, with_sumsq=False, adam=None):
         """d_outs[g]: [M, out_g] contiguous (None for a net listed in `value_heads`).  Fills bank.grad for every
         MLP parameter.  value_heads (fused path only): {g_index: (values, old_values, returns, branch_ptr, scale)}
         -- the clipped-value-loss gradient of that head is evaluated inside the backward kernel."""
@@ -371,7 +397,7 @@ class ParallelMLP:
             L.call(f"ppx_mlp3{sfx}_bwd", x.data_ptr(), x.stride(0), M, D, h, G, fa["outs"], b.p("W2"), fa["W3"], H1.data_ptr(),
                    H2.data_ptr(), dptr, vh, float(clip_range), int(B_total), b.g("W1"), b.g("b1"), b.g("W2"),
                    b.g("b2"), fa["dW3"], fa["db3"], ws.data_ptr(), ss.data_ptr() if ss is not None else None,
-                   b.step_dev.data_ptr() if ss is not None else None, L.stream())
+                   b.step_dev.data_ptr() if ss is not None else None, C.byref(adam) if adam is not None else None, L.stream())
             return
         assert not value_heads, "value_heads needs the fused MLP path"
         dP2 = sc.get("pmlp.dP2", M * G * h)[:M * G * h].view(M, G * h)
@@ -549,10 +575,12 @@ class RndNetwork:
                 sd[f"{name}.{2 * i}.bias"] = bank.view(f"{name}.{2 * i}.bias").detach().cpu().clone()
         return sd
 
-    def forward(self, x, a_norm=None):
-        """x [M,D] f32 CUDA contiguous -> (predict [M,1], target [M,1]); keeps predictor activations."""
-        self._p_acts = self.predictor.forward(x, a_norm=a_norm)
-        t_acts = self.target.forward(x, a_norm=a_norm)
+    def forward(self, x, a_norm=None, tag=""):
+        """x [M,D] f32 CUDA contiguous -> (predict [M,1], target [M,1]); keeps predictor activations.  `tag` names the
+        activation scratch: the train path (captured in CUDA graphs) and the bonus path (other batch sizes) never share
+        buffers, so growing one cannot leave the other's graph with a dangling pointer."""
+        self._p_acts = self.predictor.forward(x, tag=tag, a_norm=a_norm)
+        t_acts = self.target.forward(x, tag=tag, a_norm=a_norm)
         return self._p_acts[-1], t_acts[-1]
 
     __call__ = forward
@@ -571,7 +599,7 @@ class RndNetwork:
             else:
                 from .util import normalize_obs
                 obs = normalize_obs(obs, rms)
-        pred, tgt = self.forward(obs, a_norm)
+        pred, tgt = self.forward(obs, a_norm, tag=".bonus")
         r = torch.empty(obs.shape[0], dtype=torch.float32, device=self.device)
         L.call("ppx_rnd_sqerr", pred.data_ptr(), tgt.data_ptr(), obs.shape[0], r.data_ptr(), L.stream())
         return r
@@ -579,7 +607,7 @@ class RndNetwork:
     def train_step(self, x, loss_accum, B_total=0):
         """MSE(pred, target) forward+backward into bank.grad (algorithms.py:495-500).  x already normalised.
         Sharded: B_total = rows of the global minibatch, so the mean (and its gradient) is global."""
-        pred, tgt = self.forward(x)
+        pred, tgt = self.forward(x, tag=".train")
         M = x.shape[0]
         d_pred = self.scratch.get("rnd.dpred", M)[:M].view(M, 1)
         L.call("ppx_mse_fwd_bwd", pred.data_ptr(), tgt.data_ptr(), M, float(M) / float(B_total) if B_total else 1.0,
@@ -708,12 +736,15 @@ class IntrinsicCuriosityModule:
                rewards.data_ptr() if rewards is not None else None, ri.data_ptr(), L.stream())
         return ri
 
-    def train_step(self, obs, actions, beta, loss_accum):
+    def train_step(self, obs, actions, beta, loss_accum, pairs_total=None):
         """Forward (models.py:300-309) + 0.8*inverse + 0.2*forward loss (algorithms.py:684-688) + backward into
-        bank.grad, on the shuffled-consecutive rows obs[:-1] -> obs[1:], actions[:-1]."""
+        bank.grad, on the shuffled-consecutive rows obs[:-1] -> obs[1:], actions[:-1].  Sharded: `obs` holds this
+        rank's slice of the global minibatch (plus its halo row) and `pairs_total` the pairs of the whole minibatch,
+        so the means -- and their gradients -- are the global ones once summed over the ranks."""
         f, n, D = self.feature_size, self.n_actions, self.input_size
         B = obs.shape[0]
         M = B - 1
+        share = 1.0 if not pairs_total else float(M) / float(pairs_total)
         sc = self.scratch
         feats_acts = self.enc.forward(obs, tag=".train")                         # encoder once over all B rows
         feats = feats_acts[-1]                                                   # [B, f]
@@ -733,15 +764,15 @@ class IntrinsicCuriosityModule:
         d_a_hat = sc.get("icm.d_a_hat", M * n)[:M * n].view(M, n)
         ns_c = sc.get("icm.ns_c", M * f)[:M * f].view(M, f)
         ns_c.copy_(ns_ft)
-        L.call("ppx_mse_fwd_bwd", ns_c.data_ptr(), ns_hat.data_ptr(), M * f, float(beta), d_ns_ft.data_ptr(),
+        L.call("ppx_mse_fwd_bwd", ns_c.data_ptr(), ns_hat.data_ptr(), M * f, float(beta) * share, d_ns_ft.data_ptr(),
                d_ns_hat.data_ptr(), loss_accum.data_ptr(), L.stream())
         if self.discrete:
             tgt = actions[:M].reshape(-1).double().contiguous()
-            L.call("ppx_xent_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), 1, M, n, float(1 - beta), d_a_hat.data_ptr(),
+            L.call("ppx_xent_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), 1, M, n, float(1 - beta) * share, d_a_hat.data_ptr(),
                    loss_accum.data_ptr(), L.stream())
         else:
             tgt = actions[:M].float().reshape(M, n).contiguous()
-            L.call("ppx_mse_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), M * n, float(1 - beta), d_a_hat.data_ptr(),
+            L.call("ppx_mse_fwd_bwd", a_hat.data_ptr(), tgt.data_ptr(), M * n, float(1 - beta) * share, d_a_hat.data_ptr(),
                    None, loss_accum.data_ptr(), L.stream())
         # backward through the two heads down to their inputs
         d_fin = self.fwd.backward(fwd_acts, d_ns_hat, need_dx=True)              # [M, f+n]

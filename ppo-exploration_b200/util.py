@@ -10,7 +10,11 @@ class RunningMeanStd(object):
 
     `mean`, `var`, `count` properties copy the state to the host on demand (tests, checkpointing)."""
 
-    def __init__(self, epsilon=1e-4, shape=(), device="cuda"):
+    def __init__(self, epsilon=1e-4, shape=(), device="cuda", sharded=False):
+        # sharded (SURVEY §8e row 4): under torch.distributed every rank feeds the rows of ITS env shard; the rows of all
+        # ranks are all-gathered in rank (= global env) order first, so the update sees exactly the batch a single GPU
+        # holding every env would see and the running moments stay bit-identical replicas
+        self.sharded = bool(sharded)
         self.device = torch.device(device)
         self.shape = tuple(shape)
         self.dim = int(np.prod(shape)) if len(shape) else 1
@@ -25,6 +29,10 @@ class RunningMeanStd(object):
         if arr.dtype not in (torch.float32, torch.float64):
             arr = arr.float()
         x = arr.to(self.device).reshape(-1, self.dim).contiguous()
+        if self.sharded:
+            from . import dist as D
+            if D.world_size() > 1:
+                x = D.all_gather_cat(x).reshape(-1, self.dim)
         L.call("ppx_rms_update", x.data_ptr(), int(x.dtype == torch.float64), x.shape[0], self.dim,
                self.mean_dev.data_ptr(), self.var_dev.data_ptr(), self.count_dev.data_ptr(), None, L.stream())
 

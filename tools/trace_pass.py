@@ -9,11 +9,12 @@ from ppo_exploration_b200 import buffer as BUF
 
 dev = torch.device("cuda", 0)
 np.random.seed(0); torch.manual_seed(0)
-env = ppx.SyntheticVecEnv(B.N, B.D, ppx.Box((B.A,)), seed=0)
-m = ppx.PPO(env=env, nstep=B.T, batch_size=B.T * B.N // B.N_MINIBATCH, hidden_size=B.HIDDEN, sim_hash=True, hash_bits=B.K_BITS, device=dev, **B.HP)
+cfg = B.CONFIGS["C2"]
+env = ppx.SyntheticVecEnv(cfg["N"], cfg["D"], ppx.Box((2,)), seed=0)
+m = ppx.PPO(env=env, nstep=cfg["T"], batch_size=cfg["batch"], hidden_size=cfg["hidden"], sim_hash=True, hash_bits=cfg["hash_bits"], device=dev, **cfg["hp"])
 ro = m.rollout
-host = B.synth_rollout(100)
-ro.load_rollout(**{k: v for k, v in host.items() if k != "last_value"})
+host = B.synth_rollout(cfg, 100)
+ro.load_rollout(**{k: v for k, v in host.items() if k in B.ROLLOUT_FIELDS})
 lv = torch.as_tensor(host["last_value"]).to(dev); dn = torch.as_tensor(host["masks"][-1].copy()).to(dev)
 raw = ro.rewards.clone()
 marks = []
