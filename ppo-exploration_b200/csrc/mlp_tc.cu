@@ -685,13 +685,17 @@ namespace v2 {
 // GEMM 3 reads [V ; Q] as one M = 128 MN-major operand (4 blocks of 32 rows, 16 KB apart)
 constexpr uint32_t ACC2 = 0, ACC1 = 64, ACC3 = 128, A_RAW = 192, A_LO = 256;     // tensor-memory columns
 constexpr uint32_t W_RAW = 0, W_LO = 16384, V_RAW = 32768, Q_RAW = 65536, LO_DELTA = 65536, XE_OFF = 163840;
-constexpr int REGS_MMA = 56;
+constexpr int REGS_MMA = 24;
 template <int CW> struct Cfg {
   static constexpr int NCQ = H / CW;                // column groups
   static constexpr int NTC = TM * NCQ;              // compute threads: thread = (sample s, CW hidden columns)
   static constexpr int NTH = NTC + 128;             // + the MMA warpgroup (its first warp issues; the others only lend registers)
-  // 64 K registers: NTC x REGS + 128 x REGS_MMA <= 65536
-  static constexpr int REGS = CW == 32 ? 224 : 112;
+  // setmaxnreg moves registers through the CTA's pool only: what the compute warps take (inc) must have been released by
+  // the MMA warpgroup (dec) -- asking for more spins forever in USETMAXREG.TRY_ALLOC (measured: a hung box).
+  static constexpr int REGS_LAUNCH = (65536 / NTH) / 8 * 8;           // what ptxas gives every thread at launch (168 / 96)
+  static constexpr int REGS = CW == 32 ? 240 : 112;
+  static_assert(NTC * (REGS - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_MMA), "setmaxnreg.inc would exceed what setmaxnreg.dec releases");
+  static_assert(REGS % 8 == 0 && REGS <= 255 && REGS_MMA % 8 == 0 && REGS_MMA >= 24, "setmaxnreg operands");
 };
 }  // namespace v2
 
@@ -704,18 +708,26 @@ template <int N>
 __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&v)[N]) {
   if constexpr (N == 32) tmem_st32(taddr, v); else tmem_st16(taddr, v);
 }
-// v[CW] = columns c0 .. c0+CW-1 of row s -> MN-major BASE32B images (raw at `img`, lo at `img + lo_delta`); img = image base
+// v[CW] = columns c0 .. c0+CW-1 of row s -> MN-major BASE32B images (raw at `img`, lo at `img + lo_delta`); img = image base.
+// The kernel is bound by the shared-memory data pipe (tensor-core operand fetch + these stores: ncu r02d 82 % busy), so the
+// stores must be conflict-free: the 32-byte-chunk swizzle only separates 4 of the 8 rows of a store phase -- rows s and
+// s + 4 would hit the same 16 bytes -- so lanes with bit 2 of s set write the two 16-byte halves of every 32-byte chunk
+// in the opposite order (4 selects per store instead of a 2-way bank conflict).
 template <int CW>
 __device__ __forceinline__ void store_mn_images(uint32_t img, uint32_t lo_delta, int s, int c0, const float (&v)[CW]) {
   // bits [5,7) of the block base are zero: the 32-byte-chunk swizzle is an XOR with (s & 3) << 5
   const uint32_t row = (img + (uint32_t)((c0 >> 5) * 16384 + s * 128)) | (uint32_t)((s & 3) << 5);
-  const int j0 = (c0 & 31) >> 2;                    // first 16-byte chunk of this thread inside the 128-byte row
+  const bool swp = (s & 4) != 0;
+  const uint32_t hx = swp ? 16u : 0u;
+  const int j0 = (c0 & 31) >> 2;                    // first 16-byte chunk of this thread inside the 128-byte row (even)
 #pragma unroll
   for (int jj = 0; jj < CW / 4; ++jj) {
-    const int j = j0 + jj;
-    const uint32_t a = (row ^ (uint32_t)((j >> 1) << 5)) + (uint32_t)((j & 1) << 4);
-    sts128(a, v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-    sts128(a + lo_delta, lo_of(v[4 * jj]), lo_of(v[4 * jj + 1]), lo_of(v[4 * jj + 2]), lo_of(v[4 * jj + 3]));
+    const int j = j0 + jj, jo = jj ^ 1;             // this instruction's chunk for swp == 0; the lane's other chunk of the pair
+    const uint32_t a = ((row ^ (uint32_t)((j >> 1) << 5)) + (uint32_t)((j & 1) << 4)) ^ hx;
+    const float x0 = swp ? v[4 * jo] : v[4 * jj], x1 = swp ? v[4 * jo + 1] : v[4 * jj + 1];
+    const float x2 = swp ? v[4 * jo + 2] : v[4 * jj + 2], x3 = swp ? v[4 * jo + 3] : v[4 * jj + 3];
+    sts128(a, x0, x1, x2, x3);
+    sts128(a + lo_delta, lo_of(x0), lo_of(x1), lo_of(x2), lo_of(x3));
   }
 }
 // every lane holds v[0..CW-1]; afterwards column k's sum over the 32 lanes sits in lane k (CW = 32) or in lanes 2k and
@@ -753,7 +765,7 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
   const uint32_t Q_raw = smem + Q_RAW;                               // MN-major: dP2
   const uint32_t Xe_raw = smem + XE_OFF, Xe_lo = Xe_raw + XE_BYTES;  // K-major [4 k-blocks][NX rows][128 B]
   __shared__ __align__(16) float W3s[MAXO * H];                      // [j][c]
-  __shared__ __align__(16) float red3[4][MAXO + 1][H];               // end of kernel: per-sample-quarter dW3 / db3 partials
+  __shared__ __align__(16) float red3[4][MAXO + 2][H];               // end of kernel: per-sample-quarter dW3 / db3 / db2 partials
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
 
@@ -762,6 +774,7 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
   const uint32_t barG2 = smem_u32(&bars[0]), barG1 = smem_u32(&bars[1]), barG3 = smem_u32(&bars[2]);   // tcgen05.commit
   const uint32_t opsG2 = smem_u32(&bars[3]), opsG1 = smem_u32(&bars[4]), opsG3 = smem_u32(&bars[5]);   // one arrive per compute warp
   auto bar_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); };
+  const int nT = ((int)blockIdx.x < p.nTiles) ? (p.nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
 
   if (tid == 0) {
     mbar_init(barG2, 1); mbar_init(barG1, 1); mbar_init(barG3, 1);
@@ -797,23 +810,27 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
+  // Software pipeline over the tiles t0, t1, ... of this CTA (phases of tile t):
+  //   A(t)  dP2 -> tensor memory                    -> GEMM 2(t) = dP1pre        [needs GEMM 2(t-1) read out]
+  //   B(t)  H1 image (V), X^T image                 -> GEMM 1(t) = dW2           [needs GEMM 3(t-1) done: it read V and X^T]
+  //   D(t)  dP1 image (into V), dP2(t+1) image (Q)  -> GEMM 3(t) = dW1 | db1     [needs GEMM 2(t) and GEMM 1(t) done]
+  // One loop iteration runs B(t), dP1(t), A(t+1) + the in-warp sums of tile t+1, D(t); the tensor pipe runs
+  // GEMM 1(t), GEMM 2(t+1), GEMM 3(t) -- GEMM 2(t+1) fills the gap while the compute warps write the dP1 image.  The only
+  // serial resource is the V image: B(t) -> GEMM 1(t) -> D(t) -> GEMM 3(t) -> B(t+1).
   if (warp >= NCW) {
     // ------------------------------------------------ MMA warpgroup ------------------------------------------------
     setmaxnreg_dec<REGS_MMA>();
     if (warp == NCW) {
       // (loops deliberately not unrolled: an MMA occupies its issuer for 23-32 cycles anyway, and the unrolled form keeps
-      // ~100 precomputed descriptors alive -- spills at the 56 registers this warpgroup keeps)
+      // ~100 precomputed descriptors alive -- spills at the 24 registers this warpgroup keeps)
       const uint64_t dwr = make_desc(W_raw), dwl = make_desc(W_lo);
       const uint64_t dvr = make_desc_mn32(V_raw, 16384, 512), dvl = make_desc_mn32(V_raw + LO_DELTA, 16384, 512);
       const uint64_t dqr = make_desc_mn32(Q_raw, 16384, 512), dql = make_desc_mn32(Q_raw + LO_DELTA, 16384, 512);
       const uint64_t dxr = make_desc(Xe_raw), dxl = make_desc(Xe_lo);
-      constexpr uint32_t id2 = make_idesc_full(128, 64, 0, 0), id1 = make_idesc_full(64, 64, 1, 1), id3 = make_idesc_full(128, NX, 1, 0);
+      constexpr uint32_t id2 = make_idesc_full(128, 64, 0, 0), id1 = make_idesc_full(64, 64, 1, 1), id3 = make_idesc_full(64, NX, 1, 0);
       const bool leader = elect_one();
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
-        const uint32_t ph = (uint32_t)(it & 1);
-        // GEMM 2: dP1pre [128 x 64] = dP2 (tensor memory) . W2^T; small terms first
-        mbar_wait(opsG2, ph);
+      auto gemm2 = [&](int it) {                    // dP1pre [128 x 64] = dP2 (tensor memory) . W2^T; small terms first
+        mbar_wait(opsG2, (uint32_t)(it & 1));
         tc_fence_after();
         if (leader) {
 #pragma unroll 1
@@ -830,6 +847,10 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
           umma_commit(barG2);
         }
         __syncwarp();
+      };
+      if (nT > 0) gemm2(0);
+      for (int it = 0; it < nT; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
         // GEMM 1: dW2 [64 x 64] = H1^T dP2 over the 128 samples (both operands MN-major)
         mbar_wait(opsG1, ph);
         tc_fence_after();
@@ -848,7 +869,8 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
           umma_commit(barG1);
         }
         __syncwarp();
-        // GEMM 3: [dP1 | dP2]^T [X | 1] over the 128 samples: rows 0..63 = dW1^T | db1, rows 64..127 = (unused) | db2
+        if (it + 1 < nT) gemm2(it + 1);
+        // GEMM 3: [dW1^T | db1] [64 x NX] = dP1^T [X | 1] over the 128 samples (the dP1 image sits where H1 was)
         mbar_wait(opsG3, ph);
         tc_fence_after();
         if (leader) {
@@ -881,10 +903,9 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
     };
 
     float dW2acc[CW];                         // lanes < 16: dW2[i = q*16+lane][c0 .. c0+CW-1]
-    float acc3[NX];                           // cq == 0: row r = q*32+lane of GEMM 3: r < 64: dW1[n][r] (n < DP), db1[r] (n == DP);
-                                              //          r >= 64: db2[r - 64] (n == DP)
+    float acc3[NX];                           // cq == 0, lanes < 16: dW1[n][i = q*16+lane] (n < DP), db1[i] (n == DP)
     float a_dW3[MAXO] = {0.f, 0.f, 0.f, 0.f}; // dW3[column of this lane][j] over this warp's samples (see warp_transpose_sum)
-    float a_db3 = 0.f;                        // lane j < o: db3[j] over this warp's samples
+    float a_db3 = 0.f, a_db2 = 0.f;           // lane j < o: db3[j]; db2[column of this lane]; over this warp's samples
 #pragma unroll
     for (int c = 0; c < CW; ++c) dW2acc[c] = 0.f;
 #pragma unroll
@@ -892,23 +913,17 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
 
     float h1[CW], h2[CW], xpre[XPT];
     float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
-      // prefetches are unconditional (the tile index is clamped): a conditional load makes the compiler merge old and new
+    // prefetches are unconditional (the tile index is clamped): a conditional load makes the compiler merge old and new
     // values with register moves at the loop edge, and those moves wait for the loads
-    auto prefetch_a = [&](int tile_) {        // H2, X and the output gradient of the tile
+    auto prefetch_hd = [&](int tile_) {       // H2 and the output gradient of the tile
       const int tile = min(tile_, p.nTiles - 1);
-      const int m0 = tile * TM;
       const float4* h2t = reinterpret_cast<const float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
         const float4 b = ld_stream4(h2t + j * TM);
         h2[4 * j] = b.x; h2[4 * j + 1] = b.y; h2[4 * j + 2] = b.z; h2[4 * j + 3] = b.w;
       }
-#pragma unroll
-      for (int r = 0; r < XPT; ++r) {
-        const int e = tid + r * NTC, row = e / DP, k = e % DP;
-        xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
-      }
-      const int b = m0 + s;
+      const int b = tile * TM + s;
       float d[MAXO] = {0.f, 0.f, 0.f, 0.f};
       if (b < p.M) {
         if (p.vh_v[g] != nullptr) {           // o == 1 (checked on the host); same formula as mlp_fused.cu
@@ -927,6 +942,14 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
       }
       dpre = make_float4(d[0], d[1], d[2], d[3]);
     };
+    auto prefetch_x = [&](int tile_) {        // this thread's share of the tile's X rows
+      const int m0 = min(tile_, p.nTiles - 1) * TM;
+#pragma unroll
+      for (int r = 0; r < XPT; ++r) {
+        const int e = tid + r * NTC, row = e / DP, k = e % DP;
+        xpre[r] = (m0 + row < p.M && k < D) ? __ldg(p.X + (size_t)(m0 + row) * p.ldx + k) : 0.f;
+      }
+    };
     auto prefetch_b = [&](int tile_) {        // H1 of the tile
       const int tile = min(tile_, p.nTiles - 1);
       const float4* h1t = reinterpret_cast<const float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
@@ -936,32 +959,9 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
         h1[4 * j] = a.x; h1[4 * j + 1] = a.y; h1[4 * j + 2] = a.z; h1[4 * j + 3] = a.w;
       }
     };
-    auto drain = [&] {                        // finished GEMM 1 / GEMM 3 accumulators -> fp32 registers (round to nearest)
-      uint32_t z[CW];
-      tmem_ld_n<CW>(tlane + ACC1 + c0, z);
-#pragma unroll
-      for (int c = 0; c < CW; ++c) dW2acc[c] += __uint_as_float(z[c]);
-      if (cq == 0) {
-#pragma unroll
-        for (int n0 = 0; n0 < NX; n0 += 8) {
-          uint32_t y[8];
-          tmem_ld8_nowait(tlane + ACC3 + n0, y);
-          tmem_ld_wait();
-#pragma unroll
-          for (int n = 0; n < 8; ++n) acc3[n0 + n] += __uint_as_float(y[n]);
-        }
-      }
-    };
-
-    int it = 0;
-    prefetch_a(blockIdx.x);
-    prefetch_b(blockIdx.x);
-    for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x, ++it) {
-      const uint32_t ph = (uint32_t)(it & 1);
-      const int nxt = tile + (int)gridDim.x;
+    // A(t): dP2 = (dOut W3^T)(1 - H2^2) -> tensor memory (A operand of GEMM 2), from the prefetched h2 / dpre
+    auto phase_a = [&](float (&dp2)[CW]) {
       const float dj[MAXO] = {dpre.x, dpre.y, dpre.z, dpre.w};
-      // ---- T1: dP2 = (dOut W3^T)(1 - H2^2) -> tensor memory (A of GEMM 2) ----
-      float dp2[CW];
 #pragma unroll
       for (int c = 0; c < CW; c += 4) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -974,35 +974,21 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
         dp2[c] = a.x * (1.f - h2[c] * h2[c]); dp2[c + 1] = a.y * (1.f - h2[c + 1] * h2[c + 1]);
         dp2[c + 2] = a.z * (1.f - h2[c + 2] * h2[c + 2]); dp2[c + 3] = a.w * (1.f - h2[c + 3] * h2[c + 3]);
       }
-      {                                       // (GEMM 2 of the previous tile was waited for in its T4: the columns are free)
-        uint32_t u[CW];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) u[c] = __float_as_uint(dp2[c]);
-        tmem_st_n<CW>(tlane + A_RAW + c0, u);
+      for (int hh = 0; hh < CW; hh += 16) {    // 16 columns at a time: fewer live registers than one 32-wide store
+        uint32_t u[16];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) u[c] = __float_as_uint(lo_of(dp2[c]));
-        tmem_st_n<CW>(tlane + A_LO + c0, u);
-        tmem_st_wait();
-      }
-      arrive(opsG2);
-      // ---- T3: previous tile's accumulators out; MN-major images of dP2 and H1, the X^T image -> GEMM 1 ----
-      if (it > 0) {
-        mbar_wait(barG1, ph ^ 1);
-        mbar_wait(barG3, ph ^ 1);             // GEMM 3 has read V (dP1), Q (dP2) and the X^T image
-        tc_fence_after();
-        drain();
-      }
-      store_mn_images<CW>(Q_raw, LO_DELTA, s, c0, dp2);
-      store_mn_images<CW>(V_raw, LO_DELTA, s, c0, h1);
+        for (int c = 0; c < 16; ++c) u[c] = __float_as_uint(dp2[hh + c]);
+        tmem_st16(tlane + A_RAW + c0 + hh, u);
 #pragma unroll
-      for (int r = 0; r < XPT; ++r) {
-        const int e = tid + r * NTC, row = e / DP, k = e % DP;
-        const uint32_t off = (uint32_t)(row >> 5) * XE_KB + sw128_off(k, row & 31);
-        sts32(Xe_raw + off, xpre[r]);
-        sts32(Xe_lo + off, lo_of(xpre[r]));
+        for (int c = 0; c < 16; ++c) u[c] = __float_as_uint(lo_of(dp2[hh + c]));
+        tmem_st16(tlane + A_LO + c0 + hh, u);
       }
-      arrive(opsG1);
-      // ---- T3b (under GEMM 2 / GEMM 1): dW3 / db3 over this warp's 32 samples, inside the warp ----
+      tmem_st_wait();
+    };
+    // in-warp sums of the tile whose h2 / dpre / dp2 are in registers: dW3, db3, db2 over this warp's 32 samples
+    auto phase_c = [&](const float (&dp2)[CW]) {
+      const float dj[MAXO] = {dpre.x, dpre.y, dpre.z, dpre.w};
 #pragma unroll
       for (int j = 0; j < MAXO; ++j)
         if (j < o) {                          // CTA-uniform
@@ -1013,27 +999,99 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
           const float t = warp_sum(dj[j]);
           if (lane == j) a_db3 += t;
         }
-      prefetch_a(nxt);                        // H2 / X / dOut registers are free: next tile's loads fly under the rest of this one
-      // ---- T4: dP1 = (dP2 W2^T)(1 - H1^2) -> its MN-major image where H1 was -> GEMM 3 ----
-      mbar_wait(barG2, ph);
-      tc_fence_after();
-      float dp1[CW];
-      {
-        uint32_t z[CW];
-        tmem_ld_n<CW>(tlane + ACC2 + c0, z);
+      float v[CW];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) dp1[c] = __uint_as_float(z[c]) * (1.f - h1[c] * h1[c]);
+      for (int c = 0; c < CW; ++c) v[c] = dp2[c];
+      a_db2 += warp_transpose_sum<CW>(v, lane);
+    };
+
+    if (nT > 0) {
+      // ---- prologue: A(t0), its in-warp sums, its dP2 image ----
+      const int t0 = blockIdx.x;
+      prefetch_hd(t0);
+      prefetch_x(t0);
+      prefetch_b(t0);
+      {
+        float dp2[CW];
+        phase_a(dp2);
+        arrive(opsG2);
+        store_mn_images<CW>(Q_raw, LO_DELTA, s, c0, dp2);
+        phase_c(dp2);
       }
-      prefetch_b(nxt);                        // H1 registers are free
-      mbar_wait(barG1, ph);                   // GEMM 1 has read the H1 images
-      store_mn_images<CW>(V_raw, LO_DELTA, s, c0, dp1);
-      arrive(opsG3);
-    }
-    if (it > 0) {                             // the last tile's accumulators
-      mbar_wait(barG1, (uint32_t)((it - 1) & 1));
-      mbar_wait(barG3, (uint32_t)((it - 1) & 1));
+      prefetch_hd(t0 + (int)gridDim.x);
+      for (int it = 0; it < nT; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        const int t1 = (int)blockIdx.x + (it + 1) * (int)gridDim.x;      // next tile of this CTA (clamped by the prefetches)
+        const bool has_next = it + 1 < nT;
+        // ---- B(t): previous GEMM 3 out; H1 image + X^T image -> GEMM 1(t) ----
+        if (it > 0) {
+          mbar_wait(barG3, ph ^ 1);
+          tc_fence_after();
+          if (cq == 0) {
+#pragma unroll
+            for (int n0 = 0; n0 < NX; n0 += 8) {
+              uint32_t y[8];
+              tmem_ld8_nowait(tlane + ACC3 + n0, y);
+              tmem_ld_wait();
+#pragma unroll
+              for (int n = 0; n < 8; ++n) acc3[n0 + n] += __uint_as_float(y[n]);
+            }
+          }
+        }
+        store_mn_images<CW>(V_raw, LO_DELTA, s, c0, h1);
+#pragma unroll
+        for (int r = 0; r < XPT; ++r) {
+          const int e = tid + r * NTC, row = e / DP, k = e % DP;
+          const uint32_t off = (uint32_t)(row >> 5) * XE_KB + sw128_off(k, row & 31);
+          sts32(Xe_raw + off, xpre[r]);
+          sts32(Xe_lo + off, lo_of(xpre[r]));
+        }
+        arrive(opsG1);                        // (the dP2 image of this tile was written in the previous iteration / the prologue)
+        prefetch_x(t1);
+        // ---- dP1(t) = (dP2 W2^T)(1 - H1^2) into registers; GEMM 2's accumulator and operand columns are then free ----
+        mbar_wait(barG2, ph);
+        tc_fence_after();
+        float dp1[CW];
+        {
+          uint32_t z[CW];
+          tmem_ld_n<CW>(tlane + ACC2 + c0, z);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) dp1[c] = __uint_as_float(z[c]) * (1.f - h1[c] * h1[c]);
+        }
+        prefetch_b(t1);                       // H1 registers are free
+        // ---- A(t+1) + its in-warp sums (under GEMM 1(t)) ----
+        float dp2n[CW];
+        if (has_next) {
+          phase_a(dp2n);
+          arrive(opsG2);
+          phase_c(dp2n);
+        }
+        prefetch_hd(t1 + (int)gridDim.x);
+        // ---- D(t): GEMM 1(t) has read V and Q: dW2 out, dP1 image where H1 was -> GEMM 3(t); dP2(t+1) image ----
+        mbar_wait(barG1, ph);
+        tc_fence_after();
+        {
+          uint32_t z[CW];
+          tmem_ld_n<CW>(tlane + ACC1 + c0, z);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) dW2acc[c] += __uint_as_float(z[c]);
+        }
+        store_mn_images<CW>(V_raw, LO_DELTA, s, c0, dp1);
+        arrive(opsG3);
+        if (has_next) store_mn_images<CW>(Q_raw, LO_DELTA, s, c0, dp2n);
+      }
+      mbar_wait(barG3, (uint32_t)((nT - 1) & 1));               // the last tile's GEMM 3
       tc_fence_after();
-      drain();
+      if (cq == 0) {
+#pragma unroll
+        for (int n0 = 0; n0 < NX; n0 += 8) {
+          uint32_t y[8];
+          tmem_ld8_nowait(tlane + ACC3 + n0, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int n = 0; n < 8; ++n) acc3[n0 + n] += __uint_as_float(y[n]);
+        }
+      }
     }
     // ---- one partial per CTA ----
     float* w2 = p.ws2 + (size_t)(g * gridDim.x + blockIdx.x) * H * H;
@@ -1044,33 +1102,30 @@ __global__ void __launch_bounds__(v2::Cfg<CW>::NTH, 1) mlp3_tc_bwd2_kernel(BwdP 
 #pragma unroll
       for (int c = 0; c < CW; c += 4)
         *reinterpret_cast<float4*>(&w2[i * H + c0 + c]) = make_float4(dW2acc[c], dW2acc[c + 1], dW2acc[c + 2], dW2acc[c + 3]);
-    }
-    if (cq == 0) {
-      const int r = q * 32 + lane;
-      if (r < H) {
+      if (cq == 0) {
 #pragma unroll
         for (int n = 0; n < DP; ++n)
-          if (n < D) wr[n * H + r] = acc3[n];
-        wr[offb1 + r] = acc3[DP];
-      } else {
-        wr[offb2 + (r - H)] = acc3[DP];
+          if (n < D) wr[n * H + i] = acc3[n];
+        wr[offb1 + i] = acc3[DP];
       }
     }
-    {                                         // this warp's dW3 / db3 partials: column of lane l is c0 + l (CW = 32) or c0 + l/2
+    {                                         // this warp's dW3 / db2 / db3 partials: column of lane l is c0 + l (CW = 32) or c0 + l/2
       const bool own = CW == 32 || (lane & 1) == 0;
       const int c = c0 + (CW == 32 ? lane : (lane >> 1));
       if (own) {
 #pragma unroll
         for (int j = 0; j < MAXO; ++j) red3[q][j][c] = a_dW3[j];
+        red3[q][MAXO + 1][c] = a_db2;
       }
       if (cq == 0 && lane < MAXO) red3[q][MAXO][lane] = a_db3;
     }
     bar_compute();
-    for (int e = tid; e < (MAXO + 1) * H; e += NTC) {     // combine the four sample quarters in a fixed order
+    for (int e = tid; e < (MAXO + 2) * H; e += NTC) {     // combine the four sample quarters in a fixed order
       const int n = e >> 6, c = e & 63;
       const float v = (red3[0][n][c] + red3[1][n][c]) + (red3[2][n][c] + red3[3][n][c]);
       if (n < MAXO) { if (n < o) wr[offW3 + c * o + n] = v; }
-      else if (c < o) wr[offb3 + c] = v;
+      else if (n == MAXO) { if (c < o) wr[offb3 + c] = v; }
+      else wr[offb2 + c] = v;
     }
   }
   tc_fence_before();
@@ -1125,9 +1180,9 @@ int launch_bwd2(const BwdP& p, dim3 grid, cudaStream_t st) {
   mlp3_tc_bwd2_kernel<DP, CW><<<grid, v2::Cfg<CW>::NTH, smem, st>>>(p);
   return after_launch("mlp3_tc_bwd2");
 }
-inline int bwd2_cw() {                       // PPX_MLP_TC_CW2=32: 8 compute warps with 32 columns per thread instead of 16 x 16
+inline int bwd2_cw() {                       // PPX_MLP_TC_CW2=16: 16 compute warps with 16 columns per thread instead of 8 x 32
   static int cw = 0;
-  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW2"); cw = (e && atoi(e) == 32) ? 32 : 16; }
+  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW2"); cw = (e && atoi(e) == 16) ? 16 : 32; }
   return cw;
 }
 inline bool bwd_v1() {                       // PPX_MLP_TC_V1=1: the round-1 backward (comparison runs)
