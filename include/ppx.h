@@ -210,11 +210,12 @@ typedef struct {
   const double* branch;                                                 /* device, 2 doubles */
   float scale;                                                          /* policy_weight*vf_coef or int_vf_coef */
 } ppx_value_head;
-/* Optional optimiser tail of the backward (algorithms.py:243-244 in the SAME launch sequence, no Adam kernel): the last
- * block of the partial-sum reduce kernel combines the per-block sums of squares in a fixed order, adds the gradients
- * outside the MLP (`extra_grads`, e.g. action_log_std), bumps *step_dev and applies clip_grad_norm_(max_norm) + Adam
- * to the whole bank [0, n) (params / grads / exp_avg / exp_avg_sq are the bank's flat vectors; the MLP gradients are the
- * ones this call writes).  max_norm <= 0: no clipping.  `ticket` = one zeroed device word owned by the bank. */
+/* Optional optimiser tail of the backward (algorithms.py:243-244 in the SAME launch sequence, no Adam kernel): the
+ * blocks of the partial-sum reduce kernel (launched cooperatively) meet once, every block combines the per-block sums of
+ * squares in the same fixed order (+ the gradients outside the MLP, `extra_grads`, e.g. action_log_std, which must live
+ * inside `grads`) and applies clip_grad_norm_(max_norm) + Adam to the parameters whose gradients it has just reduced;
+ * block 0 takes the extra parameters and bumps *step_dev.  params / grads / exp_avg / exp_avg_sq are the bank's flat
+ * vectors (same offsets).  max_norm <= 0: no clipping.  `ticket` = two zeroed device words owned by the bank. */
 typedef struct {
   float* params; const float* grads; float* exp_avg; float* exp_avg_sq; int64_t n;
   double max_norm, lr, beta1, beta2, eps;

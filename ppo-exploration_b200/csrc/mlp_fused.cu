@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(NT, H == 64 ? 2 : 1) mlp3_bwd_kernel(BwdP p) {
 }
 
 template <int H>
-__device__ __forceinline__ void mlp3_reduce_finish(const RedP& p, float (&sl)[8][33], float s, int e, int R, int g, int o, int D, int el) {
+__device__ __forceinline__ float* mlp3_reduce_finish(const RedP& p, float (&sl)[8][33], float s, int e, int R, int g, int o, int D, int el,
+                                                     float* grad_value) {
   const bool live = e < H * H + R;
   if (live) {
 #pragma unroll
@@ -525,27 +526,48 @@ __device__ __forceinline__ void mlp3_reduce_finish(const RedP& p, float (&sl)[8]
     if (el == 0) p.sumsq[(size_t)g * gridDim.x + blockIdx.x] = ss;
     if (p.step_dev && el == 0 && blockIdx.x == 0 && g == 0) *p.step_dev += 1;
   }
+  float* dst = nullptr;
   if (live) {
-    if (e < H * H) p.dW2[(size_t)g * H * H + e] = s;
+    if (e < H * H) dst = p.dW2 + (size_t)g * H * H + e;
     else {
       const int r = e - H * H;
-      if (r < D * H) p.dW1[(size_t)(r / H) * (p.G * H) + g * H + r % H] = s;
-      else if (r < D * H + H) p.db1[g * H + (r - D * H)] = s;
-      else if (r < D * H + 2 * H) p.db2[g * H + (r - D * H - H)] = s;
-      else if (r < D * H + 2 * H + H * o) p.dW3[g][r - D * H - 2 * H] = s;
-      else p.db3[g][r - D * H - 2 * H - H * o] = s;
+      if (r < D * H) dst = p.dW1 + (size_t)(r / H) * (p.G * H) + g * H + r % H;
+      else if (r < D * H + H) dst = p.db1 + g * H + (r - D * H);
+      else if (r < D * H + 2 * H) dst = p.db2 + g * H + (r - D * H - H);
+      else if (r < D * H + 2 * H + H * o) dst = p.dW3[g] + (r - D * H - 2 * H);
+      else dst = p.db3[g] + (r - D * H - 2 * H - H * o);
     }
+    *dst = s;
   }
+  *grad_value = s;
+  return dst;
 }
 
-// Optimiser tail (ppx_fused_adam): every thread of every block of the reduce kernel calls this after its gradients are
-// written.  The LAST block to arrive re-reads the per-block sums of squares in a fixed order (so the clip coefficient does
-// not depend on which block that is), bumps the step counter and applies clip_grad_norm_ + torch's Adam update to the
-// whole bank.  The beta powers come from one f64 pow pair evaluated by a single thread.
-__device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, int n_partials) {
-  if (!last_block_done(a.ticket)) return;
+// Optimiser tail (ppx_fused_adam).  clip_grad_norm_ needs the norm over ALL gradients, i.e. a grid-wide dependency inside
+// the reduce kernel.  (First version: the last block to finish applied Adam to the whole bank -- one CTA walking 9732
+// parameters with dependent loads cost 53 us, more than the separate Adam launch it replaced.)  Now every block publishes
+// its sum of squares, the grid meets at a counter (the launch is COOPERATIVE, so all blocks are resident and the spin
+// cannot deadlock), every block re-reads the partials in the same fixed order -- identical clip coefficient everywhere --
+// and its first warp applies Adam to the 32 parameters whose gradients it has just produced; block (0,0) also takes the
+// parameters outside the MLP (action_log_std) and bumps the step counter.  ticket[0] = arrivals, ticket[1] = departures
+// (the last block to leave re-arms both).
+__device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, int n_partials, float* gptr, float gval, bool first_warp) {
   __shared__ double s_red[32];
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  const unsigned int total = gridDim.x * gridDim.y;
+  const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+  const int64_t t_ = *a.step_dev + 1;                          // read before the rendezvous, written (block 0) after it
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(a.ticket, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.ticket) : "memory");
+      if (seen < total) __nanosleep(64);
+    } while (seen < total);
+  }
+  __syncthreads();
   double ss = 0.0;
   if (a.max_norm > 0.0) {
     for (int k = threadIdx.x; k < n_partials; k += blockDim.x) ss += __ldcg(sumsq + k);
@@ -553,8 +575,6 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
     ss = block_sum(ss, s_red);
   }
   if (threadIdx.x == 0) {
-    const int64_t t_ = *a.step_dev + 1;
-    *a.step_dev = t_;
     const double t = (double)t_;
     s_step_size = (float)(a.lr / (1.0 - pow(a.beta1, t)));
     s_bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2, t));
@@ -562,15 +582,17 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
     if (a.max_norm > 0.0) {
       const float norm = (float)sqrt(ss);
       coef = fminf((float)a.max_norm / (norm + 1e-6f), 1.f);   // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
-      if (a.norm_out) *a.norm_out = sqrt(ss);
+      if (lead && a.norm_out) *a.norm_out = sqrt(ss);
     }
     s_coef = coef;
+    if (lead) *a.step_dev = t_;
+    if (atomicAdd(a.ticket + 1, 1u) == total - 1) { a.ticket[0] = 0u; a.ticket[1] = 0u; __threadfence(); }
   }
   __syncthreads();
   const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float w1 = (float)(1.0 - a.beta1), beta2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2), eps = (float)a.eps;
-  for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
-    const float gi = __ldcg(a.grads + i) * coef;
+  auto upd = [&](int64_t i, float gi) {
+    gi *= coef;
     float mi = a.exp_avg[i], vi = a.exp_avg_sq[i];
     mi = mi + w1 * (gi - mi);                                 // exp_avg.lerp_(grad, 1-beta1)
     vi = vi * beta2 + w2 * gi * gi;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
@@ -578,7 +600,10 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
     a.params[i] = a.params[i] - step_size * (mi / denom);     // param.addcdiv_(exp_avg, denom, -step_size)
     a.exp_avg[i] = mi;
     a.exp_avg_sq[i] = vi;
-  }
+  };
+  if (first_warp && gptr) upd((int64_t)(gptr - a.grads), gval);
+  if (lead)
+    for (int k = threadIdx.x; k < a.n_extra; k += blockDim.x) upd((int64_t)(a.extra_grads - a.grads) + k, __ldcg(a.extra_grads + k));
 }
 
 // grads[e] = sum over CTA partials in a fixed order.  Block = 32 consecutive parameters x 8 slices of the
@@ -604,8 +629,10 @@ __global__ void __launch_bounds__(256) mlp3_reduce_kernel(RedP p) {
   }
   sl[slice][el] = s;
   __syncthreads();
-  if (slice == 0) mlp3_reduce_finish<H>(p, sl, s, e, R, g, o, D, el);
-  if (p.adam.params) fused_adam_tail(p.adam, p.sumsq, (int)(gridDim.x * gridDim.y));
+  float* gptr = nullptr;
+  float gval = 0.f;
+  if (slice == 0) gptr = mlp3_reduce_finish<H>(p, sl, s, e, R, g, o, D, el, &gval);
+  if (p.adam.params) fused_adam_tail(p.adam, p.sumsq, (int)(gridDim.x * gridDim.y), gptr, gval, slice == 0);
 }
 
 inline size_t fwd_smem(int H, int D, int o) {
@@ -663,7 +690,25 @@ int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, c
   }
   for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
   dim3 rgrid((unsigned)ceil_div(H * H + rest_size(H, D, omax), 32), (unsigned)G);
-  if (H == 64) mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
+  if (adam) {                                                 // grid-wide rendezvous inside: all blocks must be resident
+    const void* fn = H == 64 ? (const void*)mlp3_reduce_kernel<64> : (const void*)mlp3_reduce_kernel<128>;
+    static int per_sm[2] = {0, 0};
+    int& occ = per_sm[H == 64 ? 0 : 1];
+    if (!occ) PPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0));
+    if ((int64_t)rgrid.x * rgrid.y > (int64_t)occ * sm_count()) {
+      // more blocks than can be resident (h = 128, three nets): plain reduce + the stand-alone clip+Adam launch
+      r.adam = ppx_fused_adam{};
+      if (H == 64) mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
+      else mlp3_reduce_kernel<128><<<rgrid, 256, 0, st>>>(r);
+      int rc = after_launch("mlp3_reduce");
+      if (rc) return rc;
+      return ppx_clip_adam(adam->params, adam->grads, adam->exp_avg, adam->exp_avg_sq, adam->n, adam->max_norm,
+                           adam->max_norm > 0.0 ? adam->n : 0, adam->lr, adam->beta1, adam->beta2, adam->eps, 0, adam->step_dev,
+                           adam->norm_out, sumsq, (void*)st);
+    }
+    void* args[] = {&r};
+    PPX_CUDA(cudaLaunchCooperativeKernel(fn, rgrid, dim3(256), args, 0, st));
+  } else if (H == 64) mlp3_reduce_kernel<64><<<rgrid, 256, 0, st>>>(r);
   else mlp3_reduce_kernel<128><<<rgrid, 256, 0, st>>>(r);
   return after_launch("mlp3_reduce");
 }

@@ -59,7 +59,7 @@ class ParamBank:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.norm_dev = torch.zeros(1, dtype=torch.float64, device=device)
         self._ws = torch.zeros(4096, dtype=torch.float64, device=device)
-        self._ticket = torch.zeros(1, dtype=torch.int32, device=device)      # last-block detection of the fused optimiser tail
+        self._ticket = torch.zeros(2, dtype=torch.int32, device=device)      # rendezvous counters of the fused optimiser tail
         self._fused = None
         self.tc_weights = []                       # TcWeight shadows to refresh after every step
 
