@@ -73,10 +73,10 @@ def _worker(rank, world, port):
     def shard(d):
         return {k: v[:, sl] for k, v in d.items()}
 
-    def finish(m, data, lvv, dual):
+    def finish(m, data, lvv, dual, livv=None):
         m.rollout.load_rollout(**data)
         if dual:
-            m.rollout.compute_returns_and_advantages(torch.tensor(lvv), torch.tensor(lvv[::-1].copy()), data["masks"][-1])
+            m.rollout.compute_returns_and_advantages(torch.tensor(lvv), torch.tensor(livv), data["masks"][-1])
         else:
             m.rollout.compute_returns_and_advantages(torch.tensor(lvv), data["masks"][-1])
         m.train(); m.train()
@@ -130,7 +130,9 @@ def _worker(rank, world, port):
     # ---------------- RND: running moments, rollout bonus, train ----------------
     fulld = _rollout(T, N * world, D_, ("Discrete", 3), 11, dual=True)
 
-    def rnd(n_envs, data, lvv, mode):
+    liv = np.random.RandomState(9).randn(N * world).astype(np.float32)
+
+    def rnd(n_envs, data, lvv, livv, mode):
         np.random.seed(4); torch.manual_seed(4)
         env = ppx.SyntheticVecEnv(n_envs, D_, ppx.Discrete(3), seed=0)
         m = ppx.PPO_RND(env=env, nstep=T, batch_size=T * n_envs // 2, hidden_size=64, int_hidden_size=16, device=dev,
@@ -140,13 +142,13 @@ def _worker(rank, world, port):
             m.obs_rms.update(data["observations"][t])
         nxt = np.concatenate([data["observations"][1:], data["observations"][:1]], 0)
         bonus = m.rnd_bonus_rollout(nxt).clone()
-        finish(m, data, lvv, True)
+        finish(m, data, lvv, True, livv)
         return m.policy.bank.flat.clone(), m.last_losses.copy(), bonus.cpu().numpy(), (m.obs_rms.mean, m.obs_rms.var, m.obs_rms.count,
                                                                                      m.int_rew_rms.var, m.int_rew_rms.count)
 
     with _single():
-        w_ref, l_ref, b_ref, st_ref = rnd(N * world, fulld, lv, "global")
-    w_g, l_g, b_g, st_g = rnd(N, shard(fulld), lv[sl], "global")
+        w_ref, l_ref, b_ref, st_ref = rnd(N * world, fulld, lv, liv, "global")
+    w_g, l_g, b_g, st_g = rnd(N, shard(fulld), lv[sl], liv[sl], "global")
     for a, b in zip(st_g, st_ref):
         np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-15, err_msg="sharded running moments")
     np.testing.assert_allclose(b_g, b_ref[:, sl], rtol=1e-6, atol=1e-9, err_msg="sharded RND rollout bonus")
