@@ -573,9 +573,9 @@ class PpxPass:
         for _ in range(warmup):
             self.step_resident()
         torch.cuda.synchronize()
-        l0 = L.launch_count()
+        l0, w0 = L.launch_count(), m.rng_wait_s
         ms = self.timed(self.step_resident, steps)
-        launches = L.launch_count() - l0
+        launches, rng_wait = L.launch_count() - l0, m.rng_wait_s - w0
         clk = clocks.stop() if clocks is not None else None
         self.step_e2e()
         ms_e2e = self.timed(self.step_e2e, steps)
@@ -593,6 +593,7 @@ class PpxPass:
                        "h2d_bytes_per_step": int(self.h2d + perm_bytes), "d2h_bytes_per_step": int(n_mb * 64),
                        "ms_per_step": ms_e2e / steps},
                "gpu_launches": int(launches), "launches_per_step": launches / steps,
+               "host_rng_wait_ms_per_step": 1e3 * rng_wait / steps,
                "roofline": roofline_of(agg, cfg, peaks) if agg else None}
         if clk is not None:
             rec["clocks"] = clk
@@ -621,8 +622,6 @@ def run_ppx(args):
     cfg = CONFIGS[args.config]
     bp = PpxPass(args.config, torch, ppx, dev, rank, world)
     m = bp.m
-    if world > 1 and os.environ.get("PPX_BENCH_SHUFFLE", "global") == "local":
-        m.shard_shuffle = "local"                               # secondary number: per-rank shuffle streams
     if args.profile:
         for _ in range(args.warmup):
             bp.step_resident()
@@ -644,7 +643,19 @@ def run_ppx(args):
                            "global_minibatch": cfg["batch"] * world,
                            "cuda_graph": "per-minibatch launch sequence replayed as a CUDA graph",
                            "shard_shuffle": (m.shard_shuffle if sharded else "n/a (1 GPU)")},
-            "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "roofline": rec["roofline"]}
+            "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "roofline": rec["roofline"],
+            "host_rng_wait_ms_per_step": rec["host_rng_wait_ms_per_step"]}
+    if sharded and cfg["alg"] != "icm":
+        # labelled secondary number: per-rank shuffle streams ("local": the usual data-parallel sampler, NOT the reference's
+        # global permutation).  The headline ("global") draws the reference's np.random.permutation(T*N*W) on every rank --
+        # a sequential MT19937 stream of W x more draws per pass, which is what bounds weak scaling at large W
+        m.shard_shuffle = "local"
+        for _ in range(3):
+            bp.step_resident()
+        ms_l = bp.timed(bp.step_resident, args.steps)
+        line["local_shuffle"] = {"value": cfg["T"] * cfg["N"] * world * args.steps / (ms_l / 1e3), "unit": "transitions/s",
+                                 "ms_per_step": ms_l / args.steps,
+                                 "note": "shard_shuffle='local': every rank shuffles its own rollout with its own numpy stream"}
     del bp, m
     torch.cuda.empty_cache()
     if args.config == "C2":

@@ -79,6 +79,7 @@ class BaseAlgorithm(object):
         self._perm_all, self._perm_events, self._perm_keep, self._copy_stream = None, [], [], None
         self._perm_j, self._perm_ws = None, None
         self._glob = None                      # sharded "global": the all-gathered rollout [W, T, N, ...] per field
+        self.rng_wait_s = 0.0                  # cumulative host time train() spent waiting for permutations
         self.device_shuffle = device_shuffle_default()         # swaps of the epoch shuffle applied on the GPU (shuffle_dev.cu)
 
     def __del__(self):
@@ -343,7 +344,9 @@ class BaseAlgorithm(object):
     def _perm_upload(self, rng, epoch, total):
         """Stage epoch `epoch`'s permutation in its slice of the all-epoch device buffer, on the copy stream (the H2D
         copy and the device-side swaps overlap the previous epoch's kernels)."""
+        t0 = time.perf_counter()
         perm = rng.next()                                       # pinned int64 [total], or the partner list (DevicePartners)
+        self.rng_wait_s += time.perf_counter() - t0             # host time blocked on the (sequential) numpy RNG stream
         on_device = isinstance(perm, DevicePartners)
         dst = self._perm_all[epoch * total:(epoch + 1) * total]
         if on_device and self._perm_j is None:
