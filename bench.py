@@ -442,15 +442,10 @@ def es_step_bench(torch, ppx, dev, world, rank, steps=20, warmup=5):
     archive = torch.randn(M, 2, dtype=torch.float64, device=dev, generator=g)
     queries = torch.randn(2, 2, dtype=torch.float64, device=dev, generator=g)
     fit_local = torch.randn(P // world, dtype=torch.float64, device=dev, generator=g)
-    step = es.make_bench_step(fit_local, archive, queries) if hasattr(es, "make_bench_step") else None
-    if step is None:
-        def step():
-            pop = es._get_population()                          # identical offsets on every rank (shared seed)
-            w = es.perturb_all(es.shard_population(pop))        # [P/W, D] f32: what the evaluators consume
-            r_all = es.gather_fitness(fit_local)
-            _, nov = es.novelty_batch(archive, queries)
-            es._update_weights(r_all, pop, novelty=nov[0:1])    # novelty stays on the device
-            return w
+    def step():
+        pop, w = es.ask()                                       # population drawn on the device; [P/W, D] f32 for the evaluators
+        es.tell(fit_local, archive, queries)                    # fitness exchange, novelty k-NN, (sharded) update
+        return w
     for _ in range(warmup):
         step()
     if world > 1:

@@ -392,6 +392,22 @@ int ppx_embedding_fwd(const float* table, int C, const void* ids, int ids_are_f6
 int ppx_embedding_bwd(const float* d_out, int ldo, const void* ids, int ids_are_f64, int id_stride, int64_t B,
                       int C, float* d_table, void* stream);
 
+/* VecNormalize on the device (the reference wraps its envs in stable_baselines3's VecNormalize with
+ * norm_reward=True, env.py:11).  obs: out = clip((obs - mean) / sqrt(var + eps), +-clip) from RunningMeanStd state
+ * (ppx_rms_update).  reward: returns = returns * gamma + r; the return statistics {mean, var, count} absorb the batch of
+ * returns (update_stats); out = clip(r / sqrt(ret_var + eps), +-clip); returns[done] = 0.  n <= any (one CTA). */
+int ppx_vecnorm_obs(const float* obs, int64_t n, int dim, const double* mean, const double* var, double eps, double clip,
+                    float* out, void* stream);
+int ppx_vecnorm_reward(const float* rewards, const uint8_t* dones, double* returns_inout, int n, double gamma,
+                       double* ret_mean, double* ret_var, double* ret_count, double eps, double clip, int update_stats,
+                       float* rewards_out, void* stream);
+/* Policy.act tail (models.py:30-50, 75-99): sample one action per env from Normal(tanh(actor_out),
+ * exp(log_std)) (Box: actions f64 [N,A], log-probs f32 [N,A]) or Categorical(softmax(actor_out)) (Discrete: action ids as
+ * f64 [N], log-probs f32 [N]) and evaluate its log-probability as torch.distributions would.  Philox4x32-10 keyed by
+ * `seed`, counter (env, draw): pass a new `draw` number per call. */
+int ppx_policy_sample(const float* actor_out, const float* log_std, int64_t N, int A, int discrete, uint64_t seed,
+                      uint64_t draw, double* actions_out, float* logp_out, void* stream);
+
 /* ---------------------------------------------------------------- ES-NSRA ------------------- */
 /* fill a shared noise table with N(0,1) f32 (Philox4x32-10 + Box-Muller); build-side design, the
  * reference draws fresh randn per member (evolution_strategies.py:172-182). */
@@ -420,6 +436,21 @@ int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, con
                   double sigma, double novelty_param, double novelty, const double* novelty_dev /* overrides `novelty` when
                   non-NULL: the k-NN result stays on the device, no host round trip */, int use_novelty, int rank_mode,
                   double decay, double* lr_inout, int* status_out, void* workspace, void* stream);
+/* The population of one ES iteration as noise-table offsets drawn ON THE DEVICE (build-side design: the reference draws
+ * fresh randn per member, :172-182): Philox4x32-10 keyed by `seed`, counter = (member, *draw_dev); *draw_dev is bumped,
+ * so the launch replays from a CUDA graph and ranks sharing (seed, draw number) draw the identical population.
+ * offsets_out[p] is a multiple of 4 in [0, table_size - D]. */
+int ppx_es_offsets(uint64_t seed, int64_t* draw_dev, int P, int64_t table_size, int D, int64_t* offsets_out, void* stream);
+/* _update_weights with the population sharded over W ranks: every rank holds all P rewards (after the
+ * fitness all-gather) and computes the identical z-scores, runs the GEMV over ITS members [p_lo, p_lo + p_n) only,
+ * leaves the partial update in `dtheta_local` (its slot of a symmetric, peer-mapped allocation) and one kernel per rank
+ * meets the others at a flag barrier, sums the W partial updates in rank order over NVLink and applies them -- theta and
+ * lr stay bit-identical replicas; the noise is streamed once over all ranks together (strong scaling). */
+int ppx_es_update_sharded(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int p_lo,
+                          int p_n, int D, double sigma, double novelty_param, double novelty, const double* novelty_dev,
+                          int use_novelty, double decay, double* lr_inout, int* status_out, void* workspace,
+                          double* dtheta_local, const void* const* peer_dtheta_host, void* const* peer_flags_host, int W,
+                          int rank, uint32_t* seq_dev, uint32_t* status_dev, void* stream);
 /* centred ranks: rank_out[p] = #{q: r_q < r_p or (r_q == r_p and q < p)}, centred_out = rank/(P-1) - 0.5 */
 int ppx_rank_center(const double* r, int P, int64_t* rank_out, double* centred_out, void* stream);
 /* get_kNN + novelty (evolution_strategies.py:264-281, 318-325), batched over Q queries:

@@ -120,11 +120,17 @@ SIGNATURES = {
     "ppx_icm_bonus_tail": (c_i, [c_p, c_p, c_l, c_i, c_d, c_p, c_p, c_p]),
     "ppx_embedding_fwd": (c_i, [c_p, c_i, c_p, c_i, c_i, c_l, c_p, c_i, c_p]),
     "ppx_embedding_bwd": (c_i, [c_p, c_i, c_p, c_i, c_i, c_l, c_i, c_p, c_p]),
+    "ppx_vecnorm_obs": (c_i, [c_p, c_l, c_i, c_p, c_p, c_d, c_d, c_p, c_p]),
+    "ppx_vecnorm_reward": (c_i, [c_p, c_p, c_p, c_i, c_d, c_p, c_p, c_p, c_d, c_d, c_i, c_p, c_p]),
+    "ppx_policy_sample": (c_i, [c_p, c_p, c_l, c_i, c_i, c_u, c_u, c_p, c_p, c_p]),
     "ppx_noise_fill": (c_i, [c_p, c_l, c_u, c_p]),
     "ppx_es_perturb": (c_i, [c_p, c_p, c_p, c_d, c_i, c_i, c_p, c_i, c_p]),
     "ppx_es_forward": (c_i, [c_p, c_p, c_p, c_d, c_i, c_p, c_i, c_p, c_i, c_p, c_p]),
     "ppx_es_update_workspace": (c_l, [c_i, c_i]),
     "ppx_es_update": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_i, c_i, c_d, c_p, c_p, c_p, c_p]),
+    "ppx_es_offsets": (c_i, [c_u, c_p, c_i, c_l, c_i, c_p, c_p]),
+    "ppx_es_update_sharded": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_d, c_p, c_i, c_d, c_p, c_p, c_p, c_p, c_p,
+                                    c_p, c_i, c_i, c_p, c_p, c_p]),
     "ppx_rank_center": (c_i, [c_p, c_i, c_p, c_p, c_p]),
     "ppx_knn_novelty": (c_i, [c_p, c_l, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
 }

@@ -433,8 +433,13 @@ class BaseAlgorithm(object):
             self._record(k, float(np.mean(losses[:, i])))
         self._n_updates += self.n_epochs
 
-    def _learn_loop(self, total_timesteps, log_interval, reward_target):
-        """algorithms.py:277-308 / 514-543 / 725-756 (logging lines trimmed to record())."""
+    def _learn_loop(self, total_timesteps, log_interval, reward_target, log_name=None, log_to_file=False):
+        """algorithms.py:261-308 / 504-543 / 715-756.  With log_to_file (or when no logger was passed) the run is logged
+        through ppx's own logger module, which writes the reference's CSV schema (logger.py:13-52, :222-246)."""
+        if log_to_file or self.logger is None:
+            from . import logger as ppx_logger
+            ppx_logger.configure(log_name or type(self).__name__, str(self.env_id), log_to_file)
+            self.logger = ppx_logger
         start, iteration = time.time(), 0
         while self.num_timesteps < total_timesteps:
             self.collect_samples()
@@ -513,7 +518,8 @@ class PPO(BaseAlgorithm):
                                   "train/entropy_loss"))
 
     def learn(self, total_timesteps, log_interval, reward_target=None, log_to_file=False):
-        return self._learn_loop(total_timesteps, log_interval, reward_target)
+        name = "PPO_SimHash" if self.sim_hash else "PPO"                       # algorithms.py:270-275
+        return self._learn_loop(total_timesteps, log_interval, reward_target, name, log_to_file)
 
 
 class PPO_RND(BaseAlgorithm):
@@ -628,7 +634,7 @@ class PPO_RND(BaseAlgorithm):
                                   "train/entropy_loss", "train/intrinsic_loss"))
 
     def learn(self, total_timesteps, log_interval, reward_target=None, log_to_file=False):
-        return self._learn_loop(total_timesteps, log_interval, reward_target)
+        return self._learn_loop(total_timesteps, log_interval, reward_target, "PPO_RND", log_to_file)
 
 
 class PPO_ICM(BaseAlgorithm):
@@ -727,4 +733,4 @@ class PPO_ICM(BaseAlgorithm):
         self._record("train/icm_loss", float(np.mean(self.last_losses[:, 5])))
 
     def learn(self, total_timesteps, log_interval=5, reward_target=None, log_to_file=False):
-        return self._learn_loop(total_timesteps, log_interval, reward_target)
+        return self._learn_loop(total_timesteps, log_interval, reward_target, "PPO_ICM", log_to_file)

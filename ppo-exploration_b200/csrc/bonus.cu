@@ -296,3 +296,76 @@ extern "C" int ppx_embedding_bwd(const float* d_out, int ldo, const void* ids, i
   else embedding_bwd_kernel<int64_t><<<grid, 128, 0, (cudaStream_t)stream>>>(d_out, ldo, (const int64_t*)ids, id_stride, B, C, d_table);
   return after_launch("embedding_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// VecNormalize on the device (the reference wraps its envs in stable_baselines3's VecNormalize with
+// norm_reward=True, env.py:11): running observation statistics + normalisation, discounted-return statistics + reward
+// normalisation, the per-env return accumulator reset on `done`.  The running moments are the RunningMeanStd state of
+// ppx_rms_update (util.py:9-44 has the same update rule as stable_baselines3's).
+namespace ppx {
+namespace {
+
+__global__ void __launch_bounds__(256)
+vecnorm_obs_kernel(const float* __restrict__ obs, int64_t n, int dim, const double* __restrict__ mean, const double* __restrict__ var,
+                   double eps, float clip, float* __restrict__ out) {
+  const int64_t total = n * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dim);
+    const double z = ((double)obs[i] - mean[d]) / sqrt(var[d] + eps);
+    out[i] = fminf(fmaxf((float)z, -clip), clip);
+  }
+}
+
+// one CTA: ret = ret * gamma + r; ret_rms.update(ret); r_out = clip(r / sqrt(ret_var + eps), +-clip); ret[done] = 0
+__global__ void __launch_bounds__(1024)
+vecnorm_reward_kernel(const float* __restrict__ r, const uint8_t* __restrict__ done, double* __restrict__ ret, int n, double gamma,
+                      double* mean, double* var, double* count, double eps, float clip, int update, float* __restrict__ out) {
+  __shared__ double s_red[32];
+  __shared__ double s_var;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = ret[i] * gamma + (double)r[i];
+    ret[i] = v;
+    a += v;
+  }
+  const double bm = block_sum(a, s_red) / (double)n;
+  a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = ret[i] - bm; a += d * d; }
+  const double bv = block_sum(a, s_red) / (double)n;
+  if (threadIdx.x == 0) {
+    double m = *mean, v = *var;
+    if (update) {
+      merge_moments(bm, bv, (double)n, m, v, *count);
+      *mean = m; *var = v; *count += (double)n;
+    }
+    s_var = v;
+  }
+  __syncthreads();
+  const double inv = 1.0 / sqrt(s_var + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    out[i] = fminf(fmaxf((float)((double)r[i] * inv), -clip), clip);
+    if (done[i]) ret[i] = 0.0;
+  }
+}
+
+}  // namespace
+}  // namespace ppx
+
+extern "C" int ppx_vecnorm_obs(const float* obs, int64_t n, int dim, const double* mean, const double* var, double eps, double clip,
+                               float* out, void* stream) {
+  PPX_REQUIRE(obs && mean && var && out && n >= 0 && dim >= 1 && clip > 0.0, "vecnorm_obs: bad arguments");
+  if (n == 0) return PPX_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n * dim, 256), (int64_t)sm_count() * 16);
+  ppx::vecnorm_obs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, n, dim, mean, var, eps, (float)clip, out);
+  return after_launch("vecnorm_obs");
+}
+
+extern "C" int ppx_vecnorm_reward(const float* rewards, const uint8_t* dones, double* returns_inout, int n, double gamma,
+                                  double* ret_mean, double* ret_var, double* ret_count, double eps, double clip, int update_stats,
+                                  float* rewards_out, void* stream) {
+  PPX_REQUIRE(rewards && dones && returns_inout && ret_mean && ret_var && ret_count && rewards_out && n >= 1 && clip > 0.0,
+              "vecnorm_reward: bad arguments");
+  ppx::vecnorm_reward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rewards, dones, returns_inout, n, gamma, ret_mean, ret_var, ret_count,
+                                                                   eps, (float)clip, update_stats, rewards_out);
+  return after_launch("vecnorm_reward");
+}

@@ -13,39 +13,39 @@
 //                                                      split over members, fixed-order reduction)
 // Parity mode passes a dense [P,D] eps (offsets == NULL) holding the very values given to the
 // reference.  All state (theta, lr) stays on device; the std==0 early-out of :225-226 is a device flag.
-#include "common.cuh"
+#include "p2p.cuh"
+#include "philox.cuh"
 
 namespace ppx {
 namespace {
 
-// ---------------- Philox4x32-10 + Box-Muller ----------------
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
-  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
-  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
-  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
-  c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
-}
 __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ table, int64_t n, uint64_t seed) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // quad index
   if (q * 4 >= n) return;
   uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), 0u, 0u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  philox4x32(c, seed);
   float z[4];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;       // (0,1]
-    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
-    const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
-  }
+  box_muller(c[0], c[1], z[0], z[1]);
+  box_muller(c[2], c[3], z[2], z[3]);
 #pragma unroll
   for (int e = 0; e < 4; ++e)
     if (q * 4 + e < n) table[q * 4 + e] = z[e];
+}
+
+// population = P offsets into the noise table, drawn on the device: Philox4x32-10 keyed by the seed, counter =
+// (member, draw number); the draw number lives on the device and is bumped here, so the launch replays from a CUDA
+// graph and every rank (same seed, same number) draws the identical population.  Offsets are multiples of 4 (16-byte
+// aligned noise rows).  One CTA: all threads read the draw number before anyone bumps it.
+__global__ void __launch_bounds__(1024) es_offsets_kernel(uint64_t seed, int64_t* draw, int P, int64_t hi, int64_t* __restrict__ out) {
+  const uint64_t n = (uint64_t)*draw;
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    uint32_t c[4] = {(uint32_t)p, (uint32_t)n, (uint32_t)(n >> 32), 0x6f666673u};
+    philox4x32(c, seed);
+    const uint64_t u = ((uint64_t)c[1] << 32) | c[0];
+    out[p] = (int64_t)(u % (uint64_t)hi) * 4;
+  }
+  if (threadIdx.x == 0) *draw = (int64_t)(n + 1);
 }
 
 // ---------------- perturb ----------------
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128)
 es_gemv_kernel(const float* __restrict__ noise, const int64_t* __restrict__ offsets, const double* __restrict__ coef, int P, int D,
                int p_chunk, double* __restrict__ partial) {
   const int j = (blockIdx.x * 128 + threadIdx.x) * 4;
-  const int p0 = blockIdx.y * p_chunk, p1 = min(P, p0 + p_chunk);
+  const int p0 = min(P, (int)blockIdx.y * p_chunk), p1 = min(P, p0 + p_chunk);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (j < D) {
 #pragma unroll 8
@@ -330,6 +330,44 @@ es_gemv_kernel(const float* __restrict__ noise, const int64_t* __restrict__ offs
     if (j + 2 < D) out[2] = a2;
     if (j + 3 < D) out[3] = a3;
   }
+}
+
+// column sums of the per-split partials in a fixed order: block = 32 columns x 8 slices of the split list (slice q takes
+// splits q, q+8, ...), slices combined 0..7.  Single GPU: theta += sum (unless the std == 0 early-out) and lr *= decay;
+// sharded: this rank's partial update over ITS members -> the peer-visible buffer (es_apply_p2p_kernel sums the ranks).
+__global__ void __launch_bounds__(256)
+es_colsum_kernel(const double* __restrict__ partial, int splits, int D, const double* __restrict__ stats, double* __restrict__ theta,
+                 double* __restrict__ dtheta, double decay, double* lr) {
+  __shared__ double sl[8][33];
+  const int c = threadIdx.x & 31, q = threadIdx.x >> 5, j = blockIdx.x * 32 + c;
+  double a = 0.0;
+  if (j < D)
+    for (int k = q; k < splits; k += 8) a += partial[(int64_t)k * D + j];
+  sl[q][c] = a;
+  __syncthreads();
+  if (q != 0 || j >= D) return;
+  const bool skip = stats[2] != 0.0;
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += sl[k][c];
+  if (dtheta) dtheta[j] = skip ? 0.0 : sum;
+  else if (!skip) theta[j] += sum;
+  if (!dtheta && j == 0 && !skip) *lr *= decay;                        // :239 (not reached on the early return)
+}
+
+// sharded update, last step: theta += sum over ranks (rank order: identical on every replica) of the peers' partial updates
+__global__ void __launch_bounds__(1024)
+es_apply_p2p_kernel(p2p::Peers P, double* __restrict__ theta, int D, const double* __restrict__ stats, double decay, double* lr) {
+  if (threadIdx.x < 32) p2p::barrier_all(P);
+  __syncthreads();
+  const bool skip = stats[2] != 0.0;
+  if (skip) return;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < P.W; ++r) s += p2p::ld_peer_f64((const double*)P.data[r] + j);
+    theta[j] += s;
+  }
+  if (threadIdx.x == 0) *lr *= decay;
 }
 
 __global__ void __launch_bounds__(256)
@@ -427,7 +465,7 @@ knn_merge_kernel(const double* __restrict__ cand, int n_cand, int64_t M, int K, 
 
 int gemv_splits(int P, int D) {
   const int64_t colblocks = ceil_div(D, 512);
-  int64_t s = ceil_div(16 * (int64_t)sm_count(), colblocks);
+  int64_t s = ceil_div(4 * (int64_t)sm_count(), colblocks);
   s = std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, P / 32)));
   return (int)s;
 }
@@ -514,6 +552,59 @@ extern "C" int64_t ppx_es_update_workspace(int P, int D) {
   return (int64_t)sizeof(double) * (8 + 2 * (int64_t)P + (int64_t)gemv_splits(P, D) * D);
 }
 
+extern "C" int ppx_es_offsets(uint64_t seed, int64_t* draw_dev, int P, int64_t table_size, int D, int64_t* offsets_out, void* stream) {
+  PPX_REQUIRE(draw_dev && offsets_out && P >= 1 && D >= 1 && table_size >= D + 4, "es_offsets: bad arguments");
+  es_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seed, draw_dev, P, (table_size - D) / 4, offsets_out);
+  return after_launch("es_offsets");
+}
+
+namespace {
+// stats + coefficients over ALL P rewards (replicated: every rank computes the identical z-scores), then the GEMV over
+// members [p_lo, p_lo + p_n) with the column-sum tail
+int es_update_core(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int p_lo, int p_n, int D,
+                   double sigma, double novelty_param, double novelty, const double* novelty_dev, int use_novelty, double decay,
+                   double* lr_inout, int* status_out, void* workspace, double* dtheta_out, cudaStream_t st) {
+  double* stats = (double*)workspace;
+  double* coef = stats + 8;
+  double* partial = coef + 2 * (int64_t)P;
+  const int splits = gemv_splits(P, D);
+  es_stats_coef_kernel<<<1, 1024, 0, st>>>(rewards, P, stats, status_out, lr_inout, sigma, novelty_param, novelty, novelty_dev,
+                                           use_novelty, coef);
+  int rc = after_launch("es_update(stats+coef)");
+  if (rc) return rc;
+  const int p_chunk = (int)ceil_div(p_n, splits);
+  dim3 grid((unsigned)ceil_div(D, 512), (unsigned)splits);
+  const bool vec = (D % 4 == 0) && ((uintptr_t)noise % 16 == 0);
+  // with offsets, vector loads need every offset to be a multiple of 4 -- the table sampler guarantees it
+  // (see host wrapper); dense parity inputs only need D % 4 == 0.
+  const float* nz = offsets ? noise : noise + (int64_t)p_lo * D;
+  if (vec) es_gemv_kernel<true><<<grid, 128, 0, st>>>(nz, offsets ? offsets + p_lo : nullptr, coef + p_lo, p_n, D, p_chunk, partial);
+  else es_gemv_kernel<false><<<grid, 128, 0, st>>>(nz, offsets ? offsets + p_lo : nullptr, coef + p_lo, p_n, D, p_chunk, partial);
+  rc = after_launch("es_update(gemv)");
+  if (rc) return rc;
+  es_colsum_kernel<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(partial, splits, D, stats, theta, dtheta_out, decay, lr_inout);
+  return after_launch("es_update(column sums)");
+}
+}  // namespace
+
+extern "C" int ppx_es_update_sharded(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int p_lo,
+                                     int p_n, int D, double sigma, double novelty_param, double novelty, const double* novelty_dev,
+                                     int use_novelty, double decay, double* lr_inout, int* status_out, void* workspace,
+                                     double* dtheta_local, const void* const* peer_dtheta_host, void* const* peer_flags_host, int W,
+                                     int rank, uint32_t* seq_dev, uint32_t* status_dev, void* stream) {
+  PPX_REQUIRE(theta && noise && rewards && lr_inout && workspace && dtheta_local, "es_update_sharded: null pointer");
+  PPX_REQUIRE(P >= 2 && D >= 1 && sigma != 0.0 && p_lo >= 0 && p_n >= 1 && p_lo + p_n <= P, "es_update_sharded: P=%d p_lo=%d p_n=%d D=%d", P, p_lo, p_n, D);
+  p2p::Peers PP;
+  int rc = p2p::fill(&PP, peer_dtheta_host, peer_flags_host, W, rank, seq_dev, status_dev);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = es_update_core(theta, noise, offsets, rewards, P, p_lo, p_n, D, sigma, novelty_param, novelty, novelty_dev, use_novelty, decay,
+                      lr_inout, status_out, workspace, dtheta_local, st);
+  if (rc) return rc;
+  es_apply_p2p_kernel<<<1, 1024, 0, st>>>(PP, theta, D, (const double*)workspace, decay, lr_inout);
+  return after_launch("es_update(p2p apply)");
+}
+
 extern "C" int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, const double* rewards, int P, int D,
                              double sigma, double novelty_param, double novelty, const double* novelty_dev, int use_novelty,
                              int rank_mode, double decay, double* lr_inout, int* status_out, void* workspace, void* stream) {
@@ -536,9 +627,9 @@ extern "C" int ppx_es_update(double* theta, const float* noise, const int64_t* o
                                                                novelty_dev, use_novelty, rank_mode, coef);
     rc = after_launch("es_update(coef)");
   } else {
-    es_stats_coef_kernel<<<1, 1024, 0, st>>>(rewards, P, stats, status_out, lr_inout, sigma, novelty_param, novelty, novelty_dev,
-                                             use_novelty, coef);
-    rc = after_launch("es_update(stats+coef)");
+    // z-score shaping (the reference's): stats + coefficients, then the GEMV whose last CTAs apply the update (2 launches)
+    return es_update_core(theta, noise, offsets, rewards, P, 0, P, D, sigma, novelty_param, novelty, novelty_dev, use_novelty, decay,
+                          lr_inout, status_out, workspace, nullptr, st);
   }
   if (rc) return rc;
   const int splits = gemv_splits(P, D);

@@ -295,6 +295,202 @@ __global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd_kernel(FwdP p) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc<64>(tmem); }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, v2
+// Round 2: BOTH dense layers of the forward on the tensor pipe, A operands in TENSOR MEMORY (tools/umma_probe3.cu):
+//   * layer 1: Z1 = [X | 1] [W1 ; b1] -- the thread that owns a sample writes its X row (raw | lo) and a ones column with
+//     tcgen05.st; B = a small K-major image of [W1 ; b1]^T staged once per CTA.  (K = DP + 8; v1 spent 256 FMAs and 72
+//     shared-memory reads per thread and tile here.)
+//   * layer 2: H1 (raw | lo) goes back into tensor memory with tcgen05.st -- no shared-memory images, no swizzle
+//     arithmetic, and the MMA reads only W2 from shared memory (32 instead of 48 cycles at M 128, N 64).
+// 48 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, one covers the other's MMA round trips.
+namespace f2 {
+constexpr uint32_t ACC = 0, A2_RAW = 64, A2_LO = 128, A1 = 192;      // tensor-memory columns (A1: raw K1 columns, then lo)
+}
+
+template <int DP>
+__global__ void __launch_bounds__(NT, 2) mlp3_tc_fwd2_kernel(FwdP p) {
+  using namespace f2;
+  constexpr int K1 = DP + 8;                      // layer-1 reduction: D inputs (padded to DP) | ones | 7 zeros
+  static_assert(2 * K1 <= 64, "layer-1 operand must fit its tensor-memory columns");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t W2_raw = smem, W2_lo = smem + 16384;            // B[n = j][k = i] = W2[i][j]: 2 k-blocks x [64 rows][128 B]
+  const uint32_t W1_raw = smem + 32768, W1_lo = smem + 40960;    // B[n = i][k] = W1[k][i] (k < D), b1[i] (k == DP): [64 rows][128 B]
+  __shared__ __align__(16) float b2s[H], W3s[H * MAXO], b3s[MAXO];
+  __shared__ __align__(16) float part[TM * MAXO];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, ch = warp >> 2, s = q * 32 + lane, c0 = ch * 32;
+  const int g = blockIdx.y, o = p.o[g], D = p.D, ldw = p.G * H;
+
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  stage_weight(W2_raw, W2_lo, p.W2 + (size_t)g * H * H, true, tid);
+  for (int e = tid; e < H * 32; e += NT) {                   // the whole 128-byte rows (unused k columns = 0)
+    const int n = e >> 5, k = e & 31;
+    float w = 0.f;
+    if (k < D) w = __ldg(p.W1 + (size_t)k * ldw + g * H + n);
+    else if (k == DP) w = __ldg(p.b1 + g * H + n);
+    const uint32_t off = sw128_off(n, k);
+    sts32(W1_raw + off, w);
+    sts32(W1_lo + off, lo_of(w));
+  }
+  for (int e = tid; e < H * MAXO; e += NT) {                 // W3s [j][c]: one 16-byte read = 4 columns of output j
+    const int j = e >> 6, c = e & 63;
+    W3s[e] = j < o ? __ldg(p.W3[g] + c * o + j) : 0.f;
+  }
+  if (tid < H) b2s[tid] = __ldg(p.b2 + g * H + tid);
+  if (tid < MAXO) b3s[tid] = tid < o ? __ldg(p.b3[g] + tid) : 0.f;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+
+  uint32_t phase = 0;
+  float x[DP];                                   // this tile's X row; the next tile's is loaded under the MMAs
+  if ((int)blockIdx.x < p.nTiles)
+    load_x_row<DP>(p.X + (size_t)(blockIdx.x * TM + s) * p.ldx, p.ldx, D, blockIdx.x * TM + s < p.M, x);
+  for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
+    const int m0 = tile * TM;
+    const bool live = m0 + s < p.M;
+    float4* h1t = reinterpret_cast<float4*>(p.H1t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;   // quad (c0/4 + j): + j*TM
+    float4* h2t = reinterpret_cast<float4*>(p.H2t + ((size_t)(g * p.nTiles + tile) * H + c0) * TM) + s;
+    // ---- layer 1 operand: [x | 1 | 0] raw (column half 0) and its lo part (column half 1) -> tensor memory ----
+    {
+#pragma unroll
+      for (int k0 = 0; k0 < K1; k0 += 8) {
+        uint32_t u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int kk = k0 + k;
+          const float v = kk < DP ? x[kk < DP ? kk : 0] : (kk == DP ? 1.f : 0.f);
+          u[k] = __float_as_uint(ch == 0 ? v : lo_of(v));
+        }
+        tmem_st8(tlane + A1 + (uint32_t)(ch * K1 + k0), u);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();                         // [A] operand complete; every thread has read the previous tile's accumulator
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t id = make_idesc_full(128, 64, 0, 0);
+        const uint64_t dr = make_desc(W1_raw), dl = make_desc(W1_lo);
+#pragma unroll
+        for (int ks = 0; ks < K1 / 8; ++ks) {
+          umma_tf32_ts(tmem + ACC, tmem + A1 + K1 + ks * 8, dr + (uint64_t)(ks * 2), id, ks ? 1u : 0u);
+          umma_tf32_ts(tmem + ACC, tmem + A1 + ks * 8, dl + (uint64_t)(ks * 2), id, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < K1 / 8; ++ks) umma_tf32_ts(tmem + ACC, tmem + A1 + ks * 8, dr + (uint64_t)(ks * 2), id, 1u);
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    {
+      const int nt = tile + (int)gridDim.x;
+      if (nt < p.nTiles) load_x_row<DP>(p.X + (size_t)(nt * TM + s) * p.ldx, p.ldx, D, nt * TM + s < p.M, x);
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- H1 = tanh(Z1) (bias came through the ones column): out to HBM, raw | lo back into tensor memory ----
+    float v[32];
+    {
+      uint32_t z[32];
+      tmem_ld32(tlane + ACC + c0, z);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = tanh_fast(__uint_as_float(z[c]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcs(h1t + j * TM, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));   // warp = 512 contiguous bytes
+#pragma unroll
+    for (int hh = 0; hh < 32; hh += 16) {
+      uint32_t u[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) u[c] = __float_as_uint(v[hh + c]);
+      tmem_st16(tlane + A2_RAW + c0 + hh, u);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) u[c] = __float_as_uint(lo_of(v[hh + c]));
+      tmem_st16(tlane + A2_LO + c0 + hh, u);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();                         // [B] layer-2 operand complete; Z1 read by everyone
+    // ---- layer 2 on the tensor core: Z2[s][j] = sum_i H1[s][i] W2[i][j] ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t id = make_idesc_full(128, 64, 0, 0);
+        const uint64_t dr = make_desc(W2_raw), dl = make_desc(W2_lo);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ob = (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+          umma_tf32_ts(tmem + ACC, tmem + A2_LO + ks * 8, dr + ob, id, ks ? 1u : 0u);
+          umma_tf32_ts(tmem + ACC, tmem + A2_RAW + ks * 8, dl + ob, id, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ob = (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+          umma_tf32_ts(tmem + ACC, tmem + A2_RAW + ks * 8, dr + ob, id, 1u);
+        }
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: bias + tanh, H2 out, head layer (o <= 4) ----
+    float po[MAXO] = {0.f, 0.f, 0.f, 0.f};
+    {
+      uint32_t z[32];
+      tmem_ld32(tlane + ACC + c0, z);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = tanh_fast(__uint_as_float(z[c]) + b2s[c0 + c]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcs(h2t + j * TM, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    auto head = [&](auto oc) {               // only the o live outputs (o is CTA-uniform)
+      constexpr int OC = decltype(oc)::value;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+        for (int j = 0; j < OC; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(&W3s[j * H + c0 + c]);
+          po[j] = fmaf(v[c + 3], w.w, fmaf(v[c + 2], w.z, fmaf(v[c + 1], w.y, fmaf(v[c], w.x, po[j]))));
+        }
+      }
+    };
+    switch (o) {
+      case 1: head(std::integral_constant<int, 1>{}); break;
+      case 2: head(std::integral_constant<int, 2>{}); break;
+      case 3: head(std::integral_constant<int, 3>{}); break;
+      default: head(std::integral_constant<int, 4>{}); break;
+    }
+    if (ch == 1) *reinterpret_cast<float4*>(&part[s * MAXO]) = make_float4(po[0], po[1], po[2], po[3]);
+    tc_fence_before();                       // the tcgen05.ld above is ordered before the next tile's MMAs
+    __syncthreads();                         // [C]
+    if (ch == 0 && live) {
+      const float4 t = *reinterpret_cast<const float4*>(&part[s * MAXO]);
+      const float r[MAXO] = {po[0] + t.x + b3s[0], po[1] + t.y + b3s[1], po[2] + t.z + b3s[2], po[3] + t.w + b3s[3]};
+      float* dst = p.out[g] + (size_t)(m0 + s) * o;
+#pragma unroll
+      for (int j = 0; j < MAXO; ++j)
+        if (j < o) dst[j] = r[j];
+    }
+    // `part` is rewritten only after the next tile's barriers [A] and [B]
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 struct BwdP {
   const float* X; int ldx; int M, D, G, nTiles;
@@ -1158,6 +1354,17 @@ int launch_fwd(const FwdP& p, dim3 grid, cudaStream_t st) {
   mlp3_tc_fwd_kernel<DP><<<grid, NT, kFwdSmem, st>>>(p);
   return after_launch("mlp3_tc_fwd");
 }
+constexpr size_t kFwd2Smem = 49152 + 1024;
+template <int DP>
+int launch_fwd2(const FwdP& p, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PPX_CUDA(cudaFuncSetAttribute(mlp3_tc_fwd2_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwd2Smem));
+    configured = true;
+  }
+  mlp3_tc_fwd2_kernel<DP><<<grid, NT, kFwd2Smem, st>>>(p);
+  return after_launch("mlp3_tc_fwd2");
+}
 template <int DP, int CW, bool MMAW>
 int launch_bwd(const BwdP& p, dim3 grid, cudaStream_t st) {
   static bool configured = false;
@@ -1228,6 +1435,9 @@ extern "C" int ppx_mlp3_tc_fwd(const float* X, int ldx, int M, int D, int H, int
   for (int g = 0; g < G; ++g) { p.W3[g] = W3[g]; p.b3[g] = b3[g]; p.o[g] = outs[g]; p.out[g] = out[g]; }
   dim3 grid((unsigned)mt::fwd_grid(M, G), (unsigned)G);
   cudaStream_t st = (cudaStream_t)stream;
+  static int v1 = -1;
+  if (v1 < 0) { const char* e = getenv("PPX_MLP_TC_FWD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }
+  if (!v1 && D <= 16) return mt::dp_of(D) == 8 ? mt::launch_fwd2<8>(p, grid, st) : mt::launch_fwd2<16>(p, grid, st);
   switch (mt::dp_of(D)) {
     case 8: return mt::launch_fwd<8>(p, grid, st);
     case 16: return mt::launch_fwd<16>(p, grid, st);

@@ -50,7 +50,10 @@ class EvolutionStrategy(object):
         self._ws = None
         self._noise = None
         self._noise_size, self._noise_seed = int(noise_table_size), int(noise_seed)
-        self._rng = np.random.RandomState(noise_seed + 1)
+        self._draw = torch.zeros(1, dtype=torch.int64, device=self.device)        # population draws made so far (device-side)
+        self._px = False                                                          # PeerExchange for the sharded update | None
+        self._graphs = {}
+        self.update_mode = "single"
 
     # ---- state views ----
     @property
@@ -84,12 +87,15 @@ class EvolutionStrategy(object):
             L.call("ppx_noise_fill", self._noise.data_ptr(), self._noise_size, self._noise_seed, L.stream())
         return self._noise
 
-    def _get_population(self):
-        """:172-182.  Returns int64 offsets [P] (multiples of 4, so rows are 16-byte aligned) into the table."""
+    def _get_population(self, out=None):
+        """:172-182.  Returns int64 offsets [P] (multiples of 4, so rows are 16-byte aligned) into the table, drawn on the
+        device (Philox keyed by the noise seed, counter = (member, draw number)): no host RNG, no H2D copy, and every rank
+        of a sharded run draws the identical population."""
         self.noise_table()
-        hi = (self._noise_size - self.D) // 4
-        off = self._rng.randint(0, hi, size=self.POPULATION_SIZE).astype(np.int64) * 4
-        return torch.as_tensor(off).to(self.device)
+        off = torch.empty(self.POPULATION_SIZE, dtype=torch.int64, device=self.device) if out is None else out
+        L.call("ppx_es_offsets", self._noise_seed + 1, self._draw.data_ptr(), self.POPULATION_SIZE, self._noise_size, self.D,
+               off.data_ptr(), L.stream())
+        return off
 
     def _as_eps(self, population):
         """-> (noise tensor f32, offsets tensor or None)."""
@@ -191,16 +197,84 @@ class EvolutionStrategy(object):
             else rewards.to(self.device, torch.float64)
         need = L.call("ppx_es_update_workspace", P, self.D)
         if self._ws is None or self._ws.numel() * 8 < need:
-            self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=self.device)
+            self._ws = torch.zeros(need // 8 + 1, dtype=torch.float64, device=self.device)     # holds self re-arming tickets
         nov_dev = None
         if isinstance(novelty, torch.Tensor):
             nov_dev = novelty.to(self.device, torch.float64).reshape(-1)[:1].contiguous()
+        W, rk = D.world_size(), D.rank()
+        px = self._peer_exchange() if (W > 1 and self.fitness_shaping != "centered_rank" and P % W == 0) else None
+        if px is not None:
+            # sharded update: identical z-scores everywhere, GEMV over this rank's P/W members only, one fused
+            # barrier + rank-ordered sum + apply over NVLink peer memory (theta / lr stay bit-identical replicas)
+            self.update_mode = "sharded: partial GEMV over P/W members + fused peer-memory all-reduce of the update"
+            L.call("ppx_es_update_sharded", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
+                   r.data_ptr(), P, rk * (P // W), P // W, self.D, float(self.SIGMA), float(self.novelty_param),
+                   float(novelty) if (novelty is not None and nov_dev is None) else 0.0,
+                   nov_dev.data_ptr() if nov_dev is not None else None, int(novelty is not None), float(self.decay),
+                   self._lr.data_ptr(), self._status.data_ptr(), self._ws.data_ptr(), self._dtheta.data_ptr(), px.peer_grad,
+                   px.peer_flags[2], px.W, px.rank, px.seq[2], px.status_ptr, L.stream())
+            return
+        self.update_mode = "single" if W == 1 else "replicated"
         L.call("ppx_es_update", self.theta.data_ptr(), noise.data_ptr(), off.data_ptr() if off is not None else None,
                r.data_ptr(), P, self.D, float(self.SIGMA), float(self.novelty_param),
                float(novelty) if (novelty is not None and nov_dev is None) else 0.0,
                nov_dev.data_ptr() if nov_dev is not None else None, int(novelty is not None),
                int(self.fitness_shaping == "centered_rank"), float(self.decay), self._lr.data_ptr(),
                self._status.data_ptr(), self._ws.data_ptr(), L.stream())
+
+    def _peer_exchange(self):
+        if self._px is False:
+            self._px = D.peer_exchange_or_none(2 * self.D, self.device, L.call("ppx_p2p_max_params"))
+            if self._px is not None:
+                self._dtheta = self._px.grad.view(torch.float64)                  # this rank's partial update, peer-visible
+        return self._px
+
+    # ---- ask / tell: the two device-side halves of one ES iteration, each replayed as ONE CUDA graph ----
+    def _graph(self, key, fn):
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "warm"
+            return fn()
+        if ent == "warm":
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = fn()
+            ent = (g, L.launch_count() - n0, out)
+            L.extra_launches -= ent[1]
+            self._graphs[key] = ent
+        ent[0].replay()
+        L.extra_launches += ent[1]
+        return ent[2]
+
+    def ask(self):
+        """First half of an iteration (:172-182, :137-145): draw the population and form theta + sigma*eps for THIS rank's
+        members.  Returns (offsets [P] int64, weights [P/W, D] f32) -- static buffers, overwritten by the next ask()."""
+        W = D.world_size()
+        if not hasattr(self, "_ask_off"):
+            self.noise_table()
+            self._ask_off = torch.empty(self.POPULATION_SIZE, dtype=torch.int64, device=self.device)
+
+        def fn():
+            pop = self._get_population(out=self._ask_off)
+            return pop, self.perturb_all(self.shard_population(pop) if W > 1 else pop)
+        return self._graph("ask", fn)
+
+    def tell(self, local_rewards, archive=None, queries=None):
+        """Second half (:217-239, :264-281, :318-325): exchange the fitness of the rank-local members, novelty k-NN of
+        `queries` against `archive` (the first query's novelty enters the update, as in run()), parameter update.
+        `local_rewards` / `archive` / `queries` must be persistent CUDA tensors (their addresses are captured)."""
+        key = ("tell", local_rewards.data_ptr(), archive.data_ptr() if archive is not None else 0,
+               queries.data_ptr() if queries is not None else 0, archive.shape[0] if archive is not None else 0)
+
+        def fn():
+            r_all = self.gather_fitness(local_rewards)
+            nov = None
+            if archive is not None:
+                _, nov = self.novelty_batch(archive, queries)
+                nov = nov[0:1]
+            self._update_weights(r_all, self._ask_off, novelty=nov)
+        return self._graph(key, fn)
 
     @property
     def update_skipped(self):

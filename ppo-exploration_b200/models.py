@@ -440,6 +440,7 @@ class Policy:
         self.scratch = _Scratch(self.device)
         self.mlp = ParallelMLP(self.bank, self.names, self.state_dim, hidden_size, self.outs, self.scratch)
         self.net = self                                           # reference code reaches policy.net.parameters()
+        self._sample_seed, self._draws = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF, 0
         self._init_like_reference()
 
     # ---- initialisation / weight exchange ----
@@ -502,12 +503,23 @@ class Policy:
         return torch.distributions.Normal(mean, torch.exp(self.bank.view("action_log_std").expand_as(mean)))
 
     def act(self, obs):
-        """models.py:30-50 / 75-99 (rollout side; sampling uses torch's CUDA generator)."""
+        """models.py:30-50 / 75-99 (rollout side).  Forward on the fused kernels, then ONE launch builds the action
+        distribution, draws an action per env and evaluates its log-probability (sample.cu; Philox stream keyed by the
+        torch seed at construction, one draw number per call) -- no torch.distributions kernels, and `obs` may already
+        be a CUDA tensor (e.g. from ppx VecNormalize), in which case nothing crosses the host here.  Returns CUDA tensors
+        shaped like the reference's: actions [N,A] (Box, f64 as the buffer stores them) / [N] int64 (Discrete),
+        log-probs [N,A] / [N], values [N]."""
         obs = torch.as_tensor(np.asarray(obs) if not isinstance(obs, torch.Tensor) else obs).to(self.device).float()
         outs = self.forward_raw(obs.contiguous())
-        dist = self._dist(outs[0])
-        actions = dist.sample()
-        lp = dist.log_prob(actions)
+        N, A = outs[0].shape
+        discrete = self.action_type == "Discrete"
+        actions = torch.empty((N,) if discrete else (N, A), dtype=torch.float64, device=self.device)
+        lp = torch.empty((N,) if discrete else (N, A), dtype=torch.float32, device=self.device)
+        self._draws += 1
+        L.call("ppx_policy_sample", outs[0].data_ptr(), None if discrete else self.bank.p("action_log_std"), N, A, int(discrete),
+               self._sample_seed, self._draws, actions.data_ptr(), lp.data_ptr(), L.stream())
+        if discrete:
+            actions = actions.long()
         vals = [o.squeeze(-1).clone() for o in outs[1:]]
         if self.intrinsic:
             return actions, vals[0], vals[1], lp

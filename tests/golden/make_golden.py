@@ -308,6 +308,21 @@ def g_rnd_bonus():
     save("rnd_bonus", **out)
 
 
+# ------------------------------------------------------------------ logger CSV schema
+LOGGER_DUMPS = [{"time/total timesteps": 2048, "rollout/ep_rew_mean": 1.5},
+                {"time/total timesteps": 4096, "train/value_loss": 0.25, "train/entropy_loss": -1.4, "plain": 3},
+                {"rollout/ep_rew_mean": 2.5, "train/value_loss": 0.125}]
+
+
+def g_logger():
+    """The reference's CSVOutputFormat (logger.py:13-52) fed a fixed record sequence -> tests/golden/logger_ref.csv"""
+    path = os.path.join(HERE, "logger_ref.csv")
+    w = reflogger.CSVOutputFormat(path)
+    for d in LOGGER_DUMPS:
+        w.write(dict(d))
+    w.close()
+
+
 # ------------------------------------------------------------------ ES
 def g_es():
     class E:
@@ -370,7 +385,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "es_predict":           # added later: regenerate this fixture alone
         g_es_predict()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "logger":               # added in round 2
+        g_logger()
+        sys.exit(0)
     g_es_predict()
+    g_logger()
     g_gae(); g_gae_dual(); g_discount(); g_simhash(); g_get(); g_rnd_bonus(); g_es()
     # C1: the reference's own CPU-runnable case (8 envs x 128 steps, obs 4, Discrete(2), defaults)
     g_ppo("ppo_c1_discrete", 8, 4, ref_shim.Discrete(2), seed=1, nstep=128)

@@ -7,7 +7,9 @@ all envs, inside the same processes (the 1-GPU answer is computed by every rank 
   * shard_shuffle="local": replicas bit-identical;
   * RolloutStorage.sim_hash_sharded: rewards and the count table equal the 1-GPU ones bit for bit;
   * sharded RunningMeanStd / RND rollout bonus: moments and bonuses equal the 1-GPU ones;
-  * PPO_RND.train and PPO_ICM.train (halo row for the shuffled-consecutive pairing), "global".
+  * PPO_RND.train and PPO_ICM.train (halo row for the shuffled-consecutive pairing), "global";
+  * ES ask / tell: identical populations on every rank, the sharded update (partial GEMV + peer-memory all-reduce) equals
+    the single-GPU update to 1e-12 and leaves bit-identical replicas.
 Run on the box with:  gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu"""
 import os
 import socket
@@ -166,6 +168,34 @@ def _worker(rank, world, port):
         w_ref, l_ref = icm(N * world, fulld, lv)
     w_g, l_g = icm(N, shard(fulld), lv[sl])
     check("ICM global", w_g, w_ref, l_g[:, :6], l_ref[:, :6], wtol=5e-4)
+    # ---------------- ES: population sharded over the ranks, fused peer-memory all-reduce of the update ----------------
+    def es_run(sharded):
+        np.random.seed(21)
+        es = ppx.EvolutionStrategy(obs_dim=8, n_actions=2, hidden_sizes=(64, 64), population_size=1000, sigma=0.1, learning_rate=0.01,
+                                   decay=0.9995, novelty_param=0.5, device=dev, noise_table_size=1 << 22, noise_seed=3)
+        fit = torch.as_tensor(np.random.RandomState(22).randn(1000)).to(dev)
+        arch = torch.as_tensor(np.random.RandomState(23).randn(500, 2)).to(dev)
+        qs = torch.as_tensor(np.random.RandomState(24).randn(2, 2)).to(dev)
+        mine = fit[rank * 500:(rank + 1) * 500].contiguous() if sharded else fit
+        pops = []
+        for _ in range(4):                                     # eager, capture, two graph replays
+            pop, w = es.ask()
+            pops.append(pop.clone())
+            es.tell(mine, arch, qs)
+        torch.cuda.synchronize()
+        return es.theta.clone(), es.learning_rate, torch.stack(pops), w.clone(), es.update_mode
+
+    with _single():
+        th_ref, lr_ref, pops_ref, w_ref1, _ = es_run(False)
+    th_s, lr_s, pops_s, w_s, mode = es_run(True)
+    assert mode.startswith("sharded"), mode
+    assert torch.equal(pops_s, pops_ref), "ranks must draw the population of the 1-GPU run"
+    assert torch.equal(w_s, w_ref1[rank * 500:(rank + 1) * 500]), "perturbed weights of this rank's members"
+    np.testing.assert_allclose(th_s.cpu().numpy(), th_ref.cpu().numpy(), rtol=1e-12, atol=1e-14, err_msg="sharded ES update")
+    assert abs(lr_s - lr_ref) < 1e-15
+    allt = [torch.empty_like(th_s) for _ in range(world)]
+    dist.all_gather(allt, th_s)
+    assert all(torch.equal(allt[0], a) for a in allt), "ES replicas diverged"
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)                                                # NCCL communicators referenced by captured graphs do not tear down cleanly

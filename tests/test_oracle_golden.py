@@ -296,3 +296,34 @@ def test_parallel_fisher_yates_equals_sequential():
         key, pos, j = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int(int(st[2])), np.zeros(n, np.int32)
         L.call("ppx_np_shuffle_draws32", key.ctypes.data, C.byref(pos), n, j.ctypes.data)
         assert np.array_equal(OR.fy_apply_parallel(j), want), n
+
+
+def test_logger_csv_schema_matches_reference(tmp_path):
+    """ppo-exploration_b200/logger.py writes the reference's CSV schema (logger.py:13-52): same columns ('group/name' ->
+    'name'), same cells per row, earlier rows padded when the header grows.  The fixture was written by the reference's
+    own CSVOutputFormat (tests/golden/make_golden.py logger); the reference appends new columns in set order (hash
+    dependent), so the comparison is by column name, which is how pandas / the notebook read the file."""
+    import csv
+    import importlib.util
+    import os
+    from conftest import GOLDEN, ROOT
+    spec = importlib.util.spec_from_file_location("ppx_logger", os.path.join(ROOT, "ppo-exploration_b200", "logger.py"))
+    lg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lg)
+    dumps = [{"time/total timesteps": 2048, "rollout/ep_rew_mean": 1.5},
+             {"time/total timesteps": 4096, "train/value_loss": 0.25, "train/entropy_loss": -1.4, "plain": 3},
+             {"rollout/ep_rew_mean": 2.5, "train/value_loss": 0.125}]
+    path = str(tmp_path / "run.csv")
+    log = lg.Logger([lg.CSVOutputFormat(path)])
+    for d in dumps:
+        for k, v in d.items():
+            log.record(k, v)
+        log.dump()
+    log.close()
+
+    def table(p):
+        with open(p) as f:
+            rows = list(csv.DictReader(f))
+        return [{k: v for k, v in r.items()} for r in rows]
+    got, want = table(path), table(os.path.join(GOLDEN, "logger_ref.csv"))
+    assert got == want
