@@ -133,17 +133,9 @@ __device__ __forceinline__ void stage_weight(uint32_t raw, uint32_t lo, const fl
 // Blocks of 32 k are A_KB / B_KB bytes apart.  Small terms first, then the hi.hi pass.  The four base descriptors are
 // built once; every MMA only adds a compile-time constant to the 14-bit address field.
 template <int A_KB, int B_KB, int KSTEPS, int MM = 128>
-__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, int dbg = 0) {
+__device__ __forceinline__ void issue_3xtf32(uint32_t tacc, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo) {
   constexpr uint32_t idesc = make_idesc(64, MM);
   const uint64_t dar = make_desc(a_raw), dal = make_desc(a_lo), dbr = make_desc(b_raw), dbl = make_desc(b_lo);
-  if (dbg & 1) {                             // timing experiment only (PPX_MLP_TC_DBG): hi.hi pass alone, wrong to ~1e-3
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
-      umma_tf32(tacc, dar + oa, dbr + ob, idesc, ks ? 1u : 0u);
-    }
-    return;
-  }
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
     const uint64_t oa = (uint64_t)(((ks >> 2) * A_KB + (ks & 3) * 32) >> 4), ob = (uint64_t)(((ks >> 2) * B_KB + (ks & 3) * 32) >> 4);
@@ -502,7 +494,6 @@ struct BwdP {
   float* ws2;        // [G][nCta][H*H]   dW2 partials
   float* wsr;        // [G][nCta][RS]    dW1 | db1 | db2 | dW3 | db3 partials
   int RS;
-  int dbg;           // timing experiments (PPX_MLP_TC_DBG): 1 = single-pass MMAs, 2 = skip dW3/db3 sums, 4 = skip dW1/db1/db2 sums
 };
 
 // byte offset of element (s, c) of the fp32 staging tile S [128][64] (16-byte chunks XOR-swizzled by the row)
@@ -634,8 +625,8 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
         if (warp == 0) {
           tc_fence_after();
           if (elect_one()) {
-            if (which == 2) { issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo, p.dbg); umma_commit(barG2); }
-            else { issue_3xtf32<8192, 8192, 16, 64>(tmem + 64, V_raw, V_lo, U_raw, U_lo, p.dbg); umma_commit(barG1); }
+            if (which == 2) { issue_3xtf32<16384, 8192, 8>(tmem, U_raw, U_lo, W_raw, W_lo); umma_commit(barG2); }
+            else { issue_3xtf32<8192, 8192, 16, 64>(tmem + 64, V_raw, V_lo, U_raw, U_lo); umma_commit(barG1); }
           }
           __syncwarp();
         }
@@ -732,7 +723,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       if constexpr (MMAW) bar_compute();      // [B2] X / dOut / H2 published to the thin reductions
       // ---- T3 (under GEMM 2): H1^T images; dW3 / db3 sums over this thread's SPG samples ----
       store_col_images_cw<CW>(V_raw, 32768u, c0, s, h1);
-      if (!(p.dbg & 2)) {
+      {
         float t3[MAXO] = {0.f, 0.f, 0.f, 0.f};
         // element (ss = sg*SPG + r, tc): the row swizzle (ss & 7) == (r & 7) is an XOR of the base with a constant
         const uint32_t sS = S + (uint32_t)(sg * SPG * 256) + (uint32_t)(((tc >> 2) << 4) | ((tc & 3) << 2));
@@ -773,7 +764,7 @@ __global__ void __launch_bounds__(128 * (64 / CW) + (MMAW ? 32 : 0), 1) mlp3_tc_
       if constexpr (MMAW) bar_compute();      // [B4] dP1 (S) and the dP2^T image published to the thin reductions
       // ---- T5 (under GEMM 1): next tile's loads in flight; dW1 / db1 / db2 sums ----
       if (tile + (int)gridDim.x < p.nTiles) prefetch(tile + gridDim.x);
-      if (!(p.dbg & 4)) {
+      {
         float t1[DP], tb = 0.f, t2 = 0.f;
 #pragma unroll
         for (int k = 0; k < DP; ++k) t1[k] = 0.f;
@@ -1387,26 +1378,6 @@ int launch_bwd2(const BwdP& p, dim3 grid, cudaStream_t st) {
   mlp3_tc_bwd2_kernel<DP, CW><<<grid, v2::Cfg<CW>::NTH, smem, st>>>(p);
   return after_launch("mlp3_tc_bwd2");
 }
-inline int bwd2_cw() {                       // PPX_MLP_TC_CW2=16: 16 compute warps with 16 columns per thread instead of 8 x 32
-  static int cw = 0;
-  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW2"); cw = (e && atoi(e) == 16) ? 16 : 32; }
-  return cw;
-}
-inline bool bwd_v1() {                       // PPX_MLP_TC_V1=1: the round-1 backward (comparison runs)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PPX_MLP_TC_V1"); v = (e && atoi(e) == 1) ? 1 : 0; }
-  return v == 1;
-}
-inline bool bwd_mmaw() {                     // PPX_MLP_TC_MMAW=1: dedicated MMA-issue warp (costs registers: 17 / 9 warps per CTA)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PPX_MLP_TC_MMAW"); v = (e && atoi(e) == 1) ? 1 : 0; }
-  return v == 1;
-}
-inline int bwd_cw() {                        // PPX_MLP_TC_CW=16: 16 compute warps per CTA (16 columns per thread) instead of 8
-  static int cw = 0;
-  if (!cw) { const char* e = getenv("PPX_MLP_TC_CW"); cw = (e && atoi(e) == 16) ? 16 : 32; }
-  return cw;
-}
 
 }  // namespace mt
 }  // namespace ppx
@@ -1436,8 +1407,8 @@ extern "C" int ppx_mlp3_tc_fwd(const float* X, int ldx, int M, int D, int H, int
   dim3 grid((unsigned)mt::fwd_grid(M, G), (unsigned)G);
   cudaStream_t st = (cudaStream_t)stream;
   static int v1 = -1;
-  if (v1 < 0) { const char* e = getenv("PPX_MLP_TC_FWD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }
-  if (!v1 && D <= 16) return mt::dp_of(D) == 8 ? mt::launch_fwd2<8>(p, grid, st) : mt::launch_fwd2<16>(p, grid, st);
+  if (v1 < 0) { const char* e = getenv("PPX_MLP_TC_FWD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }   // comparison runs only
+  if (D <= 16 && !v1) return mt::dp_of(D) == 8 ? mt::launch_fwd2<8>(p, grid, st) : mt::launch_fwd2<16>(p, grid, st);
   switch (mt::dp_of(D)) {
     case 8: return mt::launch_fwd<8>(p, grid, st);
     case 16: return mt::launch_fwd<16>(p, grid, st);
@@ -1466,7 +1437,6 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
   p.X = X; p.ldx = ldx; p.M = M; p.D = D; p.G = G; p.nTiles = mt::n_tiles(M); p.W2 = W2; p.H1t = H1t; p.H2t = H2t;
   p.ws2 = workspace; p.wsr = workspace + (size_t)G * n * mt::H * mt::H; p.RS = RS;
   p.vh_clip = clip_range; p.vh_Bt = (float)(B_total > 0 ? B_total : M);
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PPX_MLP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   for (int g = 0; g < G; ++g) {
     p.W3[g] = W3[g]; p.o[g] = outs[g]; p.dOut[g] = dOut[g];
     if (vh && vh[g].values) {
@@ -1480,22 +1450,11 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
   dim3 grid((unsigned)n, (unsigned)G);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  const bool w16 = mt::bwd_cw() == 16, mw = mt::bwd_mmaw();
-#define PPX_BWD(DPV)                                                                                          \
-  rc = w16 ? (mw ? mt::launch_bwd<DPV, 16, true>(p, grid, st) : mt::launch_bwd<DPV, 16, false>(p, grid, st))   \
-           : (mw ? mt::launch_bwd<DPV, 32, true>(p, grid, st) : mt::launch_bwd<DPV, 32, false>(p, grid, st))
-  if (!mt::bwd_v1() && D <= 16) {            // v2: A of GEMM 2 from tensor memory, MN-major images, dW1 / db1 on the tensor pipe
-    const bool w32 = mt::bwd2_cw() == 32;
-    if (mt::dp_of(D) == 8) rc = w32 ? mt::launch_bwd2<8, 32>(p, grid, st) : mt::launch_bwd2<8, 16>(p, grid, st);
-    else rc = w32 ? mt::launch_bwd2<16, 32>(p, grid, st) : mt::launch_bwd2<16, 16>(p, grid, st);
-  } else {
-    switch (mt::dp_of(D)) {
-      case 8: PPX_BWD(8); break;
-      case 16: PPX_BWD(16); break;
-      default: PPX_BWD(32); break;
-    }
+  if (D <= 16) {            // v2: A of GEMM 2 from tensor memory, MN-major images, dW1 / db1 on the tensor pipe
+    rc = mt::dp_of(D) == 8 ? mt::launch_bwd2<8, 32>(p, grid, st) : mt::launch_bwd2<16, 32>(p, grid, st);
+  } else {                  // 16 < D <= 32: the round-1 kernel (its operand images do not fit next to a 40-row X^T image)
+    rc = mt::launch_bwd<32, 32, false>(p, grid, st);
   }
-#undef PPX_BWD
   if (rc) return rc;
   return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
                                 (sumsq_partials && !adam) ? step_dev : nullptr, adam, st);

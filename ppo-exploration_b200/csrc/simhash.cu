@@ -88,9 +88,14 @@ __device__ __forceinline__ uint64_t code_of(const double* __restrict__ A, const 
   return code;
 }
 
-// codes (+ bucket ids).  DMAX > 0: A staged in shared memory as f64, the observation rows held in registers, two
-// observations per thread so every shared-memory load of A feeds two FMAs (same sequential fma order over d as
-// code_of -> identical bits).  DMAX == 0: any D, straight from global / L1.
+// codes (+ bucket ids).  The reference's sign test is on the f64 dot product (buffer.py:194: f64 A, f32 obs promoted).
+// DMAX > 0 (D <= 16): the dot products run in F32 with a rigorous error bound and fall back to the exact f64 fma chain of
+// code_of only when the f32 result is too close to zero to decide the sign -- bit-identical codes at FFMA instead of DFMA
+// speed.  With a_f = fl32(a) (relative error u = 2^-24) and a D-term f32 fma chain,
+//   |s_f32 - s_ref| <= (D + 2) u (1 + o(1)) sum_d |a_d| |x_d| <= (D + 3) u L1(a_b) max_d |x_d|  =: bound_b * xmax,
+// so |s_f32| > bound decides; the reference's own f64 rounding (D 2^-53) is far inside the margin.  A (f32) and the
+// per-bit bounds are staged in shared memory; a thread owns 4 observations (registers), so one 16-byte read of A feeds
+// 16 FMAs.  DMAX == 0: any D, the exact chain straight from global / L1.
 template <int DMAX>
 __global__ void __launch_bounds__(128)
 codes_kernel(const double* __restrict__ A, const float* __restrict__ obs, int k, int D, int64_t n,
@@ -104,39 +109,59 @@ codes_kernel(const double* __restrict__ A, const float* __restrict__ obs, int k,
     }
     return;
   }
-  constexpr int DM = DMAX > 0 ? DMAX : 1;
-  __shared__ double As[64 * DM];
+  constexpr int DM = DMAX > 0 ? DMAX : 4, OB = 4;
+  __shared__ __align__(16) float Af[64 * DM];
+  __shared__ float bnd[64];
   for (int e = threadIdx.x; e < k * DM; e += blockDim.x) {
     const int b = e / DM, d = e - b * DM;
-    As[e] = d < D ? A[(size_t)b * D + d] : 0.0;
+    Af[e] = d < D ? (float)A[(size_t)b * D + d] : 0.f;
+  }
+  for (int b = threadIdx.x; b < k; b += blockDim.x) {
+    double l1 = 0.0;
+    for (int d = 0; d < D; ++d) l1 += fabs(A[(size_t)b * D + d]);
+    bnd[b] = (float)(l1 * (double)(D + 3) * 5.9604644775390625e-08 * 1.0001);      // (D + 3) 2^-24 L1(a_b), rounded up
   }
   __syncthreads();
-  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * OB;
   if (i0 >= n) return;
-  const bool two = i0 + 1 < n;
-  double x0[DM], x1[DM];
+  float x[OB][DM], xmax[OB];
 #pragma unroll
-  for (int d = 0; d < DM; ++d) {
-    x0[d] = d < D ? (double)ld_stream(obs + i0 * D + d) : 0.0;
-    x1[d] = (two && d < D) ? (double)ld_stream(obs + (i0 + 1) * D + d) : 0.0;
-  }
-  uint64_t c0 = 0, c1 = 0;
-  for (int b = 0; b < k; ++b) {
-    double a0 = 0.0, a1 = 0.0;
+  for (int t = 0; t < OB; ++t) {
+    xmax[t] = 0.f;
 #pragma unroll
     for (int d = 0; d < DM; ++d) {
-      const double a = As[b * DM + d];
-      if (d < D) { a0 = fma(a, x0[d], a0); a1 = fma(a, x1[d], a1); }
+      x[t][d] = (i0 + t < n && d < D) ? ld_stream(obs + (i0 + t) * D + d) : 0.f;
+      xmax[t] = fmaxf(xmax[t], fabsf(x[t][d]));
     }
-    c0 |= (uint64_t)(a0 > 0.0) << b;
-    c1 |= (uint64_t)(a1 > 0.0) << b;
   }
-  codes[i0] = c0;
-  if (bucket) bucket[i0] = (uint16_t)bucket_of(c0, nb);
-  if (two) {
-    codes[i0 + 1] = c1;
-    if (bucket) bucket[i0 + 1] = (uint16_t)bucket_of(c1, nb);
+  uint64_t c[OB] = {0, 0, 0, 0};
+  for (int b = 0; b < k; ++b) {
+    float s[OB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < DM; d += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(&Af[b * DM + d]);
+#pragma unroll
+      for (int t = 0; t < OB; ++t)
+        s[t] = fmaf(a.w, x[t][d + 3], fmaf(a.z, x[t][d + 2], fmaf(a.y, x[t][d + 1], fmaf(a.x, x[t][d], s[t]))));
+    }
+    const float bb = bnd[b];
+#pragma unroll
+    for (int t = 0; t < OB; ++t) {
+      bool bit = s[t] > 0.f;
+      if (!(fabsf(s[t]) > bb * xmax[t])) {                          // too close to call in f32 (rare): the reference's own chain
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc = fma(__ldg(A + (size_t)b * D + d), (double)__ldg(obs + (i0 + t) * D + d), acc);
+        bit = acc > 0.0;
+      }
+      c[t] |= (uint64_t)bit << b;
+    }
   }
+#pragma unroll
+  for (int t = 0; t < OB; ++t)
+    if (i0 + t < n) {
+      codes[i0 + t] = c[t];
+      if (bucket) bucket[i0 + t] = (uint16_t)bucket_of(c[t], nb);
+    }
 }
 
 __global__ void __launch_bounds__(256) bucket_ids_kernel(const uint64_t* __restrict__ codes, int64_t n, uint16_t* __restrict__ bucket, uint32_t nb) {
@@ -520,8 +545,8 @@ int ensure_scratch(ppx_count_table* t, int64_t n) {
 
 int launch_codes(const double* A, const float* obs, int k, int D, int64_t n, uint64_t* codes, uint16_t* bucket, uint32_t nb,
                  cudaStream_t st) {
-  if (D <= 8) codes_kernel<8><<<(unsigned)ceil_div(n, 256), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
-  else if (D <= 16) codes_kernel<16><<<(unsigned)ceil_div(n, 256), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
+  if (D <= 8) codes_kernel<8><<<(unsigned)ceil_div(n, 512), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
+  else if (D <= 16) codes_kernel<16><<<(unsigned)ceil_div(n, 512), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
   else codes_kernel<0><<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(A, obs, k, D, n, codes, bucket, nb);
   return after_launch("simhash codes");
 }

@@ -103,3 +103,29 @@ def test_full_size_c2_checksum():
     ref = {}
     want = OR.count_update_codes(ref, codes.cpu().numpy().view(np.uint64)[:50000])
     assert np.array_equal(counts[:50000].astype(np.uint32), want)
+
+
+@pytest.mark.parametrize("D,k", [(8, 64), (13, 32), (16, 64)])
+def test_codes_exact_when_projections_are_nearly_zero(D, k):
+    """The codes kernel evaluates the projections in f32 and falls back to the reference's f64 chain when the f32 value
+    cannot decide the sign.  Adversarial inputs: observations (almost) orthogonal to rows of A, i.e. projections of the
+    order of the f32 rounding error and below, of both signs, and exact zeros -- every bit must still equal
+    (np.dot(A, obs.T).T > 0) of buffer.py:194."""
+    rs = np.random.RandomState(D * 100 + k)
+    buf = _buf(k, D, 4)
+    A = rs.randn(k, D)
+    buf.A = A
+    n = 20000
+    obs = rs.randn(n, D)
+    rows = rs.randint(0, k, size=n)
+    a = A[rows]
+    obs -= (np.sum(obs * a, axis=1) / np.sum(a * a, axis=1))[:, None] * a           # orthogonal to one row of A (in f64)
+    eps = np.concatenate([np.zeros(n // 5), 10.0 ** rs.uniform(-12, -5, size=n - n // 5) * rs.choice([-1, 1], size=n - n // 5)])
+    obs += eps[:, None] * a
+    obs = obs.astype(np.float32)
+    obs[:50] = 0.0                                                                 # all projections exactly zero
+    want = OR.pack_bits(OR.simhash_bits(A, obs))
+    got = buf.sim_hash_codes(obs).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    proj = np.abs(np.dot(A, obs.astype(np.float64).T))
+    assert (proj < 1e-6).sum() > n // 2, "the test must exercise the near-zero region"
