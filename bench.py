@@ -443,8 +443,8 @@ def es_step_bench(torch, ppx, dev, world, rank, steps=20, warmup=5):
     queries = torch.randn(2, 2, dtype=torch.float64, device=dev, generator=g)
     fit_local = torch.randn(P // world, dtype=torch.float64, device=dev, generator=g)
     def step():
-        pop, w = es.ask()                                       # population drawn on the device; [P/W, D] f32 for the evaluators
-        es.tell(fit_local, archive, queries)                    # fitness exchange, novelty k-NN, (sharded) update
+        pop, w, nov = es.ask(archive, queries)                  # population drawn on the device, [P/W, D] f32 for the evaluators, k-NN novelty
+        es.tell(fit_local)                                      # fitness exchange, (sharded) update
         return w
     for _ in range(warmup):
         step()

@@ -437,7 +437,8 @@ int ppx_es_update(double* theta, const float* noise, const int64_t* offsets, con
                   non-NULL: the k-NN result stays on the device, no host round trip */, int use_novelty, int rank_mode,
                   double decay, double* lr_inout, int* status_out, void* workspace, void* stream);
 /* The population of one ES iteration as noise-table offsets drawn ON THE DEVICE (build-side design: the reference draws
- * fresh randn per member, :172-182): Philox4x32-10 keyed by `seed`, counter = (member, *draw_dev); *draw_dev is bumped,
+ * fresh randn per member, :172-182): Philox4x32-10 keyed by `seed`, counter = (member, draw_dev[0]); draw_dev[0] is bumped
+ * (draw_dev[1] is a zeroed ticket word),
  * so the launch replays from a CUDA graph and ranks sharing (seed, draw number) draw the identical population.
  * offsets_out[p] is a multiple of 4 in [0, table_size - D]. */
 int ppx_es_offsets(uint64_t seed, int64_t* draw_dev, int P, int64_t table_size, int D, int64_t* offsets_out, void* stream);

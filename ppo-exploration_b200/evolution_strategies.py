@@ -50,7 +50,7 @@ class EvolutionStrategy(object):
         self._ws = None
         self._noise = None
         self._noise_size, self._noise_seed = int(noise_table_size), int(noise_seed)
-        self._draw = torch.zeros(1, dtype=torch.int64, device=self.device)        # population draws made so far (device-side)
+        self._draw = torch.zeros(2, dtype=torch.int64, device=self.device)        # [population draws made so far, ticket word]
         self._px = False                                                          # PeerExchange for the sharded update | None
         self._graphs = {}
         self.update_mode = "single"
@@ -247,32 +247,44 @@ class EvolutionStrategy(object):
         L.extra_launches += ent[1]
         return ent[2]
 
-    def ask(self):
-        """First half of an iteration (:172-182, :137-145): draw the population and form theta + sigma*eps for THIS rank's
-        members.  Returns (offsets [P] int64, weights [P/W, D] f32) -- static buffers, overwritten by the next ask()."""
+    def ask(self, archive=None, queries=None):
+        """First half of an iteration: draw the population (:172-182), form theta + sigma*eps for THIS rank's members
+        (:137-145) and -- as run() does before it evaluates the population (:318-325) -- the novelty of `queries` against
+        the behaviour `archive` (k-NN on a forked stream, under the perturbation).  One CUDA graph.  Returns (offsets [P]
+        int64, weights [P/W, D] f32, novelties [Q] f64 | None): static buffers, overwritten by the next ask()."""
         W = D.world_size()
         if not hasattr(self, "_ask_off"):
             self.noise_table()
             self._ask_off = torch.empty(self.POPULATION_SIZE, dtype=torch.int64, device=self.device)
+            self._side = torch.cuda.Stream(device=self.device)
+        key = ("ask", archive.data_ptr() if archive is not None else 0, queries.data_ptr() if queries is not None else 0,
+               archive.shape[0] if archive is not None else 0)
 
         def fn():
+            nov = None
+            if archive is not None:
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    _, nov = self.novelty_batch(archive, queries)
             pop = self._get_population(out=self._ask_off)
-            return pop, self.perturb_all(self.shard_population(pop) if W > 1 else pop)
-        return self._graph("ask", fn)
+            w = self.perturb_all(self.shard_population(pop) if W > 1 else pop)
+            if archive is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
+            return pop, w, nov
+        out = self._graph(key, fn)
+        self._novelty = out[2]
+        return out
 
-    def tell(self, local_rewards, archive=None, queries=None):
-        """Second half (:217-239, :264-281, :318-325): exchange the fitness of the rank-local members, novelty k-NN of
-        `queries` against `archive` (the first query's novelty enters the update, as in run()), parameter update.
-        `local_rewards` / `archive` / `queries` must be persistent CUDA tensors (their addresses are captured)."""
-        key = ("tell", local_rewards.data_ptr(), archive.data_ptr() if archive is not None else 0,
-               queries.data_ptr() if queries is not None else 0, archive.shape[0] if archive is not None else 0)
+    def tell(self, local_rewards, brain=0):
+        """Second half (:217-239): exchange the fitness of the rank-local members and update the parameters with the
+        novelty of meta-population member `brain` computed by the last ask().  `local_rewards` must be a persistent CUDA
+        tensor (its address is captured)."""
+        key = ("tell", local_rewards.data_ptr(), int(brain), self._novelty is not None)
 
         def fn():
             r_all = self.gather_fitness(local_rewards)
-            nov = None
-            if archive is not None:
-                _, nov = self.novelty_batch(archive, queries)
-                nov = nov[0:1]
+            nov = self._novelty[brain:brain + 1] if self._novelty is not None else None
             self._update_weights(r_all, self._ask_off, novelty=nov)
         return self._graph(key, fn)
 

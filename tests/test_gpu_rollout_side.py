@@ -73,7 +73,8 @@ def test_vecnormalize_matches_restatement():
         np.testing.assert_allclose(r.cpu().numpy(), wr, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(vn.ret.cpu().numpy(), ref.ret, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(vn.ret_rms.var, ref.ret_rms.var, rtol=1e-12)
-    np.testing.assert_allclose(vn.obs_rms.mean, ref.obs_rms.mean, rtol=1e-12, atol=1e-14)
+    # (numpy averages the f32 observations in f32, the device in f64: 1e-6 as in the RunningMeanStd fixture test)
+    np.testing.assert_allclose(vn.obs_rms.mean, ref.obs_rms.mean, rtol=1e-6, atol=1e-7)
     raw = vn.get_original_obs()
     back = vn.unnormalize_obs(vn.normalize_obs(raw))
     inside = (vn.normalize_obs(raw).abs() < 9.99)

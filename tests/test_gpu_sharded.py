@@ -179,9 +179,9 @@ def _worker(rank, world, port):
         mine = fit[rank * 500:(rank + 1) * 500].contiguous() if sharded else fit
         pops = []
         for _ in range(4):                                     # eager, capture, two graph replays
-            pop, w = es.ask()
+            pop, w, _ = es.ask(arch, qs)
             pops.append(pop.clone())
-            es.tell(mine, arch, qs)
+            es.tell(mine)
         torch.cuda.synchronize()
         return es.theta.clone(), es.learning_rate, torch.stack(pops), w.clone(), es.update_mode
 

@@ -21,6 +21,6 @@ for _ in range(steps):
         _, nov = es.novelty_batch(archive, queries)
         es._update_weights(fit, pop, novelty=nov[0:1])
     else:
-        es.ask(); es.tell(fit, archive, queries)
+        es.ask(archive, queries); es.tell(fit)
 torch.cuda.synchronize()
 print("ok")
