@@ -28,11 +28,13 @@ struct GatherArgs {
 };
 constexpr int kStatMax = 4096;
 
-// flat index of the (global) env-major flatten (buffer.py:49-52) -> storage row
+// flat index of the (global) env-major flatten (buffer.py:49-52) -> storage row.  T*N < 2^31 (checked on the host): the
+// index arithmetic is 32-bit -- a 64-bit division costs ~70 instructions, and this decode runs once per gathered word.
 __device__ __forceinline__ int64_t row_of(int64_t i, int T, int N, int n_shard) {
-  const int64_t t = i % T, n = i / T;
-  if (n_shard <= 0) return t * N + n;
-  return ((n / n_shard) * T + t) * n_shard + n % n_shard;
+  const uint32_t u = (uint32_t)i, n = u / (uint32_t)T, t = u - n * (uint32_t)T;
+  if (n_shard <= 0) return (int64_t)(t * (uint32_t)N + n);
+  const uint32_t r = n / (uint32_t)n_shard;
+  return (int64_t)((r * (uint32_t)T + t) * (uint32_t)n_shard + (n - r * (uint32_t)n_shard));
 }
 // this launch's index slice (step cursor: one CUDA graph serves every minibatch of a train() call)
 __device__ __forceinline__ const int64_t* idx_of(const GatherArgs& a, const int64_t* idx) {
@@ -177,7 +179,7 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
                 void* stream) {
   PPX_REQUIRE(srcs_host && dsts_host && row_bytes_host && idx, "gather_minibatch: null pointer");
   PPX_REQUIRE(n_arrays >= 1 && n_arrays <= PPX_MAX_GATHER, "gather_minibatch: n_arrays=%d (1..%d)", n_arrays, PPX_MAX_GATHER);
-  PPX_REQUIRE(B >= 0 && T > 0 && N > 0, "gather_minibatch: B=%lld T=%d N=%d", (long long)B, T, N);
+  PPX_REQUIRE(B >= 0 && T > 0 && N > 0 && (int64_t)T * N < (1ll << 31), "gather_minibatch: B=%lld T=%d N=%d", (long long)B, T, N);
   PPX_REQUIRE(n_stats >= 0 && n_stats <= 2, "gather_minibatch: at most two statistics fields");
   if (B == 0) return PPX_OK;
   ppx::GatherArgs args;

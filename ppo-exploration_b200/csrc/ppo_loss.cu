@@ -216,20 +216,29 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
       is2 += (double)(e2 * e2);
     }
   }
+  // per-CTA partial record: ONE combined reduction (warp shuffles of every quantity, one shared-memory exchange, warp 0
+  // finishes) instead of 6 + A sequential block_sum calls with two CTA barriers each
   double* out = p.partials + (int64_t)blockIdx.x * kPart;
-  double r;
-  r = block_sum(pl, s_red); if (threadIdx.x == 0) out[0] = r;
-  r = block_sum(s1, s_red); if (threadIdx.x == 0) out[1] = r;
-  r = block_sum(s2, s_red); if (threadIdx.x == 0) out[2] = r;
-  r = block_sum(is1, s_red); if (threadIdx.x == 0) out[3] = r;
-  r = block_sum(is2, s_red); if (threadIdx.x == 0) out[4] = r;
-  r = block_sum(ent_sum, s_red); if (threadIdx.x == 0) out[5] = r;
-  if (!DISCRETE) {
+  {
+    __shared__ double s_w[8][8 + kMaxBoxA];
+    double q[8 + kMaxBoxA];
+    q[0] = pl; q[1] = s1; q[2] = s2; q[3] = is1; q[4] = is2; q[5] = ent_sum; q[6] = 0.0; q[7] = 0.0;
 #pragma unroll
-    for (int a = 0; a < kMaxBoxA; ++a) {
-      if (a >= A) break;
-      r = block_sum(dls[a], s_red);
-      if (threadIdx.x == 0) out[8 + a] = r;
+    for (int a = 0; a < kMaxBoxA; ++a) q[8 + a] = DISCRETE ? 0.0 : dls[a];
+    const int nq = DISCRETE ? 6 : 8 + A;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8 + kMaxBoxA; ++k) {
+      if (k >= nq) break;
+      const double v = warp_sum(q[k]);
+      if (lane == 0) s_w[wid][k] = v;
+    }
+    __syncthreads();
+    if (wid == 0 && lane < nq) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_w[w][lane];
+      out[lane] = t;
     }
   }
   // ---- tail: the last CTA sums the partials in a fixed order (8 warps take interleaved CTAs, then 0..7) ----
