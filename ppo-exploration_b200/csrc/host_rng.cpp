@@ -28,41 +28,89 @@ constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffff
 // MT19937 with block generation: the 624-word state update and the tempering run as straight loops
 // over whole blocks (auto-vectorised), extraction is a buffered load.  Same output sequence as numpy's
 // word-at-a-time mt19937_next.
+bool has_avx512() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq");
+  return ok;
+}
+
+inline uint32_t twist(uint32_t a, uint32_t b, uint32_t far) {
+  const uint32_t y = (a & UPPER) | (b & LOWER);
+  return far ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+}
+
+void gen_block_base(uint32_t* k, uint32_t* __restrict__ o) {
+  int i;
+  for (i = 0; i < MT_N - MT_M; i++) k[i] = twist(k[i], k[i + 1], k[i + MT_M]);
+  for (; i < MT_N - 1; i++) k[i] = twist(k[i], k[i + 1], k[i + (MT_M - MT_N)]);
+  k[MT_N - 1] = twist(k[MT_N - 1], k[0], k[MT_M - 1]);
+  for (i = 0; i < MT_N; ++i) {
+    uint32_t y = k[i];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    o[i] = y;
+  }
+}
+
+// 16 state words per step.  The recurrence k[i] = f(k[i], k[i+1], k[i+397 mod 624]) reads ahead by one word and by
+// 397 (or back by 227), so a 16-wide step never reads a word the same step writes; the two scalar remainders sit
+// where the far operand wraps.  Bit-identical to gen_block_base (checked by the numpy replay test).
+#define PPX_MT_STEP16(i, src)                                                                      \
+  {                                                                                                \
+    const __m512i a = _mm512_loadu_si512((const void*)(k + (i)));                                  \
+    const __m512i b = _mm512_loadu_si512((const void*)(k + (i) + 1));                              \
+    const __m512i y = _mm512_or_si512(_mm512_and_si512(a, up), _mm512_and_si512(b, lw));           \
+    const __mmask16 odd = _mm512_test_epi32_mask(y, one);                                          \
+    __m512i r = _mm512_xor_si512(_mm512_loadu_si512((const void*)(k + (src))), _mm512_srli_epi32(y, 1)); \
+    r = _mm512_mask_xor_epi32(r, odd, r, ma);                                                      \
+    _mm512_storeu_si512((void*)(k + (i)), r);                                                      \
+  }
+
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq")))
+void gen_block_avx512(uint32_t* k, uint32_t* __restrict__ o) {
+  const __m512i up = _mm512_set1_epi32((int)UPPER), lw = _mm512_set1_epi32((int)LOWER);
+  const __m512i ma = _mm512_set1_epi32((int)MATRIX_A), one = _mm512_set1_epi32(1);
+  int i = 0;
+  for (; i + 16 <= MT_N - MT_M; i += 16) PPX_MT_STEP16(i, i + MT_M)
+  for (; i < MT_N - MT_M; i++) k[i] = twist(k[i], k[i + 1], k[i + MT_M]);
+  for (; i + 16 <= MT_N - 1; i += 16) PPX_MT_STEP16(i, i + (MT_M - MT_N))
+  for (; i < MT_N - 1; i++) k[i] = twist(k[i], k[i + 1], k[i + (MT_M - MT_N)]);
+  k[MT_N - 1] = twist(k[MT_N - 1], k[0], k[MT_M - 1]);
+  const __m512i c1 = _mm512_set1_epi32((int)0x9d2c5680u), c2 = _mm512_set1_epi32((int)0xefc60000u);
+  static_assert(MT_N % 16 == 0, "tempering runs in whole vectors");
+  for (int j = 0; j < MT_N; j += 16) {
+    __m512i v = _mm512_loadu_si512((const void*)(k + j));
+    v = _mm512_xor_si512(v, _mm512_srli_epi32(v, 11));
+    v = _mm512_xor_si512(v, _mm512_and_si512(_mm512_slli_epi32(v, 7), c1));
+    v = _mm512_xor_si512(v, _mm512_and_si512(_mm512_slli_epi32(v, 15), c2));
+    v = _mm512_xor_si512(v, _mm512_srli_epi32(v, 18));
+    _mm512_storeu_si512((void*)(o + j), v);
+  }
+}
+
+// MT19937 with block generation: the 624-word state update and the tempering run over whole blocks (16 words per
+// step with AVX-512, else straight auto-vectorised loops), extraction is a buffered load.  Same output sequence as
+// numpy's word-at-a-time mt19937_next.
 struct Mt {
   uint32_t* key;
   int pos;
-  uint32_t out[MT_N];
-  int avail_from;            // out[] holds the tempered words of the CURRENT key block for indices >= avail_from
-  Mt(uint32_t* k, int p) : key(k), pos(p), avail_from(MT_N) { temper_from(p); }
-  inline void temper_from(int from) {
-    uint32_t* __restrict__ o = out;
-    const uint32_t* __restrict__ k = key;
-    for (int i = from; i < MT_N; ++i) {
+  alignas(64) uint32_t out[MT_N];
+  Mt(uint32_t* k, int p) : key(k), pos(p) {
+    for (int i = p; i < MT_N; ++i) {               // the unread tail of the CURRENT key block
       uint32_t y = k[i];
       y ^= (y >> 11);
       y ^= (y << 7) & 0x9d2c5680u;
       y ^= (y << 15) & 0xefc60000u;
       y ^= (y >> 18);
-      o[i] = y;
+      out[i] = y;
     }
-    avail_from = from;
   }
   inline void gen() {
-    uint32_t* k = key;
-    int i;
-    uint32_t y;
-    for (i = 0; i < MT_N - MT_M; i++) {
-      y = (k[i] & UPPER) | (k[i + 1] & LOWER);
-      k[i] = k[i + MT_M] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-    }
-    for (; i < MT_N - 1; i++) {
-      y = (k[i] & UPPER) | (k[i + 1] & LOWER);
-      k[i] = k[i + (MT_M - MT_N)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-    }
-    y = (k[MT_N - 1] & UPPER) | (k[0] & LOWER);
-    k[MT_N - 1] = k[MT_M - 1] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    if (has_avx512()) gen_block_avx512(key, out);
+    else gen_block_base(key, out);
     pos = 0;
-    temper_from(0);
   }
   inline uint32_t next32() {
     if (pos == MT_N) gen();
@@ -217,8 +265,11 @@ void draw_acc_base(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress) 
   publish(progress, r);
 }
 
-// 16 draws per step: a draw is certainly accepted if v <= i-15 (at most 15 accepts precede it in the block) and
-// certainly rejected if v > i; blocks with a draw in between (probability ~ 16*15/2^k) take the scalar path.
+// 64 (then 16) draws per step: with i the position at the start of the step, a draw v is certainly accepted if
+// v <= i - (W-1) (at most W-1 accepts precede it inside the step) and certainly rejected if v > i; a step holding a draw
+// in between (probability ~ W^2 / 2^k for a k-bit mask) falls to the next narrower path.  Accepted draws are packed with
+// a register compress and a full-width store: the lanes past the packed ones land on entries a later step rewrites
+// (r + 16 <= n - 1 because the vector paths stop 16 positions above the end of the mask's range).
 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,popcnt")))
 void draw_acc_avx512(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress) {
   int64_t i = n - 1, r = 0, last_pub = 0;
@@ -230,13 +281,36 @@ void draw_acc_avx512(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress
       if (mt.pos == MT_N) mt.gen();
       const uint32_t* __restrict__ o = mt.out;
       int p = mt.pos;
-      while (p + 16 <= MT_N && i - 16 >= lo) {
+      while (p + 64 <= MT_N && i - 64 >= lo) {
+        const uint32_t ii = (uint32_t)i;
+        const __m512i top = _mm512_set1_epi32((int)ii), safe = _mm512_set1_epi32((int)(ii - 63u));
+        const __m512i v0 = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p)), maskv);
+        const __m512i v1 = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p + 16)), maskv);
+        const __m512i v2 = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p + 32)), maskv);
+        const __m512i v3 = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p + 48)), maskv);
+        const __mmask16 a0 = _mm512_cmple_epu32_mask(v0, top), a1 = _mm512_cmple_epu32_mask(v1, top);
+        const __mmask16 a2 = _mm512_cmple_epu32_mask(v2, top), a3 = _mm512_cmple_epu32_mask(v3, top);
+        const __mmask16 s0 = _mm512_cmple_epu32_mask(v0, safe), s1 = _mm512_cmple_epu32_mask(v1, safe);
+        const __mmask16 s2 = _mm512_cmple_epu32_mask(v2, safe), s3 = _mm512_cmple_epu32_mask(v3, safe);
+        if (((a0 ^ s0) | (a1 ^ s1) | (a2 ^ s2) | (a3 ^ s3)) != 0) break;            // ambiguous: 16-wide path below
+        const int64_t c0 = __builtin_popcount((unsigned)a0), c1 = __builtin_popcount((unsigned)a1);
+        const int64_t c2 = __builtin_popcount((unsigned)a2), c3 = __builtin_popcount((unsigned)a3);
+        _mm512_storeu_si512((void*)(acc + r), _mm512_maskz_compress_epi32(a0, v0));
+        _mm512_storeu_si512((void*)(acc + r + c0), _mm512_maskz_compress_epi32(a1, v1));
+        _mm512_storeu_si512((void*)(acc + r + c0 + c1), _mm512_maskz_compress_epi32(a2, v2));
+        _mm512_storeu_si512((void*)(acc + r + c0 + c1 + c2), _mm512_maskz_compress_epi32(a3, v3));
+        const int64_t c = c0 + c1 + c2 + c3;
+        r += c;
+        i -= c;
+        p += 64;
+      }
+      for (int blk = 0; blk < 4 && p + 16 <= MT_N && i - 16 >= lo; ++blk) {          // <= one 64-step's worth, then retry wide
         const __m512i v = _mm512_and_si512(_mm512_loadu_si512((const void*)(o + p)), maskv);
         const uint32_t ii = (uint32_t)i;
         const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)(ii - 15u)));
         const __mmask16 maybe = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)ii));
         if (sure == maybe) {
-          _mm512_mask_compressstoreu_epi32((void*)(acc + r), sure, v);
+          _mm512_storeu_si512((void*)(acc + r), _mm512_maskz_compress_epi32(sure, v));
           const int64_t c = (int64_t)__builtin_popcount((unsigned)sure);
           r += c;
           i -= c;
@@ -251,12 +325,6 @@ void draw_acc_avx512(Mt& mt, int64_t n, int32_t* acc, volatile int64_t* progress
     }
   }
   publish(progress, r);
-}
-
-bool has_avx512() {
-  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
-                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq");
-  return ok;
 }
 }  // namespace
 

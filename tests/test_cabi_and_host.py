@@ -116,6 +116,31 @@ def test_host_permutation_is_bit_exact_numpy_replay():
     assert np.random.randn() == tail
 
 
+def test_vectorised_draw_stream_equals_the_scalar_draws():
+    """The AVX-512 block generator / 64-wide acceptance path of ppx_np_shuffle_draws32_stream produces the scalar
+    path's partner list (in acceptance order) and leaves the MT19937 state at the same word, across sizes that cross
+    several mask ranges and end inside a state block."""
+    import ctypes as C
+    from ppo_exploration_b200 import _lib as L
+    for seed, n in ((1, 70), (2, 4097), (3, 65536), (4, 1 << 20), (5, (1 << 22) + 12345)):
+        np.random.seed(seed)
+        np.random.rand(seed * 37)                           # start part-way through a state block
+        st = np.random.get_state()
+        key1, pos1 = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int(int(st[2]))
+        key2, pos2 = key1.copy(), C.c_int(pos1.value)
+        j = np.zeros(n, np.int32)
+        acc, prog = np.zeros(n, np.int32), np.zeros(1, np.int64)
+        L.call("ppx_np_shuffle_draws32", key1.ctypes.data, C.byref(pos1), n, j.ctypes.data)
+        L.call("ppx_np_shuffle_draws32_stream", key2.ctypes.data, C.byref(pos2), n, acc.ctypes.data, prog.ctypes.data)
+        assert prog[0] == n - 1
+        assert np.array_equal(acc[:n - 1], j[:0:-1]), n      # entry r = partner of position n-1-r
+        assert pos1.value == pos2.value and np.array_equal(key1, key2), n
+        np.random.set_state(st)
+        np.random.permutation(n)
+        after = np.random.get_state()
+        assert int(after[2]) == pos1.value and np.array_equal(after[1], key1), n
+
+
 def test_speculative_rng_stream_is_exact_and_cancellable():
     """A stream pre-drawn from a snapshot gives the reference's permutations when the global state still equals the
     snapshot; after a foreign draw the snapshot no longer matches (the learner then drops the stream)."""
