@@ -483,7 +483,7 @@ class PpxPass:
         T, N, D = cfg["T"], cfg["N"], cfg["D"]
         kind, n = cfg["space"]
         space = ppx.Box((n,)) if kind == "Box" else ppx.Discrete(n)
-        np.random.seed(rank); torch.manual_seed(0)              # per-rank shuffle stream, replicated weights
+        np.random.seed(0); torch.manual_seed(0)                 # one shuffle stream ("global": identical on every rank), replicated weights
         env = ppx.SyntheticVecEnv(N, D, space, seed=rank)
         kw = dict(env=env, nstep=T, batch_size=cfg["batch"], hidden_size=cfg["hidden"], device=dev, **cfg["hp"])
         if cfg["alg"] == "ppo":
@@ -645,6 +645,7 @@ def run_ppx(args):
         # global permutation).  The headline ("global") draws the reference's np.random.permutation(T*N*W) on every rank --
         # a sequential MT19937 stream of W x more draws per pass, which is what bounds weak scaling at large W
         m.shard_shuffle = "local"
+        np.random.seed(1000 + rank)
         for _ in range(3):
             bp.step_resident()
         ms_l = bp.timed(bp.step_resident, args.steps)

@@ -143,6 +143,12 @@ int ppx_np_shuffle_apply32_stream(const int32_t* acc_host, int64_t n, const int6
 int64_t ppx_np_shuffle_apply_device_workspace(int64_t n);
 int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, int acceptance_order, void* workspace, int64_t* out_dev,
                                 void* stream);
+/* One staging step of a permutation, callable from the host thread that drew it: H2D of the pinned partner list (acceptance
+ * order) into j_dev, ppx_np_shuffle_apply_device into out_dev, and cudaEventRecord of `copied_event` (after the copy) and
+ * `ready_event` (after the swaps) when given (cudaEvent_t; NULL = skip).  Makes the device owning j_dev current for the
+ * calling thread.  2 <= n <= 2^24. */
+int ppx_np_shuffle_stage(const int32_t* j_host_pinned, int64_t n, int32_t* j_dev, void* workspace, int64_t* out_dev,
+                         void* stream, void* copied_event, void* ready_event);
 
 
 /* Sharded minibatches: rec3 = {n, mean, M2} from the local {mean, std}; after an all-gather of the

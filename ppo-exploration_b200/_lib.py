@@ -74,6 +74,7 @@ SIGNATURES = {
     "ppx_np_shuffle_apply32_stream": (c_i, [c_p, c_l, c_p, c_p, c_p]),
     "ppx_np_shuffle_apply_device_workspace": (c_l, [c_l]),
     "ppx_np_shuffle_apply_device": (c_i, [c_p, c_l, c_i, c_p, c_p, c_p]),
+    "ppx_np_shuffle_stage": (c_i, [c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_linear_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_l, c_l, c_l, c_l, c_p]),
     "ppx_linear_bwd_data": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_l, c_l, c_l, c_l, c_p]),
     "ppx_linear_bwd_weight_workspace": (c_l, [c_i, c_i, c_i, c_i]),

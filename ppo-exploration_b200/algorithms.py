@@ -17,6 +17,7 @@ The host numpy RNG is consumed in exactly the reference's order: one permutation
 """
 import ctypes as C
 import time
+import zlib
 from collections import deque
 
 import numpy as np
@@ -77,6 +78,8 @@ class BaseAlgorithm(object):
         self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)    # optimiser step of the running train() call
         self._losses_buf = None                # [steps, 8] f64, persistent (graphs keep its address)
         self._perm_all, self._perm_events, self._perm_keep, self._copy_stream = None, [], [], None
+        self._perm_gen = 0
+        self._perm_sets, self._next_set = None, 0               # two staging sets: the speculative stream of the NEXT pass fills the other one
         self._perm_j, self._perm_ws = None, None
         self._glob = None                      # sharded "global": the all-gathered rollout [W, T, N, ...] per field
         self.rng_wait_s = 0.0                  # cumulative host time train() spent waiting for permutations
@@ -277,17 +280,40 @@ class BaseAlgorithm(object):
     def _rng_open(self, script):
         """The RNG stream of this train() call.  If the stream started speculatively at the end of the previous call was
         seeded with exactly the state np.random is in now (nobody drew in between) and has the same script, its
-        permutations are already waiting; otherwise it is dropped and a fresh stream starts from the current state.
-        Either way the draws are those the reference would make from this state."""
+        permutations are already waiting (the first ones already staged on the device); otherwise it is dropped and a
+        fresh stream starts from the current state.  Either way the draws are those the reference would make from this
+        state."""
         cur = np.random.get_state()
         sp, self._spec = self._spec, None
         if sp is not None:
             stream, snapshot = sp
             if (stream.script == list(script) and rng_states_equal(cur, snapshot) and stream.err is None
-                    and stream.device_apply == self._device_apply()):
+                    and stream.device_apply == self._device_apply() and stream.generation == self._perm_gen):
                 return stream
             stream.cancel()
-        return HostRngStream(script, state=cur, device_apply=self._device_apply())
+            stream.t1.join()                                    # its uploader must not queue anything after the new stream's
+        return self._new_stream(script, cur)
+
+    def _new_stream(self, script, state):
+        """A HostRngStream whose draw thread also stages every permutation on the device as soon as it is drawn (H2D of
+        the partner list + the parallel swaps, on the copy stream) into the staging set this stream owns."""
+        set_idx, self._next_set = self._next_set, self._next_set ^ 1
+        total = next((int(op[1]) for op in script if op[0] == 'perm'), 0)
+        up = None
+        if self._device_apply() and self._perm_j is not None and 2 <= total <= (1 << 24):
+            dst_all, js, ws, cs = self._perm_sets[set_idx], self._perm_j, self._perm_ws, self._copy_stream
+            evs = self._stage_events[set_idx]
+
+            def up(k, dp):                                      # runs on the draw thread: one GIL-free C call
+                copied, ready = evs[k]
+                L.call("ppx_np_shuffle_stage", dp.j.data_ptr(), total, js[k & 1].data_ptr(), ws.data_ptr(),
+                       dst_all.data_ptr() + 8 * k * total, cs.cuda_stream, copied.cuda_event, ready.cuda_event)
+                dp.ready = ready
+                dp.release(copied)                              # the pinned partner buffer is free once the copy has run
+                return copied
+        stream = HostRngStream(script, state=state, device_apply=self._device_apply(), uploader=up)
+        stream.set_idx, stream.generation = set_idx, self._perm_gen
+        return stream
 
     def _device_apply(self):
         """The swaps of the shuffle run on the GPU (only the draws ARE the RNG stream); the permutation is only ever
@@ -298,8 +324,9 @@ class BaseAlgorithm(object):
         """Commit the consumed draws to the global numpy RNG and pre-draw the next call's stream from there."""
         final = rng.final_state()
         np.random.set_state(final)
+        self._last_rng = rng
         if speculate and self.speculative_shuffle:
-            self._spec = (HostRngStream(rng.script, state=final, device_apply=self._device_apply()), final)
+            self._spec = (self._new_stream(rng.script, final), final)
 
     def _train_geometry(self, ro):
         """(indices per permutation, rows of a global minibatch, minibatches per epoch)."""
@@ -318,15 +345,34 @@ class BaseAlgorithm(object):
             _Scratch.generation += 1
         self._losses_buf.zero_()
         self._cursor.zero_()
-        if self._perm_all is None or self._perm_all.numel() != self.n_epochs * total:
-            self._perm_all = torch.empty(self.n_epochs * total, dtype=torch.int64, device=self.device)
+        if self._perm_sets is None or self._perm_sets[0].numel() != self.n_epochs * total:
+            self._perm_sets = [torch.empty(self.n_epochs * total, dtype=torch.int64, device=self.device) for _ in range(2)]
             self._copy_stream = self._copy_stream or torch.cuda.Stream(device=self.device)
             self._perm_j = None
+            if self._device_apply() and 2 <= total <= (1 << 24):
+                self._perm_j = [torch.empty(total, dtype=torch.int32, device=self.device) for _ in range(2)]
+                self._perm_ws = torch.empty(L.call("ppx_np_shuffle_apply_device_workspace", total), dtype=torch.uint8, device=self.device)
+            # events of the staging steps (copy done, permutation ready), recorded once so that their handles exist
+            self._stage_events = [[(torch.cuda.Event(), torch.cuda.Event()) for _ in range(self.n_epochs)] for _ in range(2)]
+            for evs in self._stage_events:
+                for pair in evs:
+                    for e in pair:
+                        e.record(self._copy_stream)
             _Scratch.generation += 1
+            self._perm_gen += 1                                 # retires a speculative stream that stages into the old sets
         self._perm_events, self._perm_keep = [None] * self.n_epochs, []
-        self._copy_stream.wait_stream(torch.cuda.current_stream())      # the previous call's readers of the staging buffer
         rng = self._rng_open(self._rng_script(ro, randn_per_minibatch))
+        self._perm_set = rng.set_idx
+        self._perm_all = self._perm_sets[rng.set_idx]
+        if rng.uploader is None:                                # uploads issued by this thread: after the previous readers of the set
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+        self._rng_check = None
         if D.world_size() > 1 and self.shard_shuffle == "global":
+            # every rank must draw the SAME permutation: exchange a digest of the numpy state the stream starts from
+            # (asynchronous; compared in _finish_train, where the host synchronises anyway)
+            st = np.random.get_state()
+            digest = (zlib.crc32(np.ascontiguousarray(st[1]).tobytes()) << 16) ^ int(st[2])
+            self._rng_check = D.all_gather_cat(torch.tensor([digest], dtype=torch.int64, device=self.device))
             self._replicate_rollout(ro)
         return rng
 
@@ -348,10 +394,10 @@ class BaseAlgorithm(object):
         perm = rng.next()                                       # pinned int64 [total], or the partner list (DevicePartners)
         self.rng_wait_s += time.perf_counter() - t0             # host time blocked on the (sequential) numpy RNG stream
         on_device = isinstance(perm, DevicePartners)
+        if on_device and perm.ready is not None:                # already staged by the stream's draw thread
+            self._perm_events[epoch] = perm.ready
+            return
         dst = self._perm_all[epoch * total:(epoch + 1) * total]
-        if on_device and self._perm_j is None:
-            self._perm_j = [torch.empty(total, dtype=torch.int32, device=self.device) for _ in range(2)]
-            self._perm_ws = torch.empty(L.call("ppx_np_shuffle_apply_device_workspace", total), dtype=torch.uint8, device=self.device)
         with torch.cuda.stream(self._copy_stream):
             if on_device:                                       # 4 bytes per index up instead of 8, swaps resolved in parallel on the copy stream
                 j = self._perm_j[epoch & 1]
@@ -361,6 +407,8 @@ class BaseAlgorithm(object):
                 dst.copy_(perm, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
+        if on_device:
+            perm.release(ev)                                    # the pinned partner buffer is free once the copy has run
         self._perm_events[epoch] = ev
         self._perm_keep.append(perm)                            # keep the pinned source alive until train() has synchronised
 
@@ -385,10 +433,10 @@ class BaseAlgorithm(object):
                 if base < 2:
                     raise RuntimeError(f"a global minibatch of {bg} rows cannot be split over {W} ranks")
                 opts = L.GatherOpts(N, -lo, bg, self._cursor.data_ptr(), n_mb, total, Bg)
-                yield opts, lo, b, bg, ("g", b, bg, lo), self._glob
+                yield opts, lo, b, bg, ("g", b, bg, lo, self._perm_set), self._glob
             else:
                 opts = L.GatherOpts(0, 0, 0, self._cursor.data_ptr(), n_mb, total, Bg)
-                yield opts, 0, bg, (bg * W if W > 1 else 0), ("l", bg), None
+                yield opts, 0, bg, (bg * W if W > 1 else 0), ("l", bg, self._perm_set), None
         if epoch + 1 < n_epochs:                                # after this epoch's randn()s were consumed (RND)
             self._perm_upload(rng, epoch + 1, total)
 
@@ -425,6 +473,11 @@ class BaseAlgorithm(object):
 
     def _finish_train(self, steps, keys):
         losses = self._losses_buf[:steps].cpu().numpy()            # the only D2H sync of train()
+        if self._rng_check is not None:
+            seen = self._rng_check.cpu().numpy()
+            if not (seen == seen[0]).all():
+                raise RuntimeError("ppx: shard_shuffle='global' needs the numpy global RNG in the same state on every rank "
+                                   "(seed all ranks alike and keep rank-dependent draws off np.random); digests: %s" % seen.tolist())
         self._perm_keep = []
         if self._px and int(self._px.status.item()) != 0:
             raise RuntimeError("ppx: a peer-memory barrier timed out (a rank fell out of the sharded update)")

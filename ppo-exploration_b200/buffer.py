@@ -19,6 +19,7 @@ import ctypes as C
 import os
 import queue
 import threading
+import time
 import weakref
 from collections import namedtuple
 
@@ -50,6 +51,54 @@ def np_permutation(n):
 _live_streams = weakref.WeakSet()
 
 
+class _Task:
+    """Handle of a function running on a pooled worker thread; join() like a Thread's."""
+
+    def __init__(self, fn, args):
+        self.fn, self.args, self.done = fn, args, threading.Event()
+
+    def join(self, timeout=None):
+        self.done.wait(timeout)
+
+    def is_alive(self):
+        return not self.done.is_set()
+
+
+class _WorkerPool:
+    """Host worker threads that outlive the streams they serve.  A learner opens one HostRngStream per train() call (and
+    one speculative stream per call); starting and retiring three OS threads each time is not free for the GPU -- the
+    address-space changes of thread stacks (mmap / madvise in a process with pinned CUDA mappings) showed up as one
+    ~0.3 ms stall of the running kernels per pass on the bench host (tools/trace_sharded.py).  Idle workers are re-used;
+    the pool only grows when every worker is busy (e.g. two learners with parked speculative streams)."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.idle = []
+
+    def submit(self, fn, *args):
+        task = _Task(fn, args)
+        with self.lock:
+            box = self.idle.pop() if self.idle else None
+        if box is None:
+            box = queue.SimpleQueue()
+            threading.Thread(target=self._loop, args=(box,), daemon=True).start()
+        box.put(task)
+        return task
+
+    def _loop(self, box):
+        while True:
+            task = box.get()
+            try:
+                task.fn(*task.args)
+            finally:
+                task.done.set()
+                with self.lock:
+                    self.idle.append(box)
+
+
+_workers = _WorkerPool()
+
+
 def _stop_streams_at_exit():
     """Worker threads must not be inside torch / CUDA calls while the interpreter finalises."""
     for st in list(_live_streams):
@@ -71,11 +120,58 @@ def rng_states_equal(a, b):
 
 class DevicePartners:
     """A permutation delivered as its Fisher-Yates partner list (pinned int32 [n] in acceptance order: entry r = partner
-    of position n-1-r): the swaps are applied on the device (ppx_np_shuffle_apply_device, acceptance_order=1)."""
-    __slots__ = ("j",)
+    of position n-1-r): the swaps are applied on the device (ppx_np_shuffle_apply_device, acceptance_order=1).
 
-    def __init__(self, j):
+    The pinned buffer comes from a small per-size pool shared by the streams of this process (`_PartnerPool`): a consumer
+    that has queued its H2D copy calls `release(event)` with an event recorded after the copy; the buffer is handed out
+    again once that event has completed.  A consumer that never releases simply keeps its buffer (the pool allocates a
+    new one) until the object is collected."""
+    __slots__ = ("j", "ready", "_slot", "__weakref__")
+
+    def __init__(self, j, slot=None):
         self.j = j
+        self.ready = None                 # CUDA event: the permutation is staged on the device (set by a stream's uploader)
+        self._slot = slot
+
+    def release(self, event=None):
+        if self._slot is not None:
+            self._slot[1] = event if event is not None else True
+            self._slot = None
+
+
+class _PartnerPool:
+    """Pinned int32 partner buffers, re-used across permutations and passes.  Why: a permutation's partner list is
+    written once by the draw thread (4 bytes per draw) and read once by the H2D DMA; cycling through a few buffers that
+    stay in the host's last-level cache instead of a fresh 4-16 MB block per epoch took the stream from 0.70 to the bare
+    draw rate on the bench host (tools/host_rng_prof.py)."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.slots = {}                                         # n -> [[tensor, state, owner weakref], ...]
+        # state: None = handed out, True = free, a CUDA event = free once it has completed
+
+    def take(self, n):
+        with self.lock:
+            ring = self.slots.setdefault(n, [])
+            pick = None
+            for slot in ring:
+                owner = slot[2]() if slot[2] is not None else None
+                if slot[1] is None and owner is not None:
+                    continue                                    # in use and its consumer is alive
+                if slot[1] is not None and slot[1] is not True and not slot[1].query():
+                    continue                                    # the copy out of it has not finished yet
+                pick = slot
+                break
+            if pick is None:
+                pick = [torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available()), None, None]
+                ring.append(pick)
+            pick[1] = None
+            dp = DevicePartners(pick[0], pick)
+            pick[2] = weakref.ref(dp)
+            return dp
+
+
+_partner_pool = _PartnerPool()
 
 
 def device_shuffle_default():
@@ -115,12 +211,21 @@ class HostRngStream:
     applies the swaps into a pinned buffer, running behind stage 1's published progress inside the permutation being
     drawn.  Results come out in script order; at most `ahead` items are in flight or waiting."""
 
-    def __init__(self, script, state=None, ahead=None, workers=None, device_apply=False):
+    def __init__(self, script, state=None, ahead=None, workers=None, device_apply=False, uploader=None):
         self.script = list(script)
         self.device_apply = bool(device_apply)                  # 'perm' items come out as DevicePartners (n <= 2^24)
+        # uploader(k, partners) -> CUDA event or None: called ON THE DRAW THREAD for the k-th permutation of the script as
+        # soon as it is drawn; it queues the H2D copy + the device-side swaps, sets partners.ready and returns the event
+        # that marks the end of the copy.  Before the draw thread would go idle (queue full, script done) it waits on the
+        # last such event: the core that just wrote the partner list stays awake while the DMA reads it (a vCPU that goes
+        # idle with the list dirty in its cache made that one 2 MB copy take 380 us instead of 45 on the bench host --
+        # once per pass, after the last permutation).
+        self.uploader = uploader
+        self.profile, self.t_birth = [], time.perf_counter()    # per staged permutation: (start, wait+setup, draw, publish+stage) seconds
         nw = int(workers) if workers is not None else _apply_workers()
         self.nw = max(1, nw)
-        ahead = self.nw + 2 if ahead is None else ahead
+        if ahead is None:                                       # device_apply has no stage 2: two finished permutations in hand are enough
+            ahead = 2 if self.device_apply else self.nw + 2
         # results are delivered in script order through `q`: stage 1 enqueues one slot [event, value] per item BEFORE
         # it dispatches the work, the stage-2 worker that owns the item fills it
         self.q = queue.Queue(maxsize=max(1, int(ahead)))
@@ -139,12 +244,12 @@ class HostRngStream:
             script = sc
         self._jbufs = {}                                        # rotating partner buffers (<= ahead + 1 in flight per size)
         self._first_perm = None
-        self.t1 = threading.Thread(target=self._draw, args=(list(script),), daemon=True)
-        self.t2 = [threading.Thread(target=self._apply, args=(w,), daemon=True) for w in range(self.nw)]
         _live_streams.add(self)
-        self.t1.start()
-        for t in self.t2:
-            t.start()
+        # stage 2 is only needed when some permutation of the script is applied on the host
+        need2 = any(op[0] == 'perm' and not (self.device_apply and 2 <= int(op[1]) <= (1 << 24)) for op in script)
+        self.nw2 = self.nw if need2 else 0
+        self.t2 = [_workers.submit(self._apply, w) for w in range(self.nw2)]
+        self.t1 = _workers.submit(self._draw, list(script))
 
     def _put(self, qq, item):
         while not self.cancelled:
@@ -159,26 +264,39 @@ class HostRngStream:
         """Stage 1 (one thread, owns the RNG): draws in script order; permutations are handed round-robin to the
         stage-2 workers -- the swaps of different permutations are independent, only the draws are sequential."""
         k = 0
+        kperm = -1
+        pending = None
         try:
             for op in script:
                 if self.cancelled:
                     break
                 slot = [threading.Event(), None]
+                t_item = time.perf_counter()
+                if pending is not None and self.q.full():       # about to block: see `uploader`
+                    pending.synchronize()
+                    pending = None
                 if not self._put(self.q, slot):
                     break
                 if op[0] == 'perm':
                     n = int(op[1])
+                    kperm += 1
                     st = self.rs.get_state()
                     key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
                     pos = C.c_int(int(st[2]))
                     if self.device_apply and 2 <= n <= (1 << 24):
                         # draws only: the partner list goes to the device, which applies the swaps (shuffle_dev.cu)
-                        jt = torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+                        dp = _partner_pool.take(n)
                         prog = np.zeros(1, np.int64)
-                        L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, jt.data_ptr(), prog.ctypes.data)
+                        t0 = time.perf_counter()
+                        L.call("ppx_np_shuffle_draws32_stream", key.ctypes.data, C.byref(pos), n, dp.j.data_ptr(), prog.ctypes.data)
+                        t1 = time.perf_counter()
                         self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
-                        slot[1] = DevicePartners(jt)
+                        if self.uploader is not None and not self.cancelled:
+                            pending = self.uploader(kperm, dp)
+                        slot[1] = dp
                         slot[0].set()
+                        t2 = time.perf_counter()
+                        self.profile.append((t_item - self.t_birth, t0 - t_item, t1 - t0, t2 - t1))
                         continue
                     small = n <= 0x7fffffff
                     nbuf = self.q.maxsize + 2
@@ -219,6 +337,8 @@ class HostRngStream:
         self._put(self.q, None)
         for mid in self.mids:
             self._put(mid, None)
+        if pending is not None:
+            pending.synchronize()
 
     def _apply(self, w):
         """Stage 2 worker w: applies the swaps of the permutations dealt to it into a pinned buffer."""

@@ -25,9 +25,6 @@ namespace {
 constexpr int MT_N = 624, MT_M = 397;
 constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
 
-// MT19937 with block generation: the 624-word state update and the tempering run as straight loops
-// over whole blocks (auto-vectorised), extraction is a buffered load.  Same output sequence as numpy's
-// word-at-a-time mt19937_next.
 bool has_avx512() {
   static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
                          __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq");

@@ -146,3 +146,24 @@ extern "C" int ppx_np_shuffle_apply_device(const int32_t* j_dev, int64_t n, int 
   fy_resolve_kernel<<<g, 256, 0, st>>>(j_dev, N, rev, first, nxt, out_dev);
   return after_launch("np_shuffle_apply_device", 6);
 }
+
+// One call for a whole staging step of a permutation (made from the host thread that drew it): H2D of the pinned partner
+// list, the swaps above, and the two event records the consumer needs -- `copied` (the pinned list may be re-used) and
+// `ready` (out_dev holds the permutation).  Selects the device that owns j_dev for the calling thread first, so a
+// worker thread of a rank > 0 needs no device bookkeeping of its own.
+extern "C" int ppx_np_shuffle_stage(const int32_t* j_host_pinned, int64_t n, int32_t* j_dev, void* workspace, int64_t* out_dev,
+                                    void* stream, void* copied_event, void* ready_event) {
+  PPX_REQUIRE(n >= 2 && n <= (1ll << 24), "np_shuffle_stage: n=%lld (supported: 2 .. 2^24)", (long long)n);
+  PPX_REQUIRE(j_host_pinned && j_dev && workspace && out_dev, "np_shuffle_stage: null pointer");
+  cudaPointerAttributes at;
+  PPX_CUDA(cudaPointerGetAttributes(&at, j_dev));
+  PPX_REQUIRE(at.type == cudaMemoryTypeDevice, "np_shuffle_stage: j_dev is not device memory");
+  PPX_CUDA(cudaSetDevice(at.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  PPX_CUDA(cudaMemcpyAsync(j_dev, j_host_pinned, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (copied_event) PPX_CUDA(cudaEventRecord((cudaEvent_t)copied_event, st));
+  const int rc = ppx_np_shuffle_apply_device(j_dev, n, 1, workspace, out_dev, stream);
+  if (rc != PPX_OK) return rc;
+  if (ready_event) PPX_CUDA(cudaEventRecord((cudaEvent_t)ready_event, st));
+  return PPX_OK;
+}
