@@ -228,7 +228,22 @@ typedef struct {
   int64_t* step_dev; double* norm_out /* optional */;
   const float* extra_grads; int n_extra;
   unsigned int* ticket;
+  /* Sharded learner (W >= 2; W <= 1: single GPU): the gradient all-reduce runs inside the same kernel over peer memory
+   * (one process per GPU, NVLink-mapped symmetric buffers).  Each block pushes the 32 gradients it reduced into every
+   * rank's staging area as {f32 value, u32 sequence} 8-byte words, polls its own W slots for this launch's sequence
+   * number and sums them in rank order before the clip + Adam above -- replaces the NCCL all-reduce + optimiser launch
+   * of a data-parallel step (algorithms.py:243-244 under DDP).
+   * peer_xg_host[p]: rank p's staging area, 2 x W x n 8-byte words (sequence parity, source rank, parameter), zeroed once;
+   * seq_dev: local device word (sequence number, starts at 0, same on all ranks); status_dev: local device word set to 1
+   * when a peer did not arrive within 4 s. */
+  int W, rank;
+  void* const* peer_xg_host;
+  unsigned int* seq_dev; unsigned int* status_dev;
 } ppx_fused_adam;
+/* number of blocks of the reduce kernel that carries the optimiser tail for this shape when they can all be resident at
+ * once (the tail needs that); 0 = the tail is not available (the backward then falls back to a separate clip + Adam launch on
+ * one GPU, and must not be given a sharded ppx_fused_adam). */
+int ppx_mlp3_fused_adam_blocks(int D, int H, int G, const int* outs_host);
 int ppx_mlp3_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs_host, const float* W2,
                  const float* const* W3_host, const float* H1, const float* H2, const float* const* dOut_host,
                  const ppx_value_head* value_heads_host /* G entries or NULL */, float clip_range, int64_t B_total,
@@ -309,6 +324,13 @@ typedef struct {
    * ppx_loss_row_commit does it).  ppx_gather_minibatch_stats reads the same counter to find its index slice. */
   int64_t* row_dev;
   int row_hold;
+  /* Sharded learner, ppx_ppo_loss_head_final only (W >= 2; W <= 1: single GPU): before the finalising block evaluates the
+   * losses and the max-of-means branch, it all-reduces the 32 partial sums with its peers over NVLink-mapped memory
+   * (value + sequence number in one 8-byte store; no exchange kernel) -- B_total must then be the global row count.
+   * peer_sums_host[p]: rank p's staging, 2 x W x 64 8-byte words, zeroed once; seq_dev / status_dev as in ppx_fused_adam. */
+  int W, rank;
+  void* const* peer_sums_host;
+  unsigned int* seq_dev; unsigned int* status_dev;
 } ppx_ppo_cfg;
 /* losses[8 * row + col] = *value; losses[8 * row] += *value if add_to_total; then ++*row_dev (row = *row_dev before).
  * The ICM learner's second loss (algorithms.py:688-692) lands in the row its policy step left open (row_hold). */

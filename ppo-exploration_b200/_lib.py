@@ -22,7 +22,8 @@ c_d = C.c_double
 class PpoCfg(C.Structure):
     _fields_ = [("B", c_l), ("B_total", c_l), ("A", c_i), ("discrete", c_i), ("dual", c_i), ("clip_range", C.c_float),
                 ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("int_vf_coef", C.c_float),
-                ("policy_weight", C.c_float), ("row_dev", c_p), ("row_hold", c_i)]
+                ("policy_weight", C.c_float), ("row_dev", c_p), ("row_hold", c_i), ("W", c_i), ("rank", c_i),
+                ("peer_sums_host", c_p), ("seq_dev", c_p), ("status_dev", c_p)]
 
 
 class GatherOpts(C.Structure):
@@ -35,7 +36,8 @@ class FusedAdam(C.Structure):
     """ppx_fused_adam: the optimiser tail of the fused MLP backward (clip_grad_norm_ + Adam in the reduce kernel's last block)."""
     _fields_ = [("params", c_p), ("grads", c_p), ("exp_avg", c_p), ("exp_avg_sq", c_p), ("n", c_l), ("max_norm", c_d), ("lr", c_d),
                 ("beta1", c_d), ("beta2", c_d), ("eps", c_d), ("step_dev", c_p), ("norm_out", c_p), ("extra_grads", c_p),
-                ("n_extra", c_i), ("ticket", c_p)]
+                ("n_extra", c_i), ("ticket", c_p), ("W", c_i), ("rank", c_i), ("peer_xg_host", c_p),
+                ("seq_dev", c_p), ("status_dev", c_p)]
 
 
 class ValueHead(C.Structure):
@@ -83,6 +85,7 @@ SIGNATURES = {
     "ppx_p2p_moments_merge": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p]),
     "ppx_p2p_sums_allreduce": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ppx_p2p_clip_adam": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_d, c_l, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
+    "ppx_mlp3_fused_adam_blocks": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_supported": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i, c_p]),
@@ -135,7 +138,7 @@ SIGNATURES = {
     "ppx_rank_center": (c_i, [c_p, c_i, c_p, c_p, c_p]),
     "ppx_knn_novelty": (c_i, [c_p, c_l, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
 }
-_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n not in ("ppx_version", "ppx_tc_supported", "ppx_mlp3_supported", "ppx_mlp3_tc_supported", "ppx_tc_wgrad_supported", "ppx_mlp3_sumsq_partials")}
+_STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i and n not in ("ppx_version", "ppx_tc_supported", "ppx_mlp3_supported", "ppx_mlp3_tc_supported", "ppx_tc_wgrad_supported", "ppx_mlp3_sumsq_partials", "ppx_mlp3_fused_adam_blocks")}
 
 _lib = None
 

@@ -146,22 +146,19 @@ class BaseAlgorithm(object):
         if pol.mlp.fused():
             # head + partial sums (+ loss scalars / branch when single-GPU) in ONE launch; the value-head gradients are
             # evaluated inside the fused MLP backward from the branch weights.  Sharded: the 32 partial sums are
-            # all-reduced (256 bytes) before the finalize kernel so the max-of-means branch is the global one.
+            # all-reduced (256 bytes) by the finalising block itself so the max-of-means branch is the global one.
             Bt = int(B_total) if B_total else B
-            if not sharded:
+            px = self._peer_exchange() if sharded else None
+            if px is not None:                                  # the finalising block exchanges the sums over peer memory
+                cfg.W, cfg.rank, cfg.peer_sums_host = px.W, px.rank, C.cast(px.peer_xs, C.c_void_p)
+                cfg.seq_dev, cfg.status_dev = px.seq[1], px.status_ptr
+            if not sharded or px is not None:
                 L.call("ppx_ppo_loss_head_final", *head_args, pol.bank.g("action_log_std"), losses_row,
                        self._branch.data_ptr(), ws, L.stream())
-            else:
-                px = self._peer_exchange()
+            else:                                               # no peer memory: NCCL all-reduce between head and finalize
                 L.call("ppx_ppo_loss_head", *head_args, self._sums.data_ptr(), ws, L.stream())
-                if px is not None:
-                    L.call("ppx_p2p_sums_allreduce", px.peer_sums, px.peer_flags[1], px.W, px.rank, px.seq[1], px.status_ptr,
-                           self._sums_global.data_ptr(), L.stream())
-                    gsums = self._sums_global
-                else:
-                    D.all_reduce_sum_(self._sums)
-                    gsums = self._sums
-                L.call("ppx_ppo_loss_finalize", C.byref(cfg), gsums.data_ptr(), pol.bank.p("action_log_std"),
+                D.all_reduce_sum_(self._sums)
+                L.call("ppx_ppo_loss_finalize", C.byref(cfg), self._sums.data_ptr(), pol.bank.p("action_log_std"),
                        pol.bank.g("action_log_std"), losses_row, self._branch.data_ptr(), L.stream())
             vh = {1: (outs[1], bufs['old_values'][:B], bufs['returns'][:B], self._branch.data_ptr(),
                       float(policy_weight) * float(self.vf_coef))}
@@ -170,10 +167,13 @@ class BaseAlgorithm(object):
                          float(int_vf_coef))
             # single GPU: the reduce kernel also leaves the clip_grad_norm_ partials, and (fuse_adam) its last block
             # applies clip + Adam to the whole bank -- no sumsq launch, no Adam launch
-            self._pre_sumsq = (not sharded) and (self.max_grad_norm > 0 or fuse_adam)
+            # sharded with peer memory (fuse_adam): the same tail also all-reduces the gradient (ppx_fused_adam.W >= 2)
+            px = self._peer_exchange() if sharded else None
+            fuse_here = fuse_adam and (not sharded or (px is not None and px.flag_blocks > 0))
+            self._pre_sumsq = (self.max_grad_norm > 0 and not sharded) or fuse_here
             adam = None
-            if fuse_adam and not sharded:
-                adam = pol.bank.fused_adam(self.lr, self.max_grad_norm, extra_name="action_log_std")
+            if fuse_here:
+                adam = pol.bank.fused_adam(self.lr, self.max_grad_norm, extra_name="action_log_std", px=px)
                 self._adam_fused = True
             pol.mlp.backward([d_actor, None] + ([None] if dual else []), value_heads=vh, clip_range=self.clip_range,
                              B_total=Bt, with_sumsq=self._pre_sumsq, adam=adam)
@@ -197,7 +197,10 @@ class BaseAlgorithm(object):
             self._px = None
             if D.world_size() > 1 and self.policy.mlp.fused():
                 bank = self.policy.bank
-                px = D.peer_exchange_or_none(bank.size, self.device, L.call("ppx_p2p_max_params"))
+                mlp = self.policy.mlp
+                outs = (C.c_int * mlp.G)(*[int(o) for o in mlp.outs])
+                blocks = int(L.call("ppx_mlp3_fused_adam_blocks", int(mlp.D), int(mlp.h), int(mlp.G), outs))
+                px = D.peer_exchange_or_none(bank.size, self.device, L.call("ppx_p2p_max_params"), flag_blocks=blocks)
                 if px is not None:
                     px.grad.copy_(bank.grad)
                     bank.grad = px.grad                         # kernels now write the local gradient into peer-visible memory
@@ -469,7 +472,12 @@ class BaseAlgorithm(object):
         bank.adam_step(self.lr, self.max_grad_norm)
 
     def _fuse_adam_ok(self):
-        return D.world_size() == 1 and self.policy.mlp.fused() and not self.policy.bank.tc_weights
+        if not self.policy.mlp.fused() or self.policy.bank.tc_weights:
+            return False
+        if D.world_size() == 1:
+            return True
+        px = self._peer_exchange()
+        return px is not None and px.flag_blocks > 0
 
     def _finish_train(self, steps, keys):
         losses = self._losses_buf[:steps].cpu().numpy()            # the only D2H sync of train()

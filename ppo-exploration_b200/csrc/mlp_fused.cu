@@ -17,6 +17,7 @@
 // Replaces, for these shapes, the nn.Linear/Tanh stacks + autograd of Policy.evaluate inside train()
 // (models.py:52-73, 101-124; algorithms.py:213, 242, 425, 464, 665, 696).
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace ppx {
 namespace mf {
@@ -54,6 +55,7 @@ struct RedP {
   double* sumsq;             // optional [G * gridDim.x]: per-block sum of squares of the final gradients (clip_grad_norm_)
   int64_t* step_dev;         // optional: optimiser step counter, bumped here when the sumsq launch is skipped
   ppx_fused_adam adam;       // adam.params != nullptr: the last block applies clip + Adam to the whole bank
+  uint64_t* xg[p2p::MAXW];   // adam.W >= 2: rank r's staging area [2][W][n] of {value, seq} (device copies of adam.peer_xg_host)
 };
 
 __host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
@@ -551,12 +553,70 @@ __device__ __forceinline__ float* mlp3_reduce_finish(const RedP& p, float (&sl)[
 // and its first warp applies Adam to the 32 parameters whose gradients it has just produced; block (0,0) also takes the
 // parameters outside the MLP (action_log_std) and bumps the step counter.  ticket[0] = arrivals, ticket[1] = departures
 // (the last block to leave re-arms both).
-__device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, int n_partials, float* gptr, float gval, bool first_warp) {
+// Sharded (a.W >= 2): the gradient all-reduce happens in the same place, per block, over peer memory, with the
+// low-latency "value + tag in one 8-byte store" protocol: the first warp PUSHES the 32 gradients it has just reduced into
+// every rank's staging area (remote stores over NVLink, slot [seq parity][own rank][param] = {f32 value, u32 seq}), then
+// polls its own W slots until each carries this launch's sequence number and sums them in rank order -- every rank
+// computes bit-identical sums, so the weights stay replicas.  No fence, no flag hop, no remote load, no separate exchange
+// kernel: the cost is one one-way NVLink latency plus the skew between the ranks.  (An 8-byte aligned store is delivered
+// whole; the parity double-buffering keeps a fast rank's launch k+1 from overwriting a slot of launch k: it cannot reach
+// launch k+2 before every peer has finished launch k.)
+__device__ __forceinline__ void st_ll(uint64_t* p, float v, uint32_t tag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ float ld_ll_wait(const uint64_t* p, uint32_t tag, uint32_t* status) {
+  uint32_t v, t;
+  const uint64_t t0 = p2p::now_ns();
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
+    if (t == tag) break;
+    if (p2p::now_ns() - t0 > 4000000000ull) { atomicExch(status, 1u); break; }
+  }
+  return __uint_as_float(v);
+}
+
+__device__ void fused_adam_tail(const RedP& p, int n_partials, float* gptr, float gval, bool first_warp) {
+  const ppx_fused_adam& a = p.adam;
   __shared__ double s_red[32];
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   const unsigned int total = gridDim.x * gridDim.y;
   const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
   const int64_t t_ = *a.step_dev + 1;                          // read before the rendezvous, written (block 0) after it
+  const int extra_off = (int)(a.extra_grads - a.grads);
+  uint32_t seq = 0;
+  if (a.W >= 2) {
+    seq = *a.seq_dev + 1u;                                     // same protocol as step_dev
+    if (first_warp) {
+      const int lane = threadIdx.x & 31, W = a.W, rank = a.rank;
+      const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t slot = (size_t)(seq & 1u) * W * a.n;
+      const int64_t idx = gptr ? (int64_t)(gptr - a.grads) : -1;
+      if (gptr)
+        for (int r = 0; r < W; ++r) st_ll(p.xg[r] + slot + (size_t)rank * a.n + idx, gval, seq);
+      if (lead)
+        for (int k = lane; k < a.n_extra; k += 32) {
+          const float v = a.extra_grads[k];
+          for (int r = 0; r < W; ++r) st_ll(p.xg[r] + slot + (size_t)rank * a.n + extra_off + k, v, seq);
+        }
+      const uint64_t* mine_xg = p.xg[rank] + slot;
+      double ss = 0.0;
+      if (gptr) {
+        float g = 0.f;
+        for (int r = 0; r < W; ++r) g += ld_ll_wait(mine_xg + (size_t)r * a.n + idx, seq, a.status_dev);
+        *gptr = g;                                             // the bank's gradient vector holds the global gradient
+        gval = g;
+        ss = (double)g * (double)g;
+      }
+      if (lead)
+        for (int k = lane; k < a.n_extra; k += 32) {
+          float g = 0.f;
+          for (int r = 0; r < W; ++r) g += ld_ll_wait(mine_xg + (size_t)r * a.n + extra_off + k, seq, a.status_dev);
+          const_cast<float*>(a.extra_grads)[k] = g;            // read back (ldcg) after the grid rendezvous
+        }
+      ss = warp_sum(ss);
+      if (lane == 0) p.sumsq[blk] = ss;                        // replaces the local-gradient partial written by reduce_finish
+    }
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -570,7 +630,7 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
   __syncthreads();
   double ss = 0.0;
   if (a.max_norm > 0.0) {
-    for (int k = threadIdx.x; k < n_partials; k += blockDim.x) ss += __ldcg(sumsq + k);
+    for (int k = threadIdx.x; k < n_partials; k += blockDim.x) ss += __ldcg(p.sumsq + k);
     for (int k = threadIdx.x; k < a.n_extra; k += blockDim.x) { const double v = (double)__ldcg(a.extra_grads + k); ss += v * v; }
     ss = block_sum(ss, s_red);
   }
@@ -586,6 +646,7 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
     }
     s_coef = coef;
     if (lead) *a.step_dev = t_;
+    if (lead && a.W >= 2) *a.seq_dev = seq;
     if (atomicAdd(a.ticket + 1, 1u) == total - 1) { a.ticket[0] = 0u; a.ticket[1] = 0u; __threadfence(); }
   }
   __syncthreads();
@@ -603,7 +664,7 @@ __device__ void fused_adam_tail(const ppx_fused_adam& a, const double* sumsq, in
   };
   if (first_warp && gptr) upd((int64_t)(gptr - a.grads), gval);
   if (lead)
-    for (int k = threadIdx.x; k < a.n_extra; k += blockDim.x) upd((int64_t)(a.extra_grads - a.grads) + k, __ldcg(a.extra_grads + k));
+    for (int k = threadIdx.x; k < a.n_extra; k += blockDim.x) upd((int64_t)extra_off + k, __ldcg(a.extra_grads + k));
 }
 
 // grads[e] = sum over CTA partials in a fixed order.  Block = 32 consecutive parameters x 8 slices of the
@@ -632,7 +693,7 @@ __global__ void __launch_bounds__(256) mlp3_reduce_kernel(RedP p) {
   float* gptr = nullptr;
   float gval = 0.f;
   if (slice == 0) gptr = mlp3_reduce_finish<H>(p, sl, s, e, R, g, o, D, el, &gval);
-  if (p.adam.params) fused_adam_tail(p.adam, p.sumsq, (int)(gridDim.x * gridDim.y), gptr, gval, slice == 0);
+  if (p.adam.params) fused_adam_tail(p, (int)(gridDim.x * gridDim.y), gptr, gval, slice == 0);
 }
 
 inline size_t fwd_smem(int H, int D, int o) {
@@ -687,6 +748,14 @@ int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, c
     PPX_REQUIRE(adam->params && adam->grads && adam->exp_avg && adam->exp_avg_sq && adam->step_dev && adam->ticket && adam->n >= 1 &&
                 adam->n_extra >= 0 && (adam->n_extra == 0 || adam->extra_grads), "mlp3 fused adam: bad arguments");
     r.adam = *adam;
+    if (adam->W >= 2) {
+      PPX_REQUIRE(adam->W <= p2p::MAXW && adam->rank >= 0 && adam->rank < adam->W && adam->peer_xg_host && adam->seq_dev &&
+                  adam->status_dev && sumsq, "mlp3 fused adam: bad peer arguments (W=%d rank=%d)", adam->W, adam->rank);
+      for (int q = 0; q < adam->W; ++q) {
+        PPX_REQUIRE(adam->peer_xg_host[q], "mlp3 fused adam: null peer pointer for rank %d", q);
+        r.xg[q] = (uint64_t*)adam->peer_xg_host[q];
+      }
+    }
   }
   for (int g = 0; g < G; ++g) { r.dW3[g] = dW3[g]; r.db3[g] = db3[g]; r.o[g] = outs[g]; }
   dim3 rgrid((unsigned)ceil_div(H * H + rest_size(H, D, omax), 32), (unsigned)G);
@@ -695,6 +764,8 @@ int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, c
     static int per_sm[2] = {0, 0};
     int& occ = per_sm[H == 64 ? 0 : 1];
     if (!occ) PPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0));
+    PPX_REQUIRE(adam->W < 2 || (int64_t)rgrid.x * rgrid.y <= (int64_t)occ * sm_count(),
+                "mlp3 fused adam: the sharded tail needs %lld co-resident blocks (ppx_mlp3_fused_adam_blocks)", (long long)rgrid.x * rgrid.y);
     if ((int64_t)rgrid.x * rgrid.y > (int64_t)occ * sm_count()) {
       // more blocks than can be resident (h = 128, three nets): plain reduce + the stand-alone clip+Adam launch
       r.adam = ppx_fused_adam{};
@@ -717,6 +788,17 @@ int mlp3_reduce_launch(int H, int D, int G, const int* outs, const float* ws2, c
 }  // namespace ppx
 
 using namespace ppx;
+
+extern "C" int ppx_mlp3_fused_adam_blocks(int D, int H, int G, const int* outs) {
+  if (!outs || !mf::shape_ok(D, H, G, outs, nullptr)) return 0;
+  int omax = 0;
+  for (int g = 0; g < G; ++g) omax = std::max(omax, outs[g]);
+  const int64_t blocks = (int64_t)ceil_div(H * H + mf::rest_size(H, D, omax), 32) * G;
+  const void* fn = H == 64 ? (const void*)mf::mlp3_reduce_kernel<64> : (const void*)mf::mlp3_reduce_kernel<128>;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0) != cudaSuccess) return 0;
+  return blocks <= (int64_t)occ * sm_count() ? (int)blocks : 0;
+}
 
 extern "C" int ppx_mlp3_supported(int D, int H, int G, const int* outs) {
   return (outs && mf::shape_ok(D, H, G, outs, nullptr)) ? 1 : 0;

@@ -15,6 +15,7 @@
 // Precision: as the reference.  Box actions are stored f64 (buffer.py:154), so Normal.log_prob, the
 // ratio and the surrogate are f64; everything else f32 with f64 reductions.
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace ppx {
 namespace {
@@ -94,8 +95,26 @@ struct HeadArgs {
   int64_t B; int64_t Bt; int A; int dual;       // B = rows on this rank, Bt = rows of the global minibatch
   float clip, ent_coef, pw;
   double* sums_out;                     // [32] sum of the CTA partials (written by the last CTA to finish)
-  int do_final; FinalArgs fin;          // do_final: the last CTA also runs finalize_body (single-GPU path)
+  int do_final; FinalArgs fin;          // do_final: the last CTA also runs finalize_body
+  // sharded do_final (W >= 2): the last CTA exchanges the 32 sums with its peers first (ppx_ppo_cfg.peer_sums_host)
+  int W, rank;
+  uint64_t* xs[p2p::MAXW];              // rank r's staging [2 parities][W source ranks][64 words of {u32 half, u32 seq}]
+  uint32_t* seq_dev; uint32_t* status_dev;
 };
+
+__device__ __forceinline__ void st_ll_u32(uint64_t* p, uint32_t v, uint32_t tag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_ll_u32_wait(const uint64_t* p, uint32_t tag, uint32_t* status) {
+  uint32_t v, t;
+  const uint64_t t0 = p2p::now_ns();
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
+    if (t == tag) break;
+    if (p2p::now_ns() - t0 > 4000000000ull) { atomicExch(status, 1u); break; }
+  }
+  return v;
+}
 
 __device__ __forceinline__ float norm_adv(float a, const double* st) {
   return (a - (float)st[0]) / ((float)st[1] + 1e-8f);       // algorithms.py:219 in f32
@@ -262,6 +281,28 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs p) {
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += s_p[q][lane];
+    if (p.W >= 2) {
+      // all-reduce of the 32 sums over peer memory, value + sequence number in one 8-byte store (two per double): push
+      // to every rank, poll the own slots, add in rank order -- identical sums, hence the identical max-of-means branch,
+      // on every rank; no exchange kernel, no fence (same protocol as the optimiser tail, mlp_fused.cu)
+      const uint32_t seq = *p.seq_dev + 1u;
+      const size_t slot = (size_t)(seq & 1u) * p.W * 64;
+      const uint64_t bits = (uint64_t)__double_as_longlong(t);
+      for (int r = 0; r < p.W; ++r) {
+        uint64_t* dst = p.xs[r] + slot + (size_t)p.rank * 64 + 2 * lane;
+        st_ll_u32(dst, (uint32_t)bits, seq);
+        st_ll_u32(dst + 1, (uint32_t)(bits >> 32), seq);
+      }
+      double g = 0.0;
+      for (int r = 0; r < p.W; ++r) {
+        const uint64_t* src = p.xs[p.rank] + slot + (size_t)r * 64 + 2 * lane;
+        const uint32_t lo = ld_ll_u32_wait(src, seq, p.status_dev), hi = ld_ll_u32_wait(src + 1, seq, p.status_dev);
+        g += __longlong_as_double((long long)(((uint64_t)hi << 32) | lo));
+      }
+      t = g;
+      __syncwarp();
+      if (lane == 0) *p.seq_dev = seq;
+    }
     s_sum[lane] = t;
     p.sums_out[lane] = t;
   }
@@ -390,6 +431,16 @@ int launch_head(const ppx_ppo_cfg* c, const float* actor_out, const float* log_s
   HeadArgs h{actor_out, log_std, actions, old_log_probs, advantages, adv_stats, values, old_values, returns,
              int_advantages, int_adv_stats, int_values, old_int_values, int_returns, d_actor_out, partials,
              c->B, total_rows(c), c->A, c->dual, c->clip_range, c->ent_coef, c->policy_weight, sums_out, 0, FinalArgs{}};
+  h.W = 0;
+  if (losses_out && c->W >= 2) {
+    PPX_REQUIRE(c->W <= p2p::MAXW && c->rank >= 0 && c->rank < c->W && c->peer_sums_host && c->seq_dev && c->status_dev,
+                "ppo_loss: bad peer arguments (W=%d rank=%d)", c->W, c->rank);
+    h.W = c->W; h.rank = c->rank; h.seq_dev = c->seq_dev; h.status_dev = c->status_dev;
+    for (int q = 0; q < c->W; ++q) {
+      PPX_REQUIRE(c->peer_sums_host[q], "ppo_loss: null peer pointer for rank %d", q);
+      h.xs[q] = (uint64_t*)c->peer_sums_host[q];
+    }
+  }
   if (losses_out) {
     PPX_REQUIRE(branch_out && (c->discrete || d_log_std), "ppo_loss: fused finalize needs branch_out / d_log_std");
     h.do_final = 1;

@@ -87,12 +87,18 @@ class PeerExchange:
     FLAGS, SEQ, STATUS, REC, SUMS, GRAD = 0, 256, 272, 512, 1024, 4096       # byte offsets
     MAXW = 16
 
-    def __init__(self, n_params, device):
+    def __init__(self, n_params, device, flag_blocks=0):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         W, r = world_size(), rank()
         assert 2 <= W <= self.MAXW
-        words = self.GRAD // 4 + (int(n_params) + 3) // 4 * 4
+        n4 = (int(n_params) + 3) // 4 * 4
+        # after the gradient vector: the push staging of the fused optimiser tail, 2 parities x W source ranks x n words of
+        # {f32 value, u32 sequence} (ppx_fused_adam); flag_blocks > 0 says the tail is available for the policy's shape
+        self.XG = self.GRAD + 4 * n4
+        self.flag_blocks = int(flag_blocks)
+        self.XS = self.XG + 8 * 2 * W * int(n_params)            # the loss head's sums exchange: 2 x W x 64 words (ppx_ppo_cfg)
+        words = self.XS // 4 + 2 * (2 * W * 64) + 4
         self.buf = symm_mem.empty(words, dtype=torch.float32, device=device)
         self.buf.zero_()
         group = dist.group.WORLD
@@ -108,12 +114,13 @@ class PeerExchange:
         self.grad = w(self.GRAD, int(n_params))
         self.sums = w(self.SUMS, 64).view(torch.float64)
         self.rec = w(self.REC, 12).view(torch.float64)
-        self.seq = [self.buf.data_ptr() + self.SEQ + 4 * ch for ch in range(3)]
+        self.seq = [self.buf.data_ptr() + self.SEQ + 4 * ch for ch in range(4)]      # [3]: the fused optimiser tail; [1]: the loss head
+        self.peer_xg, self.peer_xs = arr(self.XG), arr(self.XS)
         self.status_ptr = self.buf.data_ptr() + self.STATUS
         self.status = w(self.STATUS, 1).view(torch.int32)
 
 
-def peer_exchange_or_none(n_params, device, max_params):
+def peer_exchange_or_none(n_params, device, max_params, flag_blocks=0):
     """A PeerExchange when every rank can build one (NVLink P2P, symmetric memory, bank small enough), else None --
     decided collectively so all ranks take the same path."""
     import os
@@ -123,7 +130,7 @@ def peer_exchange_or_none(n_params, device, max_params):
         ok = 0
     if ok:
         try:
-            px = PeerExchange(n_params, device)
+            px = PeerExchange(n_params, device, flag_blocks)
         except Exception:                                     # no P2P / symmetric memory on this box
             ok, px = 0, None
     flag = torch.tensor([ok], dtype=torch.int32, device=device)

@@ -77,17 +77,21 @@ class ParamBank:
     def g(self, name, extra=0):
         return self.grad.data_ptr() + (self.offsets[name] + extra) * F4
 
-    def fused_adam(self, lr, max_norm, extra_name=None, betas=(0.9, 0.999), eps=1e-8):
-        """ppx_fused_adam record for this bank: clip_grad_norm_(max_norm) + Adam applied by the last block of the fused
-        MLP backward's reduce kernel (no separate optimiser launch).  `extra_name`: a parameter outside the MLP whose
-        gradient enters the norm (action_log_std)."""
-        key = (float(lr), float(max_norm), extra_name, betas, eps, self.grad.data_ptr())
+    def fused_adam(self, lr, max_norm, extra_name=None, betas=(0.9, 0.999), eps=1e-8, px=None):
+        """ppx_fused_adam record for this bank: clip_grad_norm_(max_norm) + Adam applied by the blocks of the fused MLP
+        backward's reduce kernel (no separate optimiser launch).  `extra_name`: a parameter outside the MLP whose gradient
+        enters the norm (action_log_std).  `px` (dist.PeerExchange): sharded -- the same kernel also all-reduces the
+        gradient over peer memory."""
+        key = (float(lr), float(max_norm), extra_name, betas, eps, self.grad.data_ptr(), id(px))
         if self._fused is None or self._fused[0] != key:
             ex_ptr, ex_n = (self.g(extra_name), int(np.prod(self.shapes[extra_name]))) if extra_name else (None, 0)
+            peer = (0, 0, None, None, None)
+            if px is not None:
+                peer = (px.W, px.rank, C.cast(px.peer_xg, C.c_void_p), px.seq[3], px.status_ptr)
             rec = L.FusedAdam(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                               self.size, float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                              self.step_dev.data_ptr(), self.norm_dev.data_ptr(), ex_ptr, ex_n, self._ticket.data_ptr())
-            self._fused = (key, rec)
+                              self.step_dev.data_ptr(), self.norm_dev.data_ptr(), ex_ptr, ex_n, self._ticket.data_ptr(), *peer)
+            self._fused = (key, rec, px)                        # px: keeps the host pointer tables alive
         return self._fused[1]
 
     def adam_step_pre(self, lr, max_norm, sumsq, n_partials, extra_name=None, betas=(0.9, 0.999), eps=1e-8):
