@@ -77,6 +77,7 @@ class BaseAlgorithm(object):
         self._graphs, self._graph_state = {}, None
         self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)    # optimiser step of the running train() call
         self._losses_buf = None                # [steps, 8] f64, persistent (graphs keep its address)
+        self._readback = None                  # pinned host copy of the loss log (+ sharded status words)
         self._perm_all, self._perm_events, self._perm_keep, self._copy_stream = None, [], [], None
         self._perm_gen = 0
         self._perm_sets, self._next_set = None, 0               # two staging sets: the speculative stream of the NEXT pass fills the other one
@@ -480,14 +481,31 @@ class BaseAlgorithm(object):
         return px is not None and px.flag_blocks > 0
 
     def _finish_train(self, steps, keys):
-        losses = self._losses_buf[:steps].cpu().numpy()            # the only D2H sync of train()
+        # The only D2H read of train(): loss log (+ the RNG digests and the peer-barrier status when sharded) into PINNED
+        # memory, then an event wait.  Not `.cpu()`: a pageable cudaMemcpy waits for the stream inside the driver and keeps
+        # other host threads out of the CUDA API meanwhile -- the draw thread of the next pass's stream sat blocked in its
+        # first staging call for the ~3 ms this wait lasts (tools/trace_sharded.py), i.e. no look-ahead at all.
+        W = D.world_size()
+        n_host = steps * 8 + W + 1
+        if self._readback is None or self._readback.numel() != n_host:
+            self._readback = torch.zeros(n_host, dtype=torch.float64, pin_memory=True)
+        rb = self._readback
+        rb[:steps * 8].view(steps, 8).copy_(self._losses_buf[:steps], non_blocking=True)
         if self._rng_check is not None:
-            seen = self._rng_check.cpu().numpy()
+            rb[steps * 8:steps * 8 + W].copy_(self._rng_check.view(-1).to(torch.float64), non_blocking=True)
+        if self._px:
+            rb[steps * 8 + W:].copy_(self._px.status.to(torch.float64), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        done.synchronize()
+        losses = rb[:steps * 8].view(steps, 8).numpy().copy()
+        if self._rng_check is not None:
+            seen = rb[steps * 8:steps * 8 + W].numpy()
             if not (seen == seen[0]).all():
                 raise RuntimeError("ppx: shard_shuffle='global' needs the numpy global RNG in the same state on every rank "
                                    "(seed all ranks alike and keep rank-dependent draws off np.random); digests: %s" % seen.tolist())
         self._perm_keep = []
-        if self._px and int(self._px.status.item()) != 0:
+        if self._px and int(rb[steps * 8 + W].item()) != 0:
             raise RuntimeError("ppx: a peer-memory barrier timed out (a rank fell out of the sharded update)")
         self.last_losses = losses
         for i, k in enumerate(keys):

@@ -224,8 +224,11 @@ class HostRngStream:
         self.profile, self.t_birth = [], time.perf_counter()    # per staged permutation: (start, wait+setup, draw, publish+stage) seconds
         nw = int(workers) if workers is not None else _apply_workers()
         self.nw = max(1, nw)
-        if ahead is None:                                       # device_apply has no stage 2: two finished permutations in hand are enough
-            ahead = 2 if self.device_apply else self.nw + 2
+        if ahead is None:
+            # a stream that stages its permutations itself may run through its whole script (the staging set holds every
+            # epoch; a speculative stream then prepares the whole next pass while this one computes); device_apply without
+            # an uploader has no stage 2: two finished permutations in hand are enough
+            ahead = max(2, len(self.script)) if uploader is not None else (2 if self.device_apply else self.nw + 2)
         # results are delivered in script order through `q`: stage 1 enqueues one slot [event, value] per item BEFORE
         # it dispatches the work, the stage-2 worker that owns the item fills it
         self.q = queue.Queue(maxsize=max(1, int(ahead)))
