@@ -272,6 +272,10 @@ int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int G, const i
                     const ppx_value_head* value_heads_host, float clip_range, int64_t B_total,
                     float* dW1, float* db1, float* dW2, float* db2, float* const* dW3_host, float* const* db3_host,
                     float* workspace, double* sumsq_partials, int64_t* step_dev, const ppx_fused_adam* adam_host, void* stream);
+/* Measurement hook (bench.py's roofline): the NEXT ppx_mlp3_tc_bwd call records this cudaEvent_t on its stream between
+ * the backward kernel and the partial-sum reduce kernel, so that the dominant kernel can be timed by itself with CUDA
+ * events.  One-shot; NULL clears. */
+int ppx_mlp3_tc_bwd_probe(void* cuda_event);
 
 /* ---------------------------------------------------------------- dense layers (tcgen05) ---- */
 /* Blackwell tensor-core path for the same layers: C[M,N] = epi(A[M,R] . B[N,R]^T) with tcgen05.mma

@@ -86,6 +86,7 @@ SIGNATURES = {
     "ppx_p2p_sums_allreduce": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ppx_p2p_clip_adam": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_d, c_l, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_fused_adam_blocks": (c_i, [c_i, c_i, c_i, c_p]),
+    "ppx_mlp3_tc_bwd_probe": (c_i, [c_p]),
     "ppx_mlp3_supported": (c_i, [c_i, c_i, c_i, c_p]),
     "ppx_mlp3_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ppx_mlp3_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i, c_p]),

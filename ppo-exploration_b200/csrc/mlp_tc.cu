@@ -23,6 +23,7 @@
 //
 // Replaces, for H = 64, the nn.Linear/Tanh stacks + autograd of Policy.evaluate inside train()
 // (models.py:52-73, 101-124; algorithms.py:213, 242, 425, 464, 665, 696).
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 #include "tc_common.cuh"
@@ -1422,6 +1423,12 @@ extern "C" int64_t ppx_mlp3_tc_bwd_workspace(int M, int D, int H, int G, const i
   return (int64_t)G * n * ((int64_t)mt::H * mt::H + RS);
 }
 
+static std::atomic<void*> g_bwd_probe{nullptr};
+extern "C" int ppx_mlp3_tc_bwd_probe(void* cuda_event) {
+  g_bwd_probe.store(cuda_event);
+  return PPX_OK;
+}
+
 extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int G, const int* outs, const float* W2,
                                const float* const* W3, const float* H1t, const float* H2t, const float* const* dOut,
                                const ppx_value_head* vh, float clip_range, int64_t B_total, float* dW1, float* db1,
@@ -1456,6 +1463,7 @@ extern "C" int ppx_mlp3_tc_bwd(const float* X, int ldx, int M, int D, int H, int
     rc = mt::launch_bwd<32, 32, false>(p, grid, st);
   }
   if (rc) return rc;
+  if (void* ev = g_bwd_probe.exchange(nullptr)) PPX_CUDA(cudaEventRecord((cudaEvent_t)ev, st));   // measurement hook, see ppx.h
   return mf::mlp3_reduce_launch(H, D, G, outs, p.ws2, p.wsr, n, RS, dW1, db1, dW2, db2, dW3, db3, sumsq_partials,
                                 (sumsq_partials && !adam) ? step_dev : nullptr, adam, st);
 }
