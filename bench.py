@@ -666,9 +666,19 @@ def run_ppx(args):
         return
     clocks = ClockSampler(local_rank)                           # sampled over warm-up + timed region (same load; nvidia-smi
     clocks.start()                                              # needs a few hundred ms to produce its first line)
-    warm = max(args.warmup, 5)
-    rec = bp.measure(args.steps, warm, peaks, clocks)
+    warm = max(args.warmup, 5)                                  # two staging sets x (eager, capture) before the graphs replay
     sharded = world > 1
+    # N > 1: the headline shards the reference's unit of work the data-parallel way -- every rank is the reference's learner
+    # on its own envs (its own np.random.permutation over its T x N rollout, buffer.py:239), gradients / loss sums /
+    # advantage moments exchanged ("local").  The exact emulation of ONE reference learner over all W x N envs ("global":
+    # one permutation of W x T x N indices, identical on every rank) is timed right after as a labelled secondary number:
+    # its draws are a single sequential MT19937 stream, W x longer per pass, which no GPU work can hide beyond W = 2
+    # (DESIGN.md §5).  PPO_ICM pairs consecutive rows across the shuffle and only has the global mode.
+    headline_mode = ("local" if cfg["alg"] != "icm" else "global") if sharded else None
+    if sharded:
+        m.shard_shuffle = headline_mode
+        np.random.seed(1000 + rank if headline_mode == "local" else 0)
+    rec = bp.measure(args.steps, warm, peaks, clocks)
     line = {"metric": METRIC, "value": rec["value"], "unit": "transitions/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": cfg["workload"], "name": args.config},
@@ -680,18 +690,21 @@ def run_ppx(args):
                            "shard_shuffle": (m.shard_shuffle if sharded else "n/a (1 GPU)")},
             "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "roofline": rec["roofline"],
             "host_rng_wait_ms_per_step": rec["host_rng_wait_ms_per_step"]}
-    if sharded and cfg["alg"] != "icm":
-        # labelled secondary number: per-rank shuffle streams ("local": the usual data-parallel sampler, NOT the reference's
-        # global permutation).  The headline ("global") draws the reference's np.random.permutation(T*N*W) on every rank --
-        # a sequential MT19937 stream of W x more draws per pass, which is what bounds weak scaling at large W
-        m.shard_shuffle = "local"
-        np.random.seed(1000 + rank)
-        for _ in range(3):
+    if sharded and headline_mode == "local":
+        m.shard_shuffle = "global"
+        np.random.seed(0)                                       # one stream, identical on every rank (checked by the learner)
+        w0 = m.rng_wait_s
+        for _ in range(5):
             bp.step_resident()
-        ms_l = bp.timed(bp.step_resident, args.steps)
-        line["local_shuffle"] = {"value": cfg["T"] * cfg["N"] * world * args.steps / (ms_l / 1e3), "unit": "transitions/s",
-                                 "ms_per_step": ms_l / args.steps,
-                                 "note": "shard_shuffle='local': every rank shuffles its own rollout with its own numpy stream"}
+        w0 = m.rng_wait_s
+        ms_g = bp.timed(bp.step_resident, args.steps)
+        line["global_shuffle"] = {"value": cfg["T"] * cfg["N"] * world * args.steps / (ms_g / 1e3), "unit": "transitions/s",
+                                  "ms_per_step": ms_g / args.steps,
+                                  "host_rng_wait_ms_per_step": 1e3 * (m.rng_wait_s - w0) / args.steps,
+                                  "draws_per_step": cfg["hp"]["n_epochs"] * cfg["T"] * cfg["N"] * world,
+                                  "note": "shard_shuffle='global': ONE np.random.permutation(W*T*N) per epoch, drawn identically on every "
+                                          "rank (the reference's single learner over all envs, bit-exact index stream); rank r takes "
+                                          "its slice of every global minibatch from the all-gathered rollout"}
     del bp, m
     torch.cuda.empty_cache()
     if args.config == "C2":
@@ -704,7 +717,7 @@ def run_ppx(args):
             for name in ("C1", "C3", "C4"):
                 try:
                     sp = PpxPass(name, torch, ppx, dev, rank, world)
-                    r = sp.measure(3, 3, peaks)
+                    r = sp.measure(3, 5, peaks)
                     r["workload"] = CONFIGS[name]["workload"]
                     del sp
                     torch.cuda.empty_cache()

@@ -71,6 +71,13 @@ int ppx_count_table_clear(ppx_count_table* t, void* stream);
  * Returns PPX_ERR_CAPACITY (after syncing the stream) if the table filled up. */
 int ppx_count_table_update(ppx_count_table* t, const uint64_t* codes, int64_t n, uint32_t* counts_out,
                            void* stream);
+/* Sharded count table: W ranks each own the codes with hash(code) % W == rank.  Every rank passes the
+ * SAME globally ordered code list (t-major, env-minor over all envs); it updates only the codes it owns and writes their
+ * sequential-semantics counts, 0 for the others -- summing counts_out over the ranks (one all-reduce) gives every count
+ * of the replicated update, at 1/W of the order-dependent work per rank.  The union of the ranks' tables is the
+ * reference's dict. */
+int ppx_count_table_update_owned(ppx_count_table* t, const uint64_t* codes, int64_t n, uint32_t* counts_out, int W, int rank,
+                                 void* stream);
 /* whole sim_hash(obs, rewards), buffer.py:188-200, fused: codes from obs, sequential count update,
  * rewards[i] += beta/sqrt(count_i) (bonus in f64, stored back in the dtype of `rewards`).
  * obs is [n,D]; pass n = T*N with a [T,N,D] rollout to apply the bonus post hoc in the reference's
@@ -107,6 +114,14 @@ typedef struct {
   /* optional device step cursor: idx += (row / n_mb) * epoch_stride + (row % n_mb) * mb_stride, row = *row_dev */
   const int64_t* row_dev;
   int64_t n_mb, epoch_stride, mb_stride;
+  /* Sharded learner with per-rank shuffles (W >= 2; W <= 1: off): the statistics written to stat_outs are those of the
+   * GLOBAL minibatch -- the block that finishes the local moments pushes its {n, mean, M2} record to every rank over
+   * NVLink-mapped memory (value + sequence number per 8-byte store), polls the W records and merges them in rank order
+   * (replaces ppx_moments_pack + an exchange + ppx_moments_merge).  peer_moments_host[p]: rank p's staging, 2 x 2 x W x 8
+   * 8-byte words, zeroed once; seq_dev: TWO local device words (one per statistics slot), starting at 0. */
+  int W, rank;
+  void* const* peer_moments_host;
+  unsigned int* seq_dev; unsigned int* status_dev;
 } ppx_gather_opts;
 int ppx_gather_minibatch_stats(const void* const* srcs_host, void* const* dsts_host, const int* row_bytes_host,
                                int n_arrays, const int64_t* idx, int64_t B, int T, int N, const int* stat_fields_host,

@@ -29,7 +29,7 @@ class PpoCfg(C.Structure):
 class GatherOpts(C.Structure):
     """ppx_gather_opts: sharded source decode, statistics range, device step cursor."""
     _fields_ = [("n_shard", c_i), ("stat_lo", c_l), ("stat_n", c_l), ("row_dev", c_p), ("n_mb", c_l), ("epoch_stride", c_l),
-                ("mb_stride", c_l)]
+                ("mb_stride", c_l), ("W", c_i), ("rank", c_i), ("peer_moments_host", c_p), ("seq_dev", c_p), ("status_dev", c_p)]
 
 
 class FusedAdam(C.Structure):
@@ -58,6 +58,7 @@ SIGNATURES = {
     "ppx_count_table_destroy": (c_i, [c_p]),
     "ppx_count_table_clear": (c_i, [c_p, c_p]),
     "ppx_count_table_update": (c_i, [c_p, c_p, c_l, c_p, c_p]),
+    "ppx_count_table_update_owned": (c_i, [c_p, c_p, c_l, c_p, c_i, c_i, c_p]),
     "ppx_simhash_update": (c_i, [c_p, c_p, c_p, c_i, c_i, c_l, c_d, c_p, c_i, c_p, c_p, c_p]),
     "ppx_simhash_bonus": (c_i, [c_p, c_l, c_d, c_p, c_i, c_p]),
     "ppx_count_table_size": (c_i, [c_p, C.POINTER(c_u)]),

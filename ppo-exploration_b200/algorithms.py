@@ -110,6 +110,13 @@ class BaseAlgorithm(object):
         """Minibatch gather; the advantage moments (algorithms.py:219, :431-434) come out of the same launch."""
         B = sl.numel() if B is None else int(B)
         n_stat = opts.stat_n if (opts is not None and opts.stat_n > 0) else B
+        self._stats_merged = False
+        if D.world_size() > 1 and sources is None and opts is not None and n_stat >= 2:
+            px = self._peer_exchange()                          # per-rank shuffles: merge the moments inside the gather launch
+            if px is not None:
+                opts.W, opts.rank, opts.peer_moments_host = px.W, px.rank, C.cast(px.peer_xm, C.c_void_p)
+                opts.seq_dev, opts.status_dev = px.seq_moments, px.status_ptr
+                self._stats_merged = True
         stats = [('advantages', self._stats.data_ptr())] + ([('int_advantages', self._stats.data_ptr() + 16)] if dual else [])
         ro.gather_into(sl, bufs, stats=stats if n_stat >= 2 else None, opts=opts, sources=sources, B=B)
         return n_stat >= 2
@@ -132,7 +139,7 @@ class BaseAlgorithm(object):
             if dual:
                 iadv = bufs['int_advantages'][:B]
                 L.call("ppx_mean_std", iadv.data_ptr(), B, self._stats.data_ptr() + 16, L.stream())
-        if sharded and not stats_global:
+        if sharded and not stats_global and not (stats_ready and getattr(self, "_stats_merged", False)):
             self._merge_stats(B, dual)
         d_actor = sc.get("d_actor", B * A)[:B * A].view(B, A)
         cfg = L.PpoCfg(B, int(B_total), A, int(self.discrete), int(dual), float(self.clip_range), float(self.ent_coef),

@@ -459,6 +459,15 @@ class CountTable:
         L.call("ppx_count_table_update", self._h, codes.data_ptr(), codes.numel(), counts.data_ptr(), L.stream())
         return counts
 
+    def update_codes_owned(self, codes, W, rank):
+        """Sharded table: `codes` is the globally ordered code list (identical on every rank); this rank updates only the
+        codes it owns (hash(code) % W == rank) and returns their counts, 0 elsewhere (sum over ranks = all counts)."""
+        counts = torch.empty(codes.numel(), dtype=torch.int32, device=codes.device)
+        L.call("ppx_count_table_update_owned", self._h, codes.data_ptr(), codes.numel(), counts.data_ptr(), int(W), int(rank),
+               L.stream())
+        self.sharded = True
+        return counts
+
     def __len__(self):
         n = C.c_uint64()
         L.call("ppx_count_table_size", self._h, C.byref(n))
@@ -473,7 +482,17 @@ class CountTable:
         L.call("ppx_count_table_dump", self._h, keys.data_ptr(), counts.data_ptr(), n, C.byref(got))
         k = keys[:n].cpu().numpy().view(np.uint64)
         c = counts[:n].cpu().numpy()
-        return {int(a): int(b) for a, b in zip(k, c)}
+        mine = {int(a): int(b) for a, b in zip(k, c)}
+        if getattr(self, "sharded", False):                     # sharded table: the reference's dict is the union of the ranks' parts
+            from . import dist as D
+            if D.world_size() > 1:
+                import torch.distributed as tdist
+                parts = [None] * D.world_size()
+                tdist.all_gather_object(parts, mine)
+                mine = {}
+                for p in parts:
+                    mine.update(p)
+        return mine
 
 
 class RolloutStorage(BaseBuffer):
@@ -587,9 +606,10 @@ class RolloutStorage(BaseBuffer):
         """buffer.py:188-200 for a rollout whose env columns are sharded over the ranks: this
         rank holds columns [rank*N, (rank+1)*N) of the global [T, W*N] rollout.  Codes are computed locally; the
         count table is global and its update order-dependent (t-major, env-minor over ALL envs), so the packed codes
-        are all-gathered and every rank replays the identical, globally ordered table update (tables stay replicas)
-        and applies the counts of its own columns -- bit-identical to one GPU holding all envs.  Mutates and returns
-        `rewards` ([T,N] CUDA f32; default: the stored rollout)."""
+        are all-gathered into that order and the table is SHARDED by code: rank hash(code) % W owns a code, resolves its
+        occurrences in the global order and keeps its count; the counts come back through one all-reduce and every rank
+        applies those of its own columns -- bit-identical to one GPU holding all envs, per-rank work independent of W
+        except for the linear partition pass.  Mutates and returns `rewards` ([T,N] CUDA f32; default: the stored rollout)."""
         from . import dist as D
         obs = self.observations if obs is None else obs
         rewards = self.rewards if rewards is None else rewards
@@ -601,7 +621,11 @@ class RolloutStorage(BaseBuffer):
             raise RuntimeError("sim_hash_sharded: rewards must be a contiguous f32 CUDA tensor [T, N]")
         codes = self.sim_hash_codes(obs).view(T, N)
         allc = D.interleave_env_shards(D.all_gather_cat(codes)).reshape(-1)          # [T, W*N] in global env order
-        counts = self.count_table.update_codes(allc).view(T, W, N)[:, r].contiguous()
+        # bucket-owner ranks: every rank walks the same ordered list but resolves only the codes it owns (1/W of the
+        # order-dependent work, table sharded by hash(code) % W); one all-reduce returns every count to every rank
+        counts = self.count_table.update_codes_owned(allc, W, r)
+        D.all_reduce_sum_(counts)
+        counts = counts.view(T, W, N)[:, r].contiguous()
         L.call("ppx_simhash_bonus", counts.data_ptr(), T * N, float(self.beta), rewards.data_ptr(), 0, L.stream())
         return rewards
 

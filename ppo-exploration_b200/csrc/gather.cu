@@ -6,6 +6,7 @@
 // the fly: flat i -> (t, n) = (i % T, i / T).  One launch gathers every field of the RolloutSample.
 // Algorithmic traffic: 2 x row bytes per sample + the 8-byte index.
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace ppx {
 namespace {
@@ -18,6 +19,7 @@ struct GatherArgs {
   // optional: {mean, unbiased std} of up to two gathered f32 [B] fields (the advantages, algorithms.py:219 / :431-434),
   // computed on the way so the minibatch needs no separate moments launch
   int stat_field[2];
+  int order[PPX_MAX_GATHER];     // blockIdx.y -> field
   double* stat_out[2];
   double* stat_part;             // [2][kStatMax][2]
   unsigned int* stat_ticket;     // [2]
@@ -25,6 +27,11 @@ struct GatherArgs {
   int64_t stat_lo, stat_n;       // statistics over idx[stat_lo .. stat_lo + stat_n)
   const int64_t* row_dev;        // optional step cursor
   int64_t n_mb, epoch_stride, mb_stride;
+  // per-rank shuffles of a sharded learner (W >= 2): the finalising block merges the W ranks' moment records over peer memory
+  int W, rank;
+  uint64_t* xm[p2p::MAXW];       // rank r's staging [2 statistics slots][2 parities][W source ranks][8 words of {u32, u32 seq}]
+  uint32_t* seq_dev;             // [2]: one sequence number per statistics slot
+  uint32_t* status_dev;
 };
 constexpr int kStatMax = 4096;
 
@@ -94,16 +101,68 @@ __device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot
   for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) { s += __ldcg(part + 2 * k); q += __ldcg(part + 2 * k + 1); }
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
+  if (threadIdx.x >= 32) return;
+  double mean = s / (double)n_stat;
+  double M2 = fmax(q - s * mean, 0.0);
+  double n_tot = (double)n_stat;
+  if (args.W >= 2) {
+    // Every rank shuffled its own rollout: the statistics of the GLOBAL minibatch are the merge of the W local records
+    // {n, mean, M2} (Chan et al.), in rank order so that every rank gets the same bits.  Exchange = value + sequence
+    // number in one 8-byte store per 32-bit half, pushed to every rank; then poll the own slots (no fence, no separate
+    // kernel; same protocol as the loss sums and the gradient, ppo_loss.cu / mlp_fused.cu).
+    const int lane = threadIdx.x, W = args.W;
+    const uint32_t seq = args.seq_dev[slot] + 1u;
+    const size_t base = ((size_t)slot * 2 + (seq & 1u)) * W * 8;
+    if (lane < 6) {                                           // lane / 2 = which double, lane & 1 = which half
+      const double v = lane < 2 ? n_tot : (lane < 4 ? mean : M2);
+      const uint64_t bits = (uint64_t)__double_as_longlong(v);
+      const uint32_t half = (lane & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+      for (int r = 0; r < W; ++r)
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(args.xm[r] + base + (size_t)args.rank * 8 + lane), "r"(half), "r"(seq) : "memory");
+    }
+    double nr = 0.0, mr = 0.0, m2r = 0.0;                      // lane r < W holds rank r's record
+    if (lane < W) {
+      const uint64_t* src = args.xm[args.rank] + base + (size_t)lane * 8;
+      uint32_t w[6];
+      const uint64_t t0 = p2p::now_ns();
+      for (int k = 0; k < 6; ++k) {
+        uint32_t v, t;
+        for (;;) {
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src + k) : "memory");
+          if (t == seq) break;
+          if (p2p::now_ns() - t0 > 4000000000ull) { atomicExch(args.status_dev, 1u); break; }
+        }
+        w[k] = v;
+      }
+      nr = __longlong_as_double((long long)(((uint64_t)w[1] << 32) | w[0]));
+      mr = __longlong_as_double((long long)(((uint64_t)w[3] << 32) | w[2]));
+      m2r = __longlong_as_double((long long)(((uint64_t)w[5] << 32) | w[4]));
+    }
+    double tot = 0.0, wsum = 0.0;
+    for (int r = 0; r < W; ++r) {
+      const double a = __shfl_sync(0xffffffffu, nr, r), b = __shfl_sync(0xffffffffu, mr, r);
+      tot += a;
+      wsum += a * b;
+    }
+    mean = wsum / tot;
+    M2 = 0.0;
+    for (int r = 0; r < W; ++r) {
+      const double a = __shfl_sync(0xffffffffu, nr, r), b = __shfl_sync(0xffffffffu, mr, r), c = __shfl_sync(0xffffffffu, m2r, r);
+      const double d = b - mean;
+      M2 += c + a * d * d;
+    }
+    n_tot = tot;
+    if (lane == 0) args.seq_dev[slot] = seq;
+  }
   if (threadIdx.x == 0) {
-    const double mean = s / (double)n_stat;
     args.stat_out[slot][0] = mean;
-    args.stat_out[slot][1] = sqrt(fmax(q - s * mean, 0.0) / (double)(n_stat - 1));     // unbiased, like torch.Tensor.std()
+    args.stat_out[slot][1] = sqrt(M2 / (n_tot - 1.0));       // unbiased, like torch.Tensor.std()
   }
 }
 
 __global__ void __launch_bounds__(256)
 gather_kernel(GatherArgs args, const int64_t* __restrict__ idx_base, int64_t B, int T, int N) {
-  const int a = blockIdx.y;
+  const int a = args.order[blockIdx.y];                       // statistics fields first: their tail overlaps the other fields' rows
   const int64_t* idx = idx_of(args, idx_base);
   if (a == args.stat_field[0]) { gather_scalar_with_stats(args, a, 0, idx, B, T, N); return; }
   if (a == args.stat_field[1]) { gather_scalar_with_stats(args, a, 1, idx, B, T, N); return; }
@@ -198,6 +257,7 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
   args.stat_out[0] = args.stat_out[1] = nullptr;
   args.stat_part = nullptr; args.stat_ticket = nullptr;
   args.n_shard = 0; args.stat_lo = 0; args.stat_n = 0; args.row_dev = nullptr; args.n_mb = 1; args.epoch_stride = 0; args.mb_stride = 0;
+  args.W = 0; args.rank = 0; args.seq_dev = nullptr; args.status_dev = nullptr;
   if (opts) {
     PPX_REQUIRE(opts->n_shard >= 0 && (opts->n_shard == 0 || N % opts->n_shard == 0), "gather_minibatch: n_shard=%d does not divide N=%d", opts->n_shard, N);
     PPX_REQUIRE(opts->stat_n >= 0 && (opts->stat_n == 0 || opts->stat_n >= 2), "gather_minibatch: stat_n=%lld", (long long)opts->stat_n);
@@ -205,6 +265,15 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
     args.n_shard = opts->n_shard; args.stat_lo = opts->stat_lo; args.stat_n = opts->stat_n;
     args.row_dev = opts->row_dev; args.n_mb = opts->n_mb; args.epoch_stride = opts->epoch_stride; args.mb_stride = opts->mb_stride;
     if (opts->stat_n > max_words) max_words = opts->stat_n;
+    if (opts->W >= 2 && n_stats > 0) {
+      PPX_REQUIRE(opts->W <= ppx::p2p::MAXW && opts->rank >= 0 && opts->rank < opts->W && opts->peer_moments_host && opts->seq_dev &&
+                  opts->status_dev, "gather_minibatch: bad peer arguments (W=%d rank=%d)", opts->W, opts->rank);
+      args.W = opts->W; args.rank = opts->rank; args.seq_dev = opts->seq_dev; args.status_dev = opts->status_dev;
+      for (int q = 0; q < opts->W; ++q) {
+        PPX_REQUIRE(opts->peer_moments_host[q], "gather_minibatch: null peer pointer for rank %d", q);
+        args.xm[q] = (uint64_t*)opts->peer_moments_host[q];
+      }
+    }
   }
   int64_t gx = ppx::ceil_div(max_words, 256);
   const int64_t cap = (int64_t)ppx::sm_count() * 16;
@@ -226,6 +295,11 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
     }
     args.stat_part = part; args.stat_ticket = ticket;
     if (gx > ppx::kStatMax) gx = ppx::kStatMax;
+  }
+  {
+    int k = 0;
+    for (int q = 0; q < 2; ++q) if (args.stat_field[q] >= 0) args.order[k++] = args.stat_field[q];
+    for (int a = 0; a < n_arrays; ++a) if (a != args.stat_field[0] && a != args.stat_field[1]) args.order[k++] = a;
   }
   dim3 grid((unsigned)gx, (unsigned)n_arrays);
   ppx::gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(args, idx, B, T, N);

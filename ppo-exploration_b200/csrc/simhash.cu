@@ -436,10 +436,13 @@ __global__ void __launch_bounds__(CT)
 bucket_update_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t cap, uint32_t* ctrl,
                      const uint64_t* __restrict__ codes, const uint32_t* __restrict__ list, const uint32_t* __restrict__ bstart,
                      uint32_t n_direct, int64_t e0, double beta, void* rewards, int rewards_f64,
-                     uint32_t* __restrict__ counts_out) {
+                     uint32_t* __restrict__ counts_out, int own_W, int own_rank) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BucketSmem& S = *reinterpret_cast<BucketSmem*>(smem_raw);
   const int tid = threadIdx.x;
+  // sharded table: this rank keeps (and counts) only the codes of the buckets it owns; the bucket count is a multiple of
+  // own_W, so bucket % own_W == hash(code) % own_W whatever the call size
+  if (own_W > 1 && (int)(blockIdx.x % (unsigned)own_W) != own_rank) return;
   // list == nullptr: a single bucket holding elements 0..n_direct-1 (small calls skip the partition)
   const uint32_t lo = list ? bstart[blockIdx.x] : 0u, hi = list ? bstart[blockIdx.x + 1] : n_direct;
   for (uint32_t b0 = lo; b0 < hi; b0 += CAP) {               // batches of one bucket run in index order
@@ -552,7 +555,8 @@ int launch_codes(const double* A, const float* obs, int k, int D, int64_t n, uin
 }
 
 int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int D, const uint64_t* codes_in, int64_t n,
-               double beta, void* rewards, int rewards_f64, uint64_t* codes_out, uint32_t* counts_out, cudaStream_t st) {
+               double beta, void* rewards, int rewards_f64, uint64_t* codes_out, uint32_t* counts_out, cudaStream_t st,
+               int own_W = 1, int own_rank = 0) {
   if (n == 0) return PPX_OK;
   int rc = reserve(t, n, st);
   if (rc) return rc;
@@ -566,7 +570,8 @@ int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int
   for (int64_t e0 = 0; e0 < n; e0 += LMAX) {                  // stream-ordered launches keep the index order
     const int64_t nl = std::min<int64_t>(LMAX, n - e0);
     // <= 1024 buckets: one-CTA scan of the totals; a call that fits one sorted batch needs no partition at all
-    const uint32_t nb = nl <= CAP ? 1u : (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, TARGET), 1024));
+    uint32_t nb = nl <= CAP ? 1u : (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nl, TARGET), 1024));
+    if (own_W > 1) nb = std::max<uint32_t>((uint32_t)own_W, nb / (uint32_t)own_W * (uint32_t)own_W);   // always partitioned, W | nb
     const uint64_t* codes = codes_in ? codes_in + e0 : (codes_out ? codes_out + e0 : t->scratch_codes);
     const size_t sz = rewards_f64 ? sizeof(double) : sizeof(float);
     void* rew = rewards ? (char*)rewards + e0 * sz : nullptr;
@@ -581,7 +586,7 @@ int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int
     }
     if (nb == 1) {                                            // one bucket: no partition, elements in index order
       bucket_update_kernel<<<1, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, nullptr, nullptr,
-                                                             (uint32_t)nl, 0, beta, rew, rewards_f64, cnt);
+                                                             (uint32_t)nl, 0, beta, rew, rewards_f64, cnt, 1, 0);
     } else {
       const int tiles = (int)ceil_div(nl, TP);
       uint32_t* btot = t->scratch_bstart;
@@ -592,7 +597,7 @@ int run_update(ppx_count_table* t, const double* A, const float* obs, int k, int
       rc = after_launch("simhash partition", 3);
       if (rc) return rc;
       bucket_update_kernel<<<nb, CT, sizeof(BucketSmem), st>>>(t->keys, t->counts, t->capacity, t->ctrl, codes, t->scratch_list,
-                                                              bstart, 0u, 0, beta, rew, rewards_f64, cnt);
+                                                              bstart, 0u, 0, beta, rew, rewards_f64, cnt, own_W, own_rank);
     }
     rc = after_launch("simhash update");
     if (rc) return rc;
@@ -642,6 +647,13 @@ extern "C" int ppx_count_table_clear(ppx_count_table* t, void* stream) {
 extern "C" int ppx_count_table_update(ppx_count_table* t, const uint64_t* codes, int64_t n, uint32_t* counts_out, void* stream) {
   PPX_REQUIRE(t && codes && counts_out && n >= 0, "count_table_update: bad arguments");
   return ppx::run_update(t, nullptr, nullptr, 0, 0, codes, n, 0.0, nullptr, 0, nullptr, counts_out, (cudaStream_t)stream);
+}
+
+extern "C" int ppx_count_table_update_owned(ppx_count_table* t, const uint64_t* codes, int64_t n, uint32_t* counts_out, int W,
+                                           int rank, void* stream) {
+  PPX_REQUIRE(t && codes && counts_out && n >= 0 && W >= 1 && W <= 1024 && rank >= 0 && rank < W, "count_table_update_owned: bad arguments");
+  if (n > 0) PPX_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(uint32_t) * (size_t)n, (cudaStream_t)stream));
+  return ppx::run_update(t, nullptr, nullptr, 0, 0, codes, n, 0.0, nullptr, 0, nullptr, counts_out, (cudaStream_t)stream, W, rank);
 }
 
 extern "C" int ppx_simhash_update(ppx_count_table* t, const double* A, const float* obs, int k, int D, int64_t n, double beta,

@@ -98,7 +98,8 @@ class PeerExchange:
         self.XG = self.GRAD + 4 * n4
         self.flag_blocks = int(flag_blocks)
         self.XS = self.XG + 8 * 2 * W * int(n_params)            # the loss head's sums exchange: 2 x W x 64 words (ppx_ppo_cfg)
-        words = self.XS // 4 + 2 * (2 * W * 64) + 4
+        self.XM = self.XS + 8 * 2 * W * 64                       # the gather's moments exchange: 2 slots x 2 x W x 8 words (ppx_gather_opts)
+        words = self.XM // 4 + 2 * (2 * 2 * W * 8) + 4
         self.buf = symm_mem.empty(words, dtype=torch.float32, device=device)
         self.buf.zero_()
         group = dist.group.WORLD
@@ -114,8 +115,10 @@ class PeerExchange:
         self.grad = w(self.GRAD, int(n_params))
         self.sums = w(self.SUMS, 64).view(torch.float64)
         self.rec = w(self.REC, 12).view(torch.float64)
-        self.seq = [self.buf.data_ptr() + self.SEQ + 4 * ch for ch in range(4)]      # [3]: the fused optimiser tail; [1]: the loss head
-        self.peer_xg, self.peer_xs = arr(self.XG), arr(self.XS)
+        self.seq = [self.buf.data_ptr() + self.SEQ + 4 * ch for ch in range(4)]
+        # [1]: the loss head's sums exchange, [3]: the fused optimiser tail; two more words for the gather's moments exchange
+        self.seq_moments = self.buf.data_ptr() + self.STATUS + 8
+        self.peer_xg, self.peer_xs, self.peer_xm = arr(self.XG), arr(self.XS), arr(self.XM)
         self.status_ptr = self.buf.data_ptr() + self.STATUS
         self.status = w(self.STATUS, 1).view(torch.int32)
 
