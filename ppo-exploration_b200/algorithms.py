@@ -17,7 +17,6 @@ The host numpy RNG is consumed in exactly the reference's order: one permutation
 """
 import ctypes as C
 import time
-import zlib
 from collections import deque
 
 import numpy as np
@@ -382,7 +381,7 @@ class BaseAlgorithm(object):
             # every rank must draw the SAME permutation: exchange a digest of the numpy state the stream starts from
             # (asynchronous; compared in _finish_train, where the host synchronises anyway)
             st = np.random.get_state()
-            digest = (zlib.crc32(np.ascontiguousarray(st[1]).tobytes()) << 16) ^ int(st[2])
+            digest = D.rng_digest(st)
             self._rng_check = D.all_gather_cat(torch.tensor([digest], dtype=torch.int64, device=self.device))
             self._replicate_rollout(ro)
         return rng
@@ -439,9 +438,8 @@ class BaseAlgorithm(object):
         for k in range(n_mb):
             bg = min(Bg, total - k * Bg)
             if glob:
-                base, rem = divmod(bg, W)
-                b, lo = base + (1 if r < rem else 0), r * base + min(r, rem)
-                if base < 2:
+                lo, b = D.global_slice(bg, W, r)
+                if bg // W < 2:
                     raise RuntimeError(f"a global minibatch of {bg} rows cannot be split over {W} ranks")
                 opts = L.GatherOpts(N, -lo, bg, self._cursor.data_ptr(), n_mb, total, Bg)
                 yield opts, lo, b, bg, ("g", b, bg, lo, self._perm_set), self._glob

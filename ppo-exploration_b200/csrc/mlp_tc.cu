@@ -1407,14 +1407,9 @@ extern "C" int ppx_mlp3_tc_fwd(const float* X, int ldx, int M, int D, int H, int
   for (int g = 0; g < G; ++g) { p.W3[g] = W3[g]; p.b3[g] = b3[g]; p.o[g] = outs[g]; p.out[g] = out[g]; }
   dim3 grid((unsigned)mt::fwd_grid(M, G), (unsigned)G);
   cudaStream_t st = (cudaStream_t)stream;
-  static int v1 = -1;
-  if (v1 < 0) { const char* e = getenv("PPX_MLP_TC_FWD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }   // comparison runs only
-  if (D <= 16 && !v1) return mt::dp_of(D) == 8 ? mt::launch_fwd2<8>(p, grid, st) : mt::launch_fwd2<16>(p, grid, st);
-  switch (mt::dp_of(D)) {
-    case 8: return mt::launch_fwd<8>(p, grid, st);
-    case 16: return mt::launch_fwd<16>(p, grid, st);
-    default: return mt::launch_fwd<32>(p, grid, st);
-  }
+  // D <= 16: layer 1 on the tensor pipe, A operands in TMEM (v2); 16 < D <= 32: the round-1 kernel
+  if (D <= 16) return mt::dp_of(D) == 8 ? mt::launch_fwd2<8>(p, grid, st) : mt::launch_fwd2<16>(p, grid, st);
+  return mt::launch_fwd<32>(p, grid, st);
 }
 
 extern "C" int64_t ppx_mlp3_tc_bwd_workspace(int M, int D, int H, int G, const int* outs) {

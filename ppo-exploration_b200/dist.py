@@ -48,30 +48,19 @@ def all_gather_cat(t):
     return torch.stack(parts)
 
 
-def merge_mean_std(stats_local, n_local):
-    """Global mean / unbiased std from per-rank {mean, std(ddof=1)} of n_local samples each (n may differ).
-    stats_local: f64 tensor [2] on the compute device.  Returns f64 [2] (device), merged in rank order."""
-    W = world_size()
-    if W == 1:
-        return stats_local
-    n = torch.tensor([float(n_local)], dtype=torch.float64, device=stats_local.device)
-    m2 = stats_local[1:2] ** 2 * (n - 1.0)
-    rec = torch.cat([n, stats_local[0:1], m2])
-    allr = all_gather_cat(rec)                                    # [W, 3]
-    ns, means, m2s = allr[:, 0], allr[:, 1], allr[:, 2]
-    tot = ns.sum()
-    mean = (ns * means).sum() / tot
-    M2 = (m2s + ns * (means - mean) ** 2).sum()
-    return torch.stack([mean, torch.sqrt(M2 / (tot - 1.0))])
+def global_slice(bg, W, r):
+    """Rows [lo, lo + b) of a global minibatch of bg rows that rank r of W processes ("global" shard mode): contiguous,
+    in rank order, sizes differing by at most one.  Returns (lo, b)."""
+    base, rem = divmod(int(bg), int(W))
+    return r * base + min(r, rem), base + (1 if r < rem else 0)
 
 
-def owned_slice(global_idx, T, n_local, r):
-    """Rows of a global minibatch that live on rank r.  global_idx: numpy int64 flat indices over
-    [T, W*n_local] in the reference's env-major flatten; returns LOCAL flat indices (numpy int64)."""
-    env = global_idx // T
-    mine = (env // n_local) == r
-    g = global_idx[mine]
-    return (g // T - r * n_local) * T + g % T
+def rng_digest(state):
+    """48-bit digest of a numpy legacy RandomState state tuple (MT19937 key + position): the ranks of a "global" sharded
+    learner exchange it to check that they are about to draw the same permutation."""
+    import zlib
+    import numpy as np
+    return (zlib.crc32(np.ascontiguousarray(state[1]).tobytes()) << 16) ^ int(state[2])
 
 
 def interleave_env_shards(x):

@@ -1,6 +1,6 @@
 """World-size-2 gloo tests (CPU) of the shard-boundary host logic in ppo-exploration_b200/dist.py:
-moment merging for the advantage normalisation, owner-computes index slicing of a global permutation, env-shard
-interleaving for the replicated SimHash update, and the gather / reduce wrappers."""
+the row split of a global minibatch over the ranks, the numpy-state digest that guards the shared permutation stream,
+env-shard interleaving for the sharded SimHash update, and the gather / reduce wrappers."""
 import os
 import socket
 
@@ -32,22 +32,23 @@ def _worker(rank, world, port, q):
         assert D.world_size() == world and D.rank() == rank
         rs = np.random.RandomState(0)
         T, n_local = 16, 6
-        # ---- merge_mean_std: ragged local counts (owner-computes minibatches are ragged) ----
-        data = rs.randn(101) * 3 + 1
-        cut = 37
-        mine = data[:cut] if rank == 0 else data[cut:]
-        loc = torch.tensor([mine.mean(), mine.std(ddof=1)], dtype=torch.float64)
-        got = D.merge_mean_std(loc, len(mine))
-        assert abs(float(got[0]) - data.mean()) < 1e-12 and abs(float(got[1]) - data.std(ddof=1)) < 1e-12
-        # ---- owned_slice: every global index lands on exactly one rank, as the right local index ----
-        perm = np.random.RandomState(1).permutation(T * n_local * world)
-        g = perm[:50]
-        loc_idx = D.owned_slice(g, T, n_local, rank)
-        env, t = g // T, g % T
-        want = [(e - rank * n_local) * T + tt for e, tt in zip(env, t) if e // n_local == rank]
-        assert list(loc_idx) == want
-        counts = D.all_gather_cat(torch.tensor([len(loc_idx)]))
-        assert int(counts.sum()) == len(g)
+        # ---- global_slice: every row of a global minibatch lands on exactly one rank, contiguous, in rank order ----
+        for bg in (50, 51, 4, 131072 * world):
+            spans = [D.global_slice(bg, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(b for _, b in spans) == bg
+            assert all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            assert max(b for _, b in spans) - min(b for _, b in spans) <= 1
+        lo, b = D.global_slice(101, world, rank)
+        counts = D.all_gather_cat(torch.tensor([b]))
+        assert int(counts.sum()) == 101
+        # ---- rng_digest: equal states agree across ranks, a rank that drew on its own is found out ----
+        np.random.seed(7)
+        same = D.all_gather_cat(torch.tensor([D.rng_digest(np.random.get_state())], dtype=torch.int64))
+        assert bool((same == same[0]).all())
+        if rank == 1:
+            np.random.rand(3)
+        diff = D.all_gather_cat(torch.tensor([D.rng_digest(np.random.get_state())], dtype=torch.int64))
+        assert not bool((diff == diff[0]).all())
         # ---- interleave_env_shards: gathered per-rank [T, n_local] blocks -> global env order ----
         full = rs.randn(T, n_local * world).astype(np.float32)
         block = torch.tensor(full[:, rank * n_local:(rank + 1) * n_local])
