@@ -19,7 +19,9 @@ struct GatherArgs {
   // optional: {mean, unbiased std} of up to two gathered f32 [B] fields (the advantages, algorithms.py:219 / :431-434),
   // computed on the way so the minibatch needs no separate moments launch
   int stat_field[2];
-  int order[PPX_MAX_GATHER];     // blockIdx.y -> field
+  int order[PPX_MAX_GATHER];     // blockIdx.y (after the row-per-thread slice) -> field
+  unsigned small_mask;           // fields with rows <= 32 bytes: ONE thread gathers all of them for a row (slice blockIdx.y == 0)
+  int small_idx[8], n_small;     // the same fields as a list (at most kSmallMax)
   double* stat_out[2];
   double* stat_part;             // [2][kStatMax][2]
   unsigned int* stat_ticket;     // [2]
@@ -34,6 +36,7 @@ struct GatherArgs {
   uint32_t* status_dev;
 };
 constexpr int kStatMax = 4096;
+constexpr int kSmallMax = 8;
 
 // flat index of the (global) env-major flatten (buffer.py:49-52) -> storage row.  T*N < 2^31 (checked on the host): the
 // index arithmetic is 32-bit -- a 64-bit division costs ~70 instructions, and this decode runs once per gathered word.
@@ -63,26 +66,12 @@ __device__ __forceinline__ void gather_rows(const char* __restrict__ src, char* 
   }
 }
 
-// one f32 per row + running (sum, sum of squares) in f64; the last CTA of the field finishes the moments in a fixed order
-__device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot, const int64_t* __restrict__ idx, int64_t B,
-                                         int T, int N) {
+// Block partials of one statistics slot -> {mean, unbiased std}: every block of the slice publishes (sum, sum of squares),
+// the last one to arrive adds them in a fixed order and -- sharded with per-rank shuffles -- merges the ranks' records.
+// All threads of the block call this; n_stat = rows the statistics cover on this rank.
+__device__ void finish_stats(const GatherArgs& args, int slot, double s, double q, int64_t n_stat) {
   __shared__ double s_red[32];
   __shared__ bool s_last;
-  const float* src = reinterpret_cast<const float*>(args.src[a]);
-  float* dst = reinterpret_cast<float*>(args.dst[a]);
-  double s = 0.0, q = 0.0;
-  const int64_t lo = args.stat_n > 0 ? args.stat_lo : 0, n_stat = args.stat_n > 0 ? args.stat_n : B;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_stat; k += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = lo + k;
-    const float v = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
-    if (b >= 0 && b < B) dst[b] = v;
-    s += (double)v;
-    q += (double)v * (double)v;
-  }
-  if (args.stat_n > 0) {                                      // rows of the slice the statistics range does not cover
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
-      if (b < lo || b >= lo + n_stat) dst[b] = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
-  }
   s = block_sum(s, s_red);
   q = block_sum(q, s_red);
   double* part = args.stat_part + (size_t)slot * kStatMax * 2;
@@ -160,10 +149,89 @@ __device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot
   }
 }
 
-__global__ void __launch_bounds__(256)
+// one f32 per row + running (sum, sum of squares) in f64; the last CTA of the field finishes the moments in a fixed order
+__device__ void gather_scalar_with_stats(const GatherArgs& args, int a, int slot, const int64_t* __restrict__ idx, int64_t B,
+                                         int T, int N) {
+  const float* src = reinterpret_cast<const float*>(args.src[a]);
+  float* dst = reinterpret_cast<float*>(args.dst[a]);
+  double s = 0.0, q = 0.0;
+  const int64_t lo = args.stat_n > 0 ? args.stat_lo : 0, n_stat = args.stat_n > 0 ? args.stat_n : B;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_stat; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = lo + k;
+    const float v = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
+    if (b >= 0 && b < B) dst[b] = v;
+    s += (double)v;
+    q += (double)v * (double)v;
+  }
+  if (args.stat_n > 0) {                                      // rows of the slice the statistics range does not cover
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
+      if (b < lo || b >= lo + n_stat) dst[b] = __ldg(src + row_of(__ldg(idx + b), T, N, args.n_shard));
+  }
+  finish_stats(args, slot, s, q, n_stat);
+}
+
+// Narrow fields (rows of <= 32 bytes: at C2 every field of the RolloutSample): one thread per ROW reads the index once,
+// decodes it once and has the loads of all fields in flight together (7 independent loads at C2) before it stores;
+// the field-per-slice scheme below pays the index load, the decode and a dependent load per 4..16 bytes moved.
+__device__ void gather_small_rows(const GatherArgs& args, const int64_t* __restrict__ idx, int64_t B, int T, int N) {
+  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+  const bool st0 = args.stat_field[0] >= 0 && ((args.small_mask >> args.stat_field[0]) & 1u);
+  const bool st1 = args.stat_field[1] >= 0 && ((args.small_mask >> args.stat_field[1]) & 1u);
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = row_of(__ldg(idx + b), T, N, args.n_shard);
+#pragma unroll
+    for (int k0 = 0; k0 < kSmallMax; k0 += 4) {                // four fields' loads in flight, then their stores (32 registers)
+      if (k0 >= args.n_small) break;
+      int r[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k0 + k >= args.n_small) continue;
+        const int f = args.small_idx[k0 + k], rb = args.row_bytes[f];
+        const char* sp = args.src[f] + row * rb;
+        if (args.vec16[f]) {
+          const int4 v = __ldg(reinterpret_cast<const int4*>(sp));
+          r[k][0] = v.x; r[k][1] = v.y; r[k][2] = v.z; r[k][3] = v.w;
+          if (rb > 16) {
+            const int4 u = __ldg(reinterpret_cast<const int4*>(sp) + 1);
+            r[k][4] = u.x; r[k][5] = u.y; r[k][6] = u.z; r[k][7] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w)
+            if (4 * w < rb) r[k][w] = __ldg(reinterpret_cast<const int*>(sp) + w);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k0 + k >= args.n_small) continue;
+        const int f = args.small_idx[k0 + k], rb = args.row_bytes[f];
+        char* dp = args.dst[f] + b * rb;
+        if (args.vec16[f]) {
+          *reinterpret_cast<int4*>(dp) = make_int4(r[k][0], r[k][1], r[k][2], r[k][3]);
+          if (rb > 16) *(reinterpret_cast<int4*>(dp) + 1) = make_int4(r[k][4], r[k][5], r[k][6], r[k][7]);
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w)
+            if (4 * w < rb) reinterpret_cast<int*>(dp)[w] = r[k][w];
+        }
+        if (st0 && f == args.stat_field[0]) { const double v = (double)__int_as_float(r[k][0]); s0 += v; q0 += v * v; }
+        if (st1 && f == args.stat_field[1]) { const double v = (double)__int_as_float(r[k][0]); s1 += v; q1 += v * v; }
+      }
+    }
+  }
+  if (st0) finish_stats(args, 0, s0, q0, B);
+  if (st1) finish_stats(args, 1, s1, q1, B);
+}
+
+__global__ void __launch_bounds__(256, 4)
 gather_kernel(GatherArgs args, const int64_t* __restrict__ idx_base, int64_t B, int T, int N) {
-  const int a = args.order[blockIdx.y];                       // statistics fields first: their tail overlaps the other fields' rows
   const int64_t* idx = idx_of(args, idx_base);
+  int y = blockIdx.y;
+  if (args.small_mask) {
+    if (y == 0) { gather_small_rows(args, idx, B, T, N); return; }
+    --y;
+  }
+  const int a = args.order[y];                                // statistics fields first: their tail overlaps the other fields' rows
   if (a == args.stat_field[0]) { gather_scalar_with_stats(args, a, 0, idx, B, T, N); return; }
   if (a == args.stat_field[1]) { gather_scalar_with_stats(args, a, 1, idx, B, T, N); return; }
   if (args.vec16[a]) gather_rows<int4>(args.src[a], args.dst[a], args.row_bytes[a], idx, B, T, N, args.n_shard);
@@ -296,12 +364,35 @@ int gather_impl(const void* const* srcs_host, void* const* dsts_host, const int*
     args.stat_part = part; args.stat_ticket = ticket;
     if (gx > ppx::kStatMax) gx = ppx::kStatMax;
   }
-  {
-    int k = 0;
-    for (int q = 0; q < 2; ++q) if (args.stat_field[q] >= 0) args.order[k++] = args.stat_field[q];
-    for (int a = 0; a < n_arrays; ++a) if (a != args.stat_field[0] && a != args.stat_field[1]) args.order[k++] = a;
+  // narrow fields go to the row-per-thread slice (statistics fields too, unless their range differs from the gathered
+  // rows: the "global" shard mode takes the moments over the whole global minibatch)
+  args.small_mask = 0u;
+  int n_small = 0;
+  for (int a = 0; a < n_arrays; ++a) {
+    const bool is_stat = a == args.stat_field[0] || a == args.stat_field[1];
+    if (row_bytes_host[a] <= 32 && !(is_stat && args.stat_n > 0) && n_small < ppx::kSmallMax) {
+      args.small_mask |= 1u << a;
+      args.small_idx[n_small++] = a;
+    }
   }
-  dim3 grid((unsigned)gx, (unsigned)n_arrays);
+  if (n_small < 2) { args.small_mask = 0u; n_small = 0; }
+  args.n_small = n_small;
+  int n_slices = 0;
+  for (int q = 0; q < 2; ++q)
+    if (args.stat_field[q] >= 0 && !((args.small_mask >> args.stat_field[q]) & 1u)) args.order[n_slices++] = args.stat_field[q];
+  for (int a = 0; a < n_arrays; ++a)
+    if (a != args.stat_field[0] && a != args.stat_field[1] && !((args.small_mask >> a) & 1u)) args.order[n_slices++] = a;
+  if (n_small) {
+    int64_t big_words = 0;                                    // the slices share gridDim.x: size it for the rows and the wide fields
+    for (int k = 0; k < n_slices; ++k) {
+      const int a = args.order[k];
+      big_words = std::max<int64_t>(big_words, B * (row_bytes_host[a] / (args.vec16[a] ? 16 : 4)));
+    }
+    if (opts && opts->stat_n > big_words) big_words = opts->stat_n;
+    gx = std::min<int64_t>(std::max<int64_t>(ppx::ceil_div(std::max<int64_t>(B, big_words), 256), 1), cap);
+    if (n_stats > 0 && gx > ppx::kStatMax) gx = ppx::kStatMax;
+  }
+  dim3 grid((unsigned)gx, (unsigned)(n_slices + (n_small ? 1 : 0)));
   ppx::gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(args, idx, B, T, N);
   return ppx::after_launch("gather_minibatch");
 }
