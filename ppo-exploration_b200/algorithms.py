@@ -588,14 +588,18 @@ class PPO(BaseAlgorithm):
         fuse = self._fuse_adam_ok()
         step = 0
         for ep in range(self.n_epochs):
-            for opts, lo, b, bt, key, src in self._epoch_minibatches(ro, rng, ep, self.n_epochs):
-                def fn(opts=opts, lo=lo, b=b, bt=bt, src=src):
+            # one graph per EPOCH (the device step cursor finds each minibatch's index slice): the launches of its
+            # minibatches follow each other without the ~3 us a graph boundary costs
+            mbs = list(self._epoch_minibatches(ro, rng, ep, self.n_epochs))
+
+            def fn(mbs=mbs):
+                for opts, lo, b, bt, key, src in mbs:
                     ok = self._gather_with_stats(ro, self._perm_all[lo:], bufs, opts=opts, B=b, sources=src)
                     self._policy_step(bufs, b, self._losses_buf.data_ptr(), B_total=bt, stats_ready=ok, stats_global=src is not None,
                                       row_dev=self._cursor.data_ptr(), fuse_adam=fuse)
                     self._policy_optim_step()
-                self._graph_call(("ppo",) + key, fn)
-                step += 1
+            self._graph_call(("ppo",) + tuple(mb[4] for mb in mbs), fn)
+            step += len(mbs)
         ro.generator_ready = True
         self._rng_close(rng)
         self._finish_train(step, ("train/total_loss", "train/policy_gradient_loss", "train/value_loss",
