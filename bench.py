@@ -348,7 +348,7 @@ class OpTimer:
     # name -> indices of (M, K, N, batch) among the call's arguments (None = 1)
     SHAPE_ARGS = {"ppx_linear_fwd": (4, 5, 6, 10), "ppx_linear_bwd_data": (3, 4, 5, 11), "ppx_linear_bwd_weight": (4, 5, 6, 10),
                   "ppx_mlp3_fwd": (2, 3, 4, 5), "ppx_mlp3_bwd": (2, 3, 4, 5), "ppx_mlp3_tc_fwd": (2, 3, 4, 5),
-                  "ppx_mlp3_tc_bwd": (2, 3, 4, 5), "ppx_tc_linear": (5, 6, 7, None), "ppx_tc_wgrad": (4, 5, 6, None)}
+                  "ppx_mlp3_tc_bwd": (2, 3, 4, 5), "ppx_tc_linear": (5, 6, 7, None), "ppx_tc_linear_ws": (5, 6, 7, None), "ppx_tc_wgrad": (4, 5, 6, None)}
 
     def __init__(self, L, torch):
         self.L, self.torch, self.rec, self.orig = L, torch, [], L.call
@@ -444,7 +444,7 @@ def roofline_of(agg, cfg, peaks):
                     tf32_frac_of_bf16_peak=3.0 * achieved / tf_peak,
                     note="fused policy-MLP kernel with its 64x64 GEMMs on tcgen05 (3xTF32, fp32-equivalent); algorithmic bytes = "
                          "4 M (D + 2 G H + sum o); tf32_mma_tflops counts the three tensor passes")
-    if op in ("ppx_tc_linear", "ppx_tc_wgrad"):
+    if op in ("ppx_tc_linear", "ppx_tc_linear_ws", "ppx_tc_wgrad"):
         return dict(common, bound="tensor", kernel=f"{op} M={M_} K={K_} N={N_}", achieved=achieved, peak=tf_peak, unit="TFLOP/s",
                     frac=achieved / tf_peak, traffic=None, tf32_mma_tflops=3.0 * achieved, tf32_frac_of_bf16_peak=3.0 * achieved / tf_peak,
                     note="wide dense layer on tcgen05 (3xTF32: fp32-equivalent result from three tf32 passes); achieved = "

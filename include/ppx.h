@@ -304,8 +304,18 @@ int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, i
                   const float* bias, const float* H, int ldh, int act, int dgrad,
                   const double* a_mean, const double* a_istd, float a_clip /* optional (both or neither): A is replaced
                   by clip((A - a_mean[k]) * a_istd[k], +-a_clip) in f64 on the fly (normalize_obs fused into the
-                  A-split stage; a_istd from ppx_obs_istd) */,
+                  A-split stage;
+ a_istd from ppx_obs_istd) */,
                   float* C, int ldc, void* stream);
+/* Same with a split-K workspace: when the M x N tiles do not fill the SMs and the reduction is long (wide first layers at
+ * minibatch size: 32 tiles, 882 k-blocks) the reduction is cut S ways across CTAs (S chosen inside: fewest waves per
+ * split), raw partial sums go to `workspace` [S][M][round4(N)] and a finish pass adds them in split order and applies the
+ * epilogue -- deterministic.  ppx_tc_linear_workspace() = floats needed (0: the shape is not split; workspace may be NULL). */
+int64_t ppx_tc_linear_workspace(int M, int R, int N);
+int ppx_tc_linear_ws(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
+                     const float* bias, const float* H, int ldh, int act, int dgrad, const double* a_mean,
+                     const double* a_istd, float a_clip, float* C, int ldc, float* workspace, int64_t workspace_floats,
+                     void* stream);
 /* Weight gradient of a wide layer on the tensor cores: dW [K,N] = X^T . dY over M samples, dbias = colsum(dY)
  * (dbias may be NULL).  X is transposed and dY split/transposed into `workspace` (>= ppx_tc_wgrad_workspace floats),
  * then the 3xTF32 kernel runs with the samples as the reduction dimension.  M % 4 == 0, M >= 256, K >= 128, N >= 16. */

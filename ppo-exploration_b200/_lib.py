@@ -104,6 +104,8 @@ SIGNATURES = {
     "ppx_tc_supported": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "ppx_tc_split": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "ppx_tc_linear": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, C.c_float, c_p, c_i, c_p]),
+    "ppx_tc_linear_ws": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, C.c_float, c_p, c_i, c_p, c_l, c_p]),
+    "ppx_tc_linear_workspace": (c_l, [c_i, c_i, c_i]),
     "ppx_obs_istd": (c_i, [c_p, c_i, c_p, c_p]),
     "ppx_tc_wgrad_workspace": (c_l, [c_i, c_i, c_i]),
     "ppx_tc_wgrad_supported": (c_i, [c_i, c_i, c_i, c_p, c_p]),

@@ -60,6 +60,7 @@ struct Params {
   const double* a_mean;         // optional per-column transform of A before the hi/lo split (RND observation
   const double* a_istd;         //   normalisation, algorithms.py:111-118): A' = clip((A - mean) * istd, +-a_clip) in f64
   float a_clip;
+  float* part; int ldp;         // split-K (gridDim.z > 1): raw partial accumulators [gridDim.z][M][ldp], finished by splitk_finish_kernel
 };
 
 template <int BN, int STAGES>
@@ -77,7 +78,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // N tiles of one row block run side by side (A tile shared through L2)
-  const int num_kb = (p.R + BK - 1) / BK;
+  // split-K: CTA z of gridDim.z works on k-blocks [kb0, kb0 + num_kb) (few M x N tiles and a long reduction -- the wide
+  // first layers at minibatch size 4096 have 32 tiles for 148 SMs and 882 k-blocks)
+  const int num_kb_all = (p.R + BK - 1) / BK;
+  const int kb_per = (num_kb_all + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kb0 = (int)blockIdx.z * kb_per;
+  const int num_kb = max(0, min(num_kb_all, kb0 + kb_per) - kb0);
 
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto ready_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
@@ -117,9 +123,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
-        tma_load_2d(smem_u32(a_hi(s)), &mapA, full_bar(s), kb * BK, m0);
-        tma_load_2d(smem_u32(b_hi(s)), &mapBhi, full_bar(s), kb * BK, n0);
-        tma_load_2d(smem_u32(b_lo(s)), &mapBlo, full_bar(s), kb * BK, n0);
+        tma_load_2d(smem_u32(a_hi(s)), &mapA, full_bar(s), (kb0 + kb) * BK, m0);
+        tma_load_2d(smem_u32(b_hi(s)), &mapBhi, full_bar(s), (kb0 + kb) * BK, n0);
+        tma_load_2d(smem_u32(b_lo(s)), &mapBlo, full_bar(s), (kb0 + kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -163,7 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t ph = (kb / STAGES) & 1;
       if (norm) {                                            // fetch the column constants while the TMA is in flight
         if (t < 2 * BK) {
-          const int k = kb * BK + (t & (BK - 1));
+          const int k = (kb0 + kb) * BK + (t & (BK - 1));
           const double* src = (t < BK) ? p.a_mean : p.a_istd;
           s_norm[s][t >> 5][t & (BK - 1)] = k < p.R ? __ldg(src + k) : 0.0;
         }
@@ -221,7 +227,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
     }
-    if (row < p.M) {
+    if (row < p.M && p.part) {                               // split-K: raw partial sums; bias / activation in the finish kernel
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float* dst = p.part + ((size_t)blockIdx.z * p.M + row) * p.ldp + n0 + c0;
+        if (n0 + c0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) dst[j] = acc[c0 + j];
+        }
+      }
+    } else if (row < p.M) {
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float* dst = p.C + (size_t)row * p.ldc + n0 + c0;
@@ -298,6 +317,33 @@ split_kernel(const float* __restrict__ src, int ld, int rows, int cols, float* _
   }
 }
 
+// split-K tail: C = epi(sum over the S partials, in split order) -- same epilogue as the single-pass kernel
+__global__ void __launch_bounds__(256) splitk_finish_kernel(Params p, int S) {
+  const int64_t total4 = (int64_t)p.M * (p.ldp / 4);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e / (p.ldp / 4)), col = (int)(e % (p.ldp / 4)) * 4;
+    if (col >= p.N) continue;
+    float4 a = *reinterpret_cast<const float4*>(p.part + (size_t)row * p.ldp + col);
+    for (int z = 1; z < S; ++z) {
+      const float4 b = *reinterpret_cast<const float4*>(p.part + ((size_t)z * p.M + row) * p.ldp + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float o[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (col + j >= p.N) continue;
+      float x = o[j];
+      if (!p.dgrad) {
+        if (p.bias) x += __ldg(p.bias + col + j);
+        x = act_fwd(x, p.act);
+      } else if (p.H) {
+        x *= act_bwd(__ldg(p.H + (size_t)row * p.ldh + col + j), p.act);
+      }
+      p.C[(size_t)row * p.ldc + col + j] = x;
+    }
+  }
+}
+
 // out[c] = sum over rows of src[r, c], fixed order: block = 32 columns x 8 row slices, slices combined 0..7
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int ld, int rows, int cols, float* __restrict__ out) {
   __shared__ float sl[8][33];
@@ -343,17 +389,35 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   return PPX_OK;
 }
 
+// How many ways to cut the reduction: minimise waves(S) / S (+ a little per split for the finish pass) over S <= 8 with at
+// least 16 k-blocks per split; 1 when the tiles already fill the machine.
+static int pick_splits(int M, int R, int N, int BN) {
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN), sms = sm_count(), nkb = ceil_div(R, BK);
+  if (tiles >= 4 * sms) return 1;                             // many waves: the quantisation loss is small
+  int best = 1;
+  double best_cost = (double)ceil_div(tiles, sms);
+  for (int S = 2; S <= 8 && nkb / S >= 16; ++S) {
+    const double cost = (double)ceil_div(tiles * S, sms) / S * (1.0 + 0.03 * (S - 1));
+    if (cost < best_cost * 0.97) { best = S; best_cost = cost; }
+  }
+  return best;
+}
+
 template <int BN, int STAGES>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const Params& p, cudaStream_t st, int S = 1) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     PPX_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM));
+  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), (unsigned)S);
   tc_gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(ma, mbh, mbl, p);
-  return after_launch("tc_gemm");
+  int rc = after_launch("tc_gemm");
+  if (rc || S == 1) return rc;
+  const int64_t total4 = (int64_t)p.M * (p.ldp / 4);
+  splitk_finish_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total4, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(p, S);
+  return after_launch("tc_gemm(split-K finish)");
 }
 
 }  // namespace tc
@@ -375,9 +439,24 @@ extern "C" int ppx_tc_split(const float* src, int rows, int cols, float* hi, flo
   return after_launch("tc_split");
 }
 
+static inline int splitk_ldp(int N) { return (N + 3) & ~3; }
+
+extern "C" int64_t ppx_tc_linear_workspace(int M, int R, int N) {
+  if (M < 1 || R < 4 || N < 16) return 0;
+  const int S = tc::pick_splits(M, R, N, N <= 64 ? 64 : 128);
+  return S == 1 ? 0 : (int64_t)S * M * splitk_ldp(N);
+}
+
 extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
                              const float* bias, const float* H, int ldh, int act, int dgrad, const double* a_mean,
                              const double* a_istd, float a_clip, float* C, int ldc, void* stream) {
+  return ppx_tc_linear_ws(A, lda, Bhi, Blo, ldb, M, R, N, bias, H, ldh, act, dgrad, a_mean, a_istd, a_clip, C, ldc, nullptr, 0, stream);
+}
+
+extern "C" int ppx_tc_linear_ws(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, int M, int R, int N,
+                                const float* bias, const float* H, int ldh, int act, int dgrad, const double* a_mean,
+                                const double* a_istd, float a_clip, float* C, int ldc, float* workspace, int64_t workspace_floats,
+                                void* stream) {
   PPX_REQUIRE(A && Bhi && Blo && C, "tc_linear: null pointer");
   PPX_REQUIRE(ppx_tc_supported(M, R, N, lda, ldb, A, Bhi) && !((uintptr_t)Blo & 15), "tc_linear: shape/alignment not supported (M=%d R=%d N=%d lda=%d ldb=%d)", M, R, N, lda, ldb);
   const int BN = N <= 64 ? 64 : 128;
@@ -389,16 +468,24 @@ extern "C" int ppx_tc_linear(const float* A, int lda, const float* Bhi, const fl
   rc = tc::make_map(&mbl, Blo, N, R, ldb, BN);
   if (rc) return rc;
   PPX_REQUIRE((a_mean == nullptr) == (a_istd == nullptr), "tc_linear: a_mean / a_istd must be given together");
-  tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad, a_mean, a_istd, a_clip};
-  if (BN == 64) return tc::launch<64, 4>(ma, mbh, mbl, p, (cudaStream_t)stream);
-  return tc::launch<128, 3>(ma, mbh, mbl, p, (cudaStream_t)stream);
+  tc::Params p{M, N, R, ldc, C, bias, H, ldh, act, dgrad, a_mean, a_istd, a_clip, nullptr, 0};
+  int S = 1;
+  if (workspace && !((uintptr_t)workspace & 15)) {            // split-K only with a workspace of ppx_tc_linear_workspace() floats
+    S = tc::pick_splits(M, R, N, BN);
+    if (S > 1 && workspace_floats >= (int64_t)S * M * splitk_ldp(N)) { p.part = workspace; p.ldp = splitk_ldp(N); }
+    else S = 1;
+  }
+  if (BN == 64) return tc::launch<64, 4>(ma, mbh, mbl, p, (cudaStream_t)stream, S);
+  return tc::launch<128, 3>(ma, mbh, mbl, p, (cudaStream_t)stream, S);
 }
 
 // Weight gradient of a wide layer on the tensor cores:  dW [K,N] = X^T [K,M] . dY [M,N]  (+ dbias = colsum dY).
 // The reduction runs over the M samples, so both operands are needed K-major in M: X is transposed once
 // (Xt [K,M], split hi/lo on the fly as the A operand), dY is split and transposed (hiT/loT [N,M], the B operand), and
 // the same 3xTF32 kernel as the forward produces dW row-major [K,N] -- the in-major weight layout.
-extern "C" int64_t ppx_tc_wgrad_workspace(int M, int K, int N) { return (int64_t)M * K + 2 * (int64_t)M * N; }
+extern "C" int64_t ppx_tc_wgrad_workspace(int M, int K, int N) {
+  return (int64_t)M * K + 2 * (int64_t)M * N + ppx_tc_linear_workspace(K, M, N);       // + the split-K partials of the GEMM
+}
 
 extern "C" int ppx_tc_wgrad_supported(int M, int K, int N, const void* X, const void* dY) {
   return (M >= 256 && M % 4 == 0 && K >= 128 && N >= 16 && X && dY) ? 1 : 0;
@@ -422,5 +509,7 @@ extern "C" int ppx_tc_wgrad(const float* X, int ldx, const float* dY, int lddy, 
     rc = after_launch("tc_wgrad(colsum)");
     if (rc) return rc;
   }
-  return ppx_tc_linear(Xt, M, dYhiT, dYloT, M, K, M, N, nullptr, nullptr, 0, PPX_ACT_NONE, 0, nullptr, nullptr, 0.f, dW, N, stream);
+  float* part = dYloT + (size_t)M * N;                        // M % 4 == 0: 16-byte aligned like the workspace
+  return ppx_tc_linear_ws(Xt, M, dYhiT, dYloT, M, K, M, N, nullptr, nullptr, 0, PPX_ACT_NONE, 0, nullptr, nullptr, 0.f, dW, N,
+                          part, ppx_tc_linear_workspace(K, M, N), stream);
 }

@@ -131,13 +131,30 @@ def tc_ok(M, R, N, lda, ldb, a_ptr, b_ptr):
     return (TC_ENABLED and M >= 128 and L.call("ppx_tc_supported", M, R, N, lda, ldb, a_ptr, b_ptr) == 1)
 
 
+_splitk_ws = {}          # device -> f32 workspace of the split-K tensor-core GEMM (grows; captured graphs are retired when it moves)
+
+
+def _tc_workspace(M, R, N):
+    need = int(L.call("ppx_tc_linear_workspace", int(M), int(R), int(N)))
+    if need == 0:
+        return None, 0
+    dev = torch.cuda.current_device()
+    ws = _splitk_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=torch.device("cuda", dev))
+        _splitk_ws[dev] = ws
+        _Scratch.generation += 1
+    return ws.data_ptr(), ws.numel()
+
+
 def dense_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy, tcw=None, a_norm=None):
     """act(X @ W + b): tensor-core path when the shape allows it, SIMT fp32 otherwise.  a_norm = (mean_ptr, istd_ptr,
     clip): X is normalised on the fly inside the tensor-core kernel (only valid when can_fuse_norm() said so)."""
     if tcw is not None and tc_ok(M, K, N, ldx, K, x_ptr, tcw.hiT.data_ptr()):
         mean_ptr, istd_ptr, clip = a_norm if a_norm is not None else (None, None, 0.0)
-        L.call("ppx_tc_linear", x_ptr, ldx, tcw.hiT.data_ptr(), tcw.loT.data_ptr(), K, M, K, N, b_ptr, None, 0, act, 0,
-               mean_ptr, istd_ptr, float(clip), y_ptr, ldy, L.stream())
+        ws_ptr, ws_n = _tc_workspace(M, K, N)                    # few output tiles + long reduction: split-K
+        L.call("ppx_tc_linear_ws", x_ptr, ldx, tcw.hiT.data_ptr(), tcw.loT.data_ptr(), K, M, K, N, b_ptr, None, 0, act, 0,
+               mean_ptr, istd_ptr, float(clip), y_ptr, ldy, ws_ptr, ws_n, L.stream())
     else:
         assert a_norm is None, "fused input normalisation needs the tensor-core path"
         linear_fwd(x_ptr, ldx, w_ptr, b_ptr, M, K, N, act, y_ptr, ldy)

@@ -45,6 +45,41 @@ def test_tc_linear_matches_fp64(M, R, N, act, dgrad):
     assert err <= 4e-6 * max(scale, 1.0), (err, scale)
 
 
+@pytest.mark.parametrize("M,R,N,act,dgrad", [(4096, 28224, 128, 2, 0), (4096, 28224, 384, 0, 0), (1024, 3136, 256, 1, 0),
+                                             (1023, 1024, 100, 3, 0), (512, 2048, 64, 1, 1)])
+def test_tc_linear_split_k_matches_fp64_and_is_deterministic(M, R, N, act, dgrad):
+    """Few output tiles + a long reduction (the wide first layers at minibatch size): ppx_tc_linear_ws cuts the reduction
+    across CTAs.  Same accuracy bound as the single-pass kernel, bit-identical from run to run (fixed-order finish)."""
+    from ppo_exploration_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, R, device="cuda", generator=g)
+    W = torch.randn(N, R, device="cuda", generator=g) / np.sqrt(R)
+    bias = torch.randn(N, device="cuda", generator=g)
+    H = torch.tanh(torch.randn(M, N, device="cuda", generator=g))
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    L.call("ppx_tc_split", W.data_ptr(), N, R, hi.data_ptr(), lo.data_ptr(), None, None, L.stream())
+    need = int(L.call("ppx_tc_linear_workspace", M, R, N))
+    assert need > 0, "these shapes are meant to take the split-K path"
+    ws = torch.full((need,), float("nan"), device="cuda")
+    outs = []
+    for _ in range(2):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        L.call("ppx_tc_linear_ws", A.data_ptr(), R, hi.data_ptr(), lo.data_ptr(), R, M, R, N, bias.data_ptr(), H.data_ptr(), N, act,
+               dgrad, None, None, 0.0, C.data_ptr(), N, ws.data_ptr(), need, L.stream())
+        outs.append(C)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    acc = A.double() @ W.double().t()
+    if dgrad:
+        d = {0: torch.ones_like(H), 1: 1 - H * H, 2: torch.where(H > 0, 1.0, 0.01), 3: torch.where(H > 0, 1.0, H + 1)}[act]
+        ref = acc * d.double()
+    else:
+        ref = ACTS[act](acc + bias.double())
+    assert torch.isfinite(outs[0]).all()
+    err, scale = float((outs[0].double() - ref).abs().max()), float(acc.abs().max())
+    assert err <= 4e-6 * max(scale, 1.0), (err, scale)
+
+
 def test_tc_split_transposed():
     from ppo_exploration_b200 import _lib as L
     W = torch.randn(70, 45, device="cuda")
