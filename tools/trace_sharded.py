@@ -121,7 +121,9 @@ def main():
         barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        reps = 40 // max(1, len(gs))
+        # a graph covers one EPOCH (its minibatches find their index slices through the device step cursor): never replay more
+        # epochs than the staging buffers of a pass hold
+        reps = max(1, m.n_epochs // max(1, len(gs)))
         for _ in range(reps):
             for _, g in gs:
                 g.replay()
