@@ -28,7 +28,7 @@ extern "C" {
 #define PPX_ERR_CAPACITY (-3)
 #define PPX_ERR_UNSUPPORTED (-4)
 
-enum { PPX_ACT_NONE = 0, PPX_ACT_TANH = 1, PPX_ACT_LEAKY_RELU = 2, PPX_ACT_ELU = 3 };
+enum { PPX_ACT_NONE = 0, PPX_ACT_TANH = 1, PPX_ACT_LEAKY_RELU = 2, PPX_ACT_ELU = 3, PPX_ACT_RELU = 4 };
 
 const char* ppx_last_error(void);
 int ppx_version(void);
@@ -325,6 +325,21 @@ int ppx_tc_wgrad(const float* X, int ldx, const float* dY, int lddy, int M, int 
                  float* workspace, void* stream);
 /* istd[d] = 1/sqrt(var[d] + 1e-10) in f64 (the scale of BaseAlgorithm.normalize_obs, algorithms.py:111-118) */
 int ppx_obs_istd(const double* var, int dim, double* istd, void* stream);
+
+/* ---------------------------------------------------------------- conv front-end ------------- */
+/* Convolutional front-end of the Atari-shaped configs (spec: the reference's dead draft
+ * .ipynb_checkpoints/models-checkpoint.py:48-66, :93-121 -- no live reference arithmetic, parity is defined against
+ * torch.nn.Conv2d in fp64).  A convolution (no padding, square stride) is lowered onto the dense layers above:
+ *   cols [N*OH*OW, C*KH*KW] = im2col(x);  Y [N*OH*OW, Cout] = act(cols . Wm + b)  (ppx_tc_linear_ws / ppx_linear_fwd);
+ *   dWm = cols^T dY (ppx_tc_wgrad / ppx_linear_bwd_weight);  dcols = dY Wm^T (ppx_linear_bwd_data);  dx = col2im(dcols).
+ * nchw = 1: x is [N,C,H,W], patch entries ordered (c, kh, kw) = torch's weight.view(Cout, -1) column order (first layer);
+ * nchw = 0: x is [N,H,W,C] (= the previous layer's output rows), patch entries ordered (kh, kw, c).
+ * OH = (H - KH) / stride + 1, OW likewise.  col2im is a deterministic gather (no atomics); dx has x's layout. */
+int ppx_im2col(const float* x, int nchw, int N, int C, int H, int W, int KH, int KW, int stride, float* cols, void* stream);
+int ppx_col2im(const float* dcols, int nchw, int N, int C, int H, int W, int KH, int KW, int stride, float* dx, void* stream);
+/* out[i] = d[i] * act'(h[i]) with the derivative expressed through the post-activation value h (out may alias d): the
+ * step from a gradient w.r.t. a layer's activated output to the gradient w.r.t. its pre-activation. */
+int ppx_act_bwd_mul(const float* d, const float* h, int64_t n, int act, float* out, void* stream);
 
 /* ---------------------------------------------------------------- PPO loss ------------------ */
 /* Fused clipped-surrogate / clipped-value / entropy loss, forward and backward, for one minibatch:

@@ -7,7 +7,7 @@ the C ABI in include/ppx.h; there is no CPU fallback.
 from . import _lib
 from . import logger
 from .buffer import BaseBuffer, RolloutStorage, IntrinsicStorage, CountTable, discount_with_dones
-from .models import Policy, RndNetwork, IntrinsicCuriosityModule, ActionConverter
+from .models import Policy, RndNetwork, IntrinsicCuriosityModule, ActionConverter, ConvTrunk, ParamBank
 from .util import RunningMeanStd, normalize_obs
 from .algorithms import BaseAlgorithm, PPO, PPO_RND, PPO_ICM
 from .evolution_strategies import EvolutionStrategy
@@ -16,4 +16,4 @@ from .env import VecNormalize
 
 __all__ = ["BaseBuffer", "RolloutStorage", "IntrinsicStorage", "CountTable", "discount_with_dones", "Policy",
            "RndNetwork", "IntrinsicCuriosityModule", "ActionConverter", "RunningMeanStd", "normalize_obs",
-           "BaseAlgorithm", "PPO", "PPO_RND", "PPO_ICM", "EvolutionStrategy", "Box", "Discrete", "SyntheticVecEnv", "logger", "VecNormalize"]
+           "BaseAlgorithm", "PPO", "PPO_RND", "PPO_ICM", "EvolutionStrategy", "Box", "Discrete", "SyntheticVecEnv", "logger", "VecNormalize", "ConvTrunk", "ParamBank"]

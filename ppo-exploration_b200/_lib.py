@@ -106,6 +106,9 @@ SIGNATURES = {
     "ppx_tc_linear": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, C.c_float, c_p, c_i, c_p]),
     "ppx_tc_linear_ws": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, C.c_float, c_p, c_i, c_p, c_l, c_p]),
     "ppx_tc_linear_workspace": (c_l, [c_i, c_i, c_i]),
+    "ppx_im2col": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "ppx_col2im": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "ppx_act_bwd_mul": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
     "ppx_obs_istd": (c_i, [c_p, c_i, c_p, c_p]),
     "ppx_tc_wgrad_workspace": (c_l, [c_i, c_i, c_i]),
     "ppx_tc_wgrad_supported": (c_i, [c_i, c_i, c_i, c_p, c_p]),

@@ -37,6 +37,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
     case PPX_ACT_TANH: return tanhf(x);
     case PPX_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
     case PPX_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case PPX_ACT_RELU: return fmaxf(x, 0.f);
     default: return x;
   }
 }
@@ -45,6 +46,7 @@ __device__ __forceinline__ float act_bwd(float h, int act) {
     case PPX_ACT_TANH: return 1.f - h * h;
     case PPX_ACT_LEAKY_RELU: return h > 0.f ? 1.f : 0.01f;
     case PPX_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;
+    case PPX_ACT_RELU: return h > 0.f ? 1.f : 0.f;
     default: return 1.f;
   }
 }

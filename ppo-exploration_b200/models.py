@@ -23,7 +23,7 @@ from . import _lib as L
 import ctypes as C
 import os
 
-ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3}
+ACT = {"none": 0, "tanh": 1, "leaky_relu": 2, "elu": 3, "relu": 4}
 F4 = 4  # bytes per float
 # tcgen05 3xTF32 path (tc_gemm.cu) for the forward of WIDE dense layers -- the bonus nets' first layers (RND
 # D=28224, ICM D=3136): K >= TC_MIN_K.  PPX_TC=0 forces the SIMT fp32 kernels everywhere.  The narrow policy MLPs
@@ -283,6 +283,175 @@ class DenseStack:
                             dx.data_ptr(), K)
             d = dx
         return d
+
+
+class ConvTrunk:
+    """Convolutional feature extractor for image observations: the Nature-CNN trunk of the reference's
+    dead draft (.ipynb_checkpoints/models-checkpoint.py:48-66: Conv 8/4 -> 4/2 -> 3/1, each + activation -> Flatten ->
+    Linear(7*7*64, hidden) + activation) or the RND conv stacks (:93-121), with forward AND backward, so it can sit in
+    front of the MLP heads of `Policy` / `RndNetwork`.  The reference has no live conv arithmetic; parity is defined
+    against torch.nn.Conv2d / nn.Linear in fp64 (tests/test_gpu_conv.py).
+
+    Every layer is im2col + one of the library's dense layers (ppx_im2col / ppx_col2im + `dense_fwd` / `linear_bwd_*`:
+    tcgen05 3xTF32 for reductions >= 256, split-K where the tiles are few), activations stay NHWC between layers; only
+    layer 0 reads the caller's NCHW frames.  Parameters live in a ParamBank under `prefix` with nn.Sequential naming
+    (f"{prefix}.{2*i}.weight" ...), stored in-major [K, Cout] with the patch order of the layer's im2col.
+
+    in_shape: (C, H, W); convs: [(Cout, kernel, stride, act)]; fc: (hidden, act) or None."""
+
+    def __init__(self, bank, prefix, in_shape, convs, fc, scratch):
+        self.bank, self.prefix, self.scratch = bank, prefix, scratch
+        self.geo, self.fc = self.geometry(in_shape, convs), fc
+        C, H, W = self.geo[-1][8], self.geo[-1][6], self.geo[-1][7]
+        self.flat_dim = C * H * W
+        self.out_dim = fc[0] if fc else self.flat_dim
+        self.tc = {}
+
+    @staticmethod
+    def geometry(in_shape, convs):
+        """per conv layer: (Cin, H, W, k, stride, act, OH, OW, Cout)"""
+        C, H, W = in_shape
+        geo = []
+        for Cout, k, s, act in convs:
+            OH, OW = (H - k) // s + 1, (W - k) // s + 1
+            geo.append((C, H, W, k, s, act, OH, OW, Cout))
+            C, H, W = Cout, OH, OW
+        return geo
+
+    @staticmethod
+    def specs(prefix, in_shape, convs, fc):
+        geo, out = ConvTrunk.geometry(in_shape, convs), []
+        for i, (C, H, W, k, s, act, OH, OW, Cout) in enumerate(geo):
+            out += [(f"{prefix}.{2 * i}.weight", (C * k * k, Cout)), (f"{prefix}.{2 * i}.bias", (Cout,))]
+        if fc:
+            C, OH, OW = geo[-1][8], geo[-1][6], geo[-1][7]
+            j = 2 * len(geo) + 1                       # nn.Sequential index after the Flatten module
+            out += [(f"{prefix}.{j}.weight", (C * OH * OW, fc[0])), (f"{prefix}.{j}.bias", (fc[0],))]
+        return out
+
+    def _fc_name(self):
+        return f"{self.prefix}.{2 * len(self.geo) + 1}"
+
+    def load_torch(self, state_dict):
+        """Weights of the equivalent torch nn.Sequential(Conv2d, act, ..., Flatten, Linear, act) state_dict -> the bank
+        (patch / flatten orders converted: layer 0 keeps torch's (c, kh, kw), deeper layers and the Flatten are NHWC)."""
+        for i, (C, H, W, k, s, act, OH, OW, Cout) in enumerate(self.geo):
+            w = state_dict[f"{2 * i}.weight"].detach().to(torch.float32)           # [Cout, Cin, k, k]
+            wm = w.reshape(Cout, -1) if i == 0 else w.permute(0, 2, 3, 1).reshape(Cout, -1)
+            self.bank.view(f"{self.prefix}.{2 * i}.weight").copy_(wm.t())
+            self.bank.view(f"{self.prefix}.{2 * i}.bias").copy_(state_dict[f"{2 * i}.bias"].detach().to(torch.float32))
+        if self.fc:
+            C, OH, OW = self.geo[-1][8], self.geo[-1][6], self.geo[-1][7]
+            j = 2 * len(self.geo) + 1
+            w = state_dict[f"{j}.weight"].detach().to(torch.float32)                # [hidden, C*OH*OW] over torch's (c, h, w)
+            wm = w.reshape(-1, C, OH, OW).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+            self.bank.view(f"{self._fc_name()}.weight").copy_(wm.t())
+            self.bank.view(f"{self._fc_name()}.bias").copy_(state_dict[f"{j}.bias"].detach().to(torch.float32))
+        self.enable_tc()
+
+    def grads_as_torch(self):
+        """The bank's gradients of this trunk in the torch state_dict layouts (tests, export)."""
+        out = {}
+        for i, (C, H, W, k, s, act, OH, OW, Cout) in enumerate(self.geo):
+            g = self.bank.view(f"{self.prefix}.{2 * i}.weight", grad=True).t()      # [Cout, K]
+            out[f"{2 * i}.weight"] = (g.reshape(Cout, C, k, k) if i == 0 else g.reshape(Cout, k, k, C).permute(0, 3, 1, 2)).contiguous()
+            out[f"{2 * i}.bias"] = self.bank.view(f"{self.prefix}.{2 * i}.bias", grad=True).clone()
+        if self.fc:
+            C, OH, OW = self.geo[-1][8], self.geo[-1][6], self.geo[-1][7]
+            j = 2 * len(self.geo) + 1
+            g = self.bank.view(f"{self._fc_name()}.weight", grad=True).t()          # [hidden, OH*OW*C]
+            out[f"{j}.weight"] = g.reshape(-1, OH, OW, C).permute(0, 3, 1, 2).reshape(g.shape[0], -1).contiguous()
+            out[f"{j}.bias"] = self.bank.view(f"{self._fc_name()}.bias", grad=True).clone()
+        return out
+
+    def enable_tc(self):
+        """tensor-core weight shadows of the layers whose reduction is wide enough (refreshed after every optimiser step)"""
+        if not TC_ENABLED:
+            return
+        b = self.bank
+        b.tc_weights = [t for t in b.tc_weights if t not in self.tc.values()]
+        if self.tc:
+            _Scratch.generation += 1
+        self.tc = {}
+        names = [(f"{self.prefix}.{2 * i}.weight", g[0] * g[3] * g[3], g[8]) for i, g in enumerate(self.geo)]
+        if self.fc:
+            names.append((f"{self._fc_name()}.weight", self.flat_dim, self.fc[0]))
+        for i, (name, K, N) in enumerate(names):
+            if K >= TC_MIN_K and K % 4 == 0 and N >= 16:
+                self.tc[i] = TcWeight(b.p(name), K, N, b.device, transposed_only=True)
+        b.tc_weights += list(self.tc.values())
+
+    def forward(self, x, tag=""):
+        """x: [N, C*H*W] (or [N,C,H,W]) contiguous f32 CUDA frames.  Returns (features [N, out_dim], saved) -- `saved`
+        holds the im2col matrices and layer outputs the backward needs."""
+        N = x.shape[0]
+        cur, saved = x.reshape(N, -1), []
+        for i, (C, H, W, k, s, act, OH, OW, Cout) in enumerate(self.geo):
+            M, K = N * OH * OW, C * k * k
+            cols = self.scratch.get(f"{self.prefix}{tag}.cols{i}", M * K)[:M * K].view(M, K)
+            L.call("ppx_im2col", cur.data_ptr(), 1 if i == 0 else 0, N, C, H, W, k, k, s, cols.data_ptr(), L.stream())
+            y = self.scratch.get(f"{self.prefix}{tag}.y{i}", M * Cout)[:M * Cout].view(M, Cout)
+            dense_fwd(cols.data_ptr(), K, self.bank.p(f"{self.prefix}.{2 * i}.weight"), self.bank.p(f"{self.prefix}.{2 * i}.bias"),
+                      M, K, Cout, ACT[act], y.data_ptr(), Cout, self.tc.get(i))
+            saved.append((cols, y))
+            cur = y
+        feat = cur.view(N, self.flat_dim)
+        if self.fc:
+            hid, act = self.fc
+            f = self.scratch.get(f"{self.prefix}{tag}.feat", N * hid)[:N * hid].view(N, hid)
+            dense_fwd(feat.data_ptr(), self.flat_dim, self.bank.p(f"{self._fc_name()}.weight"), self.bank.p(f"{self._fc_name()}.bias"),
+                      N, self.flat_dim, hid, ACT[act], f.data_ptr(), hid, self.tc.get(len(self.geo)))
+            saved.append((feat, f))
+            feat = f
+        return feat, saved
+
+    def backward(self, saved, d_feat, need_dx=False, tag=""):
+        """Gradients of every layer into bank.grad (overwritten).  d_feat: [N, out_dim] gradient w.r.t. the returned
+        features (AFTER their activation).  Returns dX [N, C*H*W] in the input's NCHW layout if need_dx."""
+        N = d_feat.shape[0]
+        sc = self.scratch
+        d = d_feat
+        if self.fc:
+            hid, act = self.fc
+            flat, f = saved[-1]
+            dz = sc.get(f"{self.prefix}{tag}.dz_fc", N * hid)[:N * hid].view(N, hid)
+            L.call("ppx_act_bwd_mul", d.data_ptr(), f.data_ptr(), N * hid, ACT[act], dz.data_ptr(), L.stream())
+            name = self._fc_name()
+            linear_bwd_weight(sc, flat.data_ptr(), self.flat_dim, dz.data_ptr(), hid, N, self.flat_dim, hid,
+                              self.bank.g(f"{name}.weight"), self.bank.g(f"{name}.bias"))
+            last_act = self.geo[-1][5]
+            dflat = sc.get(f"{self.prefix}{tag}.dflat", N * self.flat_dim)[:N * self.flat_dim].view(N, self.flat_dim)
+            # dY_conv_last = (dz W_fc^T) * act'(y_last): the producer's activation derivative fused into the dgrad epilogue
+            linear_bwd_data(dz.data_ptr(), hid, self.bank.p(f"{name}.weight"), N, self.flat_dim, hid, flat.data_ptr(),
+                            self.flat_dim, ACT[last_act], dflat.data_ptr(), self.flat_dim)
+            d = dflat
+        else:
+            C, OH, OW, act = self.geo[-1][8], self.geo[-1][6], self.geo[-1][7], self.geo[-1][5]
+            y = saved[len(self.geo) - 1][1]
+            dz = sc.get(f"{self.prefix}{tag}.dz_last", N * self.flat_dim)[:N * self.flat_dim].view(N, self.flat_dim)
+            L.call("ppx_act_bwd_mul", d.data_ptr(), y.data_ptr(), N * self.flat_dim, ACT[act], dz.data_ptr(), L.stream())
+            d = dz
+        # d: gradient w.r.t. the PRE-activation output of the last conv layer, [N*OH*OW, Cout] rows (NHWC)
+        for i in range(len(self.geo) - 1, -1, -1):
+            C, H, W, k, s, act, OH, OW, Cout = self.geo[i]
+            M, K = N * OH * OW, C * k * k
+            cols, _ = saved[i]
+            dy = d.reshape(M, Cout)
+            linear_bwd_weight(sc, cols.data_ptr(), K, dy.data_ptr(), Cout, M, K, Cout,
+                              self.bank.g(f"{self.prefix}.{2 * i}.weight"), self.bank.g(f"{self.prefix}.{2 * i}.bias"))
+            if i == 0 and not need_dx:
+                return None
+            dcols = sc.get(f"{self.prefix}{tag}.dcols{i}", M * K)[:M * K].view(M, K)
+            linear_bwd_data(dy.data_ptr(), Cout, self.bank.p(f"{self.prefix}.{2 * i}.weight"), M, K, Cout, None, K, ACT["none"],
+                            dcols.data_ptr(), K)
+            dx = sc.get(f"{self.prefix}{tag}.dx{i}", N * C * H * W)[:N * C * H * W]
+            L.call("ppx_col2im", dcols.data_ptr(), 1 if i == 0 else 0, N, C, H, W, k, k, s, dx.data_ptr(), L.stream())
+            if i > 0:                                              # through the previous layer's activation
+                y_prev = saved[i - 1][1]
+                L.call("ppx_act_bwd_mul", dx.data_ptr(), y_prev.data_ptr(), dx.numel(), ACT[self.geo[i - 1][5]], dx.data_ptr(),
+                       L.stream())
+            d = dx
+        return d.view(N, -1)
 
 
 def _to_in_major(w):
