@@ -47,6 +47,23 @@ __global__ void __launch_bounds__(256) im2col_kernel(ConvShape s, const float* _
   }
 }
 
+// four consecutive k per thread (16-byte loads and stores): valid when a patch's innermost run is a multiple of 4 floats and
+// 16-byte aligned in the source -- NHWC with C % 4 == 0, or NCHW with KW % 4 == 0, stride % 4 == 0, W % 4 == 0
+__global__ void __launch_bounds__(256) im2col_vec4_kernel(ConvShape s, const float* __restrict__ x, float* __restrict__ cols) {
+  const int K = s.C * s.KH * s.KW, K4 = K / 4;
+  const int64_t total = (int64_t)s.N * s.OH * s.OW * K4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K4) * 4;
+    const int64_t row = e / K4;
+    const int ow = (int)(row % s.OW), oh = (int)((row / s.OW) % s.OH), n = (int)(row / ((int64_t)s.OW * s.OH));
+    int c, kh, kw;
+    if (s.nchw) { kw = k % s.KW; kh = (k / s.KW) % s.KH; c = k / (s.KW * s.KH); }
+    else { c = k % s.C; kw = (k / s.C) % s.KW; kh = k / (s.C * s.KW); }
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + x_index(s, n, c, oh * s.stride + kh, ow * s.stride + kw)));
+    *reinterpret_cast<float4*>(cols + row * K + k) = v;
+  }
+}
+
 // one thread per element of dx (in x's own layout): dx[n,c,h,w] = sum over the patches (oh, ow) and taps (kh, kw) with
 // oh*stride + kh == h, ow*stride + kw == w of dcols[(n,oh,ow), k(c,kh,kw)], kh then kw ascending
 __global__ void __launch_bounds__(256) col2im_kernel(ConvShape s, const float* __restrict__ dcols, float* __restrict__ dx) {
@@ -107,7 +124,10 @@ extern "C" int ppx_im2col(const float* x, int nchw, int N, int C, int H, int W, 
   int rc = make_shape(&s, nchw, N, C, H, W, KH, KW, stride, "im2col");
   if (rc) return rc;
   const int64_t total = (int64_t)N * s.OH * s.OW * C * KH * KW;
-  im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, x, cols);
+  const bool aligned = (((uintptr_t)x | (uintptr_t)cols) & 15) == 0;
+  const bool vec = aligned && (nchw ? (KW % 4 == 0 && stride % 4 == 0 && W % 4 == 0) : (C % 4 == 0));
+  if (vec) im2col_vec4_kernel<<<grid_for(total / 4), 256, 0, (cudaStream_t)stream>>>(s, x, cols);
+  else im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, x, cols);
   return after_launch("im2col");
 }
 

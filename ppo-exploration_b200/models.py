@@ -200,7 +200,10 @@ def linear_bwd_data(dy_ptr, lddy, w_ptr, M, K, N, h_ptr, ldh, act, dx_ptr, lddx,
 
 
 def linear_bwd_weight(scratch, x_ptr, ldx, dy_ptr, lddy, M, K, N, dw_ptr, db_ptr, batch=1, sx=0, sdy=0, sdw=0, sdb=0):
-    if (TC_ENABLED and batch == 1 and K >= TC_MIN_K and dw_ptr % 16 == 0
+    # the tensor-core kernel tiles dW [K, N]: a gradient with only a handful of 128 x 128 tiles and a very long sample
+    # dimension (conv layers: 256 x 32 over 1.6M rows) fills the GPU better on the SIMT kernel, which splits over the samples
+    tiles = -(-K // 128) * -(-N // (64 if N <= 64 else 128))
+    if (TC_ENABLED and batch == 1 and K >= TC_MIN_K and dw_ptr % 16 == 0 and tiles >= 12
             and L.call("ppx_tc_wgrad_supported", M, K, N, x_ptr, dy_ptr) == 1):
         # wide layer: samples as the reduction dimension of the tcgen05 3xTF32 kernel (tc_gemm.cu)
         ws = scratch.get("tc_wgrad_ws", L.call("ppx_tc_wgrad_workspace", M, K, N))
