@@ -239,14 +239,7 @@ class HostRngStream:
         self.rs = np.random.RandomState()
         self.rs.set_state(np.random.get_state() if state is None else state)
         script = self.script
-        if os.environ.get("PPX_DIAG_REUSE_PERM") == "1":        # diagnosis only: isolates the host shuffle cost
-            seen, sc = False, []
-            for op in script:
-                sc.append(('reuse',) if (op[0] == 'perm' and seen) else op)
-                seen = seen or op[0] == 'perm'
-            script = sc
         self._jbufs = {}                                        # rotating partner buffers (<= ahead + 1 in flight per size)
-        self._first_perm = None
         _live_streams.add(self)
         # stage 2 is only needed when some permutation of the script is applied on the host
         need2 = any(op[0] == 'perm' and not (self.device_apply and 2 <= int(op[1]) <= (1 << 24)) for op in script)
@@ -309,8 +302,6 @@ class HostRngStream:
                     pool[1] += 1
                     mid = self.mids[k % self.nw]
                     k += 1
-                    if self._first_perm is None:
-                        self._first_perm = slot
                     if small:
                         # streaming: hand the buffer to stage 2 first, it runs behind the published progress counter
                         prog[0] = 0
@@ -327,9 +318,6 @@ class HostRngStream:
                         if not self._put(mid, ('perm', j, n, None, slot)):
                             break
                     self.rs.set_state((st[0], key, pos.value, st[3], st[4]))
-                elif op[0] == 'reuse':
-                    slot[1] = self._first_perm                  # resolved by next(): the first permutation's slot
-                    slot[0].set()
                 else:
                     slot[1] = float(self.rs.randn())
                     slot[0].set()
@@ -377,13 +365,7 @@ class HostRngStream:
         while not slot[0].wait(timeout=0.05):
             if self.err is not None:
                 raise self.err
-        v = slot[1]
-        if isinstance(v, list):                                 # 'reuse' (diagnosis): the first permutation again
-            while not v[0].wait(timeout=0.05):
-                if self.err is not None:
-                    raise self.err
-            v = v[1]
-        return v
+        return slot[1]
 
     def final_state(self):
         """RNG state after the whole script (blocks until stage 1 has drawn everything)."""
