@@ -190,3 +190,28 @@ def test_rng_stream_device_apply_mode_delivers_exact_partner_lists():
                 assert g == w
         s.drain()
         assert rng_states_equal(s.final_state(), after)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench line the driver parses (profiles/bench_r02_n1.json is a verbatim `python bench.py` output from the B200
+    box, profiles/bench_r02_ref.json the reference arm's): every key of the measurement contract is present and typed."""
+    import json
+    from conftest import ROOT
+    line = json.loads([l for l in open(os.path.join(ROOT, "profiles", "bench_r02_n1.json")) if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["config"]["workload"].startswith("C2") and "model" not in line["config"]
+    assert line["scaling"] == "weak" and line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f32"
+    assert line["value"] > 0 and line["gpu_launches"] > 0 and abs(line["ms_per_step"] * line["value"] / 1e3 - 524288) < 1
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["value"] < line["value"] and e2e["h2d_bytes_per_step"] > 5e7 and e2e["d2h_bytes_per_step"] > 0
+    rf = line["roofline"]
+    assert rf["bound"] in ("hbm", "tensor") and rf["unit"] in ("GB/s", "TFLOP/s") and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["traffic"] is None or rf["traffic"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    ref = json.loads([l for l in open(os.path.join(ROOT, "profiles", "bench_r02_ref.json")) if l.startswith("{")][-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
