@@ -238,10 +238,15 @@ def cpu_pass_port(name, seed=0, shrink=1):
 
 
 def cpu_pass(name, seed=0, shrink=1):
+    import warnings
     from oracle import ref_runtime as RT
-    if RT.available():
-        return cpu_pass_reference(name, seed, shrink)
-    return cpu_pass_port(name, seed, shrink)
+    with warnings.catch_warnings():
+        # the reference's own numpy reductions overflow f32 on the synthetic C3-scale returns (RuntimeWarning from inside
+        # its code); irrelevant to what is timed
+        warnings.simplefilter("ignore", RuntimeWarning)
+        if RT.available():
+            return cpu_pass_reference(name, seed, shrink)
+        return cpu_pass_port(name, seed, shrink)
 
 
 def cpu_es_step(P_sample=1000, P=10000):
