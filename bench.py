@@ -543,7 +543,9 @@ class PpxPass:
         self.raw_rewards = self.ro.rewards.clone()
 
     def load(self):
-        self.ro.load_rollout(**{k: v for k, v in self.pinned.items() if k in ROLLOUT_FIELDS})
+        # overlap: the fields the bonus does not read go up on a side stream under the bonus kernels (the learner's own
+        # methods wait for them); the ICM / RND bonus legs read ro.actions / int fields directly, so they load in order
+        self.ro.load_rollout(overlap=self.cfg["alg"] == "ppo", **{k: v for k, v in self.pinned.items() if k in ROLLOUT_FIELDS})
 
     def bonus_and_gae(self):
         cfg, m, ro = self.cfg, self.m, self.ro

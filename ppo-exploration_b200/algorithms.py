@@ -348,6 +348,7 @@ class BaseAlgorithm(object):
     def _begin_train(self, ro, randn_per_minibatch=False):
         """Open the RNG stream, size the persistent per-call buffers (loss log, all-epoch permutation staging), zero the
         device step cursor and -- sharded "global" -- replicate the rollout.  Returns the RNG stream."""
+        ro.await_load()                                         # load_rollout(overlap=True): the graphs below cannot wait for it
         total, Bg, n_mb = self._train_geometry(ro)
         steps = self.n_epochs * n_mb
         if self._losses_buf is None or self._losses_buf.shape[0] != steps:

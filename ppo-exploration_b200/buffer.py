@@ -499,6 +499,7 @@ class RolloutStorage(BaseBuffer):
         self._fields = [('observations', 'observations'), ('actions', 'actions'), ('old_values', 'values'),
                         ('old_log_probs', 'action_log_probs'), ('advantages', 'advantages'), ('returns', 'returns')]
         self._mb = {}
+        self._load_stream, self._load_done = None, None     # load_rollout(overlap=True)
 
     # ------------------------------------------------------------------ storage
     def _alloc(self):
@@ -528,6 +529,7 @@ class RolloutStorage(BaseBuffer):
 
     def add(self, obs, action, reward, value, mask, log_prob):
         """buffer.py:165-186: write row `pos`; SimHash bonus first when enabled."""
+        self.await_load()
         p, dev = self.pos, self.device
         obs_d = _dev(obs, torch.float32, dev).reshape(self.n_envs, *self.obs_shape)
         self.observations[p].copy_(obs_d)
@@ -542,14 +544,41 @@ class RolloutStorage(BaseBuffer):
         if self.pos == self.buffer_size:
             self.full = True
 
-    def load_rollout(self, **arrays):
-        """Bulk fill from [T,N,...] host or device arrays (one H2D copy per field) and mark full."""
+    def load_rollout(self, overlap=False, **arrays):
+        """Bulk fill from [T,N,...] host or device arrays (one H2D copy per field) and mark full.
+        overlap=True: only what the count bonus reads (observations, rewards) is copied on the caller's stream; the other
+        fields go up on a side stream UNDER the bonus kernels, and the methods of this class that read them
+        (compute_returns_and_advantages, gather_into / get, flat, add) wait for that copy first.  Code that reads the
+        arrays directly (`ro.values`, ...) on its own stream must call `await_load()` itself, hence opt-in."""
         dt = {'actions': torch.float64, 'masks': torch.uint8}
-        for name, a in arrays.items():
+
+        def put(name, a):
             dst = getattr(self, name)
             dst.copy_(_dev(a, dt.get(name, torch.float32), self.device).reshape(dst.shape))
+        self.await_load()
+        first = ('observations', 'rewards')
+        late = [k for k in arrays if k not in first] if overlap else []
+        for name, a in arrays.items():
+            if name not in late:
+                put(name, a)
+        if late:
+            if self._load_stream is None:
+                self._load_stream = torch.cuda.Stream(device=self.device)
+            cur = torch.cuda.current_stream()
+            self._load_stream.wait_stream(cur)                  # earlier readers of these arrays were queued on the caller's stream
+            with torch.cuda.stream(self._load_stream):
+                for name in late:
+                    put(name, arrays[name])
+                self._load_done = torch.cuda.Event()
+                self._load_done.record(self._load_stream)
         self.pos, self.full = self.buffer_size, True
         self.generator_ready = False
+
+    def await_load(self):
+        """Make the caller's stream wait for the side-stream part of the last load_rollout(overlap=True)."""
+        if self._load_done is not None:
+            torch.cuda.current_stream().wait_event(self._load_done)
+            self._load_done = None
 
     # ------------------------------------------------------------------ SimHash
     def _A(self):
@@ -624,6 +653,7 @@ class RolloutStorage(BaseBuffer):
     # ------------------------------------------------------------------ GAE
     def compute_returns_and_advantages(self, last_value, dones):
         """buffer.py:203-230."""
+        self.await_load()
         lv = _dev(last_value, torch.float32, self.device).reshape(self.n_envs)
         d = _dev(dones, torch.uint8, self.device).reshape(self.n_envs)
         L.call("ppx_gae", self.rewards.data_ptr(), self.values.data_ptr(), self.masks.data_ptr(), lv.data_ptr(),
@@ -633,6 +663,7 @@ class RolloutStorage(BaseBuffer):
     # ------------------------------------------------------------------ shuffle-gather
     def flat(self, name):
         """env-major flat view of a stored array, shaped like the reference's flattened attribute."""
+        self.await_load()
         return self.swap_and_flatten(getattr(self, name))
 
     def _minibatch_buffers(self, B):
@@ -650,6 +681,7 @@ class RolloutStorage(BaseBuffer):
         """One fused launch: every RolloutSample field for the flat indices `idx_dev` (int64, CUDA).  stats: optional list
         of (field, device pointer to 2 doubles) -- {mean, unbiased std} of that gathered f32 [B] field (the advantage
         normalisation statistics) computed by the same launch."""
+        self.await_load()
         B = idx_dev.numel() if B is None else int(B)
         n = len(self._fields)
         srcs = (C.c_void_p * n)()
@@ -693,6 +725,7 @@ class RolloutStorage(BaseBuffer):
     def get(self, batch_size=None):
         """buffer.py:233-254: generator of RolloutSample minibatches (CUDA tensors; each sample owns
         fresh storage, like the reference's torch.tensor copies)."""
+        self.await_load()
         assert self.full, ''
         total = self.buffer_size * self.n_envs
         idx = self.permutation()
@@ -738,6 +771,7 @@ class IntrinsicStorage(RolloutStorage):
 
     def add(self, obs, action, reward, int_reward, value, int_value, mask, log_prob):
         """buffer.py:305-318."""
+        self.await_load()
         p, dev = self.pos, self.device
         self.int_rewards[p].copy_(_dev(int_reward, torch.float32, dev).reshape(self.n_envs))
         self.int_values[p].copy_(_dev(int_value, torch.float32, dev).reshape(self.n_envs))
@@ -746,6 +780,7 @@ class IntrinsicStorage(RolloutStorage):
     def compute_returns_and_advantages(self, last_value, last_int_value, dones):
         """buffer.py:321-362.  Returns mean(int_rewards) as a 0-d CUDA tensor (the value the reference
         logs at :335) so the caller can record it without forcing a sync here."""
+        self.await_load()
         lv = _dev(last_value, torch.float32, self.device).reshape(self.n_envs)
         liv = _dev(last_int_value, torch.float32, self.device).reshape(self.n_envs)
         d = _dev(dones, torch.uint8, self.device).reshape(self.n_envs)

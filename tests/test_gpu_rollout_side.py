@@ -102,3 +102,27 @@ def test_collect_samples_with_vecnormalize_and_csv_logger(tmp_path):
     assert len(files) == 1
     rows = list(csv.DictReader(open(files[0])))
     assert len(rows) == 2 and "total timesteps" in rows[0] and rows[1]["total timesteps"] == "256" and "value_loss" in rows[1]
+
+
+def test_overlapped_rollout_load_is_the_same_rollout():
+    """load_rollout(overlap=True) copies the fields the bonus does not read on a side stream; the learner methods wait for
+    them: bonus + GAE + train() give bit-identical losses and weights to the in-order load."""
+    import bench
+    import ppo_exploration_b200 as ppx
+    cfg = dict(bench.CONFIGS["C2"], N=64, T=64, batch=1024)
+    host = bench.synth_rollout(cfg, 7, n_envs=64)
+    pinned = {k: torch.as_tensor(v).pin_memory() for k, v in host.items() if k in bench.ROLLOUT_FIELDS}
+    res = []
+    for overlap in (False, True):
+        np.random.seed(1); torch.manual_seed(1)
+        env = ppx.SyntheticVecEnv(64, cfg["D"], ppx.Box((2,)), seed=0)
+        m = ppx.PPO(env=env, nstep=64, batch_size=1024, hidden_size=64, sim_hash=True, hash_bits=64, device="cuda", **cfg["hp"])
+        lv = torch.as_tensor(host["last_value"]).cuda()
+        dn = torch.as_tensor(host["masks"][-1].copy()).cuda()
+        for _ in range(3):                                  # eager, capture, replay
+            m.rollout.load_rollout(overlap=overlap, **pinned)
+            m.rollout.sim_hash_sharded(m.rollout.observations, m.rollout.rewards)
+            m.rollout.compute_returns_and_advantages(lv, dn)
+            m.train()
+        res.append((m.last_losses.copy(), m.policy.bank.flat.clone(), m.rollout.returns.clone()))
+    assert np.array_equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
