@@ -215,3 +215,39 @@ def test_committed_bench_lines_carry_the_contract_keys():
     ref = json.loads([l for l in open(os.path.join(ROOT, "profiles", "bench_r02_ref.json")) if l.startswith("{")][-1])
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
+
+
+def test_partner_pool_and_worker_pool_reuse():
+    """Host plumbing of the shuffle stream: pinned partner buffers are handed out again only once released (or their
+    consumer is gone), and worker threads outlive the streams they serve (no thread start / retire per train() call)."""
+    import gc
+    import threading
+    from ppo_exploration_b200 import buffer as BUF
+    pool = BUF._PartnerPool()
+    a = pool.take(1000)
+    b = pool.take(1000)
+    assert a.j.data_ptr() != b.j.data_ptr() and len(pool.slots[1000]) == 2           # both in use: two buffers
+    a_ptr = a.j.data_ptr()
+    a.release()                                                                     # consumer done with it
+    c = pool.take(1000)
+    assert c.j.data_ptr() == a_ptr and len(pool.slots[1000]) == 2                    # re-used, pool did not grow
+    b_ptr = b.j.data_ptr()
+    del b
+    gc.collect()                                                                    # a consumer that never released but is gone
+    d = pool.take(1000)
+    assert d.j.data_ptr() == b_ptr and len(pool.slots[1000]) == 2
+    assert pool.take(8).j.numel() == 8                                              # sizes do not mix
+    # worker threads: two streams in sequence run on the same pooled threads
+    np.random.seed(2)
+    before = threading.active_count()
+    s1 = BUF.HostRngStream([('perm', 100)] * 3)
+    p1 = [s1.next().numpy().copy() for _ in range(3)]
+    s1.drain()
+    mid = threading.active_count()
+    s2 = BUF.HostRngStream([('perm', 100)] * 3)
+    p2 = [s2.next().numpy().copy() for _ in range(3)]
+    s2.drain()
+    assert threading.active_count() == mid >= before                                # no new threads for the second stream
+    assert all(np.array_equal(x, y) for x, y in zip(p1, p2))                         # both started from the same global state
+    np.random.seed(2)
+    assert np.array_equal(p1[0], np.random.permutation(100))
